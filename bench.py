@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s of the batched FPV-drone dynamics step on B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[2], the config the metric is quoted on): 1,048,576 drones per GPU,
+8 physics substeps of 1 ms per control step, body drag + motor-curve shared-memory LUT + ground contact
+(initial heights 0.05..3 m so a fraction bounce and crash), auto-reset on crash, fresh random stick
+actions every control step.  A "step" is one control step of every env.  Prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ENVS_PER_GPU = 1 << 20
+SUBSTEPS = 8
+DT = 1e-3
+LUT_N = 2049
+# algorithmic work per env (SURVEY.md section 8d adapted to the matrix-state layout)
+BYTES_PER_ENV_STEP = 80 + 80 + 16 + 1          # state read + state write + action + done flag
+FLOP_PER_ENV_SUBSTEP = 252                     # 245 arithmetic + 6 sin/cos + 1 sqrt
+FP32_LANES_PER_SM = 128
+
+
+def peaks():
+    p = {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0, "source": "fallback (B200_PROFILING.md)"}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            m = json.load(f)
+        p.update(hbm_gbs=float(m["hbm_gbs"]), sm_max_mhz=float(m.get("sm_max_mhz", 1965.0)),
+                 source="measured (MEASURED_PEAKS.json)")
+    except Exception:
+        pass
+    return p
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.2] or [r for _, r in self.rows[-3:]]
+        sm = sorted(float(r[0]) for r in rows if r and r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in rows for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        pw = [float(r[2]) for r in rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(rows), "reasons": reasons}
+
+
+def synthetic_init(n, device, seed):
+    import torch
+    g = torch.Generator(device=device).manual_seed(seed)
+    pos = torch.randn(n, 3, device=device, generator=g) * torch.tensor([5.0, 5.0, 0.0], device=device)
+    pos[:, 2] = 0.05 + torch.rand(n, device=device, generator=g) * 2.95       # ground-contact config
+    vel = torch.randn(n, 3, device=device, generator=g)
+    rpy = (torch.rand(n, 3, device=device, generator=g) * 2 - 1) * 30
+    return pos, vel, rpy, g
+
+
+# --------------------------------------------------------------------------------------------
+# CPU arm: the oracle's C restatement of the reference algorithm on the host cores
+# --------------------------------------------------------------------------------------------
+def cpu_arm(steps, warmup, n_sample=65536, target_seconds=None):
+    """env-steps/s of oracle/fpv_oracle.c (float64, all host cores) on a bounded sample of the workload."""
+    import numpy as np
+    import yaml
+    from oracle import c_oracle, fpv_oracle as fo
+    c_oracle.build()
+    cfg = os.path.join(ROOT, "fpyv_b200", "config")
+    with open(os.path.join(cfg, "params.yaml")) as f:
+        params = yaml.safe_load(f)
+    c = fo.derive_consts(params, os.path.join(cfg, "t_motos_f80_motor_test.csv"), dt=DT)
+    k = c_oracle.make_consts(c)
+    cores = c_oracle.max_threads()
+    rng = np.random.default_rng(1234)
+    n = n_sample
+    pos = np.stack([rng.normal(0, 5, n), rng.normal(0, 5, n), rng.uniform(0.05, 3.0, n)], 1)
+    vel = rng.normal(0, 1, (n, 3))
+    rpy = rng.uniform(-30, 30, (n, 3))
+    s = fo.drone_reset(c, pos, vel, rpy)
+    P, V, R = s.pos.copy(), s.vel.copy(), np.ascontiguousarray(s.R)
+    pr, pt = np.zeros((n, 3)), np.zeros(n)
+    acts = [np.ascontiguousarray(rng.uniform(-1, 1, (n, 4))) for _ in range(4)]
+    for i in range(warmup):
+        c_oracle.drone_step(k, P, V, R, pr, pt, acts[i % 4], substeps=SUBSTEPS, threads=cores)
+    t0 = time.perf_counter()
+    done_steps = 0
+    for i in range(steps):
+        c_oracle.drone_step(k, P, V, R, pr, pt, acts[i % 4], substeps=SUBSTEPS, threads=cores)
+        done_steps += 1
+        if target_seconds and time.perf_counter() - t0 > target_seconds:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": n * done_steps / dt, "unit": "env-steps/s", "cores": cores, "kind": "port",
+            "sample": f"{n} envs x {SUBSTEPS} substeps x {done_steps} control steps, float64 C restatement of "
+                      f"Drone.step (oracle/fpv_oracle.c), {cores} threads, {dt:.1f} s",
+            "ms_per_step": 1e3 * dt / done_steps, "steps": done_steps}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_arm(args.steps, args.warmup)
+    line = {"impl": "reference", "metric": "env_steps_per_sec", "value": r["value"], "unit": "env-steps/s",
+            "n_gpus": args.gpus, "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.gpus, sample=r["sample"]),
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_config(n_gpus, **extra):
+    c = {"workload": "BASELINE.json configs[2]: 1,048,576 drones per GPU, 8 substeps x 1 ms per control step, "
+                     "drag + motor-curve LUT + ground contact, auto-reset, random sticks",
+         "envs_per_gpu": ENVS_PER_GPU, "total_envs": ENVS_PER_GPU * n_gpus, "substeps_per_step": SUBSTEPS,
+         "dt_substep_s": DT, "thrust_lut_entries": LUT_N, "parallelism": f"env-sharded x{n_gpus}, no data-path collective",
+         "l2": "flushed (256 MiB write) between timed steps; per-step CUDA-event intervals summed"}
+    c.update(extra)
+    return c
+
+
+# --------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from fpyv_b200 import BatchedDrone
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n, K, W = args.envs, args.steps, args.warmup
+
+    def make(substeps, lut=LUT_N):
+        d = BatchedDrone(None, num_envs=n, device=dev, substeps=substeps, dt=DT, auto_reset=True, thrust_lut=lut)
+        pos, vel, rpy, g = synthetic_init(n, dev, 1234 + rank)
+        d.reset(pos, vel, rpy)
+        return d, g
+
+    drone, gen = make(SUBSTEPS)
+    ring = [torch.rand(n, 4, device=dev, generator=gen) * 2 - 1 for _ in range(4)]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def timed_loop(d, steps, warm):
+        """returns summed per-step device ms (L2 flushed between steps)."""
+        for i in range(warm):
+            d.step(ring[i % 4], return_obs=False)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        for i in range(steps):
+            flush.zero_()
+            ev[i][0].record()
+            d.step(ring[i % 4], return_obs=False)
+            ev[i][1].record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        return sum(a.elapsed_time(b) for a, b in ev)
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    t0 = time.time()
+    ms = timed_loop(drone, K, W)
+    t1 = time.time()
+    clocks = sampler.stop(t0, t1) if sampler else None
+
+    # ---- end to end through the public API with HOST buffers (pinned): H2D actions, step, D2H done flags
+    host_actions = [torch.empty(n, 4, dtype=torch.float32, pin_memory=True).uniform_(-1, 1) for _ in range(2)]
+    host_done = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    for i in range(max(3, W)):
+        drone.step_host(host_actions[i % 2], host_done)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    crashed = 0
+    for i in range(K):
+        drone.step_host(host_actions[i % 2], host_done)
+        torch.cuda.current_stream().synchronize()      # the caller consumes the done flags every step
+        crashed += int(host_done[:64].sum())
+    e1.record()
+    torch.cuda.synchronize()
+    ms_e2e = e0.elapsed_time(e1)
+
+    # ---- HBM-bound variant of the same kernel (K = 1) for the memory-roofline placement
+    d1, _ = make(1)
+    ms_k1 = timed_loop(d1, K, W)
+
+    t = torch.tensor([ms, ms_e2e, ms_k1], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e, ms_k1 = t.tolist()
+    stats = drone.episode_stats(all_reduce=world > 1)      # the engine's only collective (NCCL), outside the timed loop
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+    total_envs = n * world
+    value = total_envs * K / (ms * 1e-3)
+    per_gpu_launch_s = ms * 1e-3 / K
+    fp32_peak = sm_count * FP32_LANES_PER_SM * 2 * pk["sm_max_mhz"] * 1e6 / 1e12
+    fp32_ach = FLOP_PER_ENV_SUBSTEP * SUBSTEPS * n / per_gpu_launch_s / 1e12
+    hbm_ach = BYTES_PER_ENV_STEP * n / per_gpu_launch_s / 1e9
+    hbm_k1 = BYTES_PER_ENV_STEP * n / (ms_k1 * 1e-3 / K) / 1e9
+    roof = {"bound": "fp32", "achieved": fp32_ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": fp32_ach / fp32_peak,
+            "traffic": None, "kernel": "fpv::drone_step_kernel<F2,SMALL,!GENERAL> (K=8)",
+            "peak_source": f"{sm_count} SMs x {FP32_LANES_PER_SM} FP32 lanes x 2 x {pk['sm_max_mhz']:.0f} MHz (clocks.max.sm); "
+                           "tensor cores unused by design (no dense contraction on this path)",
+            "algorithmic": f"{FLOP_PER_ENV_SUBSTEP} flop/env/substep x {SUBSTEPS} substeps x {n} envs per launch",
+            "hbm": {"achieved": hbm_ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": hbm_ach / pk["hbm_gbs"],
+                    "algorithmic": f"{BYTES_PER_ENV_STEP} B/env/control-step x {n} envs per launch", "peak_source": pk["source"]},
+            "hbm_bound_variant_k1": {"bound": "hbm", "achieved": hbm_k1, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                     "frac": hbm_k1 / pk["hbm_gbs"], "ms_per_step": ms_k1 / K,
+                                     "env_steps_per_sec": total_envs * K / (ms_k1 * 1e-3)}}
+    cpu = cpu_arm(steps=1000, warmup=1, target_seconds=12.0)
+    line = {"metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(world),
+            "env_substeps_per_sec": value * SUBSTEPS,
+            "e2e": {"value": total_envs * K / (ms_e2e * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": 16 * n,
+                    "d2h_bytes_per_step": n, "ms_per_step": ms_e2e / K,
+                    "api": "BatchedDrone.step_host(pinned actions) -> pinned done flags; host waits every step"},
+            "gpu_launches": K, "roofline": roof,
+            "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "clocks": clocks, "episode_stats": stats}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU (default: the BASELINE config)")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "native":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

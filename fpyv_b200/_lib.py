@@ -1,0 +1,115 @@
+"""ctypes binding of libfpyv_b200.so (include/fpv_api.h).  There is NO fallback: if the CUDA library is
+missing, stale against the header, or cannot launch on the device, every entry point raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libfpyv_b200.so")
+ABI_VERSION = 3
+
+# flags (fpv_api.h)
+F_GROUND, F_AUTO_RESET, F_FREEZE_DONE, F_THRUST_LUT, F_FAST_MATH, F_SCALAR = 1, 2, 4, 8, 16, 32
+OBJ_SPHERE, OBJ_CYLINDER = 1, 2
+MAX_OBJECTS = 16
+DRONE_PLANES, RACER_PLANES = 5, 7
+EXPORTS = ("fpv_abi_version", "fpv_last_error", "fpv_sizeof", "fpv_device_info", "fpv_drone_reset",
+           "fpv_drone_step", "fpv_drone_observe", "fpv_sticks_to_actions", "fpv_racer_reset", "fpv_racer_step")
+
+
+class FpvError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libfpyv_b200 error {code}: {msg}")
+        self.code = code
+
+
+class DroneParams(C.Structure):
+    _fields_ = [("dt", C.c_float), ("substeps", C.c_int32), ("gravity", C.c_float), ("mass", C.c_float),
+                ("max_rates", C.c_float), ("rates_transition_rate", C.c_float),
+                ("thrust_transition_rate", C.c_float), ("k_drag", C.c_float * 3),
+                ("motor_xy", (C.c_float * 2) * 4), ("motor_radius", C.c_float), ("spring_k", C.c_float),
+                ("spring_c", C.c_float), ("thrust_poly", C.c_float * 4), ("wind", C.c_float * 3),
+                ("flags", C.c_uint32), ("n_objects", C.c_int32)]
+
+
+class Object(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("x", C.c_float), ("y", C.c_float), ("z", C.c_float), ("a", C.c_float),
+                ("b", C.c_float)]
+
+
+class Stats(C.Structure):
+    _fields_ = [(k, C.c_double) for k in ("env_steps", "crashes", "episodes", "episode_len_sum", "reward_sum",
+                                          "reward_sq_sum", "nonfinite", "reserved")]
+
+
+class DroneIO(C.Structure):
+    _fields_ = [("state", C.c_void_p), ("n", C.c_int64), ("plane_stride", C.c_int64), ("actions", C.c_void_p),
+                ("wind_env", C.c_void_p), ("lut", C.c_void_p), ("lut_n", C.c_int32), ("done", C.c_void_p),
+                ("acc_out", C.c_void_p), ("reset_state", C.c_void_p), ("override_R", C.c_void_p),
+                ("objects", C.POINTER(Object)), ("stats", C.c_void_p)]
+
+
+class StickCalib(C.Structure):
+    _fields_ = [("min_vals", C.c_float * 6), ("max_vals", C.c_float * 6), ("sign_reverse", C.c_float * 6),
+                ("stick_idx", C.c_int32 * 4), ("stick_center", C.c_float * 4)]
+
+
+class RacerParams(C.Structure):
+    _fields_ = [("dt", C.c_float), ("substeps", C.c_int32), ("mass", C.c_float), ("inertia", C.c_float * 3),
+                ("gains", (C.c_float * 3) * 3), ("vel_decay", C.c_float), ("flags", C.c_uint32)]
+
+
+_STRUCTS = (DroneParams, DroneIO, Object, Stats, StickCalib, RacerParams)
+_lib = None
+
+
+def load():
+    """dlopen the library once, declare prototypes, verify ABI version and struct sizes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build it with `python -m fpyv_b200.build` "
+                          "(fpyv_b200 has no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    for name in EXPORTS:
+        if not hasattr(lib, name):
+            raise ImportError(f"{LIB_PATH} does not export {name}; rebuild it")
+    lib.fpv_abi_version.restype = C.c_int
+    lib.fpv_last_error.restype = C.c_char_p
+    lib.fpv_sizeof.argtypes = [C.c_int]
+    lib.fpv_device_info.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.fpv_drone_reset.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p]
+    lib.fpv_drone_step.argtypes = [C.POINTER(DroneParams), C.POINTER(DroneIO), C.c_void_p]
+    lib.fpv_drone_observe.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p]
+    lib.fpv_sticks_to_actions.argtypes = [C.POINTER(StickCalib), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                          C.c_void_p]
+    lib.fpv_racer_reset.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
+    lib.fpv_racer_step.argtypes = [C.POINTER(RacerParams), C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
+                                   C.c_void_p, C.c_void_p]
+    v = lib.fpv_abi_version()
+    if v != ABI_VERSION:
+        raise ImportError(f"{LIB_PATH} has ABI version {v}, this package needs {ABI_VERSION}; rebuild it")
+    for i, st in enumerate(_STRUCTS):
+        if lib.fpv_sizeof(i) != C.sizeof(st):
+            raise ImportError(f"struct {st.__name__}: library sizeof {lib.fpv_sizeof(i)} != binding {C.sizeof(st)}")
+    _lib = lib
+    return lib
+
+
+def check(rc: int):
+    if rc != 0:
+        raise FpvError(rc, load().fpv_last_error().decode("utf-8", "replace"))
+
+
+def ptr(t):
+    """device pointer of a torch tensor (or None)."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def current_stream(device):
+    import torch
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)

@@ -1,0 +1,53 @@
+"""Builds libfpyv_b200.so (hand-written sm_100a CUDA + the C ABI) in-tree with nvcc.
+
+    python -m fpyv_b200.build [--force]
+
+The library is git-ignored but travels to the GPU box with the repo snapshot."""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libfpyv_b200.so")
+SOURCES = ["fpv_api.cu"]
+HEADERS = ["drone_kernels.cuh", "misc_kernels.cuh", "vec.cuh", os.path.join("..", "..", "include", "fpv_api.h")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+def _nvcc():
+    for c in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if c and os.path.isfile(c):
+            return c
+    raise RuntimeError("nvcc not found (set NVCC=/path/to/nvcc)")
+
+
+def needs_build() -> bool:
+    if not os.path.isfile(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > t for d in deps if os.path.isfile(d))
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not needs_build():
+        return LIB
+    cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB, *[os.path.join(CSRC, s) for s in SOURCES]]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+        print(" ".join(cmd))
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    if verbose:
+        print(r.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,266 @@
+// C ABI of libfpyv_b200.so (see include/fpv_api.h).  Validation + double-precision derivation of the
+// launch constants on the host, then one kernel launch on the caller's stream.  No global state.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/fpv_api.h"
+#include "drone_kernels.cuh"
+#include "misc_kernels.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) return FPV_OK;
+  if (e == cudaErrorNoKernelImageForDevice || e == cudaErrorInvalidDeviceFunction)
+    return fail(FPV_ENODEV, "%s: no sm_100a kernel image for this device (%s)", what, cudaGetErrorString(e));
+  return fail(FPV_ECUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+constexpr int kThreads = 128;
+
+using fpv::DroneIO;
+using fpv::DroneK;
+using fpv::F2;
+
+template <class V, bool SMALL, bool GENERAL, bool FAST>
+void launch_drone(const DroneK& k, const DroneIO& io, cudaStream_t st) {
+  constexpr int L = fpv::Lane<V>::N;
+  const long long per_block = (long long)kThreads * L;
+  const unsigned grid = (unsigned)((io.n + per_block - 1) / per_block);
+  const size_t smem = (k.flags & FPV_F_THRUST_LUT) ? sizeof(float) * (size_t)k.lut_n : 0;
+  auto kern = fpv::drone_step_kernel<V, SMALL, GENERAL, FAST, kThreads>;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  kern<<<grid, kThreads, smem, st>>>(k, io);
+}
+
+template <class V, bool SMALL, bool GENERAL>
+void launch_drone_f(const DroneK& k, const DroneIO& io, cudaStream_t st) {
+  if (k.flags & FPV_F_FAST_MATH) launch_drone<V, SMALL, GENERAL, true>(k, io, st);
+  else launch_drone<V, SMALL, GENERAL, false>(k, io, st);
+}
+template <class V, bool SMALL>
+void launch_drone_g(const DroneK& k, const DroneIO& io, bool general, cudaStream_t st) {
+  if (general) launch_drone_f<V, SMALL, true>(k, io, st);
+  else launch_drone_f<V, SMALL, false>(k, io, st);
+}
+
+}  // namespace
+
+extern "C" {
+
+int fpv_abi_version(void) { return FPV_ABI_VERSION; }
+
+const char* fpv_last_error(void) { return g_err; }
+
+int fpv_sizeof(int which) {
+  switch (which) {
+    case 0: return (int)sizeof(fpv_drone_params_t);
+    case 1: return (int)sizeof(fpv_drone_io_t);
+    case 2: return (int)sizeof(fpv_object_t);
+    case 3: return (int)sizeof(fpv_stats_t);
+    case 4: return (int)sizeof(fpv_stick_calib_t);
+    case 5: return (int)sizeof(fpv_racer_params_t);
+    default: return -1;
+  }
+}
+
+int fpv_device_info(int device, int* sm_count, int* cc_major, int* cc_minor) {
+  cudaDeviceProp p;
+  cudaError_t e = cudaGetDeviceProperties(&p, device);
+  if (e != cudaSuccess) return fail(FPV_ENODEV, "cudaGetDeviceProperties(%d): %s", device, cudaGetErrorString(e));
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (cc_major) *cc_major = p.major;
+  if (cc_minor) *cc_minor = p.minor;
+  return FPV_OK;
+}
+
+int fpv_drone_reset(void* state, int64_t n, int64_t plane_stride, const float* pos, const float* vel,
+                    const float* rpy_deg, const uint8_t* mask, void* stream) {
+  if (!state || !pos || !vel || !rpy_deg) return fail(FPV_EINVAL, "fpv_drone_reset: null pointer");
+  if (n < 0 || plane_stride < n) return fail(FPV_EINVAL, "fpv_drone_reset: bad n=%lld stride=%lld", (long long)n, (long long)plane_stride);
+  if (!aligned16(state)) return fail(FPV_EINVAL, "fpv_drone_reset: state must be 16-byte aligned");
+  if (n == 0) return FPV_OK;
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  fpv::drone_reset_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((float4*)state, n, plane_stride, pos, vel, rpy_deg, mask);
+  return check_launch("fpv_drone_reset");
+}
+
+int fpv_drone_step(const fpv_drone_params_t* p, const fpv_drone_io_t* io, void* stream) {
+  if (!p || !io) return fail(FPV_EINVAL, "fpv_drone_step: null params/io");
+  if (io->n < 0 || io->plane_stride < io->n)
+    return fail(FPV_EINVAL, "fpv_drone_step: bad n=%lld stride=%lld", (long long)io->n, (long long)io->plane_stride);
+  if (io->n == 0) return FPV_OK;
+  if (!io->state || !io->actions) return fail(FPV_EINVAL, "fpv_drone_step: state/actions must not be null");
+  if (!aligned16(io->state) || !aligned16(io->actions) || !aligned16(io->wind_env) || !aligned16(io->acc_out) ||
+      !aligned16(io->reset_state) || !aligned16(io->override_R))
+    return fail(FPV_EINVAL, "fpv_drone_step: float4 planes must be 16-byte aligned");
+  if (p->substeps < 1) return fail(FPV_EINVAL, "fpv_drone_step: substeps must be >= 1 (got %d)", p->substeps);
+  if (!(p->dt > 0.f) || !(p->mass > 0.f)) return fail(FPV_EINVAL, "fpv_drone_step: dt and mass must be positive");
+  if (p->n_objects < 0 || p->n_objects > FPV_MAX_OBJECTS)
+    return fail(FPV_EINVAL, "fpv_drone_step: n_objects=%d out of range [0,%d]", p->n_objects, FPV_MAX_OBJECTS);
+  if (p->n_objects > 0 && !io->objects) return fail(FPV_EINVAL, "fpv_drone_step: n_objects > 0 but objects is null");
+  if (io->override_R && p->substeps != 1)
+    return fail(FPV_EINVAL, "fpv_drone_step: the rotation/thrust override is a per-step input; it needs substeps == 1");
+  if ((p->flags & FPV_F_AUTO_RESET) && !io->reset_state)
+    return fail(FPV_EINVAL, "fpv_drone_step: FPV_F_AUTO_RESET needs io.reset_state");
+  if ((p->flags & FPV_F_AUTO_RESET) && (p->flags & FPV_F_FREEZE_DONE))
+    return fail(FPV_EINVAL, "fpv_drone_step: AUTO_RESET and FREEZE_DONE are mutually exclusive");
+  if (p->flags & FPV_F_THRUST_LUT) {
+    if (!io->lut || io->lut_n < 2) return fail(FPV_EINVAL, "fpv_drone_step: FPV_F_THRUST_LUT needs io.lut with lut_n >= 2");
+    if ((size_t)io->lut_n * sizeof(float) > 200 * 1024) return fail(FPV_EINVAL, "fpv_drone_step: lut_n=%d does not fit in shared memory", io->lut_n);
+  }
+
+  DroneK k;
+  std::memset(&k, 0, sizeof(k));
+  const double rtr = p->rates_transition_rate, ttr = p->thrust_transition_rate;
+  k.dt = p->dt;
+  k.substeps = p->substeps;
+  k.one_minus_rtr = (float)(1.0 - rtr);
+  k.max_rates = p->max_rates;
+  k.rtr = p->rates_transition_rate;
+  k.rtr_max_rates = (float)(rtr * p->max_rates);
+  k.ttr = p->thrust_transition_rate;
+  k.one_minus_ttr = (float)(1.0 - ttr);
+  for (int i = 0; i < 3; ++i) k.k_drag[i] = p->k_drag[i];
+  for (int m = 0; m < 4; ++m) { k.motor_xy[m][0] = p->motor_xy[m][0]; k.motor_xy[m][1] = p->motor_xy[m][1]; }
+  k.motor_radius = p->motor_radius;
+  k.spring_k = p->spring_k;
+  k.spring_c = p->spring_c;
+  for (int i = 0; i < 4; ++i) k.poly[i] = p->thrust_poly[i];
+  for (int i = 0; i < 3; ++i) k.wind[i] = p->wind[i];
+  k.grav_force_z = (float)(-(double)p->gravity * (double)p->mass);
+  k.inv_mass = (float)(1.0 / (double)p->mass);
+  k.mass = p->mass;
+  k.ang_scale = (float)(0.017453292519943295 * (double)p->dt);
+  k.lut_n = (p->flags & FPV_F_THRUST_LUT) ? io->lut_n : 0;
+  k.lut_scale = (float)((io->lut_n - 1) * 0.5);
+  k.flags = p->flags;
+  k.n_objects = p->n_objects;
+  for (int i = 0; i < p->n_objects; ++i) {
+    k.objects[i] = io->objects[i];
+    if (k.objects[i].kind != FPV_OBJ_SPHERE && k.objects[i].kind != FPV_OBJ_CYLINDER)
+      return fail(FPV_EINVAL, "fpv_drone_step: object %d has unknown kind %d", i, k.objects[i].kind);
+  }
+
+  DroneIO d;
+  d.state = (float4*)io->state;
+  d.n = io->n;
+  d.stride = io->plane_stride;
+  d.actions = (const float4*)io->actions;
+  d.wind_env = (const float4*)io->wind_env;
+  d.lut = io->lut;
+  d.done = io->done;
+  d.acc_out = (float4*)io->acc_out;
+  d.reset_state = (const float4*)io->reset_state;
+  d.override_R = (const float4*)io->override_R;
+  d.stats = io->stats;
+
+  // |rates| <= max_rates is an invariant of action2force (a convex mix of clipped commands), so the
+  // per-substep Euler angles are bounded by max_rates*dt in radians: below 0.5 rad the sin/cos
+  // polynomials need no range reduction.
+  const bool small = std::fabs((double)p->max_rates) * k.ang_scale <= 0.5;
+  const bool general = p->n_objects > 0 || io->override_R != nullptr;
+  const bool scalar = (p->flags & FPV_F_SCALAR) != 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (scalar) {
+    if (small) launch_drone_g<float, true>(k, d, general, st);
+    else launch_drone_g<float, false>(k, d, general, st);
+  } else {
+    if (small) launch_drone_g<F2, true>(k, d, general, st);
+    else launch_drone_g<F2, false>(k, d, general, st);
+  }
+  return check_launch("fpv_drone_step");
+}
+
+int fpv_drone_observe(const void* state, int64_t n, int64_t plane_stride, const void* acc, float* Rt, float* gyro,
+                      float* accel, void* stream) {
+  if (!state) return fail(FPV_EINVAL, "fpv_drone_observe: null state");
+  if (n < 0 || plane_stride < n) return fail(FPV_EINVAL, "fpv_drone_observe: bad n/stride");
+  if (accel && !acc) return fail(FPV_EINVAL, "fpv_drone_observe: accel output needs the acc plane");
+  if (!aligned16(state) || !aligned16(acc)) return fail(FPV_EINVAL, "fpv_drone_observe: planes must be 16-byte aligned");
+  if (n == 0) return FPV_OK;
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  fpv::drone_observe_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)state, n, plane_stride,
+                                                                     (const float4*)acc, Rt, gyro, accel);
+  return check_launch("fpv_drone_observe");
+}
+
+int fpv_sticks_to_actions(const fpv_stick_calib_t* c, const int32_t* raw, int64_t n, void* actions, float* calibrated,
+                          void* stream) {
+  if (!c || !raw || !actions) return fail(FPV_EINVAL, "fpv_sticks_to_actions: null pointer");
+  if (n < 0) return fail(FPV_EINVAL, "fpv_sticks_to_actions: bad n");
+  if (!aligned16(actions)) return fail(FPV_EINVAL, "fpv_sticks_to_actions: actions must be 16-byte aligned");
+  fpv::StickK k;
+  for (int i = 0; i < 6; ++i) {
+    const double span = (double)c->max_vals[i] - (double)c->min_vals[i];
+    if (span == 0.0) return fail(FPV_EINVAL, "fpv_sticks_to_actions: axis %d has max == min", i);
+    k.min_v[i] = c->min_vals[i];
+    k.inv_span2[i] = (float)(2.0 / span);
+    k.sign[i] = c->sign_reverse[i];
+  }
+  for (int s = 0; s < 4; ++s) {
+    if (c->stick_idx[s] < 0 || c->stick_idx[s] > 5) return fail(FPV_EINVAL, "fpv_sticks_to_actions: stick idx out of range");
+    const double ctr = c->stick_center[s];
+    if (ctr <= -1.0 || ctr >= 1.0) return fail(FPV_EINVAL, "fpv_sticks_to_actions: stick centre must be inside (-1,1)");
+    k.idx[s] = c->stick_idx[s];
+    k.center[s] = c->stick_center[s];
+    k.inv_lo[s] = (float)(1.0 / (ctr + 1.0));
+    k.inv_hi[s] = (float)(1.0 / (1.0 - ctr));
+  }
+  if (n == 0) return FPV_OK;
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  fpv::sticks_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(k, raw, n, (float4*)actions, calibrated);
+  return check_launch("fpv_sticks_to_actions");
+}
+
+int fpv_racer_reset(void* state, int64_t n, int64_t plane_stride, const uint8_t* mask, void* stream) {
+  if (!state) return fail(FPV_EINVAL, "fpv_racer_reset: null state");
+  if (n < 0 || plane_stride < n) return fail(FPV_EINVAL, "fpv_racer_reset: bad n/stride");
+  if (!aligned16(state)) return fail(FPV_EINVAL, "fpv_racer_reset: state must be 16-byte aligned");
+  if (n == 0) return FPV_OK;
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  fpv::racer_reset_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((float4*)state, n, plane_stride, mask);
+  return check_launch("fpv_racer_reset");
+}
+
+int fpv_racer_step(const fpv_racer_params_t* p, void* state, int64_t n, int64_t plane_stride, const void* actions,
+                   void* torque_out, void* stream) {
+  if (!p || !state || !actions) return fail(FPV_EINVAL, "fpv_racer_step: null pointer");
+  if (n < 0 || plane_stride < n) return fail(FPV_EINVAL, "fpv_racer_step: bad n/stride");
+  if (!aligned16(state) || !aligned16(actions) || !aligned16(torque_out))
+    return fail(FPV_EINVAL, "fpv_racer_step: planes must be 16-byte aligned");
+  if (p->substeps < 1 || !(p->dt > 0.f) || !(p->mass > 0.f)) return fail(FPV_EINVAL, "fpv_racer_step: bad dt/mass/substeps");
+  fpv::RacerK k;
+  k.dt = p->dt;
+  k.inv_dt = (float)(1.0 / (double)p->dt);
+  k.substeps = p->substeps;
+  k.inv_mass = (float)(1.0 / (double)p->mass);
+  for (int i = 0; i < 3; ++i) {
+    if (!(p->inertia[i] > 0.f)) return fail(FPV_EINVAL, "fpv_racer_step: inertia must be positive");
+    k.dt_over_I[i] = (float)((double)p->dt / (double)p->inertia[i]);
+    for (int j = 0; j < 3; ++j) k.gains[i][j] = p->gains[i][j];
+  }
+  k.vel_decay = p->vel_decay;
+  if (n == 0) return FPV_OK;
+  const unsigned grid = (unsigned)((n + kThreads - 1) / kThreads);
+  fpv::racer_step_kernel<kThreads><<<grid, kThreads, 0, (cudaStream_t)stream>>>(k, (float4*)state, n, plane_stride,
+                                                                                   (const float4*)actions, (float4*)torque_out);
+  return check_launch("fpv_racer_step");
+}
+
+}  // extern "C"

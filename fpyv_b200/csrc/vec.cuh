@@ -1,0 +1,133 @@
+// Lane value types for the dynamics kernels.
+//   float : one env per thread.
+//   F2    : two envs per thread in one 64-bit register pair, so that add/mul/fma issue as the
+//           Blackwell packed-FP32 instructions (PTX add/mul/fma.rn.f32x2 -> SASS FADD2/FMUL2/FFMA2):
+//           half the issue slots per env for the same FP32 lane throughput.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace fpv {
+
+struct F2 {
+  float2 v;
+};
+struct B2 {
+  bool x, y;
+};
+
+// ---- construction / lanes
+template <class V> struct Lane;
+template <> struct Lane<float> {
+  static constexpr int N = 1;
+  using Mask = bool;
+  static __device__ __forceinline__ float splat(float s) { return s; }
+  static __device__ __forceinline__ float get(float v, int) { return v; }
+  static __device__ __forceinline__ float make(float a, float) { return a; }
+};
+template <> struct Lane<F2> {
+  static constexpr int N = 2;
+  using Mask = B2;
+  static __device__ __forceinline__ F2 splat(float s) { return F2{make_float2(s, s)}; }
+  static __device__ __forceinline__ float get(F2 v, int i) { return i ? v.v.y : v.v.x; }
+  static __device__ __forceinline__ F2 make(float a, float b) { return F2{make_float2(a, b)}; }
+};
+
+// ---- float
+__device__ __forceinline__ float vfma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+__device__ __forceinline__ float vneg(float a) { return -a; }
+__device__ __forceinline__ float vmin(float a, float b) { return fminf(a, b); }
+__device__ __forceinline__ float vmax(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ float vsqrt(float a) { return __fsqrt_rn(a); }
+__device__ __forceinline__ float vsqrt_fast(float a) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+  return r;
+}
+__device__ __forceinline__ bool vlt(float a, float b) { return a < b; }
+__device__ __forceinline__ bool vle(float a, float b) { return a <= b; }
+__device__ __forceinline__ bool vor(bool a, bool b) { return a || b; }
+__device__ __forceinline__ bool vand(bool a, bool b) { return a && b; }
+__device__ __forceinline__ bool vnot(bool a) { return !a; }
+__device__ __forceinline__ bool vany(bool a) { return a; }
+__device__ __forceinline__ float vsel(bool m, float a, float b) { return m ? a : b; }
+__device__ __forceinline__ float vtrunc_i(float a) { return truncf(a); }
+__device__ __forceinline__ float vabs(float a) { return fabsf(a); }
+__device__ __forceinline__ float vdiv(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ bool vfinite(float a) { return isfinite(a); }
+
+// ---- F2 (packed pair)
+__device__ __forceinline__ F2 operator+(F2 a, F2 b) { return F2{__fadd2_rn(a.v, b.v)}; }
+__device__ __forceinline__ F2 operator*(F2 a, F2 b) { return F2{__fmul2_rn(a.v, b.v)}; }
+__device__ __forceinline__ F2 vneg(F2 a) { return F2{make_float2(-a.v.x, -a.v.y)}; }
+__device__ __forceinline__ F2 operator-(F2 a, F2 b) { return F2{__fadd2_rn(a.v, make_float2(-b.v.x, -b.v.y))}; }
+__device__ __forceinline__ F2 operator-(F2 a) { return vneg(a); }
+__device__ __forceinline__ F2 vfma(F2 a, F2 b, F2 c) { return F2{__ffma2_rn(a.v, b.v, c.v)}; }
+__device__ __forceinline__ F2 vmin(F2 a, F2 b) { return F2{make_float2(fminf(a.v.x, b.v.x), fminf(a.v.y, b.v.y))}; }
+__device__ __forceinline__ F2 vmax(F2 a, F2 b) { return F2{make_float2(fmaxf(a.v.x, b.v.x), fmaxf(a.v.y, b.v.y))}; }
+__device__ __forceinline__ F2 vsqrt(F2 a) { return F2{make_float2(__fsqrt_rn(a.v.x), __fsqrt_rn(a.v.y))}; }
+__device__ __forceinline__ F2 vsqrt_fast(F2 a) { return F2{make_float2(vsqrt_fast(a.v.x), vsqrt_fast(a.v.y))}; }
+__device__ __forceinline__ B2 vlt(F2 a, F2 b) { return B2{a.v.x < b.v.x, a.v.y < b.v.y}; }
+__device__ __forceinline__ B2 vle(F2 a, F2 b) { return B2{a.v.x <= b.v.x, a.v.y <= b.v.y}; }
+__device__ __forceinline__ B2 vor(B2 a, B2 b) { return B2{a.x || b.x, a.y || b.y}; }
+__device__ __forceinline__ B2 vand(B2 a, B2 b) { return B2{a.x && b.x, a.y && b.y}; }
+__device__ __forceinline__ B2 vnot(B2 a) { return B2{!a.x, !a.y}; }
+__device__ __forceinline__ bool vany(B2 a) { return a.x || a.y; }
+__device__ __forceinline__ F2 vsel(B2 m, F2 a, F2 b) { return F2{make_float2(m.x ? a.v.x : b.v.x, m.y ? a.v.y : b.v.y)}; }
+__device__ __forceinline__ F2 vabs(F2 a) { return F2{make_float2(fabsf(a.v.x), fabsf(a.v.y))}; }
+__device__ __forceinline__ F2 vdiv(F2 a, F2 b) { return F2{make_float2(__fdiv_rn(a.v.x, b.v.x), __fdiv_rn(a.v.y, b.v.y))}; }
+__device__ __forceinline__ B2 vfinite(F2 a) { return B2{isfinite(a.v.x), isfinite(a.v.y)}; }
+
+__device__ __forceinline__ bool mask_get(bool m, int) { return m; }
+__device__ __forceinline__ bool mask_get(B2 m, int i) { return i ? m.y : m.x; }
+
+// scalar (warp-uniform parameter) with lane value
+template <class V> __device__ __forceinline__ V S(float s) { return Lane<V>::splat(s); }
+
+// ---- sin/cos
+// Polynomial kernels on |x| <= pi/4 (the same minimax coefficients a reduced-argument sinf/cosf uses);
+// max error < 1 ulp there.  Used directly when the host proves the angle bound (SMALL), otherwise
+// after a Cody-Waite reduction by pi/2 (float path only needs accurate sincosf for |x| up to ~1e5).
+template <class V> __device__ __forceinline__ void sincos_poly(V x, V& s, V& c) {
+  const V x2 = x * x;
+  V ps = vfma(S<V>(-1.95152959e-4f), x2, S<V>(8.33216087e-3f));
+  ps = vfma(ps, x2, S<V>(-1.66666546e-1f));
+  const V x3 = x2 * x;
+  s = vfma(ps, x3, x);
+  V pc = vfma(S<V>(2.44331571e-5f), x2, S<V>(-1.38873163e-3f));
+  pc = vfma(pc, x2, S<V>(4.16666457e-2f));
+  pc = vfma(pc, x2, S<V>(-0.5f));
+  c = vfma(pc, x2, S<V>(1.0f));
+}
+
+template <bool SMALL> __device__ __forceinline__ void vsincos(float x, float& s, float& c) {
+  if (SMALL) sincos_poly<float>(x, s, c);
+  else sincosf(x, &s, &c);
+}
+template <bool SMALL> __device__ __forceinline__ void vsincos(F2 x, F2& s, F2& c) {
+  if (SMALL) {
+    sincos_poly<F2>(x, s, c);
+  } else {
+    float s0, c0, s1, c1;
+    sincosf(x.v.x, &s0, &c0);
+    sincosf(x.v.y, &s1, &c1);
+    s = F2{make_float2(s0, s1)};
+    c = F2{make_float2(c0, c1)};
+  }
+}
+
+// 128-bit global access.  State/action streams are touched exactly once per control step, so they
+// bypass L1 allocation (streaming) -- L2 still serves the re-reads of small batches.
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg_stream(float4* p, float4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+
+}  // namespace fpv

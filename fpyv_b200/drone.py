@@ -1,0 +1,349 @@
+"""`BatchedDrone`: the reference's `utils.components.Drone` protocol (src/utils/components.py:72-253)
+for N independent drones on one B200.  PyTorch owns the device memory; every `reset`/`step` is one
+launch of the hand-written sm_100a kernels in libfpyv_b200.so through the C ABI (include/fpv_api.h).
+There is no CPU path: without the CUDA library or a device this module raises.
+
+Name-for-name mirror of the reference object:
+  Drone(params)                         -> BatchedDrone(params, num_envs, device=...)
+  reset(position, velocity, ypr)        -> same (ypr in DEGREES, consumed as roll, pitch, yaw: components.py:154)
+  step(action, wind_velocity_vector, object_list, rotation_matrix=None, thrust_force=None)
+                                        -> same; returns (R^T, gyro matrix, R @ acc) batched
+  .position .velocity .state .rotation_matrix .prev_rates .prev_thrust .rates .thrust .acceleration
+  .done .dt .mass .max_rates ...        -> same names, leading env axis
+`Drone(params)` (bottom of this file) is the num_envs=1 NumPy-returning stand-in for simulator.py-style loops.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib, config
+from .objects import Ground, lower_object_list
+from .sticks import Joystick
+
+
+def _as_dev(x, device, shape=None, dtype=torch.float32):
+    t = x if isinstance(x, torch.Tensor) else torch.as_tensor(np.asarray(x), dtype=dtype)
+    t = t.to(device=device, dtype=dtype, non_blocking=True)
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        t = torch.broadcast_to(t, shape)
+    return t.contiguous()
+
+
+class BatchedDrone:
+    def __init__(self, params=None, num_envs: int = 1, device="cuda:0", substeps: int = 1, dt: float | None = None,
+                 auto_reset: bool = False, freeze_done: bool = False, thrust_lut: int = 0, lut_source: str = "poly",
+                 fast_math: bool = False, packed: bool = True, ground: bool = True, joystick=None):
+        self._lib = _lib.load()
+        if isinstance(params, str) or params is None:
+            params = config.load_params(params)
+        self.params = params
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("fpyv_b200 runs on CUDA devices only (no CPU fallback)")
+        if num_envs < 1:
+            raise ValueError("num_envs must be >= 1")
+        self.num_envs = int(num_envs)
+        self.substeps = int(substeps)
+        c = self.constants = config.derive_constants(params, dt=dt)
+
+        # --- same attribute names as the reference (components.py:84-142)
+        self.dim = 3
+        self.max_rates = c.max_rates
+        self.gravity = c.gravity
+        self.dt = c.dt
+        self.mass = c.mass
+        self.drag_coef = c.drag_coef
+        self.dimensions = c.dimensions
+        self.cross_section_areas = c.cross_section_areas
+        self.rates_transition_rate = c.rates_transition_rate
+        self.thrust_transition_rate = c.thrust_transition_rate
+        self.n_motors = config.N_MOTORS
+        self.motor_radius = config.MOTOR_RADIUS
+        self.radius = config.ARM_RADIUS
+        self.motors_relative_position = c.motors_relative_position
+        self.throttle2thrust = c.throttle2thrust
+        self.thrust2throttle = c.thrust2throttle
+        self.min_throttle_in_force = c.min_throttle_in_force
+        self.max_throttle_in_force = c.max_throttle_in_force
+        # the reference writes the thrust limits back into the caller's dict (components.py:143-144)
+        if "force_multiplier_pid" in params.get("drone", {}):
+            params["drone"]["force_multiplier_pid"]["min_output"] = self.min_throttle_in_force
+            params["drone"]["force_multiplier_pid"]["max_output"] = self.max_throttle_in_force
+
+        # --- stick front-end (components.py:75-81); file problems raise exactly like the reference
+        self.rc = joystick if joystick is not None else Joystick(device=self.device)
+        if "joystick_calib_path" in params["drone"]:
+            search = (params.get("__config_dir__"),) if params.get("__config_dir__") else ()
+            try:
+                path = config.resolve_path(params["drone"]["joystick_calib_path"], search)
+            except FileNotFoundError:
+                path = params["drone"]["joystick_calib_path"]
+            self.rc.calibrate(path, load_calibration_file=True)
+
+        # --- device state: 5 float4 planes (fpv_api.h "Drone state layout")
+        n = self.num_envs
+        self._stride = (n + 3) // 4 * 4
+        dev = self.device
+        self._state = torch.zeros((_lib.DRONE_PLANES, self._stride, 4), dtype=torch.float32, device=dev)
+        self._reset_state = torch.zeros_like(self._state) if auto_reset else None
+        self._done = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self._acc = torch.zeros((n, 4), dtype=torch.float32, device=dev)
+        self._actions = torch.zeros((n, 4), dtype=torch.float32, device=dev)
+        self._stats = torch.zeros(8, dtype=torch.float64, device=dev)
+        self._lut = None
+        if thrust_lut:
+            self._lut = torch.from_numpy(config.thrust_table(c, int(thrust_lut), lut_source)).to(dev)
+        self._flags = ((_lib.F_GROUND if ground else 0) | (_lib.F_AUTO_RESET if auto_reset else 0) |
+                       (_lib.F_FREEZE_DONE if freeze_done else 0) | (_lib.F_THRUST_LUT if thrust_lut else 0) |
+                       (_lib.F_FAST_MATH if fast_math else 0) | (0 if packed else _lib.F_SCALAR))
+        self._p = self._make_params()
+        self._io = _lib.DroneIO()
+        self._host_actions = None
+        self._host_done = None
+        self.throttle = None
+        self._is_reset = False
+
+    # ------------------------------------------------------------------ parameters
+    def _make_params(self) -> _lib.DroneParams:
+        c = self.constants
+        p = _lib.DroneParams()
+        p.dt, p.substeps, p.gravity, p.mass = c.dt, self.substeps, c.gravity, c.mass
+        p.max_rates = c.max_rates
+        p.rates_transition_rate, p.thrust_transition_rate = c.rates_transition_rate, c.thrust_transition_rate
+        for i in range(3):
+            p.k_drag[i] = float(c.k_drag[i])
+        for m in range(4):
+            p.motor_xy[m][0] = float(c.motors_relative_position[m, 0])
+            p.motor_xy[m][1] = float(c.motors_relative_position[m, 1])
+        p.motor_radius, p.spring_k, p.spring_c = config.MOTOR_RADIUS, config.COLLISION_SPRING, config.COLLISION_DAMPING
+        for i in range(4):
+            p.thrust_poly[i] = float(c.thrust_poly.coeffs[i])
+        p.flags = self._flags
+        p.n_objects = 0
+        return p
+
+    # ------------------------------------------------------------------ views of the state
+    @property
+    def position(self):
+        return self._state[0, :self.num_envs, :3]
+
+    @property
+    def velocity(self):
+        return self._state[1, :self.num_envs, :3]
+
+    @property
+    def state(self):
+        """[n,6] = [x,y,z,vx,vy,vz] like Drone.state (a copy; write through .position/.velocity)."""
+        return torch.cat([self.position, self.velocity], dim=1)
+
+    @property
+    def rotation_matrix(self):
+        return self._state[2:5, :self.num_envs, :3].permute(1, 0, 2)
+
+    @property
+    def prev_rates(self):
+        return self._state[2:5, :self.num_envs, 3].t()
+
+    rates = prev_rates          # components.py:188-189: step stores the filtered rates as both
+
+    @property
+    def prev_thrust(self):
+        return self._state[0, :self.num_envs, 3]
+
+    @property
+    def thrust(self):
+        """World-frame thrust vector of the state (kinematics.thrust_vector, kinematics.py:48-49)."""
+        return self.rotation_matrix[:, :, 2] * self.prev_thrust[:, None]
+
+    @property
+    def acceleration(self):
+        return self._acc[:, :3]
+
+    @property
+    def episode_steps(self):
+        return self._state[1, :self.num_envs, 3].view(torch.int32)
+
+    @property
+    def done(self):
+        return self._done.bool()
+
+    @property
+    def motors_orientation(self):
+        m = torch.as_tensor(self.motors_relative_position, dtype=torch.float32, device=self.device)
+        return torch.einsum("mj,nij->nmi", m, self.rotation_matrix)
+
+    # ------------------------------------------------------------------ reset / step
+    def reset(self, position=None, velocity=None, ypr=None, mask=None):
+        """Drone.reset (components.py:150-169).  Arguments broadcast over envs; `mask` (bool[n]) restricts
+        the reset to a subset.  Defaults are params.yaml's initial_* (as simulator.py:59 passes them)."""
+        n, dev, dr = self.num_envs, self.device, self.params["drone"]
+        pos = _as_dev(dr["initial_position"] if position is None else position, dev, (n, 3))
+        vel = _as_dev(dr["initial_velocity"] if velocity is None else velocity, dev, (n, 3))
+        rpy = _as_dev(dr["initial_orientation"] if ypr is None else ypr, dev, (n, 3))
+        m = None if mask is None else _as_dev(mask, dev, (n,), torch.uint8)
+        _lib.check(self._lib.fpv_drone_reset(_lib.ptr(self._state), n, self._stride, _lib.ptr(pos), _lib.ptr(vel),
+                                             _lib.ptr(rpy), _lib.ptr(m), _lib.current_stream(dev)))
+        if m is None:
+            self._done.zero_()
+            self._acc.zero_()
+        else:
+            self._done.masked_fill_(m.bool(), 0)
+        if self._reset_state is not None:
+            if m is None:
+                self._reset_state.copy_(self._state)
+            else:
+                sel = m.bool()
+                self._reset_state[:, :n][:, sel] = self._state[:, :n][:, sel]
+        self._is_reset = True
+
+    def read_sticks(self):
+        """components.py:250-253 on the batched joystick source."""
+        return self.rc.read_actions()
+
+    def step(self, action, wind_velocity_vector=None, object_list=None, rotation_matrix=None, thrust_force=None,
+             return_obs: bool = True):
+        """Drone.step (components.py:220-248) for every env: `substeps` reference steps with `action` held.
+        action: [n,4] (roll, pitch, yaw, throttle) in [-1,1], or None to poll the joystick source.
+        Returns (R^T [n,3,3], euler_matrix(*rates) [n,3,3], R @ acc [n,3]) when return_obs."""
+        if not self._is_reset:
+            raise RuntimeError("call reset() before step() (the reference's state is None until reset)")
+        n, dev = self.num_envs, self.device
+        if action is None:
+            action = self.read_sticks()
+        act = _as_dev(action, dev, (n, 4))
+        self.throttle = act[:, 3]
+        p, io = self._p, self._io
+        p.flags = self._flags
+        wind_env = None
+        if wind_velocity_vector is None:
+            p.wind[0] = p.wind[1] = p.wind[2] = 0.0
+        else:
+            w = wind_velocity_vector
+            if isinstance(w, torch.Tensor) and w.dim() == 2:
+                wind_env = torch.zeros((n, 4), dtype=torch.float32, device=dev)
+                wind_env[:, :3] = w.to(dev, torch.float32)
+            else:
+                w = np.asarray(w.cpu() if isinstance(w, torch.Tensor) else w, dtype=np.float64).reshape(3)
+                p.wind[0], p.wind[1], p.wind[2] = float(w[0]), float(w[1]), float(w[2])
+        objs = None
+        p.n_objects = 0
+        if object_list is not None:
+            has_ground, lowered = lower_object_list(object_list)
+            p.flags = (p.flags & ~_lib.F_GROUND) | (_lib.F_GROUND if has_ground else 0)
+            if lowered:
+                objs = (_lib.Object * len(lowered))(*lowered)
+                p.n_objects = len(lowered)
+        ovr = None
+        if rotation_matrix is not None:
+            if thrust_force is None:
+                raise ValueError("rotation_matrix override needs thrust_force (components.py:230-232)")
+            R = _as_dev(rotation_matrix, dev, (n, 3, 3))
+            ovr = torch.zeros((3, n, 4), dtype=torch.float32, device=dev)
+            ovr[:, :, :3] = R.permute(1, 0, 2)
+            ovr[0, :, 3] = _as_dev(thrust_force, dev, (n,))
+        io.state, io.n, io.plane_stride = self._state.data_ptr(), n, self._stride
+        io.actions = act.data_ptr()
+        io.wind_env = None if wind_env is None else wind_env.data_ptr()
+        io.lut = None if self._lut is None else self._lut.data_ptr()
+        io.lut_n = 0 if self._lut is None else self._lut.numel()
+        io.done = self._done.data_ptr()
+        io.acc_out = self._acc.data_ptr()
+        io.reset_state = None if self._reset_state is None else self._reset_state.data_ptr()
+        io.override_R = None if ovr is None else ovr.data_ptr()
+        io.objects = objs if objs is not None else C.POINTER(_lib.Object)()
+        io.stats = self._stats.data_ptr()
+        _lib.check(self._lib.fpv_drone_step(C.byref(p), C.byref(io), _lib.current_stream(dev)))
+        if return_obs:
+            return self.observe()
+        return None
+
+    def observe(self):
+        """The tuple Drone.step returns (components.py:247-248)."""
+        n, dev = self.num_envs, self.device
+        Rt = torch.empty((n, 3, 3), dtype=torch.float32, device=dev)
+        gyro = torch.empty((n, 3, 3), dtype=torch.float32, device=dev)
+        accel = torch.empty((n, 3), dtype=torch.float32, device=dev)
+        _lib.check(self._lib.fpv_drone_observe(_lib.ptr(self._state), n, self._stride, _lib.ptr(self._acc), _lib.ptr(Rt),
+                                               _lib.ptr(gyro), _lib.ptr(accel), _lib.current_stream(dev)))
+        return Rt, gyro, accel
+
+    # ------------------------------------------------------------------ host-buffer entry (end-to-end path)
+    def step_host(self, actions_host: torch.Tensor, done_host: torch.Tensor | None = None):
+        """One control step with HOST buffers: pinned actions [n,4] -> device, step, done flags -> pinned host.
+        This is the call timed as `e2e` in bench.py (H2D 16 B/env, D2H 1 B/env per step)."""
+        n = self.num_envs
+        if done_host is None:
+            if self._host_done is None:
+                self._host_done = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+            done_host = self._host_done
+        self._actions.copy_(actions_host, non_blocking=True)
+        self.step(self._actions, return_obs=False)
+        done_host.copy_(self._done, non_blocking=True)
+        return done_host
+
+    # ------------------------------------------------------------------ episode statistics
+    def episode_stats(self, all_reduce: bool = False, reset: bool = False) -> dict:
+        """Device-accumulated counters (fpv_stats_t).  With all_reduce the 8 doubles are summed over the
+        torch.distributed world (NCCL on GPUs) -- the only collective of the engine, never inside step."""
+        s = self._stats.clone()
+        if all_reduce and torch.distributed.is_available() and torch.distributed.is_initialized():
+            torch.distributed.all_reduce(s, op=torch.distributed.ReduceOp.SUM)
+        if reset:
+            self._stats.zero_()
+        v = s.tolist()
+        keys = ("env_steps", "crashes", "episodes", "episode_len_sum", "reward_sum", "reward_sq_sum", "nonfinite")
+        out = dict(zip(keys, v))
+        out["mean_episode_len"] = out["episode_len_sum"] / out["episodes"] if out["episodes"] else math.nan
+        return out
+
+
+class Drone:
+    """num_envs = 1 stand-in for `utils.components.Drone` (NumPy in, NumPy out), for simulator.py-style
+    loops: `drone = Drone(params); drone.reset(p, v, ypr); drone.step(action, wind, [ground])`."""
+
+    def __init__(self, params=None, device="cuda:0", **kw):
+        self._b = BatchedDrone(params, num_envs=1, device=device, **kw)
+        for k in ("dim", "max_rates", "gravity", "dt", "mass", "drag_coef", "dimensions", "cross_section_areas",
+                  "rates_transition_rate", "thrust_transition_rate", "n_motors", "motor_radius", "radius",
+                  "motors_relative_position", "throttle2thrust", "thrust2throttle", "min_throttle_in_force",
+                  "max_throttle_in_force", "rc", "params"):
+            setattr(self, k, getattr(self._b, k))
+        self.done = None
+        self.throttle = None
+
+    def reset(self, position, velocity, ypr):
+        self._b.reset(np.asarray(position, dtype=np.float64)[None], np.asarray(velocity, dtype=np.float64)[None],
+                      np.asarray(ypr, dtype=np.float64)[None])
+        self.done = False
+
+    def step(self, action, wind_velocity_vector=None, object_list=None, rotation_matrix=None, thrust_force=None):
+        if action is not None:
+            action = np.asarray(action, dtype=np.float64)[None]
+        if rotation_matrix is not None:
+            rotation_matrix = np.asarray(rotation_matrix, dtype=np.float64)[None]
+            thrust_force = np.asarray([thrust_force], dtype=np.float64)
+        Rt, gyro, acc = self._b.step(action, wind_velocity_vector, object_list, rotation_matrix, thrust_force)
+        self.done = bool(self._b.done[0].item())
+        self.throttle = float(self._b.throttle[0].item())
+        return Rt[0].double().cpu().numpy(), gyro[0].double().cpu().numpy(), acc[0].double().cpu().numpy()
+
+    def read_sticks(self):
+        return self._b.read_sticks()[0].double().cpu().numpy()
+
+    def _np(self, t):
+        return t.double().cpu().numpy()
+
+    position = property(lambda self: self._np(self._b.position[0]))
+    velocity = property(lambda self: self._np(self._b.velocity[0]))
+    state = property(lambda self: self._np(self._b.state[0]))
+    rotation_matrix = property(lambda self: self._np(self._b.rotation_matrix[0]))
+    prev_rates = property(lambda self: self._np(self._b.prev_rates[0]))
+    rates = prev_rates
+    prev_thrust = property(lambda self: float(self._b.prev_thrust[0].item()))
+    thrust = property(lambda self: self._np(self._b.thrust[0]))
+    acceleration = property(lambda self: self._np(self._b.acceleration[0]))
+    motors_orientation = property(lambda self: self._np(self._b.motors_orientation[0]))

@@ -1,0 +1,203 @@
+/* fpv_api.h -- C ABI of libfpyv_b200.so: the batched FPV-drone dynamics step for NVIDIA B200
+ * (sm_100a).  This is the drop-in boundary for the dynamics path of omrijsharon/FpyV.
+ *
+ * The reference has no FFI for this path: its boundary is the Python object protocol of
+ * `utils.components.Drone` (src/utils/components.py:72-253) plus the free functions of
+ * src/utils/kinematics.py.  Each entry point below names the reference interface it replaces.
+ * The Python mirror of that protocol lives in fpyv_b200/drone.py and binds these symbols with
+ * ctypes; INTEGRATION.md shows the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - Every function returns 0 on success and a negative FPV_E* code otherwise; nothing throws
+ *     across the ABI.  fpv_last_error() returns a thread-local message for the last failure.
+ *   - All data pointers are DEVICE pointers owned by the caller (PyTorch owns the memory; the
+ *     library only borrows them for the launch).  Parameter structs are HOST pointers to PODs
+ *     that are copied by value into the launch (kernel-parameter constant bank): the library
+ *     keeps no per-device state, so it is re-entrant and usable from one host thread per GPU.
+ *   - Launches are asynchronous and ordered on `stream` (a cudaStream_t / CUstream handle; 0 =
+ *     legacy default stream).  No hidden synchronisation, no allocation.
+ *   - "float4 plane" = an array of n 16-byte elements, 16-byte aligned.  Env i lives at
+ *     element i of every plane.  Planes of one state buffer are `plane_stride` ELEMENTS apart.
+ *   - Arithmetic is FP32 (the reference is float64 NumPy); parity tolerance is stated in
+ *     tests/test_gpu_parity.py (<= 1e-5 relative per step).
+ */
+#ifndef FPV_API_H
+#define FPV_API_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FPV_ABI_VERSION 3
+
+/* error codes */
+#define FPV_OK 0
+#define FPV_EINVAL (-22)  /* bad argument (null/misaligned pointer, bad size, bad flag combo) */
+#define FPV_ECUDA (-5)    /* CUDA runtime error at launch; see fpv_last_error()               */
+#define FPV_ENODEV (-19)  /* no sm_100 device / kernel image not loadable on this device      */
+
+/* ---------------------------------------------------------------------------------------------
+ * Drone state layout (mode A, reference `Drone`): 5 float4 planes
+ *   plane 0: position.x  position.y  position.z  prev_thrust      components.py:151-153,:161
+ *   plane 1: velocity.x  velocity.y  velocity.z  episode (int32 bits: steps since reset; -1-steps if
+ *                                                 the env has crashed and is frozen)
+ *   plane 2: R[0][0] R[0][1] R[0][2] prev_rates[0]               components.py:154,:160
+ *   plane 3: R[1][0] R[1][1] R[1][2] prev_rates[1]
+ *   plane 4: R[2][0] R[2][1] R[2][2] prev_rates[2]
+ * R is the body->world rotation matrix exactly as the reference stores it (not a quaternion):
+ * the reference never re-orthonormalises it and lets callers overwrite it (components.py:230-231).
+ * -------------------------------------------------------------------------------------------*/
+#define FPV_DRONE_PLANES 5
+
+/* flags for fpv_drone_params_t.flags */
+#define FPV_F_GROUND 1u         /* plane z=0 in the object list (components.py:649-680)          */
+#define FPV_F_AUTO_RESET 2u     /* an env whose control step raised `done` is reloaded from
+                                   io.reset_state at the end of that control step              */
+#define FPV_F_FREEZE_DONE 4u    /* a crashed env stops integrating (the reference caller breaks
+                                   out of its loop, src/core/simulator.py:91-93); default is the
+                                   reference's own behaviour: done is reported, integration goes on */
+#define FPV_F_THRUST_LUT 8u     /* throttle->thrust through io.lut (shared-memory table, linear
+                                   interpolation) instead of the cubic                          */
+#define FPV_F_FAST_MATH 16u     /* allow approximate sqrt/division (still within tolerance)     */
+#define FPV_F_SCALAR 32u        /* one env per thread (plain FP32 instructions) instead of the
+                                   default two envs per thread on packed f32x2 instructions     */
+
+/* Mirrors what Drone.__init__ derives from params.yaml (components.py:84-142). */
+typedef struct fpv_drone_params {
+  float dt;               /* seconds per substep (reference: 1/fps, components.py:96)            */
+  int32_t substeps;       /* K >= 1 reference steps per launch, same action (north_star)         */
+  float gravity;          /* m/s^2, components.py:92                                             */
+  float mass;             /* kg, components.py:97                                                */
+  float max_rates;        /* deg/s, components.py:85                                             */
+  float rates_transition_rate;   /* components.py:105 */
+  float thrust_transition_rate;  /* components.py:106 */
+  float k_drag[3];        /* -0.5*Cd*rho*A per body axis, kinematics.py:36                       */
+  float motor_xy[4][2];   /* body-frame motor offsets (z = 0), components.py:123-125             */
+  float motor_radius;     /* components.py:121 */
+  float spring_k;         /* components.py:198 */
+  float spring_c;         /* components.py:198 */
+  float thrust_poly[4];   /* cubic in throttle PERCENT, highest power first (model_xy, flight_time_calculator.py:43-52) */
+  float wind[3];          /* uniform wind, world frame (step's wind_velocity_vector)             */
+  uint32_t flags;
+  int32_t n_objects;      /* extra obstacles after the ground plane, <= FPV_MAX_OBJECTS          */
+} fpv_drone_params_t;
+
+#define FPV_MAX_OBJECTS 16
+#define FPV_OBJ_SPHERE 1    /* Target,   components.py:773-777 : x,y,z = centre, a = radius            */
+#define FPV_OBJ_CYLINDER 2  /* Cylinder, components.py:710-729 : x,y,z = base centre, a = radius, b = height */
+typedef struct fpv_object {
+  int32_t kind;
+  float x, y, z, a, b;
+} fpv_object_t;
+
+/* Episode statistics accumulated on the device (one struct per GPU; all-reduced by the host with
+ * NCCL outside the step).  Doubles are updated with one atomicAdd per CTA. */
+typedef struct fpv_stats {
+  double env_steps;       /* control steps executed                                       */
+  double crashes;         /* control steps that raised done                               */
+  double episodes;        /* episodes ended (auto-reset or frozen)                        */
+  double episode_len_sum; /* sum of lengths (control steps) of ended episodes              */
+  double reward_sum;      /* env kernels only                                              */
+  double reward_sq_sum;
+  double nonfinite;       /* envs whose state went NaN/Inf this step                       */
+  double reserved;
+} fpv_stats_t;
+
+typedef struct fpv_drone_io {
+  void* state;              /* float4[FPV_DRONE_PLANES][plane_stride], in/out                     */
+  int64_t n;                /* number of envs                                                     */
+  int64_t plane_stride;     /* elements between planes, >= n                                      */
+  const void* actions;      /* float4[n]: roll, pitch, yaw, throttle in [-1,1] (components.py:220) */
+  const void* wind_env;     /* float4[n] per-env wind (xyz), or NULL -> params.wind               */
+  const float* lut;         /* float[lut_n] thrust [N] sampled at throttle -1..1, or NULL         */
+  int32_t lut_n;
+  uint8_t* done;            /* uint8[n] out: 1 if any substep raised done (components.py:236-240); may be NULL */
+  void* acc_out;            /* float4[n] out: world acceleration of the last substep (components.py:243); may be NULL */
+  const void* reset_state;  /* float4[FPV_DRONE_PLANES][plane_stride]: source for FPV_F_AUTO_RESET */
+  const void* override_R;   /* float4[3][n]: rows of the rotation override, .w of row 0 = thrust_force
+                               (step(rotation_matrix=, thrust_force=), components.py:230-232); NULL = none.
+                               Requires substeps == 1. */
+  const fpv_object_t* objects; /* HOST pointer, params.n_objects entries, or NULL                  */
+  fpv_stats_t* stats;       /* device, may be NULL                                                */
+} fpv_drone_io_t;
+
+int fpv_abi_version(void);
+const char* fpv_last_error(void);
+
+/* sizeof() of the ABI structs as this library was compiled, so that a foreign-language binding can
+ * verify its own struct layout: which = 0 fpv_drone_params_t, 1 fpv_drone_io_t, 2 fpv_object_t,
+ * 3 fpv_stats_t, 4 fpv_stick_calib_t, 5 fpv_racer_params_t; -1 for an unknown index. */
+int fpv_sizeof(int which);
+
+/* Number of SMs / compute capability of `device`; used by hosts to size persistent launches. */
+int fpv_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
+
+/* Drone.reset(position, velocity, ypr)  -- components.py:150-169.
+ * pos, vel, rpy_deg: float[n][3] row-major (rpy in DEGREES, consumed as roll, pitch, yaw exactly like
+ * the reference's `ypr` argument).  mask: uint8[n] or NULL; only envs with mask != 0 are reset. */
+int fpv_drone_reset(void* state, int64_t n, int64_t plane_stride, const float* pos, const float* vel,
+                    const float* rpy_deg, const uint8_t* mask, void* stream);
+
+/* Drone.step(action, wind_velocity_vector, object_list, rotation_matrix=None, thrust_force=None)
+ * -- components.py:220-248, i.e. action2force :179-196, calculate_drag kinematics.py:33-38,
+ * gravity_vector :41-45, handle_collisions components.py:198-214 (+Ground :674-680, spring_force
+ * kinematics.py:56-59), the crash test :239, the force sum :242-243 and update :216-218
+ * (update_kinematic_step kinematics.py:15-24 + rotate_body_by_rates :27-30, applied twice).
+ * Runs params->substeps reference steps per env with the state held in registers. */
+int fpv_drone_step(const fpv_drone_params_t* params, const fpv_drone_io_t* io, void* stream);
+
+/* The tuple Drone.step returns -- components.py:247-248: (R^T, euler_matrix(*rates), R @ acc).
+ * Rt, gyro: float[n][9] row-major; accel: float[n][3].  Any of the three may be NULL. */
+int fpv_drone_observe(const void* state, int64_t n, int64_t plane_stride, const void* acc /*float4[n]*/,
+                      float* Rt, float* gyro, float* accel, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stick front-end: Joystick.calib_read + Drone.read_sticks
+ * (src/utils/get_sticks.py:245-265, components.py:250-253).
+ * -------------------------------------------------------------------------------------------*/
+typedef struct fpv_stick_calib {
+  float min_vals[6], max_vals[6], sign_reverse[6];   /* calibration JSON arrays           */
+  int32_t stick_idx[4];                              /* JSON "sticks" in file order: Throttle, Roll, Pitch, Yaw */
+  float stick_center[4];
+} fpv_stick_calib_t;
+
+/* raw: int32[n][6] axis readings (dwXpos..dwVpos order, get_sticks.py:55-60).
+ * actions: float4[n] = [-roll, pitch, yaw, throttle]; calibrated: float[n][6] or NULL. */
+int fpv_sticks_to_actions(const fpv_stick_calib_t* calib, const int32_t* raw, int64_t n, void* actions,
+                          float* calibrated, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Mode B: the acro rate-PID drone of tests/racer_drone_test.py (`PID` :11-32, `Racer` :68-103).
+ * State: 7 float4 planes
+ *   0: position xyz, first-call flag of the PIDs (1.0 / 0.0)      :20, :47-51
+ *   1: velocity xyz, unused
+ *   2..4: rows of the orientation matrix, .w = angular_velocity[row]
+ *   5: PID integral per axis, unused
+ *   6: PID last error per axis, unused
+ * -------------------------------------------------------------------------------------------*/
+#define FPV_RACER_PLANES 7
+
+typedef struct fpv_racer_params {
+  float dt;              /* racer_drone_test.py:8  */
+  int32_t substeps;
+  float mass;            /* :82 */
+  float inertia[3];      /* :83 (m r^2 on every axis in the reference) */
+  float gains[3][3];     /* [axis roll/pitch/yaw][P,I,D], :113 */
+  float vel_decay;       /* :102 (0.9) */
+  uint32_t flags;        /* FPV_F_FAST_MATH only */
+} fpv_racer_params_t;
+
+/* Racer.reset -- :86-93 (mask as in fpv_drone_reset). */
+int fpv_racer_reset(void* state, int64_t n, int64_t plane_stride, const uint8_t* mask, void* stream);
+
+/* Racer.step(action) -- :95-103.  actions: float4[n] = [roll, pitch, yaw rate set-points, thrust N].
+ * torque_out: float4[n] (last substep's PID output) or NULL. */
+int fpv_racer_step(const fpv_racer_params_t* params, void* state, int64_t n, int64_t plane_stride,
+                   const void* actions, void* torque_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FPV_API_H */

@@ -1,0 +1,463 @@
+"""GPU parity: the CUDA path (through the C ABI, via fpyv_b200's Python mirror of `Drone`) against
+(1) the golden vectors produced by the unmodified reference and (2) the float64 oracle on seeded inputs.
+
+Tolerance (BASELINE.json north_star): <= 1e-5 relative per single step.  "relative" here is, per env and
+per quantity group (position, velocity, R, rates, thrust): max|gpu - ref| / max(1, max|ref|).
+The free-running divergence over the 1 s horizon is printed and bounded separately.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle import fpv_oracle as fo
+
+pytestmark = pytest.mark.gpu
+
+TOL_STEP = 1e-5
+DEV = "cuda:0"
+
+
+def load(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
+def group_err(a, b):
+    """a, b: [n, ...] -> per-env error."""
+    a = np.asarray(a, dtype=np.float64).reshape(len(a), -1)
+    b = np.asarray(b, dtype=np.float64).reshape(len(b), -1)
+    return np.max(np.abs(a - b), axis=1) / np.maximum(1.0, np.max(np.abs(b), axis=1))
+
+
+def drone_err(d, state, R, prev_rates, prev_thrust):
+    errs = [group_err(d.position.cpu().numpy(), state[:, :3]), group_err(d.velocity.cpu().numpy(), state[:, 3:]),
+            group_err(d.rotation_matrix.cpu().numpy(), R), group_err(d.prev_rates.cpu().numpy(), prev_rates),
+            group_err(d.prev_thrust.cpu().numpy()[:, None], np.asarray(prev_thrust)[:, None])]
+    return np.max(np.stack(errs), axis=0)
+
+
+def set_state(d, state, R, prev_rates, prev_thrust):
+    f = lambda x: torch.as_tensor(np.asarray(x), dtype=torch.float32, device=DEV)
+    d.position.copy_(f(state[:, :3]))
+    d.velocity.copy_(f(state[:, 3:]))
+    d.rotation_matrix.copy_(f(R))
+    d.prev_rates.copy_(f(prev_rates))
+    d.prev_thrust.copy_(f(prev_thrust))
+
+
+def make(n, **kw):
+    from fpyv_b200 import BatchedDrone
+    d = BatchedDrone(None, num_envs=n, device=DEV, **kw)
+    return d
+
+
+@pytest.mark.parametrize("packed", [True, False])
+@pytest.mark.parametrize("name", ["drone_kat", "drone_random", "drone_ground", "drone_wind", "drone_overdrive",
+                                  "drone_1ms_k8"])
+def test_single_step_vs_reference(name, packed):
+    """Every (t, env) pair of the golden rollout is one env: start from the reference's state at t-1, apply
+    action t, compare with the reference's state at t."""
+    g = load(name)
+    T, n = g["actions"].shape[:2]
+    d = make((T - 1) * n, dt=float(g["dt"]), packed=packed)
+    d.reset()
+    cat = lambda k, sl: g[k][sl].reshape((-1,) + g[k].shape[2:])
+    prev, nxt = slice(0, T - 1), slice(1, T)
+    set_state(d, cat("state", prev), cat("R", prev), cat("prev_rates", prev), cat("prev_thrust", prev))
+    wind = g["wind"] if "wind" in g else None
+    ret = d.step(cat("actions", nxt), wind_velocity_vector=wind)
+    err = drone_err(d, cat("state", nxt), cat("R", nxt), cat("prev_rates", nxt), cat("prev_thrust", nxt))
+    print(f"\n{name} packed={packed}: single-step rel err max {err.max():.3e} median {np.median(err):.3e}")
+    assert err.max() <= TOL_STEP
+    # done flag: identical, except where a motor sits within 1e-5 m of the plane in the reference itself
+    done_ref = cat("done", nxt).astype(bool)
+    done_gpu = d.done.cpu().numpy()
+    mism = done_ref != done_gpu
+    assert mism.sum() == 0, f"{mism.sum()} done flags differ"
+    if "ret_Rt" in g:
+        assert group_err(ret[0].cpu().numpy(), cat("ret_Rt", nxt)).max() <= TOL_STEP
+        assert group_err(ret[2].cpu().numpy(), cat("ret_acc", nxt)).max() <= TOL_STEP
+        # gyro matrix = euler(rates in deg/s taken as radians): |angle| up to 200 rad, so the fp32 rounding of the
+        # rates themselves (rel 6e-8 * 200 rad) bounds the achievable accuracy at ~2e-5 absolute
+        assert group_err(ret[1].cpu().numpy(), cat("ret_gyro", nxt)).max() <= 5e-5
+
+
+@pytest.mark.parametrize("name,horizon_tol", [("drone_kat", 1e-5), ("drone_random", 1e-5), ("drone_wind", 1e-5),
+                                              ("drone_overdrive", 1e-5)])
+def test_free_running_divergence(name, horizon_tol):
+    g = load(name)
+    T, n = g["actions"].shape[:2]
+    d = make(n, dt=float(g["dt"]))
+    d.reset(g["pos0"], g["vel0"], g["rpy0"])
+    wind = g["wind"] if "wind" in g else None
+    curve = []
+    for t in range(T):
+        d.step(g["actions"][t], wind_velocity_vector=wind, return_obs=False)
+        curve.append(drone_err(d, g["state"][t], g["R"][t], g["prev_rates"][t], g["prev_thrust"][t]).max())
+    marks = [t for t in (1, 2, 5, 10, 30, 60, 120) if t <= T]
+    print(f"\n{name}: divergence " + " ".join(f"@{t}:{curve[t - 1]:.2e}" for t in marks))
+    assert curve[0] <= TOL_STEP
+    assert max(curve) <= horizon_tol
+
+
+@pytest.mark.parametrize("packed", [True, False])
+def test_k8_substeps_1s_horizon(packed):
+    """config 2/3 shape: 8 substeps of 1 ms per control step, 1 s horizon (1000 reference steps)."""
+    g = load("drone_1ms_k8")
+    T, n = g["actions"].shape[:2]
+    K = int(g["hold"])
+    d = make(n, dt=float(g["dt"]), substeps=K, packed=packed)
+    d.reset(g["pos0"], g["vel0"], g["rpy0"])
+    curve = []
+    for j in range(T // K):
+        d.step(g["actions"][j * K], return_obs=False)
+        t = j * K + K - 1
+        curve.append(drone_err(d, g["state"][t], g["R"][t], g["prev_rates"][t], g["prev_thrust"][t]).max())
+        assert np.array_equal(d.done.cpu().numpy(), g["done"][j * K:t + 1].any(axis=0))
+    print(f"\nK=8 packed={packed}: divergence over 1 s: first {curve[0]:.2e} @0.5s {curve[len(curve) // 2]:.2e} "
+          f"@1s {curve[-1]:.2e} max {max(curve):.2e}")
+    assert curve[0] <= TOL_STEP
+    assert max(curve) <= 1e-4
+
+
+def test_ground_contact_free_running():
+    """Spring + crash branch (components.py:198-214, :239): trajectories match until the reference crashes."""
+    g = load("drone_ground")
+    T, n = g["actions"].shape[:2]
+    d = make(n, dt=float(g["dt"]))
+    d.reset(g["pos0"], g["vel0"], g["rpy0"])
+    crashed = np.zeros(n, dtype=bool)
+    worst = 0.0
+    for t in range(T):
+        d.step(g["actions"][t], return_obs=False)
+        dg = d.done.cpu().numpy()
+        ok = ~crashed
+        assert np.array_equal(dg[ok], g["done"][t].astype(bool)[ok]), t
+        e = drone_err(d, g["state"][t], g["R"][t], g["prev_rates"][t], g["prev_thrust"][t])
+        worst = max(worst, e[ok].max() if ok.any() else 0.0)
+        crashed |= g["done"][t].astype(bool)
+    assert crashed.any() and not crashed.all()
+    assert worst <= 1e-5, worst
+
+
+def test_override_inputs():
+    g = load("drone_override")
+    T, n = g["actions"].shape[:2]
+    d = make(n, dt=float(g["dt"]))
+    d.reset(g["pos0"], g["vel0"], g["rpy0"])
+    for t in range(T):
+        d.step(g["actions"][t], rotation_matrix=g["R_override"][t], thrust_force=g["thrust_override"][t], return_obs=False)
+        e = drone_err(d, g["state"][t], g["R"][t], g["prev_rates"][t], g["prev_thrust"][t])
+        assert e.max() <= TOL_STEP, (t, e.max())
+        assert np.array_equal(d.done.cpu().numpy(), g["done"][t].astype(bool))
+    from fpyv_b200 import FpvError
+    d2 = make(n, dt=float(g["dt"]), substeps=2)
+    d2.reset()
+    with pytest.raises(FpvError):
+        d2.step(g["actions"][0], rotation_matrix=g["R_override"][0], thrust_force=g["thrust_override"][0])
+
+
+@pytest.mark.parametrize("packed", [True, False])
+def test_obstacles(packed):
+    from fpyv_b200 import Cylinder, Ground, Target
+    g = load("drone_objects")
+    T, n = g["actions"].shape[:2]
+    objs = [Target(g["sph"][:3], g["sph"][3]), Cylinder(g["cyl"][:3], g["cyl"][3], g["cyl"][4]), Ground()]
+    # single-step form (chaotic after contact): all (t, env) pairs at once
+    d = make((T - 1) * n, dt=float(g["dt"]), packed=packed)
+    d.reset()
+    cat = lambda k, sl: g[k][sl].reshape((-1,) + g[k].shape[2:])
+    prev, nxt = slice(0, T - 1), slice(1, T)
+    set_state(d, cat("state", prev), cat("R", prev), cat("prev_rates", prev), cat("prev_thrust", prev))
+    d.step(cat("actions", nxt), object_list=objs, return_obs=False)
+    err = drone_err(d, cat("state", nxt), cat("R", nxt), cat("prev_rates", nxt), cat("prev_thrust", nxt))
+    assert err.max() <= TOL_STEP, err.max()
+    assert np.array_equal(d.done.cpu().numpy(), cat("done", nxt).astype(bool))
+    assert cat("done", nxt).any()
+
+
+@pytest.mark.parametrize("calib", ["frsky", "calibration"])
+def test_sticks(calib):
+    from fpyv_b200 import Joystick
+    from conftest import CONFIG
+    g = load("sticks_" + calib)
+    rc = Joystick(device=DEV)
+    rc.calibrate(os.path.join(CONFIG, calib + ".json"))
+    rc.feed(g["raw"].astype(np.int64))
+    cal = rc.calib_read().cpu().numpy()
+    act = rc.read_actions().cpu().numpy()
+    assert np.max(np.abs(cal - g["calibrated"])) <= 2e-6
+    assert np.max(np.abs(act - g["action"])) <= 2e-6
+
+
+def test_step_from_sticks():
+    """Drone.step(action=None): joystick -> action -> dynamics (components.py:227-228)."""
+    g = load("drone_sticks")
+    T = g["raw"].shape[0]
+    d = make(1, dt=float(g["dt"]))
+    d.reset(g["pos0"], g["vel0"], g["rpy0"])
+    for t in range(T):
+        d.rc.feed(g["raw"][t].astype(np.int64))
+        d.step(None, return_obs=False)
+        e = drone_err(d, g["state"][t], g["R"][t], g["prev_rates"][t], g["prev_thrust"][t])
+        assert e.max() <= TOL_STEP, (t, e.max())
+    d.rc._raw = None
+    with pytest.raises(ModuleNotFoundError):
+        d.step(None)
+
+
+@pytest.mark.parametrize("name", ["racer_demo", "racer_random"])
+def test_racer(name):
+    from fpyv_b200 import BatchedRacer
+    g = load(name)
+    T, n = g["actions"].shape[:2]
+    worst_step, curve = 0.0, []
+    # free-running per env (gains differ per env -> one BatchedRacer per env, batched over nothing)
+    for e in range(n):
+        gains = dict(zip(("roll", "pitch", "yaw"), g["gains"][e]))
+        r = BatchedRacer(5, gains, num_envs=1, device=DEV)
+        r.reset()
+        for t in range(T):
+            r.step(g["actions"][t, e][None])
+            if t in (0, 1, 9, 99, T - 1):
+                err = max(group_err(r.position.cpu().numpy(), g["position"][t, e][None]).max(),
+                          group_err(r.linear_velocity.cpu().numpy(), g["velocity"][t, e][None]).max(),
+                          group_err(r.orientation.cpu().numpy(), g["R"][t, e][None]).max(),
+                          group_err(r.angular_velocity.cpu().numpy(), g["omega"][t, e][None]).max())
+                if t == 0:
+                    worst_step = max(worst_step, err)
+                curve.append((t + 1, err))
+    by_t = {}
+    for t, e in curve:
+        by_t[t] = max(by_t.get(t, 0), e)
+    print(f"\n{name}: divergence " + " ".join(f"@{t}:{e:.2e}" for t, e in sorted(by_t.items())))
+    assert worst_step <= TOL_STEP
+    assert max(by_t.values()) <= 2e-4    # |omega| ~ 80 rad feeds sin/cos: fp32 argument rounding dominates
+
+
+def test_reset_and_views():
+    d = make(5)
+    rng = np.random.default_rng(0)
+    pos, vel, rpy = rng.normal(size=(5, 3)), rng.normal(size=(5, 3)), rng.uniform(-180, 180, (5, 3))
+    d.reset(pos, vel, rpy)
+    a = np.deg2rad(rpy)
+    R = fo.euler_matrix(a[:, 0], a[:, 1], a[:, 2])
+    assert np.max(np.abs(d.rotation_matrix.cpu().numpy() - R)) <= 1e-7
+    assert np.allclose(d.position.cpu().numpy(), pos.astype(np.float32))
+    assert np.allclose(d.state.cpu().numpy()[:, 3:], vel.astype(np.float32))
+    assert d.prev_rates.abs().max().item() == 0 and d.prev_thrust.abs().max().item() == 0
+    assert not d.done.any()
+    # masked reset leaves the other envs alone
+    d.step(rng.uniform(-1, 1, (5, 4)), return_obs=False)
+    before = d.position.clone()
+    d.reset(pos, vel, rpy, mask=np.array([1, 0, 0, 1, 0], dtype=bool))
+    after = d.position
+    assert torch.equal(after[[1, 2, 4]], before[[1, 2, 4]])
+    assert np.allclose(after[[0, 3]].cpu().numpy(), pos[[0, 3]].astype(np.float32))
+    # stock defaults of params.yaml
+    d.reset()
+    assert np.allclose(d.position.cpu().numpy(), [[0, 0, 10]] * 5) and np.allclose(d.velocity.cpu().numpy(), [[1, 0, 0]] * 5)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 127, 128, 129, 257, 1000])
+def test_ragged_sizes_match_between_variants(n):
+    """Packed (2 envs/thread) and scalar kernels agree to fp32 rounding for every tail shape, and nothing outside
+    [0, n) is written."""
+    rng = np.random.default_rng(n)
+    pos = np.stack([rng.normal(0, 5, n), rng.normal(0, 5, n), rng.uniform(0.05, 3, n)], 1)
+    vel, rpy = rng.normal(size=(n, 3)), rng.uniform(-30, 30, (n, 3))
+    acts = rng.uniform(-1, 1, (6, n, 4))
+    out = []
+    for packed in (True, False):
+        d = make(n, packed=packed, substeps=4, dt=1e-3)
+        d.reset(pos, vel, rpy)
+        d._state[:, n:] = 123.0
+        for a in acts:
+            d.step(a, return_obs=False)
+        assert (d._state[:, n:] == 123.0).all()
+        out.append((d._state[:, :n].clone(), d.done.clone()))
+    assert torch.allclose(out[0][0][[0, 2, 3, 4]], out[1][0][[0, 2, 3, 4]], rtol=1e-5, atol=1e-5)
+    assert torch.allclose(out[0][0][1, :, :3], out[1][0][1, :, :3], rtol=1e-5, atol=1e-5)
+    assert torch.equal(out[0][0][1, :, 3].view(torch.int32), out[1][0][1, :, 3].view(torch.int32))
+    assert torch.equal(out[0][1], out[1][1])
+    c = fo_consts(1e-3)
+    s = fo.drone_reset(c, pos, vel, rpy)
+    for a in acts:
+        fo.drone_step(c, s, a, substeps=4)
+    assert group_err(out[0][0][0, :, :3].cpu().numpy(), s.pos).max() <= 1e-5
+
+
+def fo_consts(dt=None):
+    import yaml
+    from conftest import CONFIG
+    with open(os.path.join(CONFIG, "params.yaml")) as f:
+        params = yaml.safe_load(f)
+    return fo.derive_consts(params, os.path.join(CONFIG, "t_motos_f80_motor_test.csv"), dt=dt)
+
+
+def test_thrust_lut_matches_cubic():
+    """north_star's shared-memory LUT with interpolation vs the reference cubic (n=2049: <= 6e-6 N)."""
+    n = 4096
+    rng = np.random.default_rng(5)
+    acts = rng.uniform(-1, 1, (n, 4))
+    res = []
+    for lut in (0, 2049):
+        d = make(n, thrust_lut=lut)
+        d.reset()
+        d.step(acts, return_obs=False)
+        res.append(d.prev_thrust.cpu().numpy().astype(np.float64))
+    c = fo_consts()
+    ref = fo.throttle2thrust(c, acts[:, 3]) * 0.5
+    assert np.max(np.abs(res[0] - ref)) <= 1e-5
+    assert np.max(np.abs(res[1] - ref)) <= 2e-5
+    print(f"\nLUT(2049) vs cubic: max abs {np.max(np.abs(res[1] - res[0])):.2e} N")
+
+
+def test_per_env_wind_and_fast_math():
+    n = 512
+    rng = np.random.default_rng(6)
+    pos = np.stack([rng.normal(0, 5, n), rng.normal(0, 5, n), rng.uniform(2, 12, n)], 1)
+    vel, rpy = rng.normal(0, 3, (n, 3)), rng.uniform(-30, 30, (n, 3))
+    wind = rng.normal(0, 2, (n, 3))
+    acts = rng.uniform(-1, 1, (10, n, 4))
+    c = fo_consts()
+    s = fo.drone_reset(c, pos, vel, rpy)
+    # oracle: per-env wind = loop-free because drone_substep broadcasts [n,3]
+    for a in acts:
+        fo.drone_substep(c, s, a, wind)
+    for fast in (False, True):
+        d = make(n, fast_math=fast)
+        d.reset(pos, vel, rpy)
+        w = torch.as_tensor(wind, dtype=torch.float32, device=DEV)
+        for a in acts:
+            d.step(a, wind_velocity_vector=w, return_obs=False)
+        e = drone_err(d, np.concatenate([s.pos, s.vel], 1), s.R, s.prev_rates, s.prev_thrust)
+        assert e.max() <= 1e-5, (fast, e.max())
+
+
+def test_auto_reset_freeze_and_stats():
+    n = 64
+    pos = np.tile([0.0, 0.0, 0.3], (n, 1))
+    pos[::2, 2] = 50.0                       # even envs fly high, odd envs start just above the ground
+    vel = np.tile([0.0, 0.0, -3.0], (n, 1))
+    acts = np.tile([0.0, 0.0, 0.0, -1.0], (n, 1))
+    # reference behaviour: done reported per step, integration continues
+    d = make(n)
+    d.reset(pos, vel, 0.0)
+    seen = torch.zeros(n, dtype=torch.bool, device=DEV)
+    for _ in range(30):
+        d.step(acts, return_obs=False)
+        seen |= d.done
+    assert seen[1::2].all() and not seen[::2].any()
+    # freeze: crashed envs stop, done is sticky
+    d = make(n, freeze_done=True)
+    d.reset(pos, vel, 0.0)
+    for _ in range(30):
+        d.step(acts, return_obs=False)
+    assert d.done[1::2].all() and not d.done[::2].any()
+    z = d.position[1::2, 2].clone()
+    d.step(acts, return_obs=False)
+    assert torch.equal(d.position[1::2, 2], z)
+    assert (d.episode_steps[1::2] < 0).all()
+    st = d.episode_stats()
+    assert st["episodes"] == n // 2 and st["crashes"] == n // 2 and st["nonfinite"] == 0
+    assert st["env_steps"] == pytest.approx(31 * (n // 2) + st["episode_len_sum"])
+    # auto-reset: crashed envs restart from the reset snapshot and keep counting episodes
+    d = make(n, auto_reset=True)
+    d.reset(pos, vel, 0.0)
+    for _ in range(40):
+        d.step(acts, return_obs=False)
+    st = d.episode_stats()
+    assert st["episodes"] >= n // 2 and st["env_steps"] == 40 * n
+    assert (d.position[1::2, 2] > 0).all()
+    assert st["mean_episode_len"] > 1
+
+
+def test_drone_compat_object_matches_reference_kat():
+    """num_envs=1 NumPy stand-in driven exactly like simulator.py drives the reference."""
+    from fpyv_b200 import Drone, Ground
+    from fpyv_b200.config import load_params
+    params = load_params()
+    drone = Drone(params)
+    assert params["drone"]["force_multiplier_pid"]["max_output"] == pytest.approx(81.30229036293663)
+    drone.reset(position=np.array(params["drone"]["initial_position"]), velocity=np.array(params["drone"]["initial_velocity"]),
+                ypr=np.array(params["drone"]["initial_orientation"]))
+    g = load("drone_kat")
+    for t in range(60):
+        Rt, gyro, acc = drone.step(action=np.array([0.3, -0.2, 0.1, 0.25]), wind_velocity_vector=np.zeros(3), object_list=[Ground()])
+        assert not drone.done
+    assert np.max(np.abs(drone.state - g["state"][59, 0])) / np.max(np.abs(g["state"][59, 0])) <= 1e-5
+    assert np.max(np.abs(Rt - g["ret_Rt"][59, 0])) <= 1e-5
+    assert drone.prev_thrust == pytest.approx(g["prev_thrust"][59, 0], rel=1e-5)
+
+
+def test_error_paths():
+    from fpyv_b200 import FpvError, _lib
+    import ctypes as C
+    lib = _lib.load()
+    d = make(8)
+    with pytest.raises(RuntimeError):
+        d.step(np.zeros((8, 4)))            # step before reset
+    d.reset()
+    p, io = d._p, d._io
+    d.step(np.zeros((8, 4)), return_obs=False)
+    p.substeps = 0
+    assert lib.fpv_drone_step(C.byref(p), C.byref(io), None) == -22
+    assert b"substeps" in lib.fpv_last_error()
+    p.substeps = 1
+    io.actions = io.actions + 4             # misaligned
+    assert lib.fpv_drone_step(C.byref(p), C.byref(io), None) == -22
+    io.actions = None
+    assert lib.fpv_drone_step(C.byref(p), C.byref(io), None) == -22
+    with pytest.raises(FpvError):
+        _lib.check(-22)
+    with pytest.raises(FileNotFoundError):
+        from fpyv_b200 import Joystick
+        Joystick(device=DEV).calibrate("/nonexistent/calib.json")
+    with pytest.raises(ValueError):
+        from fpyv_b200 import Ground, Target
+        d.step(np.zeros((8, 4)), object_list=[Ground(), Target([0, 0, 5], 1.0)])
+
+
+def test_full_size_properties():
+    """BASELINE config 3 size (1,048,576 envs, K=8, 1 ms): size-independent properties + a 4,096-env subsample
+    against the oracle over the 1 s horizon (125 control steps)."""
+    n, K, dt, steps = 1 << 20, 8, 1e-3, 125
+    gen = torch.Generator(device=DEV).manual_seed(1234)
+    pos = torch.randn(n, 3, device=DEV, generator=gen) * torch.tensor([5.0, 5.0, 2.0], device=DEV) + torch.tensor([0, 0, 10.0], device=DEV)
+    pos[:, 2].clamp_(min=1.0)
+    vel = torch.randn(n, 3, device=DEV, generator=gen)
+    rpy = (torch.rand(n, 3, device=DEV, generator=gen) * 2 - 1) * 30
+    # plant duplicates: env i+half == env i for the first 1000 envs
+    half = n // 2
+    for t in (pos, vel, rpy):
+        t[half:half + 1000] = t[:1000]
+    d = make(n, substeps=K, dt=dt)
+    d.reset(pos, vel, rpy)
+    sub = torch.arange(0, n, n // 4096, device=DEV)[:4096]
+    c = fo_consts(dt)
+    s = fo.drone_reset(c, pos[sub].cpu().numpy().astype(np.float64), vel[sub].cpu().numpy().astype(np.float64),
+                       rpy[sub].cpu().numpy().astype(np.float64))
+    curve = {}
+    for j in range(steps):
+        a = torch.rand(n, 4, device=DEV, generator=gen) * 2 - 1
+        a[half:half + 1000] = a[:1000]
+        d.step(a, return_obs=False)
+        fo.drone_step(c, s, a[sub].cpu().numpy().astype(np.float64), substeps=K)
+        if j + 1 in (1, 2, 5, 10, 30, 60, 125):
+            e = np.maximum.reduce([group_err(d.position[sub].cpu().numpy(), s.pos), group_err(d.velocity[sub].cpu().numpy(), s.vel),
+                                   group_err(d.rotation_matrix[sub].cpu().numpy(), s.R)])
+            curve[j + 1] = e.max()
+    print("\n1M envs, K=8: divergence vs float64 oracle (4096-env subsample) " + " ".join(f"@{k}:{v:.2e}" for k, v in curve.items()))
+    assert curve[1] <= TOL_STEP and max(curve.values()) <= 1e-4
+    # determinism across thread slots / positions in the batch
+    assert torch.equal(d._state[:, half:half + 1000], d._state[:, :1000])
+    # R stays a rotation: R R^T = I to fp32 drift
+    R = d.rotation_matrix
+    eye = torch.eye(3, device=DEV)
+    assert (R @ R.transpose(1, 2) - eye).abs().max().item() <= 1e-4
+    assert torch.isfinite(d._state[:, :n, :3]).all()
+    st = d.episode_stats()
+    assert st["env_steps"] == steps * n and st["nonfinite"] == 0

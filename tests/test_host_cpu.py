@@ -1,0 +1,171 @@
+"""CPU-side tests (no GPU): the C-ABI library loads and exports every symbol include/fpv_api.h declares,
+struct layouts agree, config front-end parses the reference's file formats, host logic of objects/sticks."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import CONFIG, GOLDEN, ROOT
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from fpyv_b200 import build, _lib
+    build.build()
+    return _lib.load()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    hdr = open(os.path.join(ROOT, "include", "fpv_api.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(fpv_[a-z_0-9]+)\s*\(", hdr))
+    assert {"fpv_drone_step", "fpv_drone_reset", "fpv_racer_step", "fpv_sticks_to_actions"} <= names
+    raw = C.CDLL(os.path.join(ROOT, "fpyv_b200", "libfpyv_b200.so"))
+    for n in sorted(names):
+        assert hasattr(raw, n), f"{n} declared in fpv_api.h but not exported"
+    from fpyv_b200 import _lib
+    assert set(_lib.EXPORTS) == names
+
+
+def test_abi_version_and_struct_sizes(lib):
+    from fpyv_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "fpv_api.h")).read()
+    assert int(re.search(r"#define FPV_ABI_VERSION (\d+)", hdr).group(1)) == lib.fpv_abi_version() == _lib.ABI_VERSION
+    for i, st in enumerate(_lib._STRUCTS):
+        assert lib.fpv_sizeof(i) == C.sizeof(st), st.__name__
+    assert lib.fpv_sizeof(99) == -1
+    for name, val in (("FPV_F_GROUND", _lib.F_GROUND), ("FPV_F_AUTO_RESET", _lib.F_AUTO_RESET),
+                      ("FPV_F_FREEZE_DONE", _lib.F_FREEZE_DONE), ("FPV_F_THRUST_LUT", _lib.F_THRUST_LUT),
+                      ("FPV_F_FAST_MATH", _lib.F_FAST_MATH), ("FPV_F_SCALAR", _lib.F_SCALAR),
+                      ("FPV_MAX_OBJECTS", _lib.MAX_OBJECTS), ("FPV_DRONE_PLANES", _lib.DRONE_PLANES),
+                      ("FPV_RACER_PLANES", _lib.RACER_PLANES)):
+        assert int(re.search(rf"#define {name} (\d+)", hdr).group(1)) == val, name
+
+
+def test_argument_validation_needs_no_gpu(lib):
+    """EINVAL paths return before any CUDA call."""
+    from fpyv_b200 import _lib
+    p, io = _lib.DroneParams(), _lib.DroneIO()
+    assert lib.fpv_drone_step(None, None, None) == -22
+    io.n, io.plane_stride = 8, 4
+    assert lib.fpv_drone_step(C.byref(p), C.byref(io), None) == -22
+    assert b"stride" in lib.fpv_last_error()
+    io.n = 0
+    io.plane_stride = 0
+    assert lib.fpv_drone_step(C.byref(p), C.byref(io), None) == 0       # empty batch is a no-op
+    assert lib.fpv_racer_step(None, None, 0, 0, None, None, None) == -22
+    assert lib.fpv_sticks_to_actions(None, None, 0, None, None, None) == -22
+
+
+def test_no_cpu_fallback():
+    import torch
+    from fpyv_b200 import BatchedDrone
+    with pytest.raises(RuntimeError):
+        BatchedDrone(None, num_envs=2, device="cpu")
+    if not torch.cuda.is_available():
+        with pytest.raises(Exception):
+            BatchedDrone(None, num_envs=2, device="cuda:0")
+
+
+def test_product_never_imports_oracle():
+    for root, _, files in os.walk(os.path.join(ROOT, "fpyv_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(root, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+                assert "/root/reference" not in src, f
+
+
+def test_config_constants_match_reference_golden():
+    from fpyv_b200 import config
+    g = np.load(os.path.join(GOLDEN, "consts.npz"))
+    params = config.load_params()
+    c = config.derive_constants(params)
+    assert c.dt == float(g["dt"]) and c.mass == float(g["mass"])
+    np.testing.assert_allclose(c.thrust_poly.coeffs, g["poly"], rtol=1e-12)
+    np.testing.assert_allclose(c.throttle_poly.coeffs, g["inv_poly"], rtol=1e-12)
+    np.testing.assert_allclose(c.motors_relative_position, g["motors_relative_position"], atol=1e-16)
+    np.testing.assert_allclose(c.cross_section_areas, g["cross_section_areas"], rtol=1e-15)
+    np.testing.assert_allclose(c.throttle2thrust(g["t2t_x"]), g["t2t_y"], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(c.thrust2throttle(g["inv_x"]), g["inv_y"], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose([c.min_throttle_in_force, c.max_throttle_in_force], [g["min_force"], g["max_force"]], rtol=1e-13)
+    np.testing.assert_allclose(c.thrust_newton, g["thrust_n"], rtol=1e-15)
+    assert c.motor_name == "F80 Pro KV1900" and c.propeller == "5055 Tri-Blade"
+
+
+def test_motor_report_reader_handles_format_quirks(tmp_path):
+    from fpyv_b200 import config
+    sweeps = config.read_motor_test_report(os.path.join(CONFIG, "t_motos_f80_motor_test.csv"))
+    assert len(sweeps) == 5 and all(len(s.throttle_percent) == 11 for s in sweeps)
+    assert sweeps[2].thrust_grams[2] == 993.47          # quoted decimal comma "993,47"
+    p = tmp_path / "m.csv"
+    p.write_text('Type,Propeller,Throttle,Thrust (g)\nX,P,50%,"10,5"\n,,100%,20\n,,50%,11\n,,100%,21\n')
+    s = config.read_motor_test_report(str(p))
+    assert len(s) == 2 and s[0].thrust_grams.tolist() == [10.5, 20.0] and s[0].motor == "X"
+
+
+def test_windows_paths_resolve_next_to_params(tmp_path):
+    from fpyv_b200 import config
+    assert config.resolve_path(r"C:\Users\omri_\PycharmProjects\FpyV\config\frsky.json").endswith("frsky.json")
+    (tmp_path / "frsky.json").write_text("{}")
+    assert config.resolve_path(r"C:\x\frsky.json", (str(tmp_path),)) == str(tmp_path / "frsky.json")
+    with pytest.raises(FileNotFoundError):
+        config.resolve_path(r"C:\x\nope.json")
+    params = config.load_params()
+    params["drone"]["motor_test_report_path"] = r"C:\Users\omri_\PycharmProjects\FpyV\config\t_motos_f80_motor_test.csv"
+    assert config.derive_constants(params).max_throttle_in_force == pytest.approx(81.30229036293663)
+
+
+def test_thrust_table():
+    from fpyv_b200 import config
+    c = config.derive_constants(config.load_params())
+    t = config.thrust_table(c, 2049)
+    x = np.linspace(-1, 1, 20001)
+    lin = np.interp(x, np.linspace(-1, 1, 2049), t.astype(np.float64))
+    assert np.max(np.abs(lin - c.throttle2thrust(x))) < 6e-6
+    b = config.thrust_table(c, 1025, "bench")
+    assert b[0] == 0 and b[-1] == pytest.approx(c.thrust_newton[-1], rel=1e-6)
+    with pytest.raises(ValueError):
+        config.thrust_table(c, 16, "nope")
+
+
+def test_stick_calibration_json():
+    from fpyv_b200 import config
+    cal = config.StickCalibration.load(os.path.join(CONFIG, "frsky.json"))
+    assert cal.stick_idx == [0, 1, 2, 5] and list(cal.sticks) == ["Throttle", "Roll", "Pitch", "Yaw"]
+    assert cal.max_vals[0] == 48371
+    with pytest.raises(FileNotFoundError):
+        config.StickCalibration.load("/nonexistent.json")
+
+
+def test_object_list_lowering():
+    from fpyv_b200 import objects, _lib
+    g, lowered = objects.lower_object_list([objects.Target([1, 2, 3], 0.5), objects.Gate([0, 0, 0], np.eye(3), 2.0),
+                                            objects.Cylinder([4, 5, 0], 1.0, 6.0), objects.Ground()])
+    assert g and [o.kind for o in lowered] == [_lib.OBJ_SPHERE, _lib.OBJ_CYLINDER]
+    assert lowered[1].b == 6.0
+    with pytest.raises(ValueError):
+        objects.lower_object_list([objects.Ground(), objects.Target([0, 0, 0], 1)])
+    with pytest.raises(ValueError):
+        objects.lower_object_list([objects.Target([0, 0, 0], 1)] * 17)
+    with pytest.raises(AssertionError):
+        objects.Cylinder([0, 0, 0], -1, 1)
+    gate = objects.Gate([1.0, 0, 0], np.eye(3), 2.0)
+    assert gate.calculate_distance(np.array([3.0, 5, 5])) == pytest.approx(2.0)
+
+
+def test_sincos_polynomial_accuracy():
+    """The small-angle kernels in csrc/vec.cuh, evaluated here in float32 with the same coefficients."""
+    x = np.linspace(-0.7854, 0.7854, 200001).astype(np.float32)
+    x2 = x * x
+    ps = np.float32(-1.95152959e-4) * x2 + np.float32(8.33216087e-3)
+    ps = ps * x2 + np.float32(-1.66666546e-1)
+    s = ps * (x2 * x) + x
+    pc = np.float32(2.44331571e-5) * x2 + np.float32(-1.38873163e-3)
+    pc = pc * x2 + np.float32(4.16666457e-2)
+    pc = pc * x2 + np.float32(-0.5)
+    c = pc * x2 + np.float32(1.0)
+    assert np.max(np.abs(s - np.sin(x.astype(np.float64)))) < 1.5e-7
+    assert np.max(np.abs(c - np.cos(x.astype(np.float64)))) < 1.5e-7

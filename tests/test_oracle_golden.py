@@ -161,3 +161,24 @@ def test_l1_kats():
     ang = np.deg2rad(np.array([[-42., 28, -14]])) / 60
     E = fo.euler_matrix(ang[:, 0], ang[:, 1], ang[:, 2])
     np.testing.assert_allclose((R @ np.swapaxes(E, 1, 2))[0], g["rot_by_rates"], rtol=1e-13, atol=1e-16)
+
+
+@pytest.mark.parametrize("name", ["drone_kat", "drone_random", "drone_ground", "drone_wind", "drone_1ms_k8"])
+def test_c_restatement_matches_reference(name):
+    """oracle/fpv_oracle.c (the CPU-baseline code) against the same golden vectors."""
+    from oracle import c_oracle
+    g = load(name)
+    c = consts(dt=float(g["dt"]))
+    k = c_oracle.make_consts(c)
+    s = fo.drone_reset(c, g["pos0"], g["vel0"], g["rpy0"])
+    pos, vel, R = s.pos.copy(), s.vel.copy(), np.ascontiguousarray(s.R)
+    pr, pt = np.zeros_like(pos), np.zeros(len(pos))
+    wind = g["wind"] if "wind" in g else None
+    worst = 0.0
+    for t in range(g["actions"].shape[0]):
+        done = c_oracle.drone_step(k, pos, vel, R, pr, pt, np.ascontiguousarray(g["actions"][t]), wind,
+                                   threads=2 if t % 2 else 1)
+        worst = max(worst, rel(np.concatenate([pos, vel], 1), g["state"][t]), rel(R, g["R"][t]),
+                    rel(pr, g["prev_rates"][t]), rel(pt, g["prev_thrust"][t]))
+        assert np.array_equal(done.astype(bool), g["done"][t].astype(bool))
+    assert worst < 1e-11, worst
