@@ -210,6 +210,13 @@ def run_gpu(args):
     t1 = time.time()
     clocks = sampler.stop(t0, t1) if sampler else None
 
+    if args.profile:      # ncu / launch-list runs: only the two timed kernel loops (K=8 then K=1)
+        d1, _ = make(1)
+        ms_k1 = timed_loop(d1, K, W)
+        if rank == 0:
+            print(json.dumps({"profile_run": True, "ms_per_step_k8": ms / K, "ms_per_step_k1": ms_k1 / K}))
+        return
+
     # ---- end to end through the public API with HOST buffers (pinned): H2D actions, step, D2H done flags
     host_actions = [torch.empty(n, 4, dtype=torch.float32, pin_memory=True).uniform_(-1, 1) for _ in range(2)]
     host_done = torch.empty(n, dtype=torch.uint8, pin_memory=True)
@@ -285,6 +292,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU (default: the BASELINE config)")
+    ap.add_argument("--profile", action="store_true", help="kernel loops only (for ncu): no e2e / CPU legs")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native":
         args.warmup = 3

@@ -6,11 +6,12 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libfpyv_b200.so")
-ABI_VERSION = 3
+# FPYV_B200_LIB: developer override used to A/B differently tuned builds of the same ABI
+LIB_PATH = os.environ.get("FPYV_B200_LIB") or os.path.join(HERE, "libfpyv_b200.so")
+ABI_VERSION = 4
 
 # flags (fpv_api.h)
-F_GROUND, F_AUTO_RESET, F_FREEZE_DONE, F_THRUST_LUT, F_FAST_MATH, F_SCALAR = 1, 2, 4, 8, 16, 32
+F_GROUND, F_AUTO_RESET, F_FREEZE_DONE, F_THRUST_LUT, F_SCALAR = 1, 2, 4, 8, 32
 OBJ_SPHERE, OBJ_CYLINDER = 1, 2
 MAX_OBJECTS = 16
 DRONE_PLANES, RACER_PLANES = 5, 7

@@ -26,6 +26,7 @@ struct DroneK {
   float wind[3];
   float grav_force_z;       // -g*m                                  kinematics.py:41-45
   float inv_mass;
+  float dt_over_mass;       // dt / m
   float mass;
   float ang_scale;          // deg2rad * dt                          kinematics.py:29
   float lut_scale;          // (lut_n-1)/2
@@ -90,7 +91,9 @@ template <class V> struct DroneRegs {
 };
 
 // K reference steps for the envs held in `s`.  Returns the OR of the per-step crash flags.
-template <class V, bool SMALL, bool GENERAL, bool FAST>
+// ANG selects the sin/cos evaluation: 0 = full-range sincosf, 1 = |angle| <= 0.5 rad (degree-7/8 kernels, no range
+// reduction), 2 = |angle| <= 0.1 rad (degree-5/4 kernels, truncation error < 2e-11).
+template <class V, int ANG, bool GENERAL>
 __device__ __forceinline__ typename Lane<V>::Mask drone_substeps(const DroneK& k, DroneRegs<V>& s, V a0, V a1, V a2,
                                                                    V thrust_target, V wx, V wy, V wz,
                                                                    bool has_override, V o_thrust,
@@ -103,9 +106,11 @@ __device__ __forceinline__ typename Lane<V>::Mask drone_substeps(const DroneK& k
   const V c2 = vmin(vmax(vneg(a2) * mr, vneg(mr)), mr) * S<V>(k.rtr);
   const V tt = thrust_target * S<V>(k.ttr);
   const V omr = S<V>(k.one_minus_rtr), omt = S<V>(k.one_minus_ttr);
-  const V dt = S<V>(k.dt), inv_m = S<V>(k.inv_mass), asc = S<V>(k.ang_scale);
+  const V dt = S<V>(k.dt), dt_m = S<V>(k.dt_over_mass), asc = S<V>(k.ang_scale);
   const V zero = S<V>(0.f);
+  const bool ground = (k.flags & FPV_F_GROUND) != 0;
   M done = vlt(S<V>(1.f), zero);  // all false
+  V Fx = zero, Fy = zero, Fz = zero;
 
 #pragma unroll 1
   for (int it = 0; it < k.substeps; ++it) {
@@ -120,39 +125,41 @@ __device__ __forceinline__ typename Lane<V>::Mask drone_substeps(const DroneK& k
       s.r20 = ovr->r20; s.r21 = ovr->r21; s.r22 = ovr->r22;
       th = o_thrust;
     }
-    // ---- drag, kinematics.py:33-38: R * (k (.) (R^T (v + wind)) * |v + wind|)
+    // ---- drag, kinematics.py:33-38: R * (k (.) (R^T (v + wind)) * |v + wind|); the thrust R[:,2]*th
+    //      (kinematics.py:48-49) is a body-z force too, so it joins the body-frame vector before the rotation
     const V ux = s.vx + wx, uy = s.vy + wy, uz = s.vz + wz;
-    const V n2 = vfma(ux, ux, vfma(uy, uy, uz * uz));
-    const V nrm = FAST ? vsqrt_fast(n2) : vsqrt(n2);
+    const V nrm = vsqrt_fast(vfma(ux, ux, vfma(uy, uy, uz * uz)));
     const V b0 = vfma(s.r00, ux, vfma(s.r10, uy, s.r20 * uz));
     const V b1 = vfma(s.r01, ux, vfma(s.r11, uy, s.r21 * uz));
     const V b2 = vfma(s.r02, ux, vfma(s.r12, uy, s.r22 * uz));
-    const V f0 = (S<V>(k.k_drag[0]) * b0) * nrm, f1 = (S<V>(k.k_drag[1]) * b1) * nrm,
-            f2 = (S<V>(k.k_drag[2]) * b2) * nrm;
-    // ---- thrust + gravity + drag (components.py:242), thrust_vector kinematics.py:48-49
-    V Fx = vfma(s.r00, f0, vfma(s.r01, f1, vfma(s.r02, f2, s.r02 * th)));
-    V Fy = vfma(s.r10, f0, vfma(s.r11, f1, vfma(s.r12, f2, s.r12 * th)));
-    V Fz = vfma(s.r20, f0, vfma(s.r21, f1, vfma(s.r22, f2, vfma(s.r22, th, S<V>(k.grav_force_z)))));
+    const V f0 = (S<V>(k.k_drag[0]) * b0) * nrm, f1 = (S<V>(k.k_drag[1]) * b1) * nrm;
+    const V f2 = vfma(S<V>(k.k_drag[2]) * b2, nrm, th);
+    // ---- thrust + gravity + drag (components.py:242)
+    Fx = vfma(s.r00, f0, vfma(s.r01, f1, s.r02 * f2));
+    Fy = vfma(s.r10, f0, vfma(s.r11, f1, s.r12 * f2));
+    Fz = vfma(s.r20, f0, vfma(s.r21, f1, vfma(s.r22, f2, S<V>(k.grav_force_z))));
     // ---- motors, collisions, crash test (components.py:235-239, :198-214)
-    M crashed = vlt(S<V>(1.f), zero);
-    V cfx = zero, cfy = zero, cfz = zero;
+    M crashed;
     if (!GENERAL) {
-      // ground only: distance = z, normal = +z (components.py:674-680); only z of M_rel @ R^T matters
-      V minz = S<V>(3.0e38f);
+      // ground only: distance = z, normal = +z (components.py:674-680); only z of M_rel @ R^T matters.
+      // t_m = motor_radius - z_m is the spring compression; spring_force (kinematics.py:56-59) per motor is
+      // k*t_m - c*vz where t_m > 0; a motor below the plane (t_m > radius) is a crash with NO force (:207-210).
+      const V h = S<V>(k.motor_radius) - s.pz;
+      V tmax = S<V>(-3.0e38f), pen_sum = zero, cnt = zero;
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
-        const V mz = vfma(S<V>(k.motor_xy[m][0]), s.r20, vfma(S<V>(k.motor_xy[m][1]), s.r21, s.pz));
-        minz = vmin(minz, mz);
-        const V pen = mz - S<V>(k.motor_radius);
-        // spring_force, kinematics.py:56-59: (-k*pen - c*(v.n)) * n
-        const V f = vneg(vfma(S<V>(k.spring_k), pen, S<V>(k.spring_c) * s.vz));
-        cfz = cfz + vsel(vlt(pen, zero), f, zero);
+        const V t = vfma(S<V>(-k.motor_xy[m][0]), s.r20, vfma(S<V>(-k.motor_xy[m][1]), s.r21, h));
+        tmax = vmax(tmax, t);
+        pen_sum = pen_sum + vmax(t, zero);
+        if (k.spring_c != 0.f) cnt = cnt + vsel(vlt(zero, t), S<V>(1.f), zero);
       }
-      crashed = vlt(minz, zero);
-      if (k.flags & FPV_F_GROUND) cfz = vsel(crashed, zero, cfz);  // early return with no force, :207-210
-      else { cfz = zero; }
-      // without the ground object the crash test of components.py:239 still applies
+      crashed = vlt(S<V>(k.motor_radius), tmax);
+      V cf = S<V>(k.spring_k) * pen_sum;
+      if (k.spring_c != 0.f) cf = vfma(vneg(S<V>(k.spring_c)) * s.vz, cnt, cf);
+      if (ground) Fz = Fz + vsel(crashed, zero, cf);
     } else {
+      crashed = vlt(S<V>(1.f), zero);
+      V cfx = zero, cfy = zero, cfz = zero;
       V mxw[4], myw[4], mzw[4];
       V minz = S<V>(3.0e38f);
 #pragma unroll
@@ -163,7 +170,7 @@ __device__ __forceinline__ typename Lane<V>::Mask drone_substeps(const DroneK& k
         mzw[m] = vfma(ox, s.r20, vfma(oy, s.r21, s.pz));
         minz = vmin(minz, mzw[m]);
       }
-      const int n_obj = k.n_objects + ((k.flags & FPV_F_GROUND) ? 1 : 0);
+      const int n_obj = k.n_objects + (ground ? 1 : 0);
       for (int o = 0; o < n_obj; ++o) {  // object order: extra objects first, ground last
         V d[4], nx[4], ny[4], nz[4];
         M hit = vlt(S<V>(1.f), zero);
@@ -192,21 +199,19 @@ __device__ __forceinline__ typename Lane<V>::Mask drone_substeps(const DroneK& k
         cfz = cfz + vsel(live, oz, zero);
       }
       crashed = vor(crashed, vlt(minz, zero));  // components.py:239
+      Fx = Fx + cfx; Fy = Fy + cfy; Fz = Fz + cfz;
     }
     done = vor(done, crashed);
-    Fx = Fx + cfx; Fy = Fy + cfy; Fz = Fz + cfz;
-    // ---- acceleration, components.py:243
-    s.ax = Fx * inv_m; s.ay = Fy * inv_m; s.az = Fz * inv_m;
-    // ---- translation: x += v*dt with the OLD v, then v += a*dt, kinematics.py:21-22
+    // ---- translation: x += v*dt with the OLD v, then v += (F/m)*dt, kinematics.py:21-22, components.py:243
     s.px = vfma(s.vx, dt, s.px); s.py = vfma(s.vy, dt, s.py); s.pz = vfma(s.vz, dt, s.pz);
-    s.vx = vfma(s.ax, dt, s.vx); s.vy = vfma(s.ay, dt, s.vy); s.vz = vfma(s.az, dt, s.vz);
+    s.vx = vfma(Fx, dt_m, s.vx); s.vy = vfma(Fy, dt_m, s.vy); s.vz = vfma(Fz, dt_m, s.vz);
     // ---- attitude: E = Rz(yaw)Ry(pitch)Rx(roll) of deg2rad(rates)*dt, R <- R E^T E^T
     //      (rotate_body_by_rates kinematics.py:27-30 runs inside update_kinematic_step :23 AND again in
     //      Drone.update components.py:218)
     V sr, cr, sp, cp, sy, cy;
-    vsincos<SMALL>(w0 * asc, sr, cr);
-    vsincos<SMALL>(w1 * asc, sp, cp);
-    vsincos<SMALL>(w2 * asc, sy, cy);
+    vsincos<ANG>(w0 * asc, sr, cr);
+    vsincos<ANG>(w1 * asc, sp, cp);
+    vsincos<ANG>(w2 * asc, sy, cy);
     const V sysp = sy * sp, cysp = cy * sp;
     const V e00 = cy * cp, e01 = vfma(cysp, sr, vneg(sy * cr)), e02 = vfma(cysp, cr, sy * sr);
     const V e10 = sy * cp, e11 = vfma(sysp, sr, cy * cr), e12 = vfma(sysp, cr, vneg(cy * sr));
@@ -228,6 +233,9 @@ __device__ __forceinline__ typename Lane<V>::Mask drone_substeps(const DroneK& k
       s.r20 = t0; s.r21 = t1; s.r22 = t2;
     }
   }
+  // acceleration of the last substep (Drone.acceleration, components.py:243)
+  const V inv_m = S<V>(k.inv_mass);
+  s.ax = Fx * inv_m; s.ay = Fy * inv_m; s.az = Fz * inv_m;
   return done;
 }
 
@@ -256,59 +264,164 @@ template <> struct Pack<float> {
   static __device__ __forceinline__ float w(const float4* q) { return q[0].w; }
 };
 template <> struct Pack<F2> {
-  static __device__ __forceinline__ F2 x(const float4* q) { return F2{make_float2(q[0].x, q[1].x)}; }
-  static __device__ __forceinline__ F2 y(const float4* q) { return F2{make_float2(q[0].y, q[1].y)}; }
-  static __device__ __forceinline__ F2 z(const float4* q) { return F2{make_float2(q[0].z, q[1].z)}; }
-  static __device__ __forceinline__ F2 w(const float4* q) { return F2{make_float2(q[0].w, q[1].w)}; }
+  static __device__ __forceinline__ F2 x(const float4* q) { return f2_pack(q[0].x, q[1].x); }
+  static __device__ __forceinline__ F2 y(const float4* q) { return f2_pack(q[0].y, q[1].y); }
+  static __device__ __forceinline__ F2 z(const float4* q) { return f2_pack(q[0].z, q[1].z); }
+  static __device__ __forceinline__ F2 w(const float4* q) { return f2_pack(q[0].w, q[1].w); }
 };
 
-// Block-level accumulation of the episode statistics: warp shuffle -> shared -> one atomic per CTA.
-__device__ __forceinline__ void stats_accumulate(fpv_stats_t* stats, float steps, float crashes, float episodes,
-                                                 float len_sum, float nonfinite) {
-  __shared__ float red[5][32];
-  float v[5] = {steps, crashes, episodes, len_sum, nonfinite};
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+// Episode statistics: every counter is a RARE event (crash / episode end / non-finite / frozen), so the common
+// path is one warp vote and no memory traffic; a warp that saw an event reduces with shuffles and issues one
+// fire-and-forget red.global.add.f64 per non-zero counter.  No block barrier.  env_steps = n per launch (added by
+// one thread of the grid) minus the frozen envs.
+__device__ __forceinline__ void stats_warp_flush(fpv_stats_t* stats, float crashes, float episodes, float len_sum,
+                                                 float nonfinite, float frozen) {
+  const bool any = (crashes != 0.f) | (nonfinite != 0.f) | (frozen != 0.f);
+  if (!__any_sync(0xffffffffu, any)) return;
+  float v[5] = {crashes, episodes, len_sum, nonfinite, frozen};
 #pragma unroll
-  for (int i = 0; i < 5; ++i) {
+  for (int i = 0; i < 5; ++i)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
-    if (lane == 0) red[i][warp] = v[i];
-  }
-  __syncthreads();
-  if (warp == 0) {
-    const int nw = (blockDim.x + 31) >> 5;
-#pragma unroll
-    for (int i = 0; i < 5; ++i) {
-      float t = lane < nw ? red[i][lane] : 0.f;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-      v[i] = t;
-    }
-    if (lane == 0) {
-      if (v[0] != 0.f) atomicAdd(&stats->env_steps, (double)v[0]);
-      if (v[1] != 0.f) atomicAdd(&stats->crashes, (double)v[1]);
-      if (v[2] != 0.f) atomicAdd(&stats->episodes, (double)v[2]);
-      if (v[3] != 0.f) atomicAdd(&stats->episode_len_sum, (double)v[3]);
-      if (v[4] != 0.f) atomicAdd(&stats->nonfinite, (double)v[4]);
-    }
+  if ((threadIdx.x & 31) == 0) {
+    if (v[0] != 0.f) atomicAdd(&stats->crashes, (double)v[0]);
+    if (v[1] != 0.f) atomicAdd(&stats->episodes, (double)v[1]);
+    if (v[2] != 0.f) atomicAdd(&stats->episode_len_sum, (double)v[2]);
+    if (v[3] != 0.f) atomicAdd(&stats->nonfinite, (double)v[3]);
+    if (v[4] != 0.f) atomicAdd(&stats->env_steps, -(double)v[4]);
   }
 }
 
-template <class V, bool SMALL, bool GENERAL, bool FAST, int THREADS>
-__global__ void __launch_bounds__(THREADS) drone_step_kernel(const __grid_constant__ DroneK k, const DroneIO io) {
+struct TileStats {
+  float crash, epi, len, nf, frozen;
+};
+
+// One tile worth of work for this thread: unpack L envs from their float4 rows, run the substeps in registers,
+// episode bookkeeping, stores.  q[p][l] = plane p of slot l; slot l is env base + l*SLOT_STRIDE (ei[l] = the same index
+// clamped to n-1, used for the side inputs of the general path).
+template <class V, int ANG, bool GENERAL, int SLOT_STRIDE>
+__device__ __forceinline__ void drone_tile(const DroneK& k, const DroneIO& io, const float* lut_s,
+                                           const float4 (&q)[FPV_DRONE_PLANES][Lane<V>::N],
+                                           const float4 (&act)[Lane<V>::N], const long long (&ei)[Lane<V>::N],
+                                           long long base, TileStats& st) {
   constexpr int L = Lane<V>::N;
-  extern __shared__ float lut_s[];
-  const bool use_lut = (k.flags & FPV_F_THRUST_LUT) != 0;
-  if (use_lut) {  // stage the motor curve in shared memory once per CTA
+  DroneRegs<V> s;
+  s.px = Pack<V>::x(q[0]); s.py = Pack<V>::y(q[0]); s.pz = Pack<V>::z(q[0]); s.pt = Pack<V>::w(q[0]);
+  s.vx = Pack<V>::x(q[1]); s.vy = Pack<V>::y(q[1]); s.vz = Pack<V>::z(q[1]);
+  s.r00 = Pack<V>::x(q[2]); s.r01 = Pack<V>::y(q[2]); s.r02 = Pack<V>::z(q[2]); s.pr0 = Pack<V>::w(q[2]);
+  s.r10 = Pack<V>::x(q[3]); s.r11 = Pack<V>::y(q[3]); s.r12 = Pack<V>::z(q[3]); s.pr1 = Pack<V>::w(q[3]);
+  s.r20 = Pack<V>::x(q[4]); s.r21 = Pack<V>::y(q[4]); s.r22 = Pack<V>::z(q[4]); s.pr2 = Pack<V>::w(q[4]);
+  s.ax = S<V>(0.f); s.ay = S<V>(0.f); s.az = S<V>(0.f);
+  int epi[L];
+#pragma unroll
+  for (int l = 0; l < L; ++l) epi[l] = __float_as_int(q[1][l].w);
+
+  V wx = S<V>(k.wind[0]), wy = S<V>(k.wind[1]), wz = S<V>(k.wind[2]);
+  if (io.wind_env) {
+    float4 w[L];
+#pragma unroll
+    for (int l = 0; l < L; ++l) w[l] = ldg_stream(io.wind_env + ei[l]);
+    wx = Pack<V>::x(w); wy = Pack<V>::y(w); wz = Pack<V>::z(w);
+  }
+  const V a0 = Pack<V>::x(act), a1 = Pack<V>::y(act), a2 = Pack<V>::z(act), a3 = Pack<V>::w(act);
+  V target;
+  if (k.flags & FPV_F_THRUST_LUT) {
+    float t[2];
+#pragma unroll
+    for (int l = 0; l < L; ++l) t[l] = thrust_lut1(k, lut_s, act[l].w);
+    target = Lane<V>::make(t[0], t[L - 1]);
+  } else {
+    target = thrust_poly<V>(k, a3);
+  }
+  DroneRegs<V> ovr;
+  V o_thrust = S<V>(0.f);
+  const bool has_ovr = GENERAL && io.override_R != nullptr;
+  if (has_ovr) {
+    float4 r0[L], r1[L], r2[L];
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+      r0[l] = ldg_stream(io.override_R + ei[l]);
+      r1[l] = ldg_stream(io.override_R + io.n + ei[l]);
+      r2[l] = ldg_stream(io.override_R + 2 * io.n + ei[l]);
+    }
+    ovr.r00 = Pack<V>::x(r0); ovr.r01 = Pack<V>::y(r0); ovr.r02 = Pack<V>::z(r0); o_thrust = Pack<V>::w(r0);
+    ovr.r10 = Pack<V>::x(r1); ovr.r11 = Pack<V>::y(r1); ovr.r12 = Pack<V>::z(r1);
+    ovr.r20 = Pack<V>::x(r2); ovr.r21 = Pack<V>::y(r2); ovr.r22 = Pack<V>::z(r2);
+  }
+
+  auto done = drone_substeps<V, ANG, GENERAL>(k, s, a0, a1, a2, target, wx, wy, wz, has_ovr, o_thrust, &ovr);
+
+  // ---- epilogue per env: episode bookkeeping, freeze / auto-reset, stores
+#pragma unroll
+  for (int l = 0; l < L; ++l) {
+    const long long e = base + (long long)l * SLOT_STRIDE;
+    if (e >= io.n) break;
+    bool d = mask_get(done, l);
+    int ep = epi[l];
+    if (ep < 0) {  // frozen after a crash (FPV_F_FREEZE_DONE): state in memory stays as it is, done is sticky
+      if (io.done) io.done[e] = 1;
+      st.frozen += 1.f;
+      continue;
+    }
+    ep += 1;
+    float4* const dst = io.state + e;
+    if (io.done) io.done[e] = d ? 1 : 0;
+    if (d) {  // rare: crash this control step
+      st.crash += 1.f;
+      if (k.flags & FPV_F_AUTO_RESET) {  // restart from the reset snapshot (plane by plane, no merge with the hot path)
+        st.epi += 1.f; st.len += (float)ep;
+        const float4* const src = io.reset_state + e;
+        float4 v[FPV_DRONE_PLANES];  // all loads in flight before the first store (one round trip, not five)
+#pragma unroll
+        for (int p = 0; p < FPV_DRONE_PLANES; ++p) v[p] = ldg_stream(src + p * io.stride);
+        v[1].w = __int_as_float(0);
+#pragma unroll
+        for (int p = 0; p < FPV_DRONE_PLANES; ++p) stg_stream(dst + p * io.stride, v[p]);
+        if (io.acc_out)
+          stg_stream(io.acc_out + e, make_float4(Lane<V>::get(s.ax, l), Lane<V>::get(s.ay, l), Lane<V>::get(s.az, l), 0.f));
+        continue;
+      }
+      if (k.flags & FPV_F_FREEZE_DONE) {
+        st.epi += 1.f; st.len += (float)ep;
+        ep = -ep - 1;
+      }
+    }
+    const float px = Lane<V>::get(s.px, l), py = Lane<V>::get(s.py, l), pz = Lane<V>::get(s.pz, l);
+    const float vx = Lane<V>::get(s.vx, l), vy = Lane<V>::get(s.vy, l), vz = Lane<V>::get(s.vz, l);
+    // NaN/Inf guard: the sum of the six components is non-finite iff one of them is (or they overflow together)
+    if (!(fabsf(((px + py) + (pz + vx)) + (vy + vz)) <= 3.0e38f)) st.nf += 1.f;
+    stg_stream(dst, make_float4(px, py, pz, Lane<V>::get(s.pt, l)));
+    stg_stream(dst + io.stride, make_float4(vx, vy, vz, __int_as_float(ep)));
+    stg_stream(dst + 2 * io.stride, make_float4(Lane<V>::get(s.r00, l), Lane<V>::get(s.r01, l), Lane<V>::get(s.r02, l), Lane<V>::get(s.pr0, l)));
+    stg_stream(dst + 3 * io.stride, make_float4(Lane<V>::get(s.r10, l), Lane<V>::get(s.r11, l), Lane<V>::get(s.r12, l), Lane<V>::get(s.pr1, l)));
+    stg_stream(dst + 4 * io.stride, make_float4(Lane<V>::get(s.r20, l), Lane<V>::get(s.r21, l), Lane<V>::get(s.r22, l), Lane<V>::get(s.pr2, l)));
+    if (io.acc_out)
+      stg_stream(io.acc_out + e, make_float4(Lane<V>::get(s.ax, l), Lane<V>::get(s.ay, l), Lane<V>::get(s.az, l), 0.f));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Kernel 1 (general path, and tiny batches): persistent CTAs, state fetched with 128-bit streaming loads.
+// gridDim.x CTAs (a multiple of the SM count chosen by the host) walk the tiles of THREADS*L envs with stride
+// gridDim.x.  The motor-curve LUT is staged into shared memory once per CTA.
+// ---------------------------------------------------------------------------------------------------------------
+template <class V, int ANG, bool GENERAL, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) drone_step_kernel(const __grid_constant__ DroneK k, const DroneIO io) {
+  constexpr int L = Lane<V>::N;
+  constexpr int TILE = THREADS * L;
+  extern __shared__ __align__(16) float lut_s[];
+  if (k.flags & FPV_F_THRUST_LUT) {
     for (int i = threadIdx.x; i < k.lut_n; i += THREADS) lut_s[i] = io.lut[i];
     __syncthreads();
   }
-  // thread t, slot l -> env blockBase + l*THREADS + t: every 128-bit access of a warp is one contiguous 512 B run
-  const long long base = (long long)blockIdx.x * (THREADS * L) + threadIdx.x;
-  const bool active = base < io.n;
-  float st_steps = 0.f, st_crash = 0.f, st_epi = 0.f, st_len = 0.f, st_nf = 0.f;
-  if (active) {
-    long long ei[L];  // slot -> env index; a slot past the end re-reads env n-1 and is never stored
+  if (io.stats && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&io.stats->env_steps, (double)io.n);
+  const long long n_tiles = (io.n + TILE - 1) / TILE;
+  TileStats st = {0.f, 0.f, 0.f, 0.f, 0.f};
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    // thread t, slot l -> env tile*TILE + l*THREADS + t: every 128-bit access of a warp is one contiguous 512 B run
+    const long long base = tile * TILE + threadIdx.x;
+    if (base >= io.n) continue;
+    long long ei[L];  // a slot past the end re-reads env n-1 and is never stored
 #pragma unroll
     for (int l = 0; l < L; ++l) ei[l] = min(base + (long long)l * THREADS, io.n - 1);
     float4 q[FPV_DRONE_PLANES][L];
@@ -319,99 +432,133 @@ __global__ void __launch_bounds__(THREADS) drone_step_kernel(const __grid_consta
       for (int l = 0; l < L; ++l) q[p][l] = ldg_stream(io.state + p * io.stride + ei[l]);
 #pragma unroll
     for (int l = 0; l < L; ++l) act[l] = ldg_stream(io.actions + ei[l]);
+    drone_tile<V, ANG, GENERAL, THREADS>(k, io, lut_s, q, act, ei, base, st);
+  }
+  if (io.stats) stats_warp_flush(io.stats, st.crash, st.epi, st.len, st.nf, st.frozen);
+}
 
-    DroneRegs<V> s;
-    s.px = Pack<V>::x(q[0]); s.py = Pack<V>::y(q[0]); s.pz = Pack<V>::z(q[0]); s.pt = Pack<V>::w(q[0]);
-    s.vx = Pack<V>::x(q[1]); s.vy = Pack<V>::y(q[1]); s.vz = Pack<V>::z(q[1]);
-    s.r00 = Pack<V>::x(q[2]); s.r01 = Pack<V>::y(q[2]); s.r02 = Pack<V>::z(q[2]); s.pr0 = Pack<V>::w(q[2]);
-    s.r10 = Pack<V>::x(q[3]); s.r11 = Pack<V>::y(q[3]); s.r12 = Pack<V>::z(q[3]); s.pr1 = Pack<V>::w(q[3]);
-    s.r20 = Pack<V>::x(q[4]); s.r21 = Pack<V>::y(q[4]); s.r22 = Pack<V>::z(q[4]); s.pr2 = Pack<V>::w(q[4]);
-    s.ax = S<V>(0.f); s.ay = S<V>(0.f); s.az = S<V>(0.f);
-    int epi[L];
-#pragma unroll
-    for (int l = 0; l < L; ++l) epi[l] = __float_as_int(q[1][l].w);
+// ---------------------------------------------------------------------------------------------------------------
+// Kernel 2 (the hot path): the six float4 rows of a chunk (5 state planes + actions) are brought into shared memory
+// by the TMA engine (cp.async.bulk, completion on an mbarrier) one chunk AHEAD of the arithmetic, so HBM latency and
+// bandwidth overlap the substep loop instead of preceding it.  STAGES ring slots per warp.
+//   smem: [ LUT | WARPS x STAGES x 6 x CHUNK float4 | WARPS x STAGES mbarriers ]
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  unsigned pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 
-    V wx = S<V>(k.wind[0]), wy = S<V>(k.wind[1]), wz = S<V>(k.wind[2]);
-    if (io.wind_env) {
-      float4 w[L];
+// Every WARP owns a private ring: its lane 0 is the producer for the warp's own 32*L-env chunks, the 32 lanes are
+// the consumers, and __syncwarp() is the only synchronisation -- warps of a CTA never wait for one another (a CTA
+// exists only to share the staged LUT).  Warp-chunk c covers envs [c*32*L, (c+1)*32*L); chunks are dealt
+// round-robin over all warps of the grid.
+template <class V, int ANG, int THREADS, int MINB, int STAGES>
+__global__ void __launch_bounds__(THREADS, MINB) drone_step_tma_kernel(const __grid_constant__ DroneK k, const DroneIO io,
+                                                                       const int lut_bytes) {
+  constexpr int L = Lane<V>::N;
+  constexpr int CHUNK = 32 * L;                 // envs per warp-chunk
+  constexpr int ROWS = FPV_DRONE_PLANES + 1;    // 5 state planes + actions
+  constexpr int WARPS = THREADS / 32;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* lut_s = reinterpret_cast<float*>(smem_raw);
+  float4* ring_all = reinterpret_cast<float4*>(smem_raw + lut_bytes);                   // [WARPS][STAGES][ROWS][CHUNK]
+  unsigned long long* full_all = reinterpret_cast<unsigned long long*>(ring_all + WARPS * STAGES * ROWS * CHUNK);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform id
+  float4* ring = ring_all + (size_t)warp * STAGES * ROWS * CHUNK;
+  unsigned long long* full = full_all + warp * STAGES;
+  if (lane == 0) {
 #pragma unroll
-      for (int l = 0; l < L; ++l) w[l] = ldg_stream(io.wind_env + ei[l]);
-      wx = Pack<V>::x(w); wy = Pack<V>::y(w); wz = Pack<V>::z(w);
+    for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (k.flags & FPV_F_THRUST_LUT)
+    for (int i = threadIdx.x; i < k.lut_n; i += THREADS) lut_s[i] = io.lut[i];
+  __syncthreads();  // the only CTA-wide barrier: LUT staged, mbarriers initialised
+  if (io.stats && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&io.stats->env_steps, (double)io.n);
+
+  const long long n_chunks = (io.n + CHUNK - 1) / CHUNK;
+  const long long first_chunk = (long long)blockIdx.x * WARPS + warp;
+  const long long chunk_stride = (long long)gridDim.x * WARPS;
+
+  // producer (lane 0): arm the slot's mbarrier with the byte count, then six bulk copies (one per row)
+  auto issue = [&](long long chunk, int slot) {
+    const long long first = chunk * CHUNK;
+    const long long rem = io.n - first;
+    const unsigned count = (unsigned)(rem < (long long)CHUNK ? rem : (long long)CHUNK);
+    const unsigned bytes = count * (unsigned)sizeof(float4);
+    float4* dst = ring + (size_t)slot * ROWS * CHUNK;
+    mbar_expect_tx(&full[slot], bytes * ROWS);
+#pragma unroll
+    for (int p = 0; p < FPV_DRONE_PLANES; ++p) tma_load_1d(dst + p * CHUNK, io.state + p * io.stride + first, bytes, &full[slot]);
+    tma_load_1d(dst + FPV_DRONE_PLANES * CHUNK, io.actions + first, bytes, &full[slot]);
+  };
+
+  const bool leader = elect_one();   // one lane per warp issues; every operand below is warp-uniform
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    const long long c = first_chunk + (long long)s * chunk_stride;
+    if (c < n_chunks && leader) issue(c, s);
+  }
+  TileStats st = {0.f, 0.f, 0.f, 0.f, 0.f};
+  int it = 0;
+  for (long long chunk = first_chunk; chunk < n_chunks; chunk += chunk_stride, ++it) {
+    const int slot = it % STAGES;
+    const unsigned parity = (unsigned)(it / STAGES) & 1u;
+    {  // keep STAGES-1 chunks in flight; the slot refilled here was drained at iteration it-1
+      const long long ahead = chunk + (long long)(STAGES - 1) * chunk_stride;
+      if (ahead < n_chunks && leader) issue(ahead, (it + STAGES - 1) % STAGES);
     }
-    const V a0 = Pack<V>::x(act), a1 = Pack<V>::y(act), a2 = Pack<V>::z(act), a3 = Pack<V>::w(act);
-    V target;
-    if (use_lut) {
-      float t[2];
-#pragma unroll
-      for (int l = 0; l < L; ++l) t[l] = thrust_lut1(k, lut_s, act[l].w);
-      target = Lane<V>::make(t[0], t[L - 1]);
-    } else {
-      target = thrust_poly<V>(k, a3);
-    }
-    DroneRegs<V> ovr;
-    V o_thrust = S<V>(0.f);
-    const bool has_ovr = GENERAL && io.override_R != nullptr;
-    if (has_ovr) {
-      float4 r0[L], r1[L], r2[L];
-#pragma unroll
-      for (int l = 0; l < L; ++l) {
-        r0[l] = ldg_stream(io.override_R + ei[l]);
-        r1[l] = ldg_stream(io.override_R + io.n + ei[l]);
-        r2[l] = ldg_stream(io.override_R + 2 * io.n + ei[l]);
-      }
-      ovr.r00 = Pack<V>::x(r0); ovr.r01 = Pack<V>::y(r0); ovr.r02 = Pack<V>::z(r0); o_thrust = Pack<V>::w(r0);
-      ovr.r10 = Pack<V>::x(r1); ovr.r11 = Pack<V>::y(r1); ovr.r12 = Pack<V>::z(r1);
-      ovr.r20 = Pack<V>::x(r2); ovr.r21 = Pack<V>::y(r2); ovr.r22 = Pack<V>::z(r2);
-    }
-
-    auto done = drone_substeps<V, SMALL, GENERAL, FAST>(k, s, a0, a1, a2, target, wx, wy, wz, has_ovr, o_thrust, &ovr);
-
-    // ---- epilogue per env: episode bookkeeping, freeze / auto-reset, stores
+    mbar_wait(&full[slot], parity);
+    const float4* src = ring + (size_t)slot * ROWS * CHUNK;
+    const long long base = chunk * CHUNK + lane;
+    long long ei[L];
+    float4 q[FPV_DRONE_PLANES][L];
+    float4 act[L];
 #pragma unroll
     for (int l = 0; l < L; ++l) {
-      const long long e = base + (long long)l * THREADS;
-      if (e >= io.n) break;
-      bool d = mask_get(done, l);
-      int ep = epi[l];
-      if (ep < 0) {  // frozen after a crash (FPV_F_FREEZE_DONE): state in memory stays as it is, done is sticky
-        if (io.done) io.done[e] = 1;
-        continue;
-      }
-      float4 o0, o1, o2, o3, o4;
-      o0 = make_float4(Lane<V>::get(s.px, l), Lane<V>::get(s.py, l), Lane<V>::get(s.pz, l), Lane<V>::get(s.pt, l));
-      o1 = make_float4(Lane<V>::get(s.vx, l), Lane<V>::get(s.vy, l), Lane<V>::get(s.vz, l), 0.f);
-      o2 = make_float4(Lane<V>::get(s.r00, l), Lane<V>::get(s.r01, l), Lane<V>::get(s.r02, l), Lane<V>::get(s.pr0, l));
-      o3 = make_float4(Lane<V>::get(s.r10, l), Lane<V>::get(s.r11, l), Lane<V>::get(s.r12, l), Lane<V>::get(s.pr1, l));
-      o4 = make_float4(Lane<V>::get(s.r20, l), Lane<V>::get(s.r21, l), Lane<V>::get(s.r22, l), Lane<V>::get(s.pr2, l));
-      ep += 1;
-      st_steps += 1.f;
-      const bool fin = isfinite(o0.x) && isfinite(o0.y) && isfinite(o0.z) && isfinite(o1.x) && isfinite(o1.y) &&
-                       isfinite(o1.z);
-      if (!fin) st_nf += 1.f;
-      if (d) {
-        st_crash += 1.f;
-        if ((k.flags & FPV_F_AUTO_RESET) && io.reset_state) {
-          st_epi += 1.f; st_len += (float)ep;
-          o0 = io.reset_state[e]; o1 = io.reset_state[io.stride + e]; o2 = io.reset_state[2 * io.stride + e];
-          o3 = io.reset_state[3 * io.stride + e]; o4 = io.reset_state[4 * io.stride + e];
-          ep = 0;
-        } else if (k.flags & FPV_F_FREEZE_DONE) {
-          st_epi += 1.f; st_len += (float)ep;
-          ep = -ep - 1;
-        }
-      }
-      o1.w = __int_as_float(ep);
-      stg_stream(io.state + e, o0);
-      stg_stream(io.state + io.stride + e, o1);
-      stg_stream(io.state + 2 * io.stride + e, o2);
-      stg_stream(io.state + 3 * io.stride + e, o3);
-      stg_stream(io.state + 4 * io.stride + e, o4);
-      if (io.done) io.done[e] = d ? 1 : 0;
-      if (io.acc_out)
-        stg_stream(io.acc_out + e, make_float4(Lane<V>::get(s.ax, l), Lane<V>::get(s.ay, l), Lane<V>::get(s.az, l), 0.f));
+      ei[l] = min(base + (long long)l * 32, io.n - 1);
+#pragma unroll
+      for (int p = 0; p < FPV_DRONE_PLANES; ++p) q[p][l] = src[p * CHUNK + l * 32 + lane];
+      act[l] = src[FPV_DRONE_PLANES * CHUNK + l * 32 + lane];
     }
+    __syncwarp();  // all lanes have drained this slot -> lane 0 may refill it next iteration
+    if (base < io.n) drone_tile<V, ANG, false, 32>(k, io, lut_s, q, act, ei, base, st);
   }
-  if (io.stats) stats_accumulate(io.stats, st_steps, st_crash, st_epi, st_len, st_nf);
+  if (io.stats) stats_warp_flush(io.stats, st.crash, st.epi, st.len, st.nf, st.frozen);
 }
 
 }  // namespace fpv

@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/fpv_api.h"
@@ -32,31 +33,99 @@ int check_launch(const char* what) {
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 constexpr int kThreads = 128;
+#ifndef FPV_MINB
+#define FPV_MINB 4  // resident CTAs per SM the compiler must fit (register budget = 65536 / (kThreads * FPV_MINB))
+#endif
 
 using fpv::DroneIO;
 using fpv::DroneK;
 using fpv::F2;
 
-template <class V, bool SMALL, bool GENERAL, bool FAST>
+int sm_count_of_current_device() {
+  static int cached[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (cached[dev] == 0) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    cached[dev] = v > 0 ? v : 148;
+  }
+  return cached[dev];
+}
+
+// Persistent launch: one wave of CTAs (SMs x resident CTAs per SM) walking the tiles.
+template <class V, int ANG, bool GENERAL>
 void launch_drone(const DroneK& k, const DroneIO& io, cudaStream_t st) {
   constexpr int L = fpv::Lane<V>::N;
-  const long long per_block = (long long)kThreads * L;
-  const unsigned grid = (unsigned)((io.n + per_block - 1) / per_block);
+  auto kern = fpv::drone_step_kernel<V, ANG, GENERAL, kThreads, GENERAL ? 1 : FPV_MINB>;
   const size_t smem = (k.flags & FPV_F_THRUST_LUT) ? sizeof(float) * (size_t)k.lut_n : 0;
-  auto kern = fpv::drone_step_kernel<V, SMALL, GENERAL, FAST, kThreads>;
-  if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static int occ_cache[2] = {0, 0};  // [lut?]; per template instantiation
+  int& occ = occ_cache[smem ? 1 : 0];
+  if (occ == 0) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    int o = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, kThreads, smem > 48 * 1024 ? 200 * 1024 : smem);
+    occ = o > 0 ? o : 1;
+  }
+  const long long per_block = (long long)kThreads * L;
+  const long long tiles = (io.n + per_block - 1) / per_block;
+  const long long wave = (long long)sm_count_of_current_device() * occ;
+  const unsigned grid = (unsigned)(tiles < wave ? tiles : wave);
   kern<<<grid, kThreads, smem, st>>>(k, io);
 }
 
-template <class V, bool SMALL, bool GENERAL>
-void launch_drone_f(const DroneK& k, const DroneIO& io, cudaStream_t st) {
-  if (k.flags & FPV_F_FAST_MATH) launch_drone<V, SMALL, GENERAL, true>(k, io, st);
-  else launch_drone<V, SMALL, GENERAL, false>(k, io, st);
+// Hot path: TMA-fed ring (drone_step_tma_kernel).  Returns false if the ring does not fit (huge LUT).
+template <class V, int ANG, int STAGES>
+bool launch_drone_tma(const DroneK& k, const DroneIO& io, cudaStream_t st) {
+  constexpr int L = fpv::Lane<V>::N;
+  constexpr int TILE = kThreads * L;
+  auto kern = fpv::drone_step_tma_kernel<V, ANG, kThreads, FPV_MINB, STAGES>;
+  const int lut_bytes = (k.flags & FPV_F_THRUST_LUT) ? (int)(((size_t)k.lut_n * sizeof(float) + 127) / 128 * 128) : 0;
+  const size_t smem = (size_t)lut_bytes + (size_t)STAGES * 6 * TILE * sizeof(float4) +
+                      (size_t)(kThreads / 32) * STAGES * sizeof(unsigned long long);
+  if (smem > 220 * 1024) return false;
+  static size_t attr_set = 0;  // per instantiation: largest dynamic smem opted in so far
+  static int occ_cache = 0;
+  static size_t occ_smem = 0;
+  if (smem > attr_set) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_set = smem;
+  }
+  if (occ_cache == 0 || occ_smem != smem) {
+    int o = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, kThreads, smem);
+    occ_cache = o > 0 ? o : 1;
+    occ_smem = smem;
+  }
+  const long long tiles = (io.n + TILE - 1) / TILE;
+  const long long wave = (long long)sm_count_of_current_device() * occ_cache;
+  const unsigned grid = (unsigned)(tiles < wave ? tiles : wave);
+  kern<<<grid, kThreads, smem, st>>>(k, io, lut_bytes);
+  return true;
 }
-template <class V, bool SMALL>
+
+int tune_env(const char* name, int dflt) {
+  const char* v = std::getenv(name);
+  return v ? std::atoi(v) : dflt;
+}
+
+template <class V, int ANG>
 void launch_drone_g(const DroneK& k, const DroneIO& io, bool general, cudaStream_t st) {
-  if (general) launch_drone_f<V, SMALL, true>(k, io, st);
-  else launch_drone_f<V, SMALL, false>(k, io, st);
+  static const int no_tma = tune_env("FPV_TUNE_NOTMA", 0);     // developer A/B switches, not part of the ABI
+  static const int stages = tune_env("FPV_TUNE_STAGES", 2);
+  if (general) { launch_drone<V, ANG, true>(k, io, st); return; }
+  if (!no_tma) {
+    const bool ok = stages >= 3 ? launch_drone_tma<V, ANG, 3>(k, io, st) : launch_drone_tma<V, ANG, 2>(k, io, st);
+    if (ok) return;
+  }
+  launch_drone<V, ANG, false>(k, io, st);
+}
+template <class V>
+void launch_drone_a(const DroneK& k, const DroneIO& io, int ang, bool general, cudaStream_t st) {
+  if (ang == 2) launch_drone_g<V, 2>(k, io, general, st);
+  else if (ang == 1) launch_drone_g<V, 1>(k, io, general, st);
+  else launch_drone_g<V, 0>(k, io, general, st);
 }
 
 }  // namespace
@@ -145,6 +214,7 @@ int fpv_drone_step(const fpv_drone_params_t* p, const fpv_drone_io_t* io, void* 
   for (int i = 0; i < 3; ++i) k.wind[i] = p->wind[i];
   k.grav_force_z = (float)(-(double)p->gravity * (double)p->mass);
   k.inv_mass = (float)(1.0 / (double)p->mass);
+  k.dt_over_mass = (float)((double)p->dt / (double)p->mass);
   k.mass = p->mass;
   k.ang_scale = (float)(0.017453292519943295 * (double)p->dt);
   k.lut_n = (p->flags & FPV_F_THRUST_LUT) ? io->lut_n : 0;
@@ -171,19 +241,14 @@ int fpv_drone_step(const fpv_drone_params_t* p, const fpv_drone_io_t* io, void* 
   d.stats = io->stats;
 
   // |rates| <= max_rates is an invariant of action2force (a convex mix of clipped commands), so the
-  // per-substep Euler angles are bounded by max_rates*dt in radians: below 0.5 rad the sin/cos
-  // polynomials need no range reduction.
-  const bool small = std::fabs((double)p->max_rates) * k.ang_scale <= 0.5;
+  // per-substep Euler angles are bounded by max_rates*dt in radians.  Below 0.1 rad degree-5/4 Taylor kernels are
+  // exact to fp32; below 0.5 rad the reduced-argument minimax kernels need no range reduction; otherwise sincosf.
+  const double max_angle = std::fabs((double)p->max_rates) * 0.017453292519943295 * (double)p->dt;
+  const int ang = max_angle <= 0.1 ? 2 : (max_angle <= 0.5 ? 1 : 0);
   const bool general = p->n_objects > 0 || io->override_R != nullptr;
-  const bool scalar = (p->flags & FPV_F_SCALAR) != 0;
   cudaStream_t st = (cudaStream_t)stream;
-  if (scalar) {
-    if (small) launch_drone_g<float, true>(k, d, general, st);
-    else launch_drone_g<float, false>(k, d, general, st);
-  } else {
-    if (small) launch_drone_g<F2, true>(k, d, general, st);
-    else launch_drone_g<F2, false>(k, d, general, st);
-  }
+  if (p->flags & FPV_F_SCALAR) launch_drone_a<float>(k, d, ang, general, st);
+  else launch_drone_a<F2>(k, d, ang, general, st);
   return check_launch("fpv_drone_step");
 }
 

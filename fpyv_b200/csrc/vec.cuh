@@ -8,9 +8,19 @@
 
 namespace fpv {
 
+// F2 is ONE 64-bit value (an aligned register pair) so that the allocator never splits the halves; all
+// arithmetic is inline PTX add/mul/fma.rn.f32x2 on .b64 operands.
 struct F2 {
-  float2 v;
+  unsigned long long v;
 };
+__device__ __forceinline__ F2 f2_pack(float lo, float hi) {
+  F2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(F2 a, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v));
+}
 struct B2 {
   bool x, y;
 };
@@ -27,9 +37,13 @@ template <> struct Lane<float> {
 template <> struct Lane<F2> {
   static constexpr int N = 2;
   using Mask = B2;
-  static __device__ __forceinline__ F2 splat(float s) { return F2{make_float2(s, s)}; }
-  static __device__ __forceinline__ float get(F2 v, int i) { return i ? v.v.y : v.v.x; }
-  static __device__ __forceinline__ F2 make(float a, float b) { return F2{make_float2(a, b)}; }
+  static __device__ __forceinline__ F2 splat(float s) { return f2_pack(s, s); }
+  static __device__ __forceinline__ float get(F2 v, int i) {
+    float lo, hi;
+    f2_unpack(v, lo, hi);
+    return i ? hi : lo;
+  }
+  static __device__ __forceinline__ F2 make(float a, float b) { return f2_pack(a, b); }
 };
 
 // ---- float
@@ -56,26 +70,76 @@ __device__ __forceinline__ float vdiv(float a, float b) { return __fdiv_rn(a, b)
 __device__ __forceinline__ bool vfinite(float a) { return isfinite(a); }
 
 // ---- F2 (packed pair)
-__device__ __forceinline__ F2 operator+(F2 a, F2 b) { return F2{__fadd2_rn(a.v, b.v)}; }
-__device__ __forceinline__ F2 operator*(F2 a, F2 b) { return F2{__fmul2_rn(a.v, b.v)}; }
-__device__ __forceinline__ F2 vneg(F2 a) { return F2{make_float2(-a.v.x, -a.v.y)}; }
-__device__ __forceinline__ F2 operator-(F2 a, F2 b) { return F2{__fadd2_rn(a.v, make_float2(-b.v.x, -b.v.y))}; }
+__device__ __forceinline__ F2 operator+(F2 a, F2 b) {
+  F2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
+}
+__device__ __forceinline__ F2 operator*(F2 a, F2 b) {
+  F2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
+}
+__device__ __forceinline__ F2 vfma(F2 a, F2 b, F2 c) {
+  F2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+  return r;
+}
+__device__ __forceinline__ F2 vneg(F2 a) { return F2{a.v ^ 0x8000000080000000ull}; }
+__device__ __forceinline__ F2 operator-(F2 a, F2 b) { return a + vneg(b); }
 __device__ __forceinline__ F2 operator-(F2 a) { return vneg(a); }
-__device__ __forceinline__ F2 vfma(F2 a, F2 b, F2 c) { return F2{__ffma2_rn(a.v, b.v, c.v)}; }
-__device__ __forceinline__ F2 vmin(F2 a, F2 b) { return F2{make_float2(fminf(a.v.x, b.v.x), fminf(a.v.y, b.v.y))}; }
-__device__ __forceinline__ F2 vmax(F2 a, F2 b) { return F2{make_float2(fmaxf(a.v.x, b.v.x), fmaxf(a.v.y, b.v.y))}; }
-__device__ __forceinline__ F2 vsqrt(F2 a) { return F2{make_float2(__fsqrt_rn(a.v.x), __fsqrt_rn(a.v.y))}; }
-__device__ __forceinline__ F2 vsqrt_fast(F2 a) { return F2{make_float2(vsqrt_fast(a.v.x), vsqrt_fast(a.v.y))}; }
-__device__ __forceinline__ B2 vlt(F2 a, F2 b) { return B2{a.v.x < b.v.x, a.v.y < b.v.y}; }
-__device__ __forceinline__ B2 vle(F2 a, F2 b) { return B2{a.v.x <= b.v.x, a.v.y <= b.v.y}; }
+#define FPV_F2_MAP1(name, expr)                              \
+  __device__ __forceinline__ F2 name(F2 a) {                 \
+    float x, y;                                              \
+    f2_unpack(a, x, y);                                      \
+    float rx, ry;                                            \
+    { const float v = x; rx = (expr); }                      \
+    { const float v = y; ry = (expr); }                      \
+    return f2_pack(rx, ry);                                  \
+  }
+#define FPV_F2_MAP2(name, expr)                              \
+  __device__ __forceinline__ F2 name(F2 a, F2 b) {           \
+    float ax, ay, bx, by;                                    \
+    f2_unpack(a, ax, ay);                                    \
+    f2_unpack(b, bx, by);                                    \
+    float rx, ry;                                            \
+    { const float u = ax, v = bx; rx = (expr); }             \
+    { const float u = ay, v = by; ry = (expr); }             \
+    return f2_pack(rx, ry);                                  \
+  }
+FPV_F2_MAP2(vmin, fminf(u, v))
+FPV_F2_MAP2(vmax, fmaxf(u, v))
+FPV_F2_MAP2(vdiv, __fdiv_rn(u, v))
+FPV_F2_MAP1(vsqrt, __fsqrt_rn(v))
+FPV_F2_MAP1(vsqrt_fast, vsqrt_fast(v))
+FPV_F2_MAP1(vabs, fabsf(v))
+__device__ __forceinline__ B2 vlt(F2 a, F2 b) {
+  float ax, ay, bx, by;
+  f2_unpack(a, ax, ay);
+  f2_unpack(b, bx, by);
+  return B2{ax < bx, ay < by};
+}
+__device__ __forceinline__ B2 vle(F2 a, F2 b) {
+  float ax, ay, bx, by;
+  f2_unpack(a, ax, ay);
+  f2_unpack(b, bx, by);
+  return B2{ax <= bx, ay <= by};
+}
 __device__ __forceinline__ B2 vor(B2 a, B2 b) { return B2{a.x || b.x, a.y || b.y}; }
 __device__ __forceinline__ B2 vand(B2 a, B2 b) { return B2{a.x && b.x, a.y && b.y}; }
 __device__ __forceinline__ B2 vnot(B2 a) { return B2{!a.x, !a.y}; }
 __device__ __forceinline__ bool vany(B2 a) { return a.x || a.y; }
-__device__ __forceinline__ F2 vsel(B2 m, F2 a, F2 b) { return F2{make_float2(m.x ? a.v.x : b.v.x, m.y ? a.v.y : b.v.y)}; }
-__device__ __forceinline__ F2 vabs(F2 a) { return F2{make_float2(fabsf(a.v.x), fabsf(a.v.y))}; }
-__device__ __forceinline__ F2 vdiv(F2 a, F2 b) { return F2{make_float2(__fdiv_rn(a.v.x, b.v.x), __fdiv_rn(a.v.y, b.v.y))}; }
-__device__ __forceinline__ B2 vfinite(F2 a) { return B2{isfinite(a.v.x), isfinite(a.v.y)}; }
+__device__ __forceinline__ F2 vsel(B2 m, F2 a, F2 b) {
+  float ax, ay, bx, by;
+  f2_unpack(a, ax, ay);
+  f2_unpack(b, bx, by);
+  return f2_pack(m.x ? ax : bx, m.y ? ay : by);
+}
+__device__ __forceinline__ B2 vfinite(F2 a) {
+  float x, y;
+  f2_unpack(a, x, y);
+  return B2{isfinite(x), isfinite(y)};
+}
 
 __device__ __forceinline__ bool mask_get(bool m, int) { return m; }
 __device__ __forceinline__ bool mask_get(B2 m, int i) { return i ? m.y : m.x; }
@@ -99,19 +163,32 @@ template <class V> __device__ __forceinline__ void sincos_poly(V x, V& s, V& c) 
   c = vfma(pc, x2, S<V>(1.0f));
 }
 
-template <bool SMALL> __device__ __forceinline__ void vsincos(float x, float& s, float& c) {
-  if (SMALL) sincos_poly<float>(x, s, c);
+// |x| <= 0.1 rad: x - x^3/6 + x^5/120 and 1 - x^2/2 + x^4/24 (next terms: 2e-11 and 1.4e-9 * x^6 -> < 1.4e-15)
+template <class V> __device__ __forceinline__ void sincos_tiny(V x, V& s, V& c) {
+  const V x2 = x * x;
+  const V ps = vfma(x2, S<V>(8.3333333e-3f), S<V>(-1.6666667e-1f));
+  s = vfma(ps, x2 * x, x);
+  const V pc = vfma(x2, S<V>(4.1666668e-2f), S<V>(-0.5f));
+  c = vfma(pc, x2, S<V>(1.0f));
+}
+
+template <int ANG> __device__ __forceinline__ void vsincos(float x, float& s, float& c) {
+  if (ANG == 2) sincos_tiny<float>(x, s, c);
+  else if (ANG == 1) sincos_poly<float>(x, s, c);
   else sincosf(x, &s, &c);
 }
-template <bool SMALL> __device__ __forceinline__ void vsincos(F2 x, F2& s, F2& c) {
-  if (SMALL) {
+template <int ANG> __device__ __forceinline__ void vsincos(F2 x, F2& s, F2& c) {
+  if (ANG == 2) {
+    sincos_tiny<F2>(x, s, c);
+  } else if (ANG == 1) {
     sincos_poly<F2>(x, s, c);
   } else {
-    float s0, c0, s1, c1;
-    sincosf(x.v.x, &s0, &c0);
-    sincosf(x.v.y, &s1, &c1);
-    s = F2{make_float2(s0, s1)};
-    c = F2{make_float2(c0, c1)};
+    float x0, x1, s0, c0, s1, c1;
+    f2_unpack(x, x0, x1);
+    sincosf(x0, &s0, &c0);
+    sincosf(x1, &s1, &c1);
+    s = f2_pack(s0, s1);
+    c = f2_pack(c0, c1);
   }
 }
 

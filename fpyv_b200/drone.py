@@ -36,7 +36,7 @@ def _as_dev(x, device, shape=None, dtype=torch.float32):
 class BatchedDrone:
     def __init__(self, params=None, num_envs: int = 1, device="cuda:0", substeps: int = 1, dt: float | None = None,
                  auto_reset: bool = False, freeze_done: bool = False, thrust_lut: int = 0, lut_source: str = "poly",
-                 fast_math: bool = False, packed: bool = True, ground: bool = True, joystick=None):
+                 packed: bool = True, ground: bool = True, joystick=None):
         self._lib = _lib.load()
         if isinstance(params, str) or params is None:
             params = config.load_params(params)
@@ -99,7 +99,7 @@ class BatchedDrone:
             self._lut = torch.from_numpy(config.thrust_table(c, int(thrust_lut), lut_source)).to(dev)
         self._flags = ((_lib.F_GROUND if ground else 0) | (_lib.F_AUTO_RESET if auto_reset else 0) |
                        (_lib.F_FREEZE_DONE if freeze_done else 0) | (_lib.F_THRUST_LUT if thrust_lut else 0) |
-                       (_lib.F_FAST_MATH if fast_math else 0) | (0 if packed else _lib.F_SCALAR))
+                       (0 if packed else _lib.F_SCALAR))
         self._p = self._make_params()
         self._io = _lib.DroneIO()
         self._host_actions = None

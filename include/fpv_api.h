@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define FPV_ABI_VERSION 3
+#define FPV_ABI_VERSION 4
 
 /* error codes */
 #define FPV_OK 0
@@ -60,7 +60,6 @@ extern "C" {
                                    reference's own behaviour: done is reported, integration goes on */
 #define FPV_F_THRUST_LUT 8u     /* throttle->thrust through io.lut (shared-memory table, linear
                                    interpolation) instead of the cubic                          */
-#define FPV_F_FAST_MATH 16u     /* allow approximate sqrt/division (still within tolerance)     */
 #define FPV_F_SCALAR 32u        /* one env per thread (plain FP32 instructions) instead of the
                                    default two envs per thread on packed f32x2 instructions     */
 
@@ -186,7 +185,7 @@ typedef struct fpv_racer_params {
   float inertia[3];      /* :83 (m r^2 on every axis in the reference) */
   float gains[3][3];     /* [axis roll/pitch/yaw][P,I,D], :113 */
   float vel_decay;       /* :102 (0.9) */
-  uint32_t flags;        /* FPV_F_FAST_MATH only */
+  uint32_t flags;        /* reserved, must be 0 */
 } fpv_racer_params_t;
 
 /* Racer.reset -- :86-93 (mask as in fpv_drone_reset). */

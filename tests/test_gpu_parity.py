@@ -244,7 +244,7 @@ def test_reset_and_views():
     d.reset(pos, vel, rpy)
     a = np.deg2rad(rpy)
     R = fo.euler_matrix(a[:, 0], a[:, 1], a[:, 2])
-    assert np.max(np.abs(d.rotation_matrix.cpu().numpy() - R)) <= 1e-7
+    assert np.max(np.abs(d.rotation_matrix.cpu().numpy() - R)) <= 2.5e-7   # float32 rounding of |R_ij| <= 1 products
     assert np.allclose(d.position.cpu().numpy(), pos.astype(np.float32))
     assert np.allclose(d.state.cpu().numpy()[:, 3:], vel.astype(np.float32))
     assert d.prev_rates.abs().max().item() == 0 and d.prev_thrust.abs().max().item() == 0
@@ -315,7 +315,7 @@ def test_thrust_lut_matches_cubic():
     print(f"\nLUT(2049) vs cubic: max abs {np.max(np.abs(res[1] - res[0])):.2e} N")
 
 
-def test_per_env_wind_and_fast_math():
+def test_per_env_wind():
     n = 512
     rng = np.random.default_rng(6)
     pos = np.stack([rng.normal(0, 5, n), rng.normal(0, 5, n), rng.uniform(2, 12, n)], 1)
@@ -327,14 +327,14 @@ def test_per_env_wind_and_fast_math():
     # oracle: per-env wind = loop-free because drone_substep broadcasts [n,3]
     for a in acts:
         fo.drone_substep(c, s, a, wind)
-    for fast in (False, True):
-        d = make(n, fast_math=fast)
+    for packed in (False, True):
+        d = make(n, packed=packed)
         d.reset(pos, vel, rpy)
         w = torch.as_tensor(wind, dtype=torch.float32, device=DEV)
         for a in acts:
             d.step(a, wind_velocity_vector=w, return_obs=False)
         e = drone_err(d, np.concatenate([s.pos, s.vel], 1), s.R, s.prev_rates, s.prev_thrust)
-        assert e.max() <= 1e-5, (fast, e.max())
+        assert e.max() <= 1e-5, (packed, e.max())
 
 
 def test_auto_reset_freeze_and_stats():

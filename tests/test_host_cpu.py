@@ -38,7 +38,7 @@ def test_abi_version_and_struct_sizes(lib):
     assert lib.fpv_sizeof(99) == -1
     for name, val in (("FPV_F_GROUND", _lib.F_GROUND), ("FPV_F_AUTO_RESET", _lib.F_AUTO_RESET),
                       ("FPV_F_FREEZE_DONE", _lib.F_FREEZE_DONE), ("FPV_F_THRUST_LUT", _lib.F_THRUST_LUT),
-                      ("FPV_F_FAST_MATH", _lib.F_FAST_MATH), ("FPV_F_SCALAR", _lib.F_SCALAR),
+                      ("FPV_F_SCALAR", _lib.F_SCALAR),
                       ("FPV_MAX_OBJECTS", _lib.MAX_OBJECTS), ("FPV_DRONE_PLANES", _lib.DRONE_PLANES),
                       ("FPV_RACER_PLANES", _lib.RACER_PLANES)):
         assert int(re.search(rf"#define {name} (\d+)", hdr).group(1)) == val, name

@@ -26,7 +26,8 @@ for f in funcs:
                 if tgt < a:
                     body = [x for x in ins if tgt <= x[0] <= a]
                     nf = sum(1 for x in body if "FFMA" in x[1] or "FMUL" in x[1] or "FADD" in x[1])
-                    if best is None or nf > best[0]:
+                    # innermost loop with real FP work: smallest body holding >= 40 FP instructions
+                    if nf >= 40 and (best is None or len(body) < len(best[3])):
                         best = (nf, tgt, a, body)
     def hist(body):
         c = collections.Counter()
