@@ -26,8 +26,8 @@ ENVS_PER_GPU = 1 << 20
 SUBSTEPS = 8
 DT = 1e-3
 LUT_N = 2049
-# algorithmic work per env (SURVEY.md section 8d adapted to the matrix-state layout)
-BYTES_PER_ENV_STEP = 80 + 80 + 16 + 1          # state read + state write + action + done flag
+# algorithmic work per env (quaternion state, 64 B each way)
+BYTES_PER_ENV_STEP = 64 + 64 + 16 + 1          # state read + state write + action + done flag
 FLOP_PER_ENV_SUBSTEP = 252                     # 245 arithmetic + 6 sin/cos + 1 sqrt
 FP32_LANES_PER_SM = 128
 

@@ -8,15 +8,15 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 # FPYV_B200_LIB: developer override used to A/B differently tuned builds of the same ABI
 LIB_PATH = os.environ.get("FPYV_B200_LIB") or os.path.join(HERE, "libfpyv_b200.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 # flags (fpv_api.h)
 F_GROUND, F_AUTO_RESET, F_FREEZE_DONE, F_THRUST_LUT, F_SCALAR = 1, 2, 4, 8, 32
 OBJ_SPHERE, OBJ_CYLINDER = 1, 2
 MAX_OBJECTS = 16
-DRONE_PLANES, RACER_PLANES = 5, 7
+DRONE_PLANES, RACER_PLANES = 4, 7
 EXPORTS = ("fpv_abi_version", "fpv_last_error", "fpv_sizeof", "fpv_device_info", "fpv_drone_reset",
-           "fpv_drone_step", "fpv_drone_observe", "fpv_sticks_to_actions", "fpv_racer_reset", "fpv_racer_step")
+           "fpv_drone_step", "fpv_drone_observe", "fpv_drone_get_rotation", "fpv_drone_set_rotation", "fpv_matrix_to_quat", "fpv_sticks_to_actions", "fpv_racer_reset", "fpv_racer_step")
 
 
 class FpvError(RuntimeError):
@@ -47,7 +47,8 @@ class Stats(C.Structure):
 class DroneIO(C.Structure):
     _fields_ = [("state", C.c_void_p), ("n", C.c_int64), ("plane_stride", C.c_int64), ("actions", C.c_void_p),
                 ("wind_env", C.c_void_p), ("lut", C.c_void_p), ("lut_n", C.c_int32), ("done", C.c_void_p),
-                ("acc_out", C.c_void_p), ("reset_state", C.c_void_p), ("override_R", C.c_void_p),
+                ("acc_out", C.c_void_p), ("reset_state", C.c_void_p), ("override_q", C.c_void_p),
+                ("override_thrust", C.c_void_p),
                 ("objects", C.POINTER(Object)), ("stats", C.c_void_p)]
 
 
@@ -86,6 +87,9 @@ def load():
     lib.fpv_drone_step.argtypes = [C.POINTER(DroneParams), C.POINTER(DroneIO), C.c_void_p]
     lib.fpv_drone_observe.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p]
+    lib.fpv_drone_get_rotation.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
+    lib.fpv_drone_set_rotation.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.fpv_matrix_to_quat.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     lib.fpv_sticks_to_actions.argtypes = [C.POINTER(StickCalib), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                           C.c_void_p]
     lib.fpv_racer_reset.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]

@@ -1,25 +1,31 @@
 // Mode A: the reference `Drone.step` (src/utils/components.py:220-248) for a batch of envs.
-// One thread owns LANES envs (1 = float, 2 = packed F2), loads their state once (5 x 128-bit per env),
+// One thread owns L envs (1 = float, 2 = packed F2), takes their state once per control step (4 x 128-bit per env),
 // runs K substeps entirely in registers and stores the state once.
+//
+// Attitude is carried as a unit quaternion q = [w,x,y,z] (the reference's own convention,
+// src/utils/helper_functions.py:65-117) instead of the 3x3 matrix the reference mutates: R(q1 (x) q2) = R(q1) R(q2),
+// so the reference's  R <- R E^T E^T  (kinematics.py:27-30 applied twice, components.py:216-218) is
+// q <- q (x) conj(qE)^2  with qE the quaternion of E = Rz Ry Rx.  Same rotation, 4 floats instead of 9 in HBM and
+// ~30 fewer FP32 operations per substep.  q is re-normalised once per control step.
 #pragma once
 #include "../../include/fpv_api.h"
 #include "vec.cuh"
 
 namespace fpv {
 
-// Launch-constant parameters, derived on the host in double precision (api.cu) and passed by value
+// Launch-constant parameters, derived on the host in double precision (fpv_api.cu) and passed by value
 // (kernel-parameter constant bank => uniform loads, no __constant__ global state).
 struct DroneK {
   float dt;
   int substeps;
   float one_minus_rtr;      // 1 - rates_transition_rate            components.py:187-188
-  float rtr_max_rates;      // unused by the kernel maths; kept for debugging
   float max_rates;
   float rtr;
   float ttr;
   float one_minus_ttr;      // components.py:192-193
-  float k_drag[3];          // kinematics.py:36
-  float motor_xy[4][2];     // components.py:123-125
+  float kd0, kd_a, kd_b;    // k_drag[0], k_drag[1]-k_drag[0], k_drag[2]-k_drag[0]   (kinematics.py:36)
+  float neg_motor_xy[4][2]; // -motor offsets                       components.py:123-125
+  float motor_xy[4][2];
   float motor_radius;
   float spring_k, spring_c; // components.py:198
   float poly[4];            // throttle% -> N, high->low; evaluated at 100*(x+1)/2   components.py:136
@@ -27,8 +33,7 @@ struct DroneK {
   float grav_force_z;       // -g*m                                  kinematics.py:41-45
   float inv_mass;
   float dt_over_mass;       // dt / m
-  float mass;
-  float ang_scale;          // deg2rad * dt                          kinematics.py:29
+  float half_ang_scale;     // 0.5 * deg2rad * dt                    kinematics.py:29
   float lut_scale;          // (lut_n-1)/2
   int lut_n;
   unsigned flags;
@@ -45,12 +50,9 @@ struct DroneIO {
   unsigned char* done;
   float4* acc_out;
   const float4* reset_state;
-  const float4* override_R;
+  const float4* override_q;      // [n]: rotation override as a quaternion (w,x,y,z)
+  const float* override_thrust;  // [n]
   fpv_stats_t* stats;
-};
-
-template <class V> struct Vec3 {
-  V x, y, z;
 };
 
 // Obstacle SDF + normal for one motor point (GENERAL path only; warp-uniform object loop).
@@ -85,19 +87,20 @@ __device__ __forceinline__ void object_sdf(const fpv_object_t& o, V px, V py, V 
 
 template <class V> struct DroneRegs {
   V px, py, pz, vx, vy, vz;
-  V r00, r01, r02, r10, r11, r12, r20, r21, r22;
+  V qw, qx, qy, qz;
   V pr0, pr1, pr2, pt;
   V ax, ay, az;  // last substep's acceleration
 };
 
 // K reference steps for the envs held in `s`.  Returns the OR of the per-step crash flags.
-// ANG selects the sin/cos evaluation: 0 = full-range sincosf, 1 = |angle| <= 0.5 rad (degree-7/8 kernels, no range
-// reduction), 2 = |angle| <= 0.1 rad (degree-5/4 kernels, truncation error < 2e-11).
-template <class V, int ANG, bool GENERAL>
+// ANG selects the sin/cos evaluation of the half Euler angles: 0 = full-range sincosf, 1 = |angle| <= 0.5 rad
+// (degree-7/8 kernels, no range reduction), 2 = |angle| <= 0.1 rad (degree-5/4 kernels, truncation < 2e-11).
+// WIND = false drops the "+ wind" adds when the launch has no wind at all.
+template <class V, int ANG, bool GENERAL, bool WIND>
 __device__ __forceinline__ typename Lane<V>::Mask drone_substeps(const DroneK& k, DroneRegs<V>& s, V a0, V a1, V a2,
                                                                    V thrust_target, V wx, V wy, V wz,
-                                                                   bool has_override, V o_thrust,
-                                                                   const DroneRegs<V>* ovr) {
+                                                                   bool has_override, V o_thrust, V oqw, V oqx, V oqy,
+                                                                   V oqz) {
   using M = typename Lane<V>::Mask;
   // action2force invariants (the action is held for the whole control step), components.py:185-193
   const V mr = S<V>(k.max_rates);
@@ -106,10 +109,10 @@ __device__ __forceinline__ typename Lane<V>::Mask drone_substeps(const DroneK& k
   const V c2 = vmin(vmax(vneg(a2) * mr, vneg(mr)), mr) * S<V>(k.rtr);
   const V tt = thrust_target * S<V>(k.ttr);
   const V omr = S<V>(k.one_minus_rtr), omt = S<V>(k.one_minus_ttr);
-  const V dt = S<V>(k.dt), dt_m = S<V>(k.dt_over_mass), asc = S<V>(k.ang_scale);
-  const V zero = S<V>(0.f);
+  const V dt = S<V>(k.dt), dt_m = S<V>(k.dt_over_mass), hasc = S<V>(k.half_ang_scale);
+  const V zero = S<V>(0.f), one = S<V>(1.f);
   const bool ground = (k.flags & FPV_F_GROUND) != 0;
-  M done = vlt(S<V>(1.f), zero);  // all false
+  M done = vlt(one, zero);  // all false
   V Fx = zero, Fy = zero, Fz = zero;
 
 #pragma unroll 1
@@ -120,24 +123,33 @@ __device__ __forceinline__ typename Lane<V>::Mask drone_substeps(const DroneK& k
     V th = vfma(s.pt, omt, tt);
     s.pt = th;
     if (GENERAL && has_override) {  // components.py:230-232
-      s.r00 = ovr->r00; s.r01 = ovr->r01; s.r02 = ovr->r02;
-      s.r10 = ovr->r10; s.r11 = ovr->r11; s.r12 = ovr->r12;
-      s.r20 = ovr->r20; s.r21 = ovr->r21; s.r22 = ovr->r22;
+      s.qw = oqw; s.qx = oqx; s.qy = oqy; s.qz = oqz;
       th = o_thrust;
     }
-    // ---- drag, kinematics.py:33-38: R * (k (.) (R^T (v + wind)) * |v + wind|); the thrust R[:,2]*th
-    //      (kinematics.py:48-49) is a body-z force too, so it joins the body-frame vector before the rotation
-    const V ux = s.vx + wx, uy = s.vy + wy, uz = s.vz + wz;
+    // ---- the entries of R(q) this step reads: columns 1 and 2 and R[2][0]  (helper_functions.py:100-117)
+    const V x2 = s.qx + s.qx, y2 = s.qy + s.qy, z2 = s.qz + s.qz;
+    const V nqw = vneg(s.qw);
+    const V xz = s.qx * z2, yz = s.qy * z2, xy = s.qx * y2;
+    const V r02 = vfma(s.qw, y2, xz), r20 = vfma(nqw, y2, xz);
+    const V r21 = vfma(s.qw, x2, yz), r12 = vfma(nqw, x2, yz);
+    const V r01 = vfma(nqw, z2, xy);
+    const V tx = vfma(vneg(s.qx), x2, one);  // 1 - 2x^2
+    const V r11 = vfma(vneg(s.qz), z2, tx), r22 = vfma(vneg(s.qy), y2, tx);
+    // ---- drag + thrust + gravity (components.py:242).  calculate_drag (kinematics.py:33-38) is
+    //      R diag(k)|u| R^T u with u = v + wind; with R orthonormal that equals
+    //      |u| (k0 u + (k1-k0)(c1.u) c1 + (k2-k0)(c2.u) c2), c_j the columns of R -- and the thrust
+    //      R[:,2]*th (kinematics.py:48-49) rides on the c2 coefficient.
+    V ux = s.vx, uy = s.vy, uz = s.vz;
+    if (WIND) { ux = ux + wx; uy = uy + wy; uz = uz + wz; }
     const V nrm = vsqrt_fast(vfma(ux, ux, vfma(uy, uy, uz * uz)));
-    const V b0 = vfma(s.r00, ux, vfma(s.r10, uy, s.r20 * uz));
-    const V b1 = vfma(s.r01, ux, vfma(s.r11, uy, s.r21 * uz));
-    const V b2 = vfma(s.r02, ux, vfma(s.r12, uy, s.r22 * uz));
-    const V f0 = (S<V>(k.k_drag[0]) * b0) * nrm, f1 = (S<V>(k.k_drag[1]) * b1) * nrm;
-    const V f2 = vfma(S<V>(k.k_drag[2]) * b2, nrm, th);
-    // ---- thrust + gravity + drag (components.py:242)
-    Fx = vfma(s.r00, f0, vfma(s.r01, f1, s.r02 * f2));
-    Fy = vfma(s.r10, f0, vfma(s.r11, f1, s.r12 * f2));
-    Fz = vfma(s.r20, f0, vfma(s.r21, f1, vfma(s.r22, f2, S<V>(k.grav_force_z))));
+    const V d1 = vfma(r01, ux, vfma(r11, uy, r21 * uz));
+    const V d2 = vfma(r02, ux, vfma(r12, uy, r22 * uz));
+    const V ks = S<V>(k.kd0) * nrm;
+    const V g1 = (S<V>(k.kd_a) * nrm) * d1;
+    const V g2 = vfma(S<V>(k.kd_b) * nrm, d2, th);
+    Fx = vfma(g2, r02, vfma(g1, r01, ks * ux));
+    Fy = vfma(g2, r12, vfma(g1, r11, ks * uy));
+    Fz = vfma(g2, r22, vfma(g1, r21, vfma(ks, uz, S<V>(k.grav_force_z))));
     // ---- motors, collisions, crash test (components.py:235-239, :198-214)
     M crashed;
     if (!GENERAL) {
@@ -148,36 +160,38 @@ __device__ __forceinline__ typename Lane<V>::Mask drone_substeps(const DroneK& k
       V tmax = S<V>(-3.0e38f), pen_sum = zero, cnt = zero;
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
-        const V t = vfma(S<V>(-k.motor_xy[m][0]), s.r20, vfma(S<V>(-k.motor_xy[m][1]), s.r21, h));
+        const V t = vfma(S<V>(k.neg_motor_xy[m][0]), r20, vfma(S<V>(k.neg_motor_xy[m][1]), r21, h));
         tmax = vmax(tmax, t);
-        pen_sum = pen_sum + vmax(t, zero);
-        if (k.spring_c != 0.f) cnt = cnt + vsel(vlt(zero, t), S<V>(1.f), zero);
+        pen_sum = m == 0 ? vmax(t, zero) : pen_sum + vmax(t, zero);
+        if (k.spring_c != 0.f) cnt = cnt + vsel(vlt(zero, t), one, zero);
       }
       crashed = vlt(S<V>(k.motor_radius), tmax);
-      V cf = S<V>(k.spring_k) * pen_sum;
-      if (k.spring_c != 0.f) cf = vfma(vneg(S<V>(k.spring_c)) * s.vz, cnt, cf);
-      if (ground) Fz = Fz + vsel(crashed, zero, cf);
+      if (ground) {
+        if (k.spring_c != 0.f) Fz = vfma(vneg(S<V>(k.spring_c)) * s.vz, vsel(crashed, zero, cnt), Fz);
+        Fz = vfma(S<V>(k.spring_k), vsel(crashed, zero, pen_sum), Fz);
+      }
     } else {
-      crashed = vlt(S<V>(1.f), zero);
+      crashed = vlt(one, zero);
+      const V r00 = vfma(vneg(s.qy), y2, vfma(vneg(s.qz), z2, one)), r10 = vfma(s.qw, z2, xy);
       V cfx = zero, cfy = zero, cfz = zero;
       V mxw[4], myw[4], mzw[4];
       V minz = S<V>(3.0e38f);
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
         const V ox = S<V>(k.motor_xy[m][0]), oy = S<V>(k.motor_xy[m][1]);
-        mxw[m] = vfma(ox, s.r00, vfma(oy, s.r01, s.px));
-        myw[m] = vfma(ox, s.r10, vfma(oy, s.r11, s.py));
-        mzw[m] = vfma(ox, s.r20, vfma(oy, s.r21, s.pz));
+        mxw[m] = vfma(ox, r00, vfma(oy, r01, s.px));
+        myw[m] = vfma(ox, r10, vfma(oy, r11, s.py));
+        mzw[m] = vfma(ox, r20, vfma(oy, r21, s.pz));
         minz = vmin(minz, mzw[m]);
       }
       const int n_obj = k.n_objects + (ground ? 1 : 0);
       for (int o = 0; o < n_obj; ++o) {  // object order: extra objects first, ground last
         V d[4], nx[4], ny[4], nz[4];
-        M hit = vlt(S<V>(1.f), zero);
+        M hit = vlt(one, zero);
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
           if (o < k.n_objects) object_sdf<V>(k.objects[o], mxw[m], myw[m], mzw[m], d[m], nx[m], ny[m], nz[m]);
-          else { d[m] = mzw[m]; nx[m] = zero; ny[m] = zero; nz[m] = S<V>(1.f); }
+          else { d[m] = mzw[m]; nx[m] = zero; ny[m] = zero; nz[m] = one; }
           hit = vor(hit, vlt(d[m], zero));
         }
         hit = vand(hit, vnot(crashed));
@@ -207,35 +221,34 @@ __device__ __forceinline__ typename Lane<V>::Mask drone_substeps(const DroneK& k
     s.vx = vfma(Fx, dt_m, s.vx); s.vy = vfma(Fy, dt_m, s.vy); s.vz = vfma(Fz, dt_m, s.vz);
     // ---- attitude: E = Rz(yaw)Ry(pitch)Rx(roll) of deg2rad(rates)*dt, R <- R E^T E^T
     //      (rotate_body_by_rates kinematics.py:27-30 runs inside update_kinematic_step :23 AND again in
-    //      Drone.update components.py:218)
+    //      Drone.update components.py:218).  Quaternion form: qE from the half angles, q <- q (x) conj(qE)^2.
     V sr, cr, sp, cp, sy, cy;
-    vsincos<ANG>(w0 * asc, sr, cr);
-    vsincos<ANG>(w1 * asc, sp, cp);
-    vsincos<ANG>(w2 * asc, sy, cy);
-    const V sysp = sy * sp, cysp = cy * sp;
-    const V e00 = cy * cp, e01 = vfma(cysp, sr, vneg(sy * cr)), e02 = vfma(cysp, cr, sy * sr);
-    const V e10 = sy * cp, e11 = vfma(sysp, sr, cy * cr), e12 = vfma(sysp, cr, vneg(cy * sr));
-    const V e20 = vneg(sp), e21 = cp * sr, e22 = cp * cr;
-#pragma unroll
-    for (int rep = 0; rep < 2; ++rep) {
-      V t0, t1, t2;
-      t0 = vfma(s.r00, e00, vfma(s.r01, e01, s.r02 * e02));
-      t1 = vfma(s.r00, e10, vfma(s.r01, e11, s.r02 * e12));
-      t2 = vfma(s.r00, e20, vfma(s.r01, e21, s.r02 * e22));
-      s.r00 = t0; s.r01 = t1; s.r02 = t2;
-      t0 = vfma(s.r10, e00, vfma(s.r11, e01, s.r12 * e02));
-      t1 = vfma(s.r10, e10, vfma(s.r11, e11, s.r12 * e12));
-      t2 = vfma(s.r10, e20, vfma(s.r11, e21, s.r12 * e22));
-      s.r10 = t0; s.r11 = t1; s.r12 = t2;
-      t0 = vfma(s.r20, e00, vfma(s.r21, e01, s.r22 * e02));
-      t1 = vfma(s.r20, e10, vfma(s.r21, e11, s.r22 * e12));
-      t2 = vfma(s.r20, e20, vfma(s.r21, e21, s.r22 * e22));
-      s.r20 = t0; s.r21 = t1; s.r22 = t2;
-    }
+    vsincos<ANG>(w0 * hasc, sr, cr);
+    vsincos<ANG>(w1 * hasc, sp, cp);
+    vsincos<ANG>(w2 * hasc, sy, cy);
+    const V A = cy * cp, B = sy * sp, C = cy * sp, D = sy * cp;
+    const V ew = vfma(A, cr, B * sr);  // qE = qz (x) qy (x) qx
+    const V ex = vfma(A, sr, vneg(B * cr));
+    const V ey = vfma(C, cr, D * sr);
+    const V ez = vfma(D, cr, vneg(C * sr));
+    // p = conj(qE)^2 = (ew^2 - |ev|^2, -2 ew ev)
+    const V pw = vfma(ew, ew, vneg(vfma(ex, ex, vfma(ey, ey, ez * ez))));
+    const V m2 = ew * S<V>(-2.f);
+    const V px_ = m2 * ex, py_ = m2 * ey, pz_ = m2 * ez;
+    // q <- q (x) p   (Hamilton product)
+    const V nw = vfma(s.qw, pw, vneg(vfma(s.qx, px_, vfma(s.qy, py_, s.qz * pz_))));
+    const V nx_ = vfma(s.qw, px_, vfma(s.qx, pw, vfma(s.qy, pz_, vneg(s.qz * py_))));
+    const V ny_ = vfma(s.qw, py_, vfma(s.qy, pw, vfma(s.qz, px_, vneg(s.qx * pz_))));
+    const V nz_ = vfma(s.qw, pz_, vfma(s.qz, pw, vfma(s.qx, py_, vneg(s.qy * px_))));
+    s.qw = nw; s.qx = nx_; s.qy = ny_; s.qz = nz_;
   }
   // acceleration of the last substep (Drone.acceleration, components.py:243)
   const V inv_m = S<V>(k.inv_mass);
   s.ax = Fx * inv_m; s.ay = Fy * inv_m; s.az = Fz * inv_m;
+  // keep q on the unit sphere (the reference's R is orthonormal to 1e-14; fp32 products drift by ~1e-7 per step)
+  const V n2 = vfma(s.qw, s.qw, vfma(s.qx, s.qx, vfma(s.qy, s.qy, s.qz * s.qz)));
+  const V rn = vrsqrt_fast(n2);
+  s.qw = s.qw * rn; s.qx = s.qx * rn; s.qy = s.qy * rn; s.qz = s.qz * rn;
   return done;
 }
 
@@ -274,11 +287,13 @@ template <> struct Pack<F2> {
 // path is one warp vote and no memory traffic; a warp that saw an event reduces with shuffles and issues one
 // fire-and-forget red.global.add.f64 per non-zero counter.  No block barrier.  env_steps = n per launch (added by
 // one thread of the grid) minus the frozen envs.
-__device__ __forceinline__ void stats_warp_flush(fpv_stats_t* stats, float crashes, float episodes, float len_sum,
-                                                 float nonfinite, float frozen) {
-  const bool any = (crashes != 0.f) | (nonfinite != 0.f) | (frozen != 0.f);
+struct TileStats {
+  float crash, epi, len, nf, frozen;
+};
+__device__ __forceinline__ void stats_warp_flush(fpv_stats_t* stats, const TileStats& t) {
+  const bool any = (t.crash != 0.f) | (t.nf != 0.f) | (t.frozen != 0.f);
   if (!__any_sync(0xffffffffu, any)) return;
-  float v[5] = {crashes, episodes, len_sum, nonfinite, frozen};
+  float v[5] = {t.crash, t.epi, t.len, t.nf, t.frozen};
 #pragma unroll
   for (int i = 0; i < 5; ++i)
 #pragma unroll
@@ -292,13 +307,9 @@ __device__ __forceinline__ void stats_warp_flush(fpv_stats_t* stats, float crash
   }
 }
 
-struct TileStats {
-  float crash, epi, len, nf, frozen;
-};
-
 // One tile worth of work for this thread: unpack L envs from their float4 rows, run the substeps in registers,
-// episode bookkeeping, stores.  q[p][l] = plane p of slot l; slot l is env base + l*SLOT_STRIDE (ei[l] = the same index
-// clamped to n-1, used for the side inputs of the general path).
+// episode bookkeeping, stores.  q[p][l] = plane p of slot l; slot l is env base + l*SLOT_STRIDE (ei[l] = the same
+// index clamped to n-1, used for the side inputs).
 template <class V, int ANG, bool GENERAL, int SLOT_STRIDE>
 __device__ __forceinline__ void drone_tile(const DroneK& k, const DroneIO& io, const float* lut_s,
                                            const float4 (&q)[FPV_DRONE_PLANES][Lane<V>::N],
@@ -308,14 +319,15 @@ __device__ __forceinline__ void drone_tile(const DroneK& k, const DroneIO& io, c
   DroneRegs<V> s;
   s.px = Pack<V>::x(q[0]); s.py = Pack<V>::y(q[0]); s.pz = Pack<V>::z(q[0]); s.pt = Pack<V>::w(q[0]);
   s.vx = Pack<V>::x(q[1]); s.vy = Pack<V>::y(q[1]); s.vz = Pack<V>::z(q[1]);
-  s.r00 = Pack<V>::x(q[2]); s.r01 = Pack<V>::y(q[2]); s.r02 = Pack<V>::z(q[2]); s.pr0 = Pack<V>::w(q[2]);
-  s.r10 = Pack<V>::x(q[3]); s.r11 = Pack<V>::y(q[3]); s.r12 = Pack<V>::z(q[3]); s.pr1 = Pack<V>::w(q[3]);
-  s.r20 = Pack<V>::x(q[4]); s.r21 = Pack<V>::y(q[4]); s.r22 = Pack<V>::z(q[4]); s.pr2 = Pack<V>::w(q[4]);
+  s.qw = Pack<V>::x(q[2]); s.qx = Pack<V>::y(q[2]); s.qy = Pack<V>::z(q[2]); s.qz = Pack<V>::w(q[2]);
+  s.pr0 = Pack<V>::x(q[3]); s.pr1 = Pack<V>::y(q[3]); s.pr2 = Pack<V>::z(q[3]);
   s.ax = S<V>(0.f); s.ay = S<V>(0.f); s.az = S<V>(0.f);
   int epi[L];
+  float spare[L];
 #pragma unroll
-  for (int l = 0; l < L; ++l) epi[l] = __float_as_int(q[1][l].w);
+  for (int l = 0; l < L; ++l) { epi[l] = __float_as_int(q[1][l].w); spare[l] = q[3][l].w; }
 
+  const bool wind_on = io.wind_env != nullptr || k.wind[0] != 0.f || k.wind[1] != 0.f || k.wind[2] != 0.f;
   V wx = S<V>(k.wind[0]), wy = S<V>(k.wind[1]), wz = S<V>(k.wind[2]);
   if (io.wind_env) {
     float4 w[L];
@@ -333,30 +345,27 @@ __device__ __forceinline__ void drone_tile(const DroneK& k, const DroneIO& io, c
   } else {
     target = thrust_poly<V>(k, a3);
   }
-  DroneRegs<V> ovr;
-  V o_thrust = S<V>(0.f);
-  const bool has_ovr = GENERAL && io.override_R != nullptr;
+  V o_thrust = S<V>(0.f), oqw = S<V>(1.f), oqx = S<V>(0.f), oqy = S<V>(0.f), oqz = S<V>(0.f);
+  const bool has_ovr = GENERAL && io.override_q != nullptr;
   if (has_ovr) {
-    float4 r0[L], r1[L], r2[L];
+    float4 oq[L];
+    float ot[2];
 #pragma unroll
-    for (int l = 0; l < L; ++l) {
-      r0[l] = ldg_stream(io.override_R + ei[l]);
-      r1[l] = ldg_stream(io.override_R + io.n + ei[l]);
-      r2[l] = ldg_stream(io.override_R + 2 * io.n + ei[l]);
-    }
-    ovr.r00 = Pack<V>::x(r0); ovr.r01 = Pack<V>::y(r0); ovr.r02 = Pack<V>::z(r0); o_thrust = Pack<V>::w(r0);
-    ovr.r10 = Pack<V>::x(r1); ovr.r11 = Pack<V>::y(r1); ovr.r12 = Pack<V>::z(r1);
-    ovr.r20 = Pack<V>::x(r2); ovr.r21 = Pack<V>::y(r2); ovr.r22 = Pack<V>::z(r2);
+    for (int l = 0; l < L; ++l) { oq[l] = ldg_stream(io.override_q + ei[l]); ot[l] = io.override_thrust[ei[l]]; }
+    oqw = Pack<V>::x(oq); oqx = Pack<V>::y(oq); oqy = Pack<V>::z(oq); oqz = Pack<V>::w(oq);
+    o_thrust = Lane<V>::make(ot[0], ot[L - 1]);
   }
 
-  auto done = drone_substeps<V, ANG, GENERAL>(k, s, a0, a1, a2, target, wx, wy, wz, has_ovr, o_thrust, &ovr);
+  typename Lane<V>::Mask done;
+  if (wind_on) done = drone_substeps<V, ANG, GENERAL, true>(k, s, a0, a1, a2, target, wx, wy, wz, has_ovr, o_thrust, oqw, oqx, oqy, oqz);
+  else done = drone_substeps<V, ANG, GENERAL, false>(k, s, a0, a1, a2, target, wx, wy, wz, has_ovr, o_thrust, oqw, oqx, oqy, oqz);
 
   // ---- epilogue per env: episode bookkeeping, freeze / auto-reset, stores
 #pragma unroll
   for (int l = 0; l < L; ++l) {
     const long long e = base + (long long)l * SLOT_STRIDE;
     if (e >= io.n) break;
-    bool d = mask_get(done, l);
+    const bool d = mask_get(done, l);
     int ep = epi[l];
     if (ep < 0) {  // frozen after a crash (FPV_F_FREEZE_DONE): state in memory stays as it is, done is sticky
       if (io.done) io.done[e] = 1;
@@ -366,19 +375,19 @@ __device__ __forceinline__ void drone_tile(const DroneK& k, const DroneIO& io, c
     ep += 1;
     float4* const dst = io.state + e;
     if (io.done) io.done[e] = d ? 1 : 0;
+    if (io.acc_out)
+      stg_stream(io.acc_out + e, make_float4(Lane<V>::get(s.ax, l), Lane<V>::get(s.ay, l), Lane<V>::get(s.az, l), 0.f));
     if (d) {  // rare: crash this control step
       st.crash += 1.f;
-      if (k.flags & FPV_F_AUTO_RESET) {  // restart from the reset snapshot (plane by plane, no merge with the hot path)
+      if (k.flags & FPV_F_AUTO_RESET) {  // restart from the reset snapshot
         st.epi += 1.f; st.len += (float)ep;
         const float4* const src = io.reset_state + e;
-        float4 v[FPV_DRONE_PLANES];  // all loads in flight before the first store (one round trip, not five)
+        float4 v[FPV_DRONE_PLANES];  // all loads in flight before the first store (one round trip, not four)
 #pragma unroll
         for (int p = 0; p < FPV_DRONE_PLANES; ++p) v[p] = ldg_stream(src + p * io.stride);
         v[1].w = __int_as_float(0);
 #pragma unroll
         for (int p = 0; p < FPV_DRONE_PLANES; ++p) stg_stream(dst + p * io.stride, v[p]);
-        if (io.acc_out)
-          stg_stream(io.acc_out + e, make_float4(Lane<V>::get(s.ax, l), Lane<V>::get(s.ay, l), Lane<V>::get(s.az, l), 0.f));
         continue;
       }
       if (k.flags & FPV_F_FREEZE_DONE) {
@@ -392,16 +401,13 @@ __device__ __forceinline__ void drone_tile(const DroneK& k, const DroneIO& io, c
     if (!(fabsf(((px + py) + (pz + vx)) + (vy + vz)) <= 3.0e38f)) st.nf += 1.f;
     stg_stream(dst, make_float4(px, py, pz, Lane<V>::get(s.pt, l)));
     stg_stream(dst + io.stride, make_float4(vx, vy, vz, __int_as_float(ep)));
-    stg_stream(dst + 2 * io.stride, make_float4(Lane<V>::get(s.r00, l), Lane<V>::get(s.r01, l), Lane<V>::get(s.r02, l), Lane<V>::get(s.pr0, l)));
-    stg_stream(dst + 3 * io.stride, make_float4(Lane<V>::get(s.r10, l), Lane<V>::get(s.r11, l), Lane<V>::get(s.r12, l), Lane<V>::get(s.pr1, l)));
-    stg_stream(dst + 4 * io.stride, make_float4(Lane<V>::get(s.r20, l), Lane<V>::get(s.r21, l), Lane<V>::get(s.r22, l), Lane<V>::get(s.pr2, l)));
-    if (io.acc_out)
-      stg_stream(io.acc_out + e, make_float4(Lane<V>::get(s.ax, l), Lane<V>::get(s.ay, l), Lane<V>::get(s.az, l), 0.f));
+    stg_stream(dst + 2 * io.stride, make_float4(Lane<V>::get(s.qw, l), Lane<V>::get(s.qx, l), Lane<V>::get(s.qy, l), Lane<V>::get(s.qz, l)));
+    stg_stream(dst + 3 * io.stride, make_float4(Lane<V>::get(s.pr0, l), Lane<V>::get(s.pr1, l), Lane<V>::get(s.pr2, l), spare[l]));
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Kernel 1 (general path, and tiny batches): persistent CTAs, state fetched with 128-bit streaming loads.
+// Kernel 1 (general path: obstacles / overrides): persistent CTAs, state fetched with 128-bit streaming loads.
 // gridDim.x CTAs (a multiple of the SM count chosen by the host) walk the tiles of THREADS*L envs with stride
 // gridDim.x.  The motor-curve LUT is staged into shared memory once per CTA.
 // ---------------------------------------------------------------------------------------------------------------
@@ -409,9 +415,9 @@ template <class V, int ANG, bool GENERAL, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) drone_step_kernel(const __grid_constant__ DroneK k, const DroneIO io) {
   constexpr int L = Lane<V>::N;
   constexpr int TILE = THREADS * L;
-  extern __shared__ __align__(16) float lut_s[];
+  extern __shared__ __align__(16) float lut_dyn[];
   if (k.flags & FPV_F_THRUST_LUT) {
-    for (int i = threadIdx.x; i < k.lut_n; i += THREADS) lut_s[i] = io.lut[i];
+    for (int i = threadIdx.x; i < k.lut_n; i += THREADS) lut_dyn[i] = io.lut[i];
     __syncthreads();
   }
   if (io.stats && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&io.stats->env_steps, (double)io.n);
@@ -432,16 +438,16 @@ __global__ void __launch_bounds__(THREADS, MINB) drone_step_kernel(const __grid_
       for (int l = 0; l < L; ++l) q[p][l] = ldg_stream(io.state + p * io.stride + ei[l]);
 #pragma unroll
     for (int l = 0; l < L; ++l) act[l] = ldg_stream(io.actions + ei[l]);
-    drone_tile<V, ANG, GENERAL, THREADS>(k, io, lut_s, q, act, ei, base, st);
+    drone_tile<V, ANG, GENERAL, THREADS>(k, io, lut_dyn, q, act, ei, base, st);
   }
-  if (io.stats) stats_warp_flush(io.stats, st.crash, st.epi, st.len, st.nf, st.frozen);
+  if (io.stats) stats_warp_flush(io.stats, st);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Kernel 2 (the hot path): the six float4 rows of a chunk (5 state planes + actions) are brought into shared memory
-// by the TMA engine (cp.async.bulk, completion on an mbarrier) one chunk AHEAD of the arithmetic, so HBM latency and
-// bandwidth overlap the substep loop instead of preceding it.  STAGES ring slots per warp.
-//   smem: [ LUT | WARPS x STAGES x 6 x CHUNK float4 | WARPS x STAGES mbarriers ]
+// Kernel 2 (the hot path): the five float4 rows of a chunk (4 state planes + actions) are brought into shared
+// memory by the TMA engine (cp.async.bulk, completion on an mbarrier) one chunk AHEAD of the arithmetic, so HBM
+// latency and bandwidth overlap the substep loop instead of preceding it.  STAGES ring slots per warp.
+//   smem: [ LUT | WARPS x STAGES x 5 x CHUNK float4 | WARPS x STAGES mbarriers ]
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
@@ -481,23 +487,23 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
                : "memory");
 }
 
-// Every WARP owns a private ring: its lane 0 is the producer for the warp's own 32*L-env chunks, the 32 lanes are
-// the consumers, and __syncwarp() is the only synchronisation -- warps of a CTA never wait for one another (a CTA
-// exists only to share the staged LUT).  Warp-chunk c covers envs [c*32*L, (c+1)*32*L); chunks are dealt
+// Every WARP owns a private ring: one elected lane is the producer for the warp's own 32*L-env chunks, the 32 lanes
+// are the consumers, and __syncwarp() is the only synchronisation -- warps of a CTA never wait for one another (a
+// CTA exists only to share the staged LUT).  Warp-chunk c covers envs [c*32*L, (c+1)*32*L); chunks are dealt
 // round-robin over all warps of the grid.
 template <class V, int ANG, int THREADS, int MINB, int STAGES>
 __global__ void __launch_bounds__(THREADS, MINB) drone_step_tma_kernel(const __grid_constant__ DroneK k, const DroneIO io,
                                                                        const int lut_bytes) {
   constexpr int L = Lane<V>::N;
-  constexpr int CHUNK = 32 * L;                 // envs per warp-chunk
-  constexpr int ROWS = FPV_DRONE_PLANES + 1;    // 5 state planes + actions
+  constexpr int CHUNK = 32 * L;               // envs per warp-chunk
+  constexpr int ROWS = FPV_DRONE_PLANES + 1;  // 4 state planes + actions
   constexpr int WARPS = THREADS / 32;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* lut_s = reinterpret_cast<float*>(smem_raw);
-  float4* ring_all = reinterpret_cast<float4*>(smem_raw + lut_bytes);                   // [WARPS][STAGES][ROWS][CHUNK]
+  float4* ring_all = reinterpret_cast<float4*>(smem_raw + lut_bytes);  // [WARPS][STAGES][ROWS][CHUNK]
   unsigned long long* full_all = reinterpret_cast<unsigned long long*>(ring_all + WARPS * STAGES * ROWS * CHUNK);
 
-  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform id
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // warp-uniform id
   float4* ring = ring_all + (size_t)warp * STAGES * ROWS * CHUNK;
   unsigned long long* full = full_all + warp * STAGES;
   if (lane == 0) {
@@ -514,7 +520,7 @@ __global__ void __launch_bounds__(THREADS, MINB) drone_step_tma_kernel(const __g
   const long long first_chunk = (long long)blockIdx.x * WARPS + warp;
   const long long chunk_stride = (long long)gridDim.x * WARPS;
 
-  // producer (lane 0): arm the slot's mbarrier with the byte count, then six bulk copies (one per row)
+  // producer: arm the slot's mbarrier with the byte count, then one bulk copy per row (all operands warp-uniform)
   auto issue = [&](long long chunk, int slot) {
     const long long first = chunk * CHUNK;
     const long long rem = io.n - first;
@@ -527,7 +533,7 @@ __global__ void __launch_bounds__(THREADS, MINB) drone_step_tma_kernel(const __g
     tma_load_1d(dst + FPV_DRONE_PLANES * CHUNK, io.actions + first, bytes, &full[slot]);
   };
 
-  const bool leader = elect_one();   // one lane per warp issues; every operand below is warp-uniform
+  const bool leader = elect_one();
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
     const long long c = first_chunk + (long long)s * chunk_stride;
@@ -555,10 +561,10 @@ __global__ void __launch_bounds__(THREADS, MINB) drone_step_tma_kernel(const __g
       for (int p = 0; p < FPV_DRONE_PLANES; ++p) q[p][l] = src[p * CHUNK + l * 32 + lane];
       act[l] = src[FPV_DRONE_PLANES * CHUNK + l * 32 + lane];
     }
-    __syncwarp();  // all lanes have drained this slot -> lane 0 may refill it next iteration
+    __syncwarp();  // all lanes have drained this slot -> the producer lane may refill it next iteration
     if (base < io.n) drone_tile<V, ANG, false, 32>(k, io, lut_s, q, act, ei, base, st);
   }
-  if (io.stats) stats_warp_flush(io.stats, st.crash, st.epi, st.len, st.nf, st.frozen);
+  if (io.stats) stats_warp_flush(io.stats, st);
 }
 
 }  // namespace fpv

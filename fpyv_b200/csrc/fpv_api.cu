@@ -82,7 +82,7 @@ bool launch_drone_tma(const DroneK& k, const DroneIO& io, cudaStream_t st) {
   constexpr int TILE = kThreads * L;
   auto kern = fpv::drone_step_tma_kernel<V, ANG, kThreads, FPV_MINB, STAGES>;
   const int lut_bytes = (k.flags & FPV_F_THRUST_LUT) ? (int)(((size_t)k.lut_n * sizeof(float) + 127) / 128 * 128) : 0;
-  const size_t smem = (size_t)lut_bytes + (size_t)STAGES * 6 * TILE * sizeof(float4) +
+  const size_t smem = (size_t)lut_bytes + (size_t)STAGES * (FPV_DRONE_PLANES + 1) * TILE * sizeof(float4) +
                       (size_t)(kThreads / 32) * STAGES * sizeof(unsigned long long);
   if (smem > 220 * 1024) return false;
   static size_t attr_set = 0;  // per instantiation: largest dynamic smem opted in so far
@@ -176,15 +176,17 @@ int fpv_drone_step(const fpv_drone_params_t* p, const fpv_drone_io_t* io, void* 
   if (io->n == 0) return FPV_OK;
   if (!io->state || !io->actions) return fail(FPV_EINVAL, "fpv_drone_step: state/actions must not be null");
   if (!aligned16(io->state) || !aligned16(io->actions) || !aligned16(io->wind_env) || !aligned16(io->acc_out) ||
-      !aligned16(io->reset_state) || !aligned16(io->override_R))
+      !aligned16(io->reset_state) || !aligned16(io->override_q))
     return fail(FPV_EINVAL, "fpv_drone_step: float4 planes must be 16-byte aligned");
   if (p->substeps < 1) return fail(FPV_EINVAL, "fpv_drone_step: substeps must be >= 1 (got %d)", p->substeps);
   if (!(p->dt > 0.f) || !(p->mass > 0.f)) return fail(FPV_EINVAL, "fpv_drone_step: dt and mass must be positive");
   if (p->n_objects < 0 || p->n_objects > FPV_MAX_OBJECTS)
     return fail(FPV_EINVAL, "fpv_drone_step: n_objects=%d out of range [0,%d]", p->n_objects, FPV_MAX_OBJECTS);
   if (p->n_objects > 0 && !io->objects) return fail(FPV_EINVAL, "fpv_drone_step: n_objects > 0 but objects is null");
-  if (io->override_R && p->substeps != 1)
+  if (io->override_q && p->substeps != 1)
     return fail(FPV_EINVAL, "fpv_drone_step: the rotation/thrust override is a per-step input; it needs substeps == 1");
+  if (io->override_q && !io->override_thrust)
+    return fail(FPV_EINVAL, "fpv_drone_step: override_q needs override_thrust (components.py:230-232)");
   if ((p->flags & FPV_F_AUTO_RESET) && !io->reset_state)
     return fail(FPV_EINVAL, "fpv_drone_step: FPV_F_AUTO_RESET needs io.reset_state");
   if ((p->flags & FPV_F_AUTO_RESET) && (p->flags & FPV_F_FREEZE_DONE))
@@ -202,11 +204,13 @@ int fpv_drone_step(const fpv_drone_params_t* p, const fpv_drone_io_t* io, void* 
   k.one_minus_rtr = (float)(1.0 - rtr);
   k.max_rates = p->max_rates;
   k.rtr = p->rates_transition_rate;
-  k.rtr_max_rates = (float)(rtr * p->max_rates);
   k.ttr = p->thrust_transition_rate;
   k.one_minus_ttr = (float)(1.0 - ttr);
-  for (int i = 0; i < 3; ++i) k.k_drag[i] = p->k_drag[i];
-  for (int m = 0; m < 4; ++m) { k.motor_xy[m][0] = p->motor_xy[m][0]; k.motor_xy[m][1] = p->motor_xy[m][1]; }
+  k.kd0 = p->k_drag[0];
+  k.kd_a = (float)((double)p->k_drag[1] - (double)p->k_drag[0]);
+  k.kd_b = (float)((double)p->k_drag[2] - (double)p->k_drag[0]);
+  for (int m = 0; m < 4; ++m)
+    for (int j = 0; j < 2; ++j) { k.motor_xy[m][j] = p->motor_xy[m][j]; k.neg_motor_xy[m][j] = -p->motor_xy[m][j]; }
   k.motor_radius = p->motor_radius;
   k.spring_k = p->spring_k;
   k.spring_c = p->spring_c;
@@ -215,8 +219,7 @@ int fpv_drone_step(const fpv_drone_params_t* p, const fpv_drone_io_t* io, void* 
   k.grav_force_z = (float)(-(double)p->gravity * (double)p->mass);
   k.inv_mass = (float)(1.0 / (double)p->mass);
   k.dt_over_mass = (float)((double)p->dt / (double)p->mass);
-  k.mass = p->mass;
-  k.ang_scale = (float)(0.017453292519943295 * (double)p->dt);
+  k.half_ang_scale = (float)(0.5 * 0.017453292519943295 * (double)p->dt);
   k.lut_n = (p->flags & FPV_F_THRUST_LUT) ? io->lut_n : 0;
   k.lut_scale = (float)((io->lut_n - 1) * 0.5);
   k.flags = p->flags;
@@ -237,7 +240,8 @@ int fpv_drone_step(const fpv_drone_params_t* p, const fpv_drone_io_t* io, void* 
   d.done = io->done;
   d.acc_out = (float4*)io->acc_out;
   d.reset_state = (const float4*)io->reset_state;
-  d.override_R = (const float4*)io->override_R;
+  d.override_q = (const float4*)io->override_q;
+  d.override_thrust = io->override_thrust;
   d.stats = io->stats;
 
   // |rates| <= max_rates is an invariant of action2force (a convex mix of clipped commands), so the
@@ -245,11 +249,38 @@ int fpv_drone_step(const fpv_drone_params_t* p, const fpv_drone_io_t* io, void* 
   // exact to fp32; below 0.5 rad the reduced-argument minimax kernels need no range reduction; otherwise sincosf.
   const double max_angle = std::fabs((double)p->max_rates) * 0.017453292519943295 * (double)p->dt;
   const int ang = max_angle <= 0.1 ? 2 : (max_angle <= 0.5 ? 1 : 0);
-  const bool general = p->n_objects > 0 || io->override_R != nullptr;
+  const bool general = p->n_objects > 0 || io->override_q != nullptr;
   cudaStream_t st = (cudaStream_t)stream;
   if (p->flags & FPV_F_SCALAR) launch_drone_a<float>(k, d, ang, general, st);
   else launch_drone_a<F2>(k, d, ang, general, st);
   return check_launch("fpv_drone_step");
+}
+
+int fpv_drone_get_rotation(const void* state, int64_t n, int64_t plane_stride, float* R, void* stream) {
+  if (!state || !R) return fail(FPV_EINVAL, "fpv_drone_get_rotation: null pointer");
+  if (n < 0 || plane_stride < n) return fail(FPV_EINVAL, "fpv_drone_get_rotation: bad n/stride");
+  if (!aligned16(state)) return fail(FPV_EINVAL, "fpv_drone_get_rotation: state must be 16-byte aligned");
+  if (n == 0) return FPV_OK;
+  fpv::drone_get_rotation_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const float4*)state, n, plane_stride, R);
+  return check_launch("fpv_drone_get_rotation");
+}
+
+int fpv_drone_set_rotation(void* state, int64_t n, int64_t plane_stride, const float* R, const uint8_t* mask,
+                           void* stream) {
+  if (!state || !R) return fail(FPV_EINVAL, "fpv_drone_set_rotation: null pointer");
+  if (n < 0 || plane_stride < n) return fail(FPV_EINVAL, "fpv_drone_set_rotation: bad n/stride");
+  if (!aligned16(state)) return fail(FPV_EINVAL, "fpv_drone_set_rotation: state must be 16-byte aligned");
+  if (n == 0) return FPV_OK;
+  fpv::drone_set_rotation_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((float4*)state, n, plane_stride, R, mask);
+  return check_launch("fpv_drone_set_rotation");
+}
+
+int fpv_matrix_to_quat(const float* R, int64_t n, void* q, void* stream) {
+  if (!R || !q) return fail(FPV_EINVAL, "fpv_matrix_to_quat: null pointer");
+  if (n < 0 || !aligned16(q)) return fail(FPV_EINVAL, "fpv_matrix_to_quat: bad n or misaligned q");
+  if (n == 0) return FPV_OK;
+  fpv::matrix_to_quat_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(R, n, (float4*)q);
+  return check_launch("fpv_matrix_to_quat");
 }
 
 int fpv_drone_observe(const void* state, int64_t n, int64_t plane_stride, const void* acc, float* Rt, float* gyro,

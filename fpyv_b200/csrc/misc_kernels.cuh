@@ -6,26 +6,83 @@
 namespace fpv {
 
 // ---------------------------------------------------------------------------------------------
+// Quaternion <-> matrix (reference conventions: src/utils/helper_functions.py:65-80, :100-117)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void quat_to_matrix(float4 q, float (&R)[9]) {  // q = (w,x,y,z) in .x .y .z .w
+  const float w = q.x, x = q.y, y = q.z, z = q.w;
+  R[0] = 1.f - 2.f * y * y - 2.f * z * z; R[1] = 2.f * x * y - 2.f * z * w;       R[2] = 2.f * x * z + 2.f * y * w;
+  R[3] = 2.f * x * y + 2.f * z * w;       R[4] = 1.f - 2.f * x * x - 2.f * z * z; R[5] = 2.f * y * z - 2.f * x * w;
+  R[6] = 2.f * x * z - 2.f * y * w;       R[7] = 2.f * y * z + 2.f * x * w;       R[8] = 1.f - 2.f * x * x - 2.f * y * y;
+}
+
+// Robust matrix -> unit quaternion (Shepperd's branch on the largest diagonal term; the reference's
+// rotation_matrix_to_quaternion, helper_functions.py:65-80, is the trace branch only and divides by zero at 180 deg).
+// Evaluated in double and normalised; sign fixed to w >= 0.
+__device__ __forceinline__ float4 matrix_to_quat(const float* R) {
+  const double m00 = R[0], m01 = R[1], m02 = R[2], m10 = R[3], m11 = R[4], m12 = R[5], m20 = R[6], m21 = R[7], m22 = R[8];
+  double w, x, y, z;
+  const double tr = m00 + m11 + m22;
+  if (tr > 0.0) {
+    const double s = sqrt(tr + 1.0) * 2.0;
+    w = 0.25 * s; x = (m21 - m12) / s; y = (m02 - m20) / s; z = (m10 - m01) / s;
+  } else if (m00 > m11 && m00 > m22) {
+    const double s = sqrt(1.0 + m00 - m11 - m22) * 2.0;
+    w = (m21 - m12) / s; x = 0.25 * s; y = (m01 + m10) / s; z = (m02 + m20) / s;
+  } else if (m11 > m22) {
+    const double s = sqrt(1.0 + m11 - m00 - m22) * 2.0;
+    w = (m02 - m20) / s; x = (m01 + m10) / s; y = 0.25 * s; z = (m12 + m21) / s;
+  } else {
+    const double s = sqrt(1.0 + m22 - m00 - m11) * 2.0;
+    w = (m10 - m01) / s; x = (m02 + m20) / s; y = (m12 + m21) / s; z = 0.25 * s;
+  }
+  double n = rsqrt(w * w + x * x + y * y + z * z);
+  if (w < 0.0) n = -n;
+  return make_float4((float)(w * n), (float)(x * n), (float)(y * n), (float)(z * n));
+}
+
+// ---------------------------------------------------------------------------------------------
 // Drone.reset, components.py:150-169.  R = Rz(yaw) Ry(pitch) Rx(roll) from degrees
-// (helper_functions.py:39-44).  Rare path: evaluated in double, stored as float.
+// (helper_functions.py:39-44), stored as its quaternion.  Rare path: evaluated in double.
 // ---------------------------------------------------------------------------------------------
 __global__ void drone_reset_kernel(float4* state, long long n, long long stride, const float* pos, const float* vel,
                                    const float* rpy_deg, const unsigned char* mask) {
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n) return;
   if (mask && !mask[e]) return;
-  const double d2r = 0.017453292519943295;
-  const double roll = (double)rpy_deg[3 * e] * d2r, pitch = (double)rpy_deg[3 * e + 1] * d2r,
-               yaw = (double)rpy_deg[3 * e + 2] * d2r;
+  const double d2r = 0.017453292519943295 * 0.5;
   double sr, cr, sp, cp, sy, cy;
-  sincos(roll, &sr, &cr);
-  sincos(pitch, &sp, &cp);
-  sincos(yaw, &sy, &cy);
+  sincos((double)rpy_deg[3 * e] * d2r, &sr, &cr);
+  sincos((double)rpy_deg[3 * e + 1] * d2r, &sp, &cp);
+  sincos((double)rpy_deg[3 * e + 2] * d2r, &sy, &cy);
+  double w = cy * cp * cr + sy * sp * sr, x = cy * cp * sr - sy * sp * cr;
+  double y = cy * sp * cr + sy * cp * sr, z = sy * cp * cr - cy * sp * sr;
+  if (w < 0.0) { w = -w; x = -x; y = -y; z = -z; }
   state[e] = make_float4(pos[3 * e], pos[3 * e + 1], pos[3 * e + 2], 0.f);
   state[stride + e] = make_float4(vel[3 * e], vel[3 * e + 1], vel[3 * e + 2], __int_as_float(0));
-  state[2 * stride + e] = make_float4((float)(cy * cp), (float)(cy * sp * sr - sy * cr), (float)(cy * sp * cr + sy * sr), 0.f);
-  state[3 * stride + e] = make_float4((float)(sy * cp), (float)(sy * sp * sr + cy * cr), (float)(sy * sp * cr - cy * sr), 0.f);
-  state[4 * stride + e] = make_float4((float)(-sp), (float)(cp * sr), (float)(cp * cr), 0.f);
+  state[2 * stride + e] = make_float4((float)w, (float)x, (float)y, (float)z);
+  state[3 * stride + e] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// rotation_matrix attribute of the reference object (components.py:154): read / write through the quaternion plane
+__global__ void drone_get_rotation_kernel(const float4* state, long long n, long long stride, float* R) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  float m[9];
+  quat_to_matrix(state[2 * stride + e], m);
+#pragma unroll
+  for (int i = 0; i < 9; ++i) R[9 * e + i] = m[i];
+}
+__global__ void drone_set_rotation_kernel(float4* state, long long n, long long stride, const float* R,
+                                          const unsigned char* mask) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  if (mask && !mask[e]) return;
+  state[2 * stride + e] = matrix_to_quat(R + 9 * e);
+}
+// free-standing conversion for override inputs: R[n][9] -> q[n] (float4)
+__global__ void matrix_to_quat_kernel(const float* R, long long n, float4* q) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n) q[e] = matrix_to_quat(R + 9 * e);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -36,18 +93,20 @@ __global__ void drone_observe_kernel(const float4* state, long long n, long long
                                      float* gyro, float* accel) {
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n) return;
-  const float4 r0 = state[2 * stride + e], r1 = state[3 * stride + e], r2 = state[4 * stride + e];
+  float R[9];
+  quat_to_matrix(state[2 * stride + e], R);
+  const float4 rates = state[3 * stride + e];
   if (Rt) {
     float* o = Rt + 9 * e;
-    o[0] = r0.x; o[1] = r1.x; o[2] = r2.x;
-    o[3] = r0.y; o[4] = r1.y; o[5] = r2.y;
-    o[6] = r0.z; o[7] = r1.z; o[8] = r2.z;
+    o[0] = R[0]; o[1] = R[3]; o[2] = R[6];
+    o[3] = R[1]; o[4] = R[4]; o[5] = R[7];
+    o[6] = R[2]; o[7] = R[5]; o[8] = R[8];
   }
   if (gyro) {
     float sr, cr, sp, cp, sy, cy;
-    sincosf(r0.w, &sr, &cr);
-    sincosf(r1.w, &sp, &cp);
-    sincosf(r2.w, &sy, &cy);
+    sincosf(rates.x, &sr, &cr);
+    sincosf(rates.y, &sp, &cp);
+    sincosf(rates.z, &sy, &cy);
     float* o = gyro + 9 * e;
     o[0] = cy * cp; o[1] = cy * sp * sr - sy * cr; o[2] = cy * sp * cr + sy * sr;
     o[3] = sy * cp; o[4] = sy * sp * sr + cy * cr; o[5] = sy * sp * cr - cy * sr;
@@ -55,9 +114,9 @@ __global__ void drone_observe_kernel(const float4* state, long long n, long long
   }
   if (accel && acc) {
     const float4 a = acc[e];
-    accel[3 * e] = r0.x * a.x + r0.y * a.y + r0.z * a.z;
-    accel[3 * e + 1] = r1.x * a.x + r1.y * a.y + r1.z * a.z;
-    accel[3 * e + 2] = r2.x * a.x + r2.y * a.y + r2.z * a.z;
+    accel[3 * e] = R[0] * a.x + R[1] * a.y + R[2] * a.z;
+    accel[3 * e + 1] = R[3] * a.x + R[4] * a.y + R[5] * a.z;
+    accel[3 * e + 2] = R[6] * a.x + R[7] * a.y + R[8] * a.z;
   }
 }
 

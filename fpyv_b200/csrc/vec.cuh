@@ -57,6 +57,11 @@ __device__ __forceinline__ float vsqrt_fast(float a) {
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
   return r;
 }
+__device__ __forceinline__ float vrsqrt_fast(float a) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+  return r;
+}
 __device__ __forceinline__ bool vlt(float a, float b) { return a < b; }
 __device__ __forceinline__ bool vle(float a, float b) { return a <= b; }
 __device__ __forceinline__ bool vor(bool a, bool b) { return a || b; }
@@ -112,6 +117,7 @@ FPV_F2_MAP2(vmax, fmaxf(u, v))
 FPV_F2_MAP2(vdiv, __fdiv_rn(u, v))
 FPV_F2_MAP1(vsqrt, __fsqrt_rn(v))
 FPV_F2_MAP1(vsqrt_fast, vsqrt_fast(v))
+FPV_F2_MAP1(vrsqrt_fast, vrsqrt_fast(v))
 FPV_F2_MAP1(vabs, fabsf(v))
 __device__ __forceinline__ B2 vlt(F2 a, F2 b) {
   float ax, ay, bx, by;

@@ -10,6 +10,8 @@ Name-for-name mirror of the reference object:
                                         -> same; returns (R^T, gyro matrix, R @ acc) batched
   .position .velocity .state .rotation_matrix .prev_rates .prev_thrust .rates .thrust .acceleration
   .done .dt .mass .max_rates ...        -> same names, leading env axis
+Attitude lives on the device as the unit quaternion of the rotation (`.quaternion`, reference convention
+helper_functions.py:65-117); `.rotation_matrix` converts on read and `set_rotation_matrix` on write.
 `Drone(params)` (bottom of this file) is the num_envs=1 NumPy-returning stand-in for simulator.py-style loops.
 """
 from __future__ import annotations
@@ -84,7 +86,7 @@ class BatchedDrone:
                 path = params["drone"]["joystick_calib_path"]
             self.rc.calibrate(path, load_calibration_file=True)
 
-        # --- device state: 5 float4 planes (fpv_api.h "Drone state layout")
+        # --- device state: 4 float4 planes (fpv_api.h "Drone state layout")
         n = self.num_envs
         self._stride = (n + 3) // 4 * 4
         dev = self.device
@@ -141,12 +143,30 @@ class BatchedDrone:
         return torch.cat([self.position, self.velocity], dim=1)
 
     @property
+    def quaternion(self):
+        """[n,4] view: attitude as (w, x, y, z)."""
+        return self._state[2, :self.num_envs]
+
+    @property
     def rotation_matrix(self):
-        return self._state[2:5, :self.num_envs, :3].permute(1, 0, 2)
+        """[n,3,3] body->world rotation (Drone.rotation_matrix); converted from the quaternion plane on every read.
+        Write with set_rotation_matrix()."""
+        n = self.num_envs
+        R = torch.empty((n, 3, 3), dtype=torch.float32, device=self.device)
+        _lib.check(self._lib.fpv_drone_get_rotation(_lib.ptr(self._state), n, self._stride, _lib.ptr(R),
+                                                    _lib.current_stream(self.device)))
+        return R
+
+    def set_rotation_matrix(self, R, mask=None):
+        n, dev = self.num_envs, self.device
+        R = _as_dev(R, dev, (n, 3, 3))
+        m = None if mask is None else _as_dev(mask, dev, (n,), torch.uint8)
+        _lib.check(self._lib.fpv_drone_set_rotation(_lib.ptr(self._state), n, self._stride, _lib.ptr(R), _lib.ptr(m),
+                                                    _lib.current_stream(dev)))
 
     @property
     def prev_rates(self):
-        return self._state[2:5, :self.num_envs, 3].t()
+        return self._state[3, :self.num_envs, :3]
 
     rates = prev_rates          # components.py:188-189: step stores the filtered rates as both
 
@@ -237,14 +257,14 @@ class BatchedDrone:
             if lowered:
                 objs = (_lib.Object * len(lowered))(*lowered)
                 p.n_objects = len(lowered)
-        ovr = None
+        ovr_q = ovr_t = None
         if rotation_matrix is not None:
             if thrust_force is None:
                 raise ValueError("rotation_matrix override needs thrust_force (components.py:230-232)")
             R = _as_dev(rotation_matrix, dev, (n, 3, 3))
-            ovr = torch.zeros((3, n, 4), dtype=torch.float32, device=dev)
-            ovr[:, :, :3] = R.permute(1, 0, 2)
-            ovr[0, :, 3] = _as_dev(thrust_force, dev, (n,))
+            ovr_q = torch.empty((n, 4), dtype=torch.float32, device=dev)
+            _lib.check(self._lib.fpv_matrix_to_quat(_lib.ptr(R), n, _lib.ptr(ovr_q), _lib.current_stream(dev)))
+            ovr_t = _as_dev(thrust_force, dev, (n,))
         io.state, io.n, io.plane_stride = self._state.data_ptr(), n, self._stride
         io.actions = act.data_ptr()
         io.wind_env = None if wind_env is None else wind_env.data_ptr()
@@ -253,7 +273,8 @@ class BatchedDrone:
         io.done = self._done.data_ptr()
         io.acc_out = self._acc.data_ptr()
         io.reset_state = None if self._reset_state is None else self._reset_state.data_ptr()
-        io.override_R = None if ovr is None else ovr.data_ptr()
+        io.override_q = None if ovr_q is None else ovr_q.data_ptr()
+        io.override_thrust = None if ovr_t is None else ovr_t.data_ptr()
         io.objects = objs if objs is not None else C.POINTER(_lib.Object)()
         io.stats = self._stats.data_ptr()
         _lib.check(self._lib.fpv_drone_step(C.byref(p), C.byref(io), _lib.current_stream(dev)))

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define FPV_ABI_VERSION 4
+#define FPV_ABI_VERSION 5
 
 /* error codes */
 #define FPV_OK 0
@@ -39,17 +39,19 @@ extern "C" {
 #define FPV_ENODEV (-19)  /* no sm_100 device / kernel image not loadable on this device      */
 
 /* ---------------------------------------------------------------------------------------------
- * Drone state layout (mode A, reference `Drone`): 5 float4 planes
+ * Drone state layout (mode A, reference `Drone`): 4 float4 planes = 64 B per env
  *   plane 0: position.x  position.y  position.z  prev_thrust      components.py:151-153,:161
- *   plane 1: velocity.x  velocity.y  velocity.z  episode (int32 bits: steps since reset; -1-steps if
- *                                                 the env has crashed and is frozen)
- *   plane 2: R[0][0] R[0][1] R[0][2] prev_rates[0]               components.py:154,:160
- *   plane 3: R[1][0] R[1][1] R[1][2] prev_rates[1]
- *   plane 4: R[2][0] R[2][1] R[2][2] prev_rates[2]
- * R is the body->world rotation matrix exactly as the reference stores it (not a quaternion):
- * the reference never re-orthonormalises it and lets callers overwrite it (components.py:230-231).
+ *   plane 1: velocity.x  velocity.y  velocity.z  episode (int32 bits: control steps since reset; -1-steps
+ *                                                 once the env has crashed and is frozen)
+ *   plane 2: attitude as a unit quaternion  w x y z               components.py:154 (rotation_matrix)
+ *   plane 3: prev_rates[0..2] (deg/s, components.py:160), one spare float preserved by the step
+ * The reference stores the body->world rotation MATRIX and multiplies it by an Euler increment twice per
+ * step (components.py:216-218, kinematics.py:27-30).  The same rotation is carried here as the quaternion
+ * of the reference's own convention (helper_functions.py:65-117): R(q1 q2) = R(q1) R(q2), so the update is a
+ * quaternion product; fpv_drone_get_rotation / fpv_drone_set_rotation convert at the boundary.
+ * Consequence: a rotation override must be a proper rotation (the reference would accept any 3x3).
  * -------------------------------------------------------------------------------------------*/
-#define FPV_DRONE_PLANES 5
+#define FPV_DRONE_PLANES 4
 
 /* flags for fpv_drone_params_t.flags */
 #define FPV_F_GROUND 1u         /* plane z=0 in the object list (components.py:649-680)          */
@@ -115,9 +117,10 @@ typedef struct fpv_drone_io {
   uint8_t* done;            /* uint8[n] out: 1 if any substep raised done (components.py:236-240); may be NULL */
   void* acc_out;            /* float4[n] out: world acceleration of the last substep (components.py:243); may be NULL */
   const void* reset_state;  /* float4[FPV_DRONE_PLANES][plane_stride]: source for FPV_F_AUTO_RESET */
-  const void* override_R;   /* float4[3][n]: rows of the rotation override, .w of row 0 = thrust_force
+  const void* override_q;   /* float4[n]: rotation override as quaternion (w,x,y,z), see fpv_matrix_to_quat
                                (step(rotation_matrix=, thrust_force=), components.py:230-232); NULL = none.
-                               Requires substeps == 1. */
+                               Requires substeps == 1 and override_thrust. */
+  const float* override_thrust; /* float[n]: thrust_force of the same call */
   const fpv_object_t* objects; /* HOST pointer, params.n_objects entries, or NULL                  */
   fpv_stats_t* stats;       /* device, may be NULL                                                */
 } fpv_drone_io_t;
@@ -146,6 +149,14 @@ int fpv_drone_reset(void* state, int64_t n, int64_t plane_stride, const float* p
  * (update_kinematic_step kinematics.py:15-24 + rotate_body_by_rates :27-30, applied twice).
  * Runs params->substeps reference steps per env with the state held in registers. */
 int fpv_drone_step(const fpv_drone_params_t* params, const fpv_drone_io_t* io, void* stream);
+
+/* Drone.rotation_matrix (components.py:154) read / write: R is float[n][9] row-major, body->world.
+ * set: robust matrix->quaternion (all four Shepperd branches), normalised; mask as in fpv_drone_reset. */
+int fpv_drone_get_rotation(const void* state, int64_t n, int64_t plane_stride, float* R, void* stream);
+int fpv_drone_set_rotation(void* state, int64_t n, int64_t plane_stride, const float* R, const uint8_t* mask,
+                           void* stream);
+/* R float[n][9] -> q float4[n] (w,x,y,z); for override inputs. */
+int fpv_matrix_to_quat(const float* R, int64_t n, void* q, void* stream);
 
 /* The tuple Drone.step returns -- components.py:247-248: (R^T, euler_matrix(*rates), R @ acc).
  * Rt, gyro: float[n][9] row-major; accel: float[n][3].  Any of the three may be NULL. */
