@@ -493,7 +493,8 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
 // round-robin over all warps of the grid.
 template <class V, int ANG, int THREADS, int MINB, int STAGES>
 __global__ void __launch_bounds__(THREADS, MINB) drone_step_tma_kernel(const __grid_constant__ DroneK k, const DroneIO io,
-                                                                       const int lut_bytes) {
+                                                                       const int lut_bytes, const int stagger_ns,
+                                                                       const int n_sms) {
   constexpr int L = Lane<V>::N;
   constexpr int CHUNK = 32 * L;               // envs per warp-chunk
   constexpr int ROWS = FPV_DRONE_PLANES + 1;  // 4 state planes + actions
@@ -538,6 +539,13 @@ __global__ void __launch_bounds__(THREADS, MINB) drone_step_tma_kernel(const __g
   for (int s = 0; s < STAGES - 1; ++s) {
     const long long c = first_chunk + (long long)s * chunk_stride;
     if (c < n_chunks && leader) issue(c, s);
+  }
+  // Identical warps started together stay in lock-step: they would all sit in the (ALU/LSU-heavy) unpack/store
+  // phase at the same time and all in the FMA-bound substep loop at the same time.  Co-resident CTAs of one SM are
+  // therefore phase-shifted once at start, so one warp's I/O phase overlaps the others' arithmetic.
+  if (stagger_ns > 0) {
+    const int slot = (int)(blockIdx.x / (unsigned)n_sms);
+    if (slot > 0) __nanosleep((unsigned)(slot * stagger_ns));
   }
   TileStats st = {0.f, 0.f, 0.f, 0.f, 0.f};
   int it = 0;

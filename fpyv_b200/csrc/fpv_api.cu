@@ -75,6 +75,11 @@ void launch_drone(const DroneK& k, const DroneIO& io, cudaStream_t st) {
   kern<<<grid, kThreads, smem, st>>>(k, io);
 }
 
+int tune_env(const char* name, int dflt) {
+  const char* v = std::getenv(name);
+  return v ? std::atoi(v) : dflt;
+}
+
 // Hot path: TMA-fed ring (drone_step_tma_kernel).  Returns false if the ring does not fit (huge LUT).
 template <class V, int ANG, int STAGES>
 bool launch_drone_tma(const DroneK& k, const DroneIO& io, cudaStream_t st) {
@@ -101,13 +106,9 @@ bool launch_drone_tma(const DroneK& k, const DroneIO& io, cudaStream_t st) {
   const long long tiles = (io.n + TILE - 1) / TILE;
   const long long wave = (long long)sm_count_of_current_device() * occ_cache;
   const unsigned grid = (unsigned)(tiles < wave ? tiles : wave);
-  kern<<<grid, kThreads, smem, st>>>(k, io, lut_bytes);
+  static const int stagger = tune_env("FPV_TUNE_STAGGER_NS", 0);
+  kern<<<grid, kThreads, smem, st>>>(k, io, lut_bytes, stagger, sm_count_of_current_device());
   return true;
-}
-
-int tune_env(const char* name, int dflt) {
-  const char* v = std::getenv(name);
-  return v ? std::atoi(v) : dflt;
 }
 
 template <class V, int ANG>
