@@ -53,6 +53,8 @@ struct DroneIO {
   const float4* override_q;      // [n]: rotation override as a quaternion (w,x,y,z)
   const float* override_thrust;  // [n]
   fpv_stats_t* stats;
+  unsigned* work;              // [0] next-chunk counter, [1] finished-warp counter (dynamic scheduling), or null
+  unsigned long long* trace;
 };
 
 // Obstacle SDF + normal for one motor point (GENERAL path only; warp-uniform object loop).
@@ -493,8 +495,7 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
 // round-robin over all warps of the grid.
 template <class V, int ANG, int THREADS, int MINB, int STAGES>
 __global__ void __launch_bounds__(THREADS, MINB) drone_step_tma_kernel(const __grid_constant__ DroneK k, const DroneIO io,
-                                                                       const int lut_bytes, const int stagger_ns,
-                                                                       const int n_sms) {
+                                                                       const int lut_bytes) {
   constexpr int L = Lane<V>::N;
   constexpr int CHUNK = 32 * L;               // envs per warp-chunk
   constexpr int ROWS = FPV_DRONE_PLANES + 1;  // 4 state planes + actions
@@ -518,8 +519,8 @@ __global__ void __launch_bounds__(THREADS, MINB) drone_step_tma_kernel(const __g
   if (io.stats && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&io.stats->env_steps, (double)io.n);
 
   const long long n_chunks = (io.n + CHUNK - 1) / CHUNK;
-  const long long first_chunk = (long long)blockIdx.x * WARPS + warp;
-  const long long chunk_stride = (long long)gridDim.x * WARPS;
+  const long long my_warp = (long long)blockIdx.x * WARPS + warp;
+  const long long total_warps = (long long)gridDim.x * WARPS;
 
   // producer: arm the slot's mbarrier with the byte count, then one bulk copy per row (all operands warp-uniform)
   auto issue = [&](long long chunk, int slot) {
@@ -534,29 +535,45 @@ __global__ void __launch_bounds__(THREADS, MINB) drone_step_tma_kernel(const __g
     tma_load_1d(dst + FPV_DRONE_PLANES * CHUNK, io.actions + first, bytes, &full[slot]);
   };
 
+  // Work distribution.  The SM's warp arbiter is not fair (among the warps sharing a scheduler one runs ahead and
+  // the last one finishes alone at a fraction of the pipe rate), so chunks are PULLED: the first STAGES chunks of a
+  // warp are static (no start-up burst of atomics), every further one comes from a global counter.  The last warp
+  // to finish puts the two counters back to zero for the next launch.
+  const bool dynamic = io.work != nullptr;
+  unsigned long long t_start = 0;
+  if (io.trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
   const bool leader = elect_one();
+  auto grab = [&](long long static_next) -> long long {
+    if (!dynamic) return static_next;
+    unsigned v = 0;
+    if (leader) v = atomicAdd(io.work, 1u);
+    v = __shfl_sync(0xffffffffu, v, __ffs(__ballot_sync(0xffffffffu, leader)) - 1);
+    return (long long)STAGES * total_warps + (long long)v;
+  };
+
+  long long pending[STAGES];  // chunk index resident (or in flight) in each ring slot
 #pragma unroll
-  for (int s = 0; s < STAGES - 1; ++s) {
-    const long long c = first_chunk + (long long)s * chunk_stride;
-    if (c < n_chunks && leader) issue(c, s);
+  for (int s = 0; s < STAGES; ++s) {
+    pending[s] = my_warp + (long long)s * total_warps;
+    if (pending[s] < n_chunks && leader) issue(pending[s], s);
   }
-  // Identical warps started together stay in lock-step: they would all sit in the (ALU/LSU-heavy) unpack/store
-  // phase at the same time and all in the FMA-bound substep loop at the same time.  Co-resident CTAs of one SM are
-  // therefore phase-shifted once at start, so one warp's I/O phase overlaps the others' arithmetic.
-  if (stagger_ns > 0) {
-    const int slot = (int)(blockIdx.x / (unsigned)n_sms);
-    if (slot > 0) __nanosleep((unsigned)(slot * stagger_ns));
-  }
+  long long static_next = my_warp + (long long)STAGES * total_warps;
   TileStats st = {0.f, 0.f, 0.f, 0.f, 0.f};
-  int it = 0;
-  for (long long chunk = first_chunk; chunk < n_chunks; chunk += chunk_stride, ++it) {
+  unsigned use[STAGES];
+#pragma unroll
+  for (int s = 0; s < STAGES; ++s) use[s] = 0;
+  for (int it = 0;; ++it) {
     const int slot = it % STAGES;
-    const unsigned parity = (unsigned)(it / STAGES) & 1u;
-    {  // keep STAGES-1 chunks in flight; the slot refilled here was drained at iteration it-1
-      const long long ahead = chunk + (long long)(STAGES - 1) * chunk_stride;
-      if (ahead < n_chunks && leader) issue(ahead, (it + STAGES - 1) % STAGES);
-    }
-    mbar_wait(&full[slot], parity);
+    long long chunk = pending[0];
+#pragma unroll
+    for (int s = 1; s < STAGES; ++s) if (slot == s) chunk = pending[s];
+    if (chunk >= n_chunks) break;
+    const long long nxt = grab(static_next);  // the atomic's round trip overlaps the wait and the shared-memory reads
+    static_next += total_warps;
+    unsigned parity = use[0];
+#pragma unroll
+    for (int s = 1; s < STAGES; ++s) if (slot == s) parity = use[s];
+    mbar_wait(&full[slot], parity & 1u);
     const float4* src = ring + (size_t)slot * ROWS * CHUNK;
     const long long base = chunk * CHUNK + lane;
     long long ei[L];
@@ -569,10 +586,25 @@ __global__ void __launch_bounds__(THREADS, MINB) drone_step_tma_kernel(const __g
       for (int p = 0; p < FPV_DRONE_PLANES; ++p) q[p][l] = src[p * CHUNK + l * 32 + lane];
       act[l] = src[FPV_DRONE_PLANES * CHUNK + l * 32 + lane];
     }
-    __syncwarp();  // all lanes have drained this slot -> the producer lane may refill it next iteration
+    __syncwarp();  // all lanes have drained this slot -> refill it right away with the chunk just pulled
+    if (nxt < n_chunks && leader) issue(nxt, slot);
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) if (slot == s) { pending[s] = nxt; use[s] += 1; }
     if (base < io.n) drone_tile<V, ANG, false, 32>(k, io, lut_s, q, act, ei, base, st);
   }
+  if (dynamic && leader) {
+    const unsigned finished = atomicAdd(io.work + 1, 1u);
+    if (finished == (unsigned)total_warps - 1u) { io.work[0] = 0u; io.work[1] = 0u; }
+  }
   if (io.stats) stats_warp_flush(io.stats, st);
+  if (io.trace && lane == 0) {
+    unsigned long long t_end;
+    unsigned smid;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    unsigned long long* o = io.trace + 3 * ((size_t)blockIdx.x * WARPS + warp);
+    o[0] = t_start; o[1] = t_end; o[2] = smid;
+  }
 }
 
 }  // namespace fpv

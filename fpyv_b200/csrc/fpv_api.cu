@@ -106,8 +106,7 @@ bool launch_drone_tma(const DroneK& k, const DroneIO& io, cudaStream_t st) {
   const long long tiles = (io.n + TILE - 1) / TILE;
   const long long wave = (long long)sm_count_of_current_device() * occ_cache;
   const unsigned grid = (unsigned)(tiles < wave ? tiles : wave);
-  static const int stagger = tune_env("FPV_TUNE_STAGGER_NS", 0);
-  kern<<<grid, kThreads, smem, st>>>(k, io, lut_bytes, stagger, sm_count_of_current_device());
+  kern<<<grid, kThreads, smem, st>>>(k, io, lut_bytes);
   return true;
 }
 
@@ -244,6 +243,10 @@ int fpv_drone_step(const fpv_drone_params_t* p, const fpv_drone_io_t* io, void* 
   d.override_q = (const float4*)io->override_q;
   d.override_thrust = io->override_thrust;
   d.stats = io->stats;
+  // pulled chunks pay one atomic round trip per chunk: worth it once a chunk carries enough arithmetic to hide it
+  static const int no_dyn = tune_env("FPV_TUNE_STATIC", 0);
+  d.work = (no_dyn || p->substeps < 4) ? nullptr : (unsigned*)io->work;
+  d.trace = (unsigned long long*)io->trace;
 
   // |rates| <= max_rates is an invariant of action2force (a convex mix of clipped commands), so the
   // per-substep Euler angles are bounded by max_rates*dt in radians.  Below 0.1 rad degree-5/4 Taylor kernels are

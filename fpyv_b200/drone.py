@@ -96,6 +96,7 @@ class BatchedDrone:
         self._acc = torch.zeros((n, 4), dtype=torch.float32, device=dev)
         self._actions = torch.zeros((n, 4), dtype=torch.float32, device=dev)
         self._stats = torch.zeros(8, dtype=torch.float64, device=dev)
+        self._work = torch.zeros(2, dtype=torch.int32, device=dev)      # dynamic chunk counter (fpv_drone_io_t.work)
         self._lut = None
         if thrust_lut:
             self._lut = torch.from_numpy(config.thrust_table(c, int(thrust_lut), lut_source)).to(dev)
@@ -277,6 +278,8 @@ class BatchedDrone:
         io.override_thrust = None if ovr_t is None else ovr_t.data_ptr()
         io.objects = objs if objs is not None else C.POINTER(_lib.Object)()
         io.stats = self._stats.data_ptr()
+        io.work = self._work.data_ptr()
+        io.trace = None if getattr(self, "_trace", None) is None else self._trace.data_ptr()
         _lib.check(self._lib.fpv_drone_step(C.byref(p), C.byref(io), _lib.current_stream(dev)))
         if return_obs:
             return self.observe()

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define FPV_ABI_VERSION 5
+#define FPV_ABI_VERSION 7
 
 /* error codes */
 #define FPV_OK 0
@@ -123,6 +123,11 @@ typedef struct fpv_drone_io {
   const float* override_thrust; /* float[n]: thrust_force of the same call */
   const fpv_object_t* objects; /* HOST pointer, params.n_objects entries, or NULL                  */
   fpv_stats_t* stats;       /* device, may be NULL                                                */
+  void* work;               /* device uint32[2], zeroed ONCE by the caller: chunk counter for dynamic load balancing
+                               (warps pull the next 64-env chunk with one atomic); every launch leaves it zeroed.
+                               NULL = static round-robin distribution.                                     */
+  void* trace;              /* developer profiling hook: device uint64[3 * warps] receiving per-warp
+                               (start ns, end ns, SM id) of the hot kernel; NULL in production           */
 } fpv_drone_io_t;
 
 int fpv_abi_version(void);
