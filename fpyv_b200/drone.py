@@ -313,16 +313,11 @@ class BatchedDrone:
     def episode_stats(self, all_reduce: bool = False, reset: bool = False) -> dict:
         """Device-accumulated counters (fpv_stats_t).  With all_reduce the 8 doubles are summed over the
         torch.distributed world (NCCL on GPUs) -- the only collective of the engine, never inside step."""
-        s = self._stats.clone()
-        if all_reduce and torch.distributed.is_available() and torch.distributed.is_initialized():
-            torch.distributed.all_reduce(s, op=torch.distributed.ReduceOp.SUM)
+        from .shard import reduce_stats, stats_dict
+        s = reduce_stats(self._stats) if all_reduce else self._stats.clone()
         if reset:
             self._stats.zero_()
-        v = s.tolist()
-        keys = ("env_steps", "crashes", "episodes", "episode_len_sum", "reward_sum", "reward_sq_sum", "nonfinite")
-        out = dict(zip(keys, v))
-        out["mean_episode_len"] = out["episode_len_sum"] / out["episodes"] if out["episodes"] else math.nan
-        return out
+        return stats_dict(s)
 
 
 class Drone:

@@ -1,6 +1,6 @@
 """dev helper: flush-mode and size sweeps on the GPU box"""
 import sys, torch
-sys.path.insert(0, '.')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 from fpyv_b200 import BatchedDrone
 dev = 'cuda:0'
 fl = torch.empty(256 << 20, dtype=torch.uint8, device=dev)

@@ -1,6 +1,6 @@
 """dev helper: per-warp start/end timeline of the hot kernel"""
 import sys, torch, numpy as np
-sys.path.insert(0, '.')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 from fpyv_b200 import BatchedDrone
 dev='cuda:0'; n=1<<20
 for K in (8, 1):
