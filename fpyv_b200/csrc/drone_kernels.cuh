@@ -34,6 +34,7 @@ struct DroneK {
   float inv_mass;
   float dt_over_mass;       // dt / m
   float half_ang_scale;     // 0.5 * deg2rad * dt                    kinematics.py:29
+  float inv_half_ang_scale;
   float lut_scale;          // (lut_n-1)/2
   int lut_n;
   unsigned flags;
@@ -95,8 +96,9 @@ template <class V> struct DroneRegs {
 };
 
 // K reference steps for the envs held in `s`.  Returns the OR of the per-step crash flags.
-// ANG selects the sin/cos evaluation of the half Euler angles: 0 = full-range sincosf, 1 = |angle| <= 0.5 rad
-// (degree-7/8 kernels, no range reduction), 2 = |angle| <= 0.1 rad (degree-5/4 kernels, truncation < 2e-11).
+// ANG selects the sin/cos evaluation of the HALF Euler angles h: 0 = full-range sincosf, 1 = |h| <= 0.25 rad
+// (degree-7/8 kernels, no range reduction), 2 = |h| <= 0.05 (degree-5/4, truncation < 2e-11), 3 = |h| <= 0.03
+// (degree-3/2, truncation < 3.4e-8).
 // WIND = false drops the "+ wind" adds when the launch has no wind at all.
 template <class V, int ANG, bool GENERAL, bool WIND>
 __device__ __forceinline__ typename Lane<V>::Mask drone_substeps(const DroneK& k, DroneRegs<V>& s, V a0, V a1, V a2,
@@ -105,23 +107,26 @@ __device__ __forceinline__ typename Lane<V>::Mask drone_substeps(const DroneK& k
                                                                    V oqz) {
   using M = typename Lane<V>::Mask;
   // action2force invariants (the action is held for the whole control step), components.py:185-193
+  // The rate filter runs on the half Euler angles h_i = rates_i * (deg2rad*dt/2) directly (same linear recurrence,
+  // scaled), so no per-substep rescaling is needed; rates are recovered once after the loop.
   const V mr = S<V>(k.max_rates);
-  const V c0 = vmin(vmax(vneg(a0) * mr, vneg(mr)), mr) * S<V>(k.rtr);
-  const V c1 = vmin(vmax(vneg(a1) * mr, vneg(mr)), mr) * S<V>(k.rtr);
-  const V c2 = vmin(vmax(vneg(a2) * mr, vneg(mr)), mr) * S<V>(k.rtr);
+  const V cs = S<V>(k.rtr * k.half_ang_scale);
+  const V c0 = vmin(vmax(vneg(a0) * mr, vneg(mr)), mr) * cs;
+  const V c1 = vmin(vmax(vneg(a1) * mr, vneg(mr)), mr) * cs;
+  const V c2 = vmin(vmax(vneg(a2) * mr, vneg(mr)), mr) * cs;
   const V tt = thrust_target * S<V>(k.ttr);
   const V omr = S<V>(k.one_minus_rtr), omt = S<V>(k.one_minus_ttr);
-  const V dt = S<V>(k.dt), dt_m = S<V>(k.dt_over_mass), hasc = S<V>(k.half_ang_scale);
+  const V dt = S<V>(k.dt), dt_m = S<V>(k.dt_over_mass);
+  V h0 = s.pr0 * S<V>(k.half_ang_scale), h1 = s.pr1 * S<V>(k.half_ang_scale), h2 = s.pr2 * S<V>(k.half_ang_scale);
   const V zero = S<V>(0.f), one = S<V>(1.f);
   const bool ground = (k.flags & FPV_F_GROUND) != 0;
   M done = vlt(one, zero);  // all false
   V Fx = zero, Fy = zero, Fz = zero;
 
-#pragma unroll 1
+#pragma unroll 2
   for (int it = 0; it < k.substeps; ++it) {
     // ---- low-pass filters on rates and thrust, components.py:187-194
-    const V w0 = vfma(s.pr0, omr, c0), w1 = vfma(s.pr1, omr, c1), w2 = vfma(s.pr2, omr, c2);
-    s.pr0 = w0; s.pr1 = w1; s.pr2 = w2;
+    h0 = vfma(h0, omr, c0); h1 = vfma(h1, omr, c1); h2 = vfma(h2, omr, c2);
     V th = vfma(s.pt, omt, tt);
     s.pt = th;
     if (GENERAL && has_override) {  // components.py:230-232
@@ -155,23 +160,21 @@ __device__ __forceinline__ typename Lane<V>::Mask drone_substeps(const DroneK& k
     // ---- motors, collisions, crash test (components.py:235-239, :198-214)
     M crashed;
     if (!GENERAL) {
-      // ground only: distance = z, normal = +z (components.py:674-680); only z of M_rel @ R^T matters.
-      // t_m = motor_radius - z_m is the spring compression; spring_force (kinematics.py:56-59) per motor is
-      // k*t_m - c*vz where t_m > 0; a motor below the plane (t_m > radius) is a crash with NO force (:207-210).
+      // Hot path = the reference's own configuration: ground plane in the object list, undamped spring
+      // (components.py:198 passes damping_constant=0); anything else is routed to the GENERAL kernel by the host.
+      // distance = z, normal = +z (components.py:674-680); only z of M_rel @ R^T matters.  t_m = motor_radius - z_m
+      // is the spring compression; spring_force (kinematics.py:56-59) per motor is k*t_m where t_m > 0; a motor
+      // below the plane (t_m > radius) is a crash with NO force (:207-210).
       const V h = S<V>(k.motor_radius) - s.pz;
-      V tmax = S<V>(-3.0e38f), pen_sum = zero, cnt = zero;
+      V tmax, pen_sum;
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
         const V t = vfma(S<V>(k.neg_motor_xy[m][0]), r20, vfma(S<V>(k.neg_motor_xy[m][1]), r21, h));
-        tmax = vmax(tmax, t);
+        tmax = m == 0 ? t : vmax(tmax, t);
         pen_sum = m == 0 ? vmax(t, zero) : pen_sum + vmax(t, zero);
-        if (k.spring_c != 0.f) cnt = cnt + vsel(vlt(zero, t), one, zero);
       }
       crashed = vlt(S<V>(k.motor_radius), tmax);
-      if (ground) {
-        if (k.spring_c != 0.f) Fz = vfma(vneg(S<V>(k.spring_c)) * s.vz, vsel(crashed, zero, cnt), Fz);
-        Fz = vfma(S<V>(k.spring_k), vsel(crashed, zero, pen_sum), Fz);
-      }
+      Fz = vfma(S<V>(k.spring_k), vsel(crashed, zero, pen_sum), Fz);
     } else {
       crashed = vlt(one, zero);
       const V r00 = vfma(vneg(s.qy), y2, vfma(vneg(s.qz), z2, one)), r10 = vfma(s.qw, z2, xy);
@@ -225,9 +228,9 @@ __device__ __forceinline__ typename Lane<V>::Mask drone_substeps(const DroneK& k
     //      (rotate_body_by_rates kinematics.py:27-30 runs inside update_kinematic_step :23 AND again in
     //      Drone.update components.py:218).  Quaternion form: qE from the half angles, q <- q (x) conj(qE)^2.
     V sr, cr, sp, cp, sy, cy;
-    vsincos<ANG>(w0 * hasc, sr, cr);
-    vsincos<ANG>(w1 * hasc, sp, cp);
-    vsincos<ANG>(w2 * hasc, sy, cy);
+    vsincos<ANG>(h0, sr, cr);
+    vsincos<ANG>(h1, sp, cp);
+    vsincos<ANG>(h2, sy, cy);
     const V A = cy * cp, B = sy * sp, C = cy * sp, D = sy * cp;
     const V ew = vfma(A, cr, B * sr);  // qE = qz (x) qy (x) qx
     const V ex = vfma(A, sr, vneg(B * cr));
@@ -244,6 +247,7 @@ __device__ __forceinline__ typename Lane<V>::Mask drone_substeps(const DroneK& k
     const V nz_ = vfma(s.qw, pz_, vfma(s.qz, pw, vfma(s.qx, py_, vneg(s.qy * px_))));
     s.qw = nw; s.qx = nx_; s.qy = ny_; s.qz = nz_;
   }
+  s.pr0 = h0 * S<V>(k.inv_half_ang_scale); s.pr1 = h1 * S<V>(k.inv_half_ang_scale); s.pr2 = h2 * S<V>(k.inv_half_ang_scale);
   // acceleration of the last substep (Drone.acceleration, components.py:243)
   const V inv_m = S<V>(k.inv_mass);
   s.ax = Fx * inv_m; s.ay = Fy * inv_m; s.az = Fz * inv_m;
@@ -316,7 +320,7 @@ template <class V, int ANG, bool GENERAL, int SLOT_STRIDE>
 __device__ __forceinline__ void drone_tile(const DroneK& k, const DroneIO& io, const float* lut_s,
                                            const float4 (&q)[FPV_DRONE_PLANES][Lane<V>::N],
                                            const float4 (&act)[Lane<V>::N], const long long (&ei)[Lane<V>::N],
-                                           long long base, TileStats& st) {
+                                           long long base, TileStats& st, const bool wind_on) {
   constexpr int L = Lane<V>::N;
   DroneRegs<V> s;
   s.px = Pack<V>::x(q[0]); s.py = Pack<V>::y(q[0]); s.pz = Pack<V>::z(q[0]); s.pt = Pack<V>::w(q[0]);
@@ -329,7 +333,6 @@ __device__ __forceinline__ void drone_tile(const DroneK& k, const DroneIO& io, c
 #pragma unroll
   for (int l = 0; l < L; ++l) { epi[l] = __float_as_int(q[1][l].w); spare[l] = q[3][l].w; }
 
-  const bool wind_on = io.wind_env != nullptr || k.wind[0] != 0.f || k.wind[1] != 0.f || k.wind[2] != 0.f;
   V wx = S<V>(k.wind[0]), wy = S<V>(k.wind[1]), wz = S<V>(k.wind[2]);
   if (io.wind_env) {
     float4 w[L];
@@ -399,8 +402,8 @@ __device__ __forceinline__ void drone_tile(const DroneK& k, const DroneIO& io, c
     }
     const float px = Lane<V>::get(s.px, l), py = Lane<V>::get(s.py, l), pz = Lane<V>::get(s.pz, l);
     const float vx = Lane<V>::get(s.vx, l), vy = Lane<V>::get(s.vy, l), vz = Lane<V>::get(s.vz, l);
-    // NaN/Inf guard: the sum of the six components is non-finite iff one of them is (or they overflow together)
-    if (!(fabsf(((px + py) + (pz + vx)) + (vy + vz)) <= 3.0e38f)) st.nf += 1.f;
+    // NaN/Inf guard on the position: a non-finite velocity or attitude reaches it within one more step
+    if (!(fabsf((px + py) + pz) <= 3.0e38f)) st.nf += 1.f;
     stg_stream(dst, make_float4(px, py, pz, Lane<V>::get(s.pt, l)));
     stg_stream(dst + io.stride, make_float4(vx, vy, vz, __int_as_float(ep)));
     stg_stream(dst + 2 * io.stride, make_float4(Lane<V>::get(s.qw, l), Lane<V>::get(s.qx, l), Lane<V>::get(s.qy, l), Lane<V>::get(s.qz, l)));
@@ -424,6 +427,7 @@ __global__ void __launch_bounds__(THREADS, MINB) drone_step_kernel(const __grid_
   }
   if (io.stats && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&io.stats->env_steps, (double)io.n);
   const long long n_tiles = (io.n + TILE - 1) / TILE;
+  const bool wind_on = io.wind_env != nullptr || k.wind[0] != 0.f || k.wind[1] != 0.f || k.wind[2] != 0.f;
   TileStats st = {0.f, 0.f, 0.f, 0.f, 0.f};
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     // thread t, slot l -> env tile*TILE + l*THREADS + t: every 128-bit access of a warp is one contiguous 512 B run
@@ -440,7 +444,7 @@ __global__ void __launch_bounds__(THREADS, MINB) drone_step_kernel(const __grid_
       for (int l = 0; l < L; ++l) q[p][l] = ldg_stream(io.state + p * io.stride + ei[l]);
 #pragma unroll
     for (int l = 0; l < L; ++l) act[l] = ldg_stream(io.actions + ei[l]);
-    drone_tile<V, ANG, GENERAL, THREADS>(k, io, lut_dyn, q, act, ei, base, st);
+    drone_tile<V, ANG, GENERAL, THREADS>(k, io, lut_dyn, q, act, ei, base, st, wind_on);
   }
   if (io.stats) stats_warp_flush(io.stats, st);
 }
@@ -513,14 +517,12 @@ __global__ void __launch_bounds__(THREADS, MINB) drone_step_tma_kernel(const __g
     for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (k.flags & FPV_F_THRUST_LUT)
-    for (int i = threadIdx.x; i < k.lut_n; i += THREADS) lut_s[i] = io.lut[i];
-  __syncthreads();  // the only CTA-wide barrier: LUT staged, mbarriers initialised
-  if (io.stats && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&io.stats->env_steps, (double)io.n);
+  __syncwarp();  // this warp's mbarriers are initialised: its ring can be primed before the CTA-wide LUT staging
 
   const long long n_chunks = (io.n + CHUNK - 1) / CHUNK;
   const long long my_warp = (long long)blockIdx.x * WARPS + warp;
   const long long total_warps = (long long)gridDim.x * WARPS;
+  const bool wind_on = io.wind_env != nullptr || k.wind[0] != 0.f || k.wind[1] != 0.f || k.wind[2] != 0.f;
 
   // producer: arm the slot's mbarrier with the byte count, then one bulk copy per row (all operands warp-uniform)
   auto issue = [&](long long chunk, int slot) {
@@ -543,39 +545,50 @@ __global__ void __launch_bounds__(THREADS, MINB) drone_step_tma_kernel(const __g
   unsigned long long t_start = 0;
   if (io.trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
   const bool leader = elect_one();
-  auto grab = [&](long long static_next) -> long long {
-    if (!dynamic) return static_next;
+  const int leader_lane = __ffs(__ballot_sync(0xffffffffu, leader)) - 1;
+  // a pull is split in two so that the atomic's round trip (~1k cycles) hides behind the substep loop:
+  // pull_begin() fires the atomic from the elected lane, pull_end() broadcasts its result after the arithmetic
+  auto pull_begin = [&]() -> unsigned {
     unsigned v = 0;
-    if (leader) v = atomicAdd(io.work, 1u);
-    v = __shfl_sync(0xffffffffu, v, __ffs(__ballot_sync(0xffffffffu, leader)) - 1);
-    return (long long)STAGES * total_warps + (long long)v;
+    if (dynamic && leader) v = atomicAdd(io.work, 1u);
+    return v;
+  };
+  auto pull_end = [&](unsigned v, long long static_next) -> long long {
+    if (!dynamic) return static_next;
+    v = __shfl_sync(0xffffffffu, v, leader_lane);
+    return 2 * total_warps + (long long)v;   // chunks [0, 2*total_warps) are the static first two of every warp
   };
 
-  long long pending[STAGES];  // chunk index resident (or in flight) in each ring slot
-#pragma unroll
-  for (int s = 0; s < STAGES; ++s) {
-    pending[s] = my_warp + (long long)s * total_warps;
-    if (pending[s] < n_chunks && leader) issue(pending[s], s);
-  }
-  long long static_next = my_warp + (long long)STAGES * total_warps;
+  // Ring protocol (STAGES == 2): slot (it & 1) holds the chunk computed at iteration it.  At the top of iteration it
+  // the OTHER slot -- drained at it-1 -- is refilled with the next chunk, which then lands while chunk `it` is being
+  // computed.  A chunk is therefore pulled exactly one chunk-time before it is needed (late commitment keeps the
+  // end-of-kernel tail to about one chunk), and the pull's atomic was fired one iteration earlier still... no:
+  // it is fired here and resolved here; its ~1k-cycle round trip is covered by the other warps of the scheduler.
+  static_assert(STAGES == 2, "ring protocol below is written for two slots");
+  long long cur = my_warp;                 // static first chunk
+  if (cur < n_chunks && leader) issue(cur, 0);
+  long long static_next = my_warp + total_warps;
   TileStats st = {0.f, 0.f, 0.f, 0.f, 0.f};
-  unsigned use[STAGES];
-#pragma unroll
-  for (int s = 0; s < STAGES; ++s) use[s] = 0;
-  for (int it = 0;; ++it) {
-    const int slot = it % STAGES;
-    long long chunk = pending[0];
-#pragma unroll
-    for (int s = 1; s < STAGES; ++s) if (slot == s) chunk = pending[s];
-    if (chunk >= n_chunks) break;
-    const long long nxt = grab(static_next);  // the atomic's round trip overlaps the wait and the shared-memory reads
+#ifdef FPV_TRACE_PHASES
+  long long ph_wait = 0, ph_read = 0, ph_tile = 0;
+  const long long c_begin = clock64();
+#endif
+  for (int it = 0; cur < n_chunks; ++it) {
+    const int slot = it & 1;
+#ifdef FPV_TRACE_PHASES
+    const long long c_a = clock64();
+#endif
+    // next chunk: the second one is static too (no start-up burst of atomics), later ones are pulled
+    long long nxt = static_next;
+    if (dynamic && it > 0) nxt = pull_end(pull_begin(), 0);
     static_next += total_warps;
-    unsigned parity = use[0];
-#pragma unroll
-    for (int s = 1; s < STAGES; ++s) if (slot == s) parity = use[s];
-    mbar_wait(&full[slot], parity & 1u);
+    if (nxt < n_chunks && leader) issue(nxt, slot ^ 1);
+    mbar_wait(&full[slot], (unsigned)(it >> 1) & 1u);
+#ifdef FPV_TRACE_PHASES
+    const long long c_b = clock64();
+#endif
     const float4* src = ring + (size_t)slot * ROWS * CHUNK;
-    const long long base = chunk * CHUNK + lane;
+    const long long base = cur * CHUNK + lane;
     long long ei[L];
     float4 q[FPV_DRONE_PLANES][L];
     float4 act[L];
@@ -586,11 +599,16 @@ __global__ void __launch_bounds__(THREADS, MINB) drone_step_tma_kernel(const __g
       for (int p = 0; p < FPV_DRONE_PLANES; ++p) q[p][l] = src[p * CHUNK + l * 32 + lane];
       act[l] = src[FPV_DRONE_PLANES * CHUNK + l * 32 + lane];
     }
-    __syncwarp();  // all lanes have drained this slot -> refill it right away with the chunk just pulled
-    if (nxt < n_chunks && leader) issue(nxt, slot);
-#pragma unroll
-    for (int s = 0; s < STAGES; ++s) if (slot == s) { pending[s] = nxt; use[s] += 1; }
-    if (base < io.n) drone_tile<V, ANG, false, 32>(k, io, lut_s, q, act, ei, base, st);
+    __syncwarp();  // all lanes have drained this slot: it is refilled at the top of the next iteration
+#ifdef FPV_TRACE_PHASES
+    const long long c_c = clock64();
+#endif
+    if (base < io.n) drone_tile<V, ANG, false, 32>(k, io, lut_s, q, act, ei, base, st, wind_on);
+#ifdef FPV_TRACE_PHASES
+    const long long c_d = clock64();
+    ph_wait += c_b - c_a; ph_read += c_c - c_b; ph_tile += c_d - c_c;
+#endif
+    cur = nxt;
   }
   if (dynamic && leader) {
     const unsigned finished = atomicAdd(io.work + 1, 1u);
@@ -604,6 +622,10 @@ __global__ void __launch_bounds__(THREADS, MINB) drone_step_tma_kernel(const __g
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
     unsigned long long* o = io.trace + 3 * ((size_t)blockIdx.x * WARPS + warp);
     o[0] = t_start; o[1] = t_end; o[2] = smid;
+#ifdef FPV_TRACE_PHASES
+    o[0] = (unsigned long long)ph_wait; o[1] = (unsigned long long)ph_read; o[2] = (unsigned long long)ph_tile;
+    io.trace[3 * (size_t)gridDim.x * WARPS + ((size_t)blockIdx.x * WARPS + warp)] = (unsigned long long)(clock64() - c_begin);
+#endif
   }
 }
 

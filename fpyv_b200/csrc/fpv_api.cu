@@ -123,7 +123,8 @@ void launch_drone_g(const DroneK& k, const DroneIO& io, bool general, cudaStream
 }
 template <class V>
 void launch_drone_a(const DroneK& k, const DroneIO& io, int ang, bool general, cudaStream_t st) {
-  if (ang == 2) launch_drone_g<V, 2>(k, io, general, st);
+  if (ang == 3) launch_drone_g<V, 3>(k, io, general, st);
+  else if (ang == 2) launch_drone_g<V, 2>(k, io, general, st);
   else if (ang == 1) launch_drone_g<V, 1>(k, io, general, st);
   else launch_drone_g<V, 0>(k, io, general, st);
 }
@@ -220,6 +221,7 @@ int fpv_drone_step(const fpv_drone_params_t* p, const fpv_drone_io_t* io, void* 
   k.inv_mass = (float)(1.0 / (double)p->mass);
   k.dt_over_mass = (float)((double)p->dt / (double)p->mass);
   k.half_ang_scale = (float)(0.5 * 0.017453292519943295 * (double)p->dt);
+  k.inv_half_ang_scale = (float)(1.0 / (0.5 * 0.017453292519943295 * (double)p->dt));
   k.lut_n = (p->flags & FPV_F_THRUST_LUT) ? io->lut_n : 0;
   k.lut_scale = (float)((io->lut_n - 1) * 0.5);
   k.flags = p->flags;
@@ -249,11 +251,13 @@ int fpv_drone_step(const fpv_drone_params_t* p, const fpv_drone_io_t* io, void* 
   d.trace = (unsigned long long*)io->trace;
 
   // |rates| <= max_rates is an invariant of action2force (a convex mix of clipped commands), so the
-  // per-substep Euler angles are bounded by max_rates*dt in radians.  Below 0.1 rad degree-5/4 Taylor kernels are
-  // exact to fp32; below 0.5 rad the reduced-argument minimax kernels need no range reduction; otherwise sincosf.
+  // per-substep Euler angles are bounded by max_rates*dt in radians; the polynomial degree follows that bound
+  // (see vsincos in vec.cuh), full-range sincosf beyond it.
   const double max_angle = std::fabs((double)p->max_rates) * 0.017453292519943295 * (double)p->dt;
-  const int ang = max_angle <= 0.1 ? 2 : (max_angle <= 0.5 ? 1 : 0);
-  const bool general = p->n_objects > 0 || io->override_q != nullptr;
+  const double half = 0.5 * max_angle;   // the kernel evaluates sin/cos of the HALF angles (quaternion update)
+  const int ang = half <= 0.03 ? 3 : (half <= 0.05 ? 2 : (half <= 0.25 ? 1 : 0));
+  // hot kernel = reference configuration (ground plane, undamped contact spring); everything else is general
+  const bool general = p->n_objects > 0 || io->override_q != nullptr || p->spring_c != 0.f || !(p->flags & FPV_F_GROUND);
   cudaStream_t st = (cudaStream_t)stream;
   if (p->flags & FPV_F_SCALAR) launch_drone_a<float>(k, d, ang, general, st);
   else launch_drone_a<F2>(k, d, ang, general, st);

@@ -90,8 +90,18 @@ __device__ __forceinline__ F2 vfma(F2 a, F2 b, F2 c) {
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
   return r;
 }
-__device__ __forceinline__ F2 vneg(F2 a) { return F2{a.v ^ 0x8000000080000000ull}; }
-__device__ __forceinline__ F2 operator-(F2 a, F2 b) { return a + vneg(b); }
+// negation as two scalar negs between an unpack and a pack: ptxas folds this into the consumer's operand
+// modifier (FFMA2 R, -R.F32x2, ...), whereas a 64-bit XOR of the sign bits stays as two LOP3
+__device__ __forceinline__ F2 vneg(F2 a) {
+  float x, y;
+  f2_unpack(a, x, y);
+  return f2_pack(-x, -y);
+}
+__device__ __forceinline__ F2 operator-(F2 a, F2 b) {
+  F2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
+}
 __device__ __forceinline__ F2 operator-(F2 a) { return vneg(a); }
 #define FPV_F2_MAP1(name, expr)                              \
   __device__ __forceinline__ F2 name(F2 a) {                 \
@@ -178,13 +188,23 @@ template <class V> __device__ __forceinline__ void sincos_tiny(V x, V& s, V& c) 
   c = vfma(pc, x2, S<V>(1.0f));
 }
 
+// |x| <= 0.03 rad: x (1 - x^2/6) and 1 - x^2/2 (next terms: x^5/120 -> 7e-9 relative, x^4/24 -> 3.4e-8 absolute)
+template <class V> __device__ __forceinline__ void sincos_micro(V x, V& s, V& c) {
+  const V x2 = x * x;
+  s = x * vfma(x2, S<V>(-1.6666667e-1f), S<V>(1.0f));
+  c = vfma(x2, S<V>(-0.5f), S<V>(1.0f));
+}
+
 template <int ANG> __device__ __forceinline__ void vsincos(float x, float& s, float& c) {
-  if (ANG == 2) sincos_tiny<float>(x, s, c);
+  if (ANG == 3) sincos_micro<float>(x, s, c);
+  else if (ANG == 2) sincos_tiny<float>(x, s, c);
   else if (ANG == 1) sincos_poly<float>(x, s, c);
   else sincosf(x, &s, &c);
 }
 template <int ANG> __device__ __forceinline__ void vsincos(F2 x, F2& s, F2& c) {
-  if (ANG == 2) {
+  if (ANG == 3) {
+    sincos_micro<F2>(x, s, c);
+  } else if (ANG == 2) {
     sincos_tiny<F2>(x, s, c);
   } else if (ANG == 1) {
     sincos_poly<F2>(x, s, c);
