@@ -162,7 +162,11 @@ def workload_config(n_gpus, **extra):
                      "drag + motor-curve LUT + ground contact, auto-reset, random sticks",
          "envs_per_gpu": ENVS_PER_GPU, "total_envs": ENVS_PER_GPU * n_gpus, "substeps_per_step": SUBSTEPS,
          "dt_substep_s": DT, "thrust_lut_entries": LUT_N, "parallelism": f"env-sharded x{n_gpus}, no data-path collective",
-         "l2": "flushed between timed steps (256 MiB write, then a 256 MiB read so the flush leaves no dirty lines); per-step CUDA-event intervals summed"}
+         "l2": "cold by working-set size: 4 independent batches of envs_per_gpu drones are stepped round-robin (each step "
+               "= one control step of ONE batch; 4 x (64 MiB state + 16 MiB actions) read + 4 x 64 MiB written per "
+               "rotation > 126 MB L2), steps back to back in one CUDA-event bracket; ms_per_step_flushed is the "
+               "cross-check with ONE batch and an explicit L2 flush (256 MiB write + 256 MiB read) before every step, "
+               "per-step event intervals summed"}
     c.update(extra)
     return c
 
@@ -184,26 +188,52 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=dev)
     n, K, W = args.envs, args.steps, args.warmup
 
-    def make(substeps, lut=LUT_N):
+    NB = 4   # independent 1,048,576-env batches stepped round-robin: the working set (4 x 80 MiB read per step set)
+             # exceeds the 126 MB L2, so every step finds its state cold WITHOUT flush kernels between the steps
+
+    def make(substeps, lut=LUT_N, seed_off=0):
         d = BatchedDrone(None, num_envs=n, device=dev, substeps=substeps, dt=DT, auto_reset=True, thrust_lut=lut)
-        pos, vel, rpy, g = synthetic_init(n, dev, 1234 + rank)
+        pos, vel, rpy, g = synthetic_init(n, dev, 1234 + rank + 1000 * seed_off)
         d.reset(pos, vel, rpy)
         return d, g
 
-    drone, gen = make(SUBSTEPS)
+    drones, gen = [], None
+    for j in range(NB):
+        d, g = make(SUBSTEPS, seed_off=j)
+        drones.append(d)
+        gen = gen or g
+    drone = drones[0]
     ring = [torch.rand(n, 4, device=dev, generator=gen) * 2 - 1 for _ in range(4)]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     flush_r = torch.ones(64 << 20, dtype=torch.float32, device=dev)
 
+    def timed_rotation(ds, steps, warm):
+        """The contract's timed region: `steps` control steps back to back inside ONE CUDA-event bracket (barrier +
+        synchronize on both sides).  Step i advances batch i % NB, so its state was evicted from L2 by the other
+        batches' traffic (inputs larger than L2)."""
+        for i in range(warm):
+            ds[i % len(ds)].step(ring[i % 4], return_obs=False)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(steps):
+            ds[i % len(ds)].step(ring[i % 4], return_obs=False)
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        return e0.elapsed_time(e1)
+
     def timed_loop(d, steps, warm):
-        """returns summed per-step device ms (L2 flushed between steps)."""
+        """Cross-check: ONE batch, L2 flushed explicitly before every step, per-step CUDA-event intervals summed
+        (each interval then also contains the launch latency that back-to-back steps hide)."""
         for i in range(warm):   # warm-up mirrors the timed iteration exactly (flush kernels included)
             flush.zero_()
             flush_r.sum()
             d.step(ring[i % 4], return_obs=False)
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        if world > 1:
-            dist.barrier()
         torch.cuda.synchronize()
         for i in range(steps):
             flush.zero_()        # evict the state from L2 (write > L2 size) ...
@@ -212,8 +242,6 @@ def run_gpu(args):
             d.step(ring[i % 4], return_obs=False)
             ev[i][1].record()
         torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
         per = [a.elapsed_time(b) for a, b in ev]
         timed_loop.last = sorted(per)
         return sum(per)
@@ -223,18 +251,22 @@ def run_gpu(args):
         sampler.start()
         time.sleep(0.3)
     t0 = time.time()
-    ms = timed_loop(drone, K, W)
+    ms = timed_rotation(drones, K, W)
+    ms_flushed = timed_loop(drone, min(K, 200), W)
+    K_fl = min(K, 200)
 
-    if args.profile:      # ncu / launch-list runs: only the two timed kernel loops (K=8 then K=1)
+    if args.profile:      # ncu / launch-list runs: only the kernel loops (K=8 then K=1)
         if sampler:
             sampler.stop(t0, time.time())
         k8_sorted = [round(x, 4) for x in timed_loop.last]
-        d1, _ = make(1)
-        ms_k1 = timed_loop(d1, K, W)
+        d1s = [make(1, seed_off=j)[0] for j in range(NB)]
+        ms_k1 = timed_rotation(d1s, K, W)
+        ms_k1_fl = timed_loop(d1s[0], K_fl, W)
         if rank == 0:
             p = timed_loop.last
             print(json.dumps({"profile_run": True, "ms_per_step_k8": ms / K, "ms_per_step_k1": ms_k1 / K,
-                              "k1_min_med_max": [p[0], p[len(p) // 2], p[-1]], "k8_sorted": k8_sorted}))
+                              "flushed_k8": ms_flushed / K_fl, "flushed_k1": ms_k1_fl / K_fl,
+                              "k1_fl_min_med_max": [p[0], p[len(p) // 2], p[-1]], "k8_fl_sorted": k8_sorted[:3] + k8_sorted[-3:]}))
         return
 
     # ---- end to end through the public API with HOST buffers (pinned): H2D actions, step, D2H done flags
@@ -257,8 +289,8 @@ def run_gpu(args):
     ms_e2e = e0.elapsed_time(e1)
 
     # ---- HBM-bound variant of the same kernel (K = 1) for the memory-roofline placement
-    d1, _ = make(1)
-    ms_k1 = timed_loop(d1, K, W)
+    d1s = [make(1, seed_off=j)[0] for j in range(NB)]
+    ms_k1 = timed_rotation(d1s, K, W)
 
     t1 = time.time()
     clocks = sampler.stop(t0, t1) if sampler else None      # covers the K=8 loop, the e2e loop and the K=1 loop
@@ -267,6 +299,7 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e, ms_k1 = t.tolist()
     stats = drone.episode_stats(all_reduce=world > 1)      # the engine's only collective (NCCL), outside the timed loop
+    ms_flushed_per_step = ms_flushed / K_fl
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -301,6 +334,7 @@ def run_gpu(args):
             "e2e": {"value": total_envs * K / (ms_e2e * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": 16 * n,
                     "d2h_bytes_per_step": n, "ms_per_step": ms_e2e / K,
                     "api": "BatchedDrone.step_host(pinned actions) -> pinned done flags; host waits every step"},
+            "ms_per_step_flushed": ms_flushed_per_step,
             "gpu_launches": K, "roofline": roof,
             "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "clocks": clocks, "episode_stats": stats}
