@@ -8,7 +8,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 # FPYV_B200_LIB: developer override used to A/B differently tuned builds of the same ABI
 LIB_PATH = os.environ.get("FPYV_B200_LIB") or os.path.join(HERE, "libfpyv_b200.so")
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 # flags (fpv_api.h)
 F_GROUND, F_AUTO_RESET, F_FREEZE_DONE, F_THRUST_LUT, F_SCALAR = 1, 2, 4, 8, 32
@@ -16,7 +16,7 @@ OBJ_SPHERE, OBJ_CYLINDER = 1, 2
 MAX_OBJECTS = 16
 DRONE_PLANES, RACER_PLANES = 4, 7
 EXPORTS = ("fpv_abi_version", "fpv_last_error", "fpv_sizeof", "fpv_device_info", "fpv_drone_reset",
-           "fpv_drone_step", "fpv_drone_observe", "fpv_drone_get_rotation", "fpv_drone_set_rotation", "fpv_matrix_to_quat", "fpv_sticks_to_actions", "fpv_racer_reset", "fpv_racer_step")
+           "fpv_drone_step", "fpv_drone_observe", "fpv_drone_get_rotation", "fpv_drone_set_rotation", "fpv_matrix_to_quat", "fpv_sticks_to_actions", "fpv_racer_reset", "fpv_racer_step", "fpv_gate_env_reset", "fpv_gate_env_step")
 
 
 class FpvError(RuntimeError):
@@ -62,7 +62,19 @@ class RacerParams(C.Structure):
                 ("gains", (C.c_float * 3) * 3), ("vel_decay", C.c_float), ("flags", C.c_uint32)]
 
 
-_STRUCTS = (DroneParams, DroneIO, Object, Stats, StickCalib, RacerParams)
+MAX_GATES, ENV_OBS_FLOATS = 32, 16
+
+
+class Gate(C.Structure):
+    _fields_ = [(k, C.c_float) for k in ("cx", "cy", "cz", "nx", "ny", "nz", "half_size", "pad")]
+
+
+class GateEnvParams(C.Structure):
+    _fields_ = [("n_gates", C.c_int32), ("agents_per_env", C.c_int32), ("laps_to_finish", C.c_int32),
+                ("w_gate", C.c_float), ("w_progress", C.c_float), ("w_crash", C.c_float), ("gates", Gate * MAX_GATES)]
+
+
+_STRUCTS = (DroneParams, DroneIO, Object, Stats, StickCalib, RacerParams, GateEnvParams)
 _lib = None
 
 
@@ -95,6 +107,10 @@ def load():
     lib.fpv_racer_reset.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
     lib.fpv_racer_step.argtypes = [C.POINTER(RacerParams), C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
                                    C.c_void_p, C.c_void_p]
+    lib.fpv_gate_env_reset.argtypes = [C.POINTER(GateEnvParams), C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p]
+    lib.fpv_gate_env_step.argtypes = [C.POINTER(GateEnvParams), C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     v = lib.fpv_abi_version()
     if v != ABI_VERSION:
         raise ImportError(f"{LIB_PATH} has ABI version {v}, this package needs {ABI_VERSION}; rebuild it")

@@ -561,13 +561,18 @@ __global__ void __launch_bounds__(THREADS, MINB) drone_step_tma_kernel(const __g
 
   // Ring protocol (STAGES == 2): slot (it & 1) holds the chunk computed at iteration it.  At the top of iteration it
   // the OTHER slot -- drained at it-1 -- is refilled with the next chunk, which then lands while chunk `it` is being
-  // computed.  A chunk is therefore pulled exactly one chunk-time before it is needed (late commitment keeps the
-  // end-of-kernel tail to about one chunk), and the pull's atomic was fired one iteration earlier still... no:
-  // it is fired here and resolved here; its ~1k-cycle round trip is covered by the other warps of the scheduler.
+  // computed.  A chunk is therefore pulled one chunk-time before it is needed (late commitment keeps the
+  // end-of-kernel tail to about one chunk); the pull's ~1k-cycle atomic round trip is covered by the other warps
+  // of the scheduler.
   static_assert(STAGES == 2, "ring protocol below is written for two slots");
   long long cur = my_warp;                 // static first chunk
   if (cur < n_chunks && leader) issue(cur, 0);
   long long static_next = my_warp + total_warps;
+  // while the first chunk is in flight: stage the motor curve (the only CTA-wide barrier of the kernel)
+  if (k.flags & FPV_F_THRUST_LUT)
+    for (int i = threadIdx.x; i < k.lut_n; i += THREADS) lut_s[i] = io.lut[i];
+  __syncthreads();
+  if (io.stats && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&io.stats->env_steps, (double)io.n);
   TileStats st = {0.f, 0.f, 0.f, 0.f, 0.f};
 #ifdef FPV_TRACE_PHASES
   long long ph_wait = 0, ph_read = 0, ph_tile = 0;

@@ -9,6 +9,7 @@
 #include "../../include/fpv_api.h"
 #include "drone_kernels.cuh"
 #include "misc_kernels.cuh"
+#include "env_kernels.cuh"
 
 namespace {
 
@@ -113,11 +114,9 @@ bool launch_drone_tma(const DroneK& k, const DroneIO& io, cudaStream_t st) {
 template <class V, int ANG>
 void launch_drone_g(const DroneK& k, const DroneIO& io, bool general, cudaStream_t st) {
   static const int no_tma = tune_env("FPV_TUNE_NOTMA", 0);     // developer A/B switches, not part of the ABI
-  static const int stages = tune_env("FPV_TUNE_STAGES", 2);
   if (general) { launch_drone<V, ANG, true>(k, io, st); return; }
   if (!no_tma) {
-    const bool ok = stages >= 3 ? launch_drone_tma<V, ANG, 3>(k, io, st) : launch_drone_tma<V, ANG, 2>(k, io, st);
-    if (ok) return;
+    if (launch_drone_tma<V, ANG, 2>(k, io, st)) return;
   }
   launch_drone<V, ANG, false>(k, io, st);
 }
@@ -145,6 +144,7 @@ int fpv_sizeof(int which) {
     case 3: return (int)sizeof(fpv_stats_t);
     case 4: return (int)sizeof(fpv_stick_calib_t);
     case 5: return (int)sizeof(fpv_racer_params_t);
+    case 6: return (int)sizeof(fpv_gate_env_params_t);
     default: return -1;
   }
 }
@@ -365,6 +365,43 @@ int fpv_racer_step(const fpv_racer_params_t* p, void* state, int64_t n, int64_t 
   fpv::racer_step_kernel<kThreads><<<grid, kThreads, 0, (cudaStream_t)stream>>>(k, (float4*)state, n, plane_stride,
                                                                                    (const float4*)actions, (float4*)torque_out);
   return check_launch("fpv_racer_step");
+}
+
+namespace {
+int check_gate_params(const fpv_gate_env_params_t* p, int64_t n, const char* who) {
+  if (!p) return fail(FPV_EINVAL, "%s: null params", who);
+  if (p->n_gates < 1 || p->n_gates > FPV_MAX_GATES) return fail(FPV_EINVAL, "%s: n_gates=%d out of [1,%d]", who, p->n_gates, FPV_MAX_GATES);
+  const int A = p->agents_per_env;
+  if (A < 1 || A > 32 || (A & (A - 1)) != 0) return fail(FPV_EINVAL, "%s: agents_per_env=%d must be a power of two <= 32", who, A);
+  if (n < 0 || n % A != 0) return fail(FPV_EINVAL, "%s: n_agents=%lld must be a multiple of agents_per_env=%d", who, (long long)n, A);
+  return FPV_OK;
+}
+}  // namespace
+
+int fpv_gate_env_reset(const fpv_gate_env_params_t* p, const void* state, int64_t n, int64_t plane_stride,
+                       const uint8_t* mask, void* prev, int32_t* progress, void* stream) {
+  if (int rc = check_gate_params(p, n, "fpv_gate_env_reset")) return rc;
+  if (!state || !prev || !progress) return fail(FPV_EINVAL, "fpv_gate_env_reset: null pointer");
+  if (plane_stride < n || !aligned16(state)) return fail(FPV_EINVAL, "fpv_gate_env_reset: bad stride/alignment");
+  if (n == 0) return FPV_OK;
+  fpv::gate_env_reset_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*p, (const float4*)state, n, plane_stride,
+                                                                                              mask, (float2*)prev, progress);
+  return check_launch("fpv_gate_env_reset");
+}
+
+int fpv_gate_env_step(const fpv_gate_env_params_t* p, const void* state, int64_t n, int64_t plane_stride,
+                      const uint8_t* agent_done, void* prev, int32_t* progress, float* agent_reward, float* env_reward,
+                      uint8_t* env_done, float* obs, fpv_stats_t* stats, void* stream) {
+  if (int rc = check_gate_params(p, n, "fpv_gate_env_step")) return rc;
+  if (!state || !agent_done || !prev || !progress || !env_reward || !env_done)
+    return fail(FPV_EINVAL, "fpv_gate_env_step: null pointer");
+  if (plane_stride < n || !aligned16(state) || !aligned16(obs)) return fail(FPV_EINVAL, "fpv_gate_env_step: bad stride/alignment");
+  if (n == 0) return FPV_OK;
+  constexpr int T = 256;
+  fpv::gate_env_step_kernel<T><<<(unsigned)((n + T - 1) / T), T, 0, (cudaStream_t)stream>>>(
+      *p, (const float4*)state, n, plane_stride, agent_done, (float2*)prev, progress, agent_reward, env_reward, env_done,
+      (float4*)obs, stats);
+  return check_launch("fpv_gate_env_step");
 }
 
 }  // extern "C"

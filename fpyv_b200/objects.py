@@ -83,3 +83,22 @@ def lower_object_list(object_list):
     if len(out) > _lib.MAX_OBJECTS:
         raise ValueError(f"at most {_lib.MAX_OBJECTS} obstacles per launch (got {len(out)})")
     return has_ground, out
+
+
+def generate_track(count, radius, gate_size, gate_resolution=17):
+    """Gate layout of the reference's generators.generate_track (src/utils/generators.py:7-18): gates on the
+    ellipse [cos(t)*gate_size, sin(t)*radius, 0], yaw t + pi/2, shapes cycling rectangle / circle / half_circle.
+    Reproduced as written, including its argument quirk: circle gates are raised by gate_size/2 and get size
+    gate_size/2, while rectangle and half-circle gates receive `gate_resolution` as their size (:15-16)."""
+    theta = np.linspace(0, 2 * np.pi, count + 1)[:-1]
+    shapes = ["rectangle", "circle", "half_circle"]
+    gates = []
+    for i, t in enumerate(theta):
+        p = np.array([np.cos(t) * gate_size, np.sin(t) * radius, 0.0])
+        yaw = t + np.pi / 2
+        rot = np.array([[np.cos(yaw), -np.sin(yaw), 0.0], [np.sin(yaw), np.cos(yaw), 0.0], [0.0, 0.0, 1.0]])
+        if shapes[i % 3] == "circle":
+            gates.append(Gate(p + np.array([0.0, 0.0, gate_size / 2]), rot, gate_size / 2, shape="circle", resolution=gate_resolution))
+        else:
+            gates.append(Gate(p, rot, gate_resolution, shape=shapes[i % 3], resolution=gate_resolution))
+    return gates

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define FPV_ABI_VERSION 7
+#define FPV_ABI_VERSION 8
 
 /* error codes */
 #define FPV_OK 0
@@ -211,6 +211,52 @@ int fpv_racer_reset(void* state, int64_t n, int64_t plane_stride, const uint8_t*
  * torque_out: float4[n] (last substep's PID output) or NULL. */
 int fpv_racer_step(const fpv_racer_params_t* params, void* state, int64_t n, int64_t plane_stride,
                    const void* actions, void* torque_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Multi-agent gate-race environment (BASELINE.json configs[4]; API style of tests/ma_com_simple_env.py:17-57:
+ * reset() -> obs, step(a) -> (obs, reward, done, {}) with one observation per agent and ONE reward / done per env).
+ * Gate geometry is the reference's: a gate is a plane through `position` with normal = rotation_matrix[:,0]
+ * (components.py:811-822), tracks come from generate_track (generators.py:7-18).
+ * The reference has NO gate-passing reward anywhere: the reward / termination below are OUR
+ * definition -- PARITY UNPINNED, checked only against our own float64 model (oracle/gate_env_oracle.py):
+ *   agent a (next gate g): d = n_g.(p - c_g), r = |p - c_g|
+ *   passed  = d_prev < 0 <= d  and  r^2 - d^2 <= half_size_g^2            (plane crossed inside the aperture)
+ *   reward_a = w_gate*passed + w_progress*(r_prev - r) - w_crash*crashed_a
+ *   passed -> g = (g+1) mod n_gates (a wrap counts a lap); crashed -> g = 0, laps = 0 (the drone step already
+ *   re-spawned the agent when auto-reset is on); (d_prev, r_prev) are then re-based on the agent's next gate
+ *   env reward = sum over its agents (warp shuffle reduction), env done = any agent crashed or reached `laps_to_finish`
+ * agents_per_env must be a power of two <= 32: one warp (or an aligned sub-warp) per env.
+ * -------------------------------------------------------------------------------------------*/
+#define FPV_MAX_GATES 32
+#define FPV_ENV_OBS_FLOATS 16
+typedef struct fpv_gate {
+  float cx, cy, cz;      /* Gate.position                      components.py:786 */
+  float nx, ny, nz;      /* Gate.normal = rotation_matrix[:,0] components.py:807-809 */
+  float half_size;       /* aperture half-width: Gate.size / 2 components.py:790 */
+  float pad;
+} fpv_gate_t;
+
+typedef struct fpv_gate_env_params {
+  int32_t n_gates;
+  int32_t agents_per_env;
+  int32_t laps_to_finish;  /* <= 0: never finishes */
+  float w_gate, w_progress, w_crash;
+  fpv_gate_t gates[FPV_MAX_GATES];
+} fpv_gate_env_params_t;
+
+/* (Re)base the per-agent race bookkeeping on gate 0 from the current positions.  prev: float2[n] (d_prev, r_prev);
+ * progress: int32[n] (low 16 bits next gate, high 16 bits laps); mask: uint8[n] or NULL. */
+int fpv_gate_env_reset(const fpv_gate_env_params_t* params, const void* state, int64_t n_agents, int64_t plane_stride,
+                       const uint8_t* mask, void* prev, int32_t* progress, void* stream);
+
+/* One env step AFTER fpv_drone_step: rewards, terminations, observations.
+ * agent_done: uint8[n_agents] (the done output of fpv_drone_step); agent_reward: float[n_agents] or NULL;
+ * env_reward: float[n_envs]; env_done: uint8[n_envs]; obs: float[n_agents][FPV_ENV_OBS_FLOATS] or NULL:
+ *   [0:3] R^T (c_g - p)  [3:6] R^T n_g  [6:9] R^T v  [9:12] R^T e_z  [12:15] rates (deg/s)  [15] prev_thrust
+ * stats (may be NULL): reward_sum / reward_sq_sum accumulate the env rewards. */
+int fpv_gate_env_step(const fpv_gate_env_params_t* params, const void* state, int64_t n_agents, int64_t plane_stride,
+                      const uint8_t* agent_done, void* prev, int32_t* progress, float* agent_reward, float* env_reward,
+                      uint8_t* env_done, float* obs, fpv_stats_t* stats, void* stream);
 
 #ifdef __cplusplus
 }

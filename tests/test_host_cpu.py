@@ -169,3 +169,29 @@ def test_sincos_polynomial_accuracy():
     c = pc * x2 + np.float32(1.0)
     assert np.max(np.abs(s - np.sin(x.astype(np.float64)))) < 1.5e-7
     assert np.max(np.abs(c - np.cos(x.astype(np.float64)))) < 1.5e-7
+
+
+def test_generate_track_matches_reference_layout():
+    """generators.generate_track (src/utils/generators.py:7-18) incl. its size quirk."""
+    from fpyv_b200.objects import generate_track
+    gates = generate_track(count=6, radius=12, gate_size=5, gate_resolution=17)
+    assert len(gates) == 6
+    th = np.linspace(0, 2 * np.pi, 7)[:-1]
+    for i, g in enumerate(gates):
+        base = np.array([np.cos(th[i]) * 5, np.sin(th[i]) * 12, 0.0])
+        if i % 3 == 1:      # circle
+            assert np.allclose(g.position, base + [0, 0, 2.5]) and g.size == 2.5
+        else:
+            assert np.allclose(g.position, base) and g.size == 17
+        yaw = th[i] + np.pi / 2
+        assert np.allclose(g.normal, [np.cos(yaw), np.sin(yaw), 0.0])
+
+
+def test_gate_env_model_basics():
+    from oracle import gate_env_oracle as go
+    gates = np.array([[2.0, 0, 0, 1, 0, 0, 1.0], [4.0, 0, 0, 1, 0, 0, 1.0]])
+    p0 = np.array([[1.0, 0.2, 0.0], [1.0, 3.0, 0.0]])
+    prev, g, laps = go.reset(gates, p0)
+    p1 = p0 + [1.5, 0, 0]
+    r, re, de, prev, g, laps = go.step(gates, p1, np.array([False, False]), prev, g, laps, 2, 10.0, 1.0, 5.0, 0)
+    assert g.tolist() == [1, 0] and r[0] > 10 and r[1] < 10 and re[0] == r.sum() and not de[0]
