@@ -518,6 +518,11 @@ __global__ void __launch_bounds__(THREADS, MINB) drone_step_tma_kernel(const __g
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();  // this warp's mbarriers are initialised: its ring can be primed before the CTA-wide LUT staging
+  // Programmatic dependent launch: let the NEXT launch on the stream become resident as our CTAs retire (its
+  // prologue then overlaps our tail), and wait for the PREVIOUS launch -- which may have written this very state --
+  // before the first byte of state is touched.  Without the launch attribute both instructions are no-ops.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   const long long n_chunks = (io.n + CHUNK - 1) / CHUNK;
   const long long my_warp = (long long)blockIdx.x * WARPS + warp;

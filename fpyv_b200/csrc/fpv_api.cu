@@ -107,7 +107,23 @@ bool launch_drone_tma(const DroneK& k, const DroneIO& io, cudaStream_t st) {
   const long long tiles = (io.n + TILE - 1) / TILE;
   const long long wave = (long long)sm_count_of_current_device() * occ_cache;
   const unsigned grid = (unsigned)(tiles < wave ? tiles : wave);
-  kern<<<grid, kThreads, smem, st>>>(k, io, lut_bytes);
+  static const int no_pdl = tune_env("FPV_TUNE_NOPDL", 0);
+  if (no_pdl) {
+    kern<<<grid, kThreads, smem, st>>>(k, io, lut_bytes);
+    return true;
+  }
+  // programmatic dependent launch: this grid may become resident while the previous one on the stream drains
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kern, k, io, lut_bytes);
   return true;
 }
 

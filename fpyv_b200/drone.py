@@ -107,8 +107,12 @@ class BatchedDrone:
         self._io = _lib.DroneIO()
         self._host_actions = None
         self._host_done = None
-        self.throttle = None
+        self._last_action = None
         self._is_reset = False
+        self._fast_ok = False
+        self._act_shape = torch.Size((n, 4))
+        self._step_fn = self._lib.fpv_drone_step
+        self._p_ref, self._io_ref = C.byref(self._p), C.byref(self._io)
 
     # ------------------------------------------------------------------ parameters
     def _make_params(self) -> _lib.DroneParams:
@@ -185,6 +189,11 @@ class BatchedDrone:
         return self._acc[:, :3]
 
     @property
+    def throttle(self):
+        """Drone.throttle (components.py:186): the throttle stick of the last action."""
+        return None if self._last_action is None else self._last_action[:, 3]
+
+    @property
     def episode_steps(self):
         return self._state[1, :self.num_envs, 3].view(torch.int32)
 
@@ -233,10 +242,21 @@ class BatchedDrone:
         if not self._is_reset:
             raise RuntimeError("call reset() before step() (the reference's state is None until reset)")
         n, dev = self.num_envs, self.device
+        # fast path (the RL inner loop): device float32 actions, nothing else changed since the last full call --
+        # one pointer store and one C call, no allocation (so it can be captured in a CUDA graph)
+        if (self._fast_ok and wind_velocity_vector is None and object_list is None and rotation_matrix is None
+                and type(action) is torch.Tensor and action.dtype is torch.float32 and action.is_cuda
+                and action.shape == self._act_shape and action.is_contiguous()):
+            self._last_action = action
+            self._io.actions = action.data_ptr()
+            rc = self._step_fn(self._p_ref, self._io_ref, torch.cuda.current_stream(dev).cuda_stream)
+            if rc:
+                _lib.check(rc)
+            return self.observe() if return_obs else None
         if action is None:
             action = self.read_sticks()
         act = _as_dev(action, dev, (n, 4))
-        self.throttle = act[:, 3]
+        self._last_action = act
         p, io = self._p, self._io
         p.flags = self._flags
         wind_env = None
@@ -281,6 +301,9 @@ class BatchedDrone:
         io.work = self._work.data_ptr()
         io.trace = None if getattr(self, "_trace", None) is None else self._trace.data_ptr()
         _lib.check(self._lib.fpv_drone_step(C.byref(p), C.byref(io), _lib.current_stream(dev)))
+        # the fast path may reuse p / io as they are only if this call left them in the plain configuration
+        self._fast_ok = (wind_velocity_vector is None and object_list is None and rotation_matrix is None
+                         and getattr(self, "_trace", None) is None)
         if return_obs:
             return self.observe()
         return None

@@ -398,6 +398,40 @@ def test_auto_reset_freeze_and_stats():
     assert st["mean_episode_len"] > 1
 
 
+def test_fast_path_and_cuda_graph_capture():
+    """The allocation-free fast path of step() (device float32 actions) is what an RL loop calls; it must be
+    capturable in a CUDA graph and produce exactly the same states as the general path."""
+    n, K = 4096, 8
+    rng = np.random.default_rng(11)
+    pos = np.stack([rng.normal(0, 5, n), rng.normal(0, 5, n), rng.uniform(0.5, 3, n)], 1)
+    acts = torch.as_tensor(rng.uniform(-1, 1, (6, n, 4)), dtype=torch.float32, device=DEV)
+    ref = make(n, substeps=K, dt=1e-3, auto_reset=True, thrust_lut=2049)
+    ref.reset(pos, 0.0, 0.0)
+    for a in acts:
+        ref.step(a.cpu().numpy(), return_obs=False)          # general path (host array -> conversion)
+    d = make(n, substeps=K, dt=1e-3, auto_reset=True, thrust_lut=2049)
+    d.reset(pos, 0.0, 0.0)
+    d.step(acts[0], return_obs=False)
+    assert d._fast_ok
+    static = torch.zeros(n, 4, device=DEV)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        static.copy_(acts[1])
+        d.step(static, return_obs=False)                      # warm-up on the side stream (fast path)
+    torch.cuda.current_stream().wait_stream(s)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):                             # capture records the launch, it does not run it
+        d.step(static, return_obs=False)
+    for a in acts[2:]:
+        static.copy_(a)
+        graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(d._state, ref._state)
+    assert torch.equal(d.done, ref.done)
+    assert d.throttle is static[:, 3] or torch.equal(d.throttle, static[:, 3])
+
+
 def test_drone_compat_object_matches_reference_kat():
     """num_envs=1 NumPy stand-in driven exactly like simulator.py drives the reference."""
     from fpyv_b200 import Drone, Ground
