@@ -185,6 +185,9 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # keep stdout to the ONE JSON line: NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION/INFO
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and not os.environ.get("FPV_KEEP_NCCL_DEBUG"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     n, K, W = args.envs, args.steps, args.warmup
 
@@ -331,14 +334,15 @@ def run_gpu(args):
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(world),
             "env_substeps_per_sec": value * SUBSTEPS,
-            "e2e": {"value": total_envs * K / (ms_e2e * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": 16 * n,
-                    "d2h_bytes_per_step": n, "ms_per_step": ms_e2e / K,
+            "e2e": {"value": total_envs * K / (ms_e2e * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": 16 * n * world,
+                    "d2h_bytes_per_step": n * world, "ms_per_step": ms_e2e / K,
                     "api": "BatchedDrone.step_host(pinned actions) -> pinned done flags; host waits every step"},
             "ms_per_step_flushed": ms_flushed_per_step,
             "gpu_launches": K, "roofline": roof,
             "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "clocks": clocks, "episode_stats": stats}
-    print(json.dumps(line))
+    sys.stdout.flush()
+    print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
