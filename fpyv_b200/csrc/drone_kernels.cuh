@@ -118,6 +118,10 @@ __device__ __forceinline__ typename Lane<V>::Mask drone_substeps(const DroneK& k
   const V omr = S<V>(k.one_minus_rtr), omt = S<V>(k.one_minus_ttr);
   const V dt = S<V>(k.dt), dt_m = S<V>(k.dt_over_mass);
   V h0 = s.pr0 * S<V>(k.half_ang_scale), h1 = s.pr1 * S<V>(k.half_ang_scale), h2 = s.pr2 * S<V>(k.half_ang_scale);
+  {  // s = sqrt(2) q for the duration of the loop (see the R(q) entries below)
+    const V r2 = S<V>(1.41421356237f);
+    s.qw = s.qw * r2; s.qx = s.qx * r2; s.qy = s.qy * r2; s.qz = s.qz * r2;
+  }
   const V zero = S<V>(0.f), one = S<V>(1.f);
   const bool ground = (k.flags & FPV_F_GROUND) != 0;
   M done = vlt(one, zero);  // all false
@@ -130,18 +134,20 @@ __device__ __forceinline__ typename Lane<V>::Mask drone_substeps(const DroneK& k
     V th = vfma(s.pt, omt, tt);
     s.pt = th;
     if (GENERAL && has_override) {  // components.py:230-232
-      s.qw = oqw; s.qx = oqx; s.qy = oqy; s.qz = oqz;
+      const V r2 = S<V>(1.41421356237f);
+      s.qw = oqw * r2; s.qx = oqx * r2; s.qy = oqy * r2; s.qz = oqz * r2;
       th = o_thrust;
     }
-    // ---- the entries of R(q) this step reads: columns 1 and 2 and R[2][0]  (helper_functions.py:100-117)
-    const V x2 = s.qx + s.qx, y2 = s.qy + s.qy, z2 = s.qz + s.qz;
+    // ---- the entries of R(q) this step reads: columns 1 and 2 and R[2][0]  (helper_functions.py:100-117).
+    //      The loop carries s = sqrt(2) q, so every "2 q_a q_b" of the matrix is the plain product s_a s_b
+    //      (the Hamilton update is linear in q, the scale rides along; undone by the normalisation after the loop).
     const V nqw = vneg(s.qw);
-    const V xz = s.qx * z2, yz = s.qy * z2, xy = s.qx * y2;
-    const V r02 = vfma(s.qw, y2, xz), r20 = vfma(nqw, y2, xz);
-    const V r21 = vfma(s.qw, x2, yz), r12 = vfma(nqw, x2, yz);
-    const V r01 = vfma(nqw, z2, xy);
-    const V tx = vfma(vneg(s.qx), x2, one);  // 1 - 2x^2
-    const V r11 = vfma(vneg(s.qz), z2, tx), r22 = vfma(vneg(s.qy), y2, tx);
+    const V xz = s.qx * s.qz, yz = s.qy * s.qz, xy = s.qx * s.qy;
+    const V r02 = vfma(s.qw, s.qy, xz), r20 = vfma(nqw, s.qy, xz);
+    const V r21 = vfma(s.qw, s.qx, yz), r12 = vfma(nqw, s.qx, yz);
+    const V r01 = vfma(nqw, s.qz, xy);
+    const V tx = vfma(vneg(s.qx), s.qx, one);  // 1 - 2x^2
+    const V r11 = vfma(vneg(s.qz), s.qz, tx), r22 = vfma(vneg(s.qy), s.qy, tx);
     // ---- drag + thrust + gravity (components.py:242).  calculate_drag (kinematics.py:33-38) is
     //      R diag(k)|u| R^T u with u = v + wind; with R orthonormal that equals
     //      |u| (k0 u + (k1-k0)(c1.u) c1 + (k2-k0)(c2.u) c2), c_j the columns of R -- and the thrust
@@ -177,7 +183,7 @@ __device__ __forceinline__ typename Lane<V>::Mask drone_substeps(const DroneK& k
       Fz = vfma(S<V>(k.spring_k), vsel(crashed, zero, pen_sum), Fz);
     } else {
       crashed = vlt(one, zero);
-      const V r00 = vfma(vneg(s.qy), y2, vfma(vneg(s.qz), z2, one)), r10 = vfma(s.qw, z2, xy);
+      const V r00 = vfma(vneg(s.qy), s.qy, vfma(vneg(s.qz), s.qz, one)), r10 = vfma(s.qw, s.qz, xy);
       V cfx = zero, cfy = zero, cfz = zero;
       V mxw[4], myw[4], mzw[4];
       V minz = S<V>(3.0e38f);
