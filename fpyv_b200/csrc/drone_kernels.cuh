@@ -98,7 +98,7 @@ template <class V> struct DroneRegs {
 // K reference steps for the envs held in `s`.  Returns the OR of the per-step crash flags.
 // ANG selects the sin/cos evaluation of the HALF Euler angles h: 0 = full-range sincosf, 1 = |h| <= 0.25 rad
 // (degree-7/8 kernels, no range reduction), 2 = |h| <= 0.05 (degree-5/4, truncation < 2e-11), 3 = |h| <= 0.03
-// (degree-3/2, truncation < 3.4e-8).
+// (degree-3/2, truncation < 3.4e-8), 4 = |h| <= 0.008 (qE from its own series, no sin/cos at all).
 // WIND = false drops the "+ wind" adds when the launch has no wind at all.
 template <class V, int ANG, bool GENERAL, bool WIND>
 __device__ __forceinline__ typename Lane<V>::Mask drone_substeps(const DroneK& k, DroneRegs<V>& s, V a0, V a1, V a2,
@@ -233,15 +233,29 @@ __device__ __forceinline__ typename Lane<V>::Mask drone_substeps(const DroneK& k
     // ---- attitude: E = Rz(yaw)Ry(pitch)Rx(roll) of deg2rad(rates)*dt, R <- R E^T E^T
     //      (rotate_body_by_rates kinematics.py:27-30 runs inside update_kinematic_step :23 AND again in
     //      Drone.update components.py:218).  Quaternion form: qE from the half angles, q <- q (x) conj(qE)^2.
-    V sr, cr, sp, cp, sy, cy;
-    vsincos<ANG>(h0, sr, cr);
-    vsincos<ANG>(h1, sp, cp);
-    vsincos<ANG>(h2, sy, cy);
-    const V A = cy * cp, B = sy * sp, C = cy * sp, D = sy * cp;
-    const V ew = vfma(A, cr, B * sr);  // qE = qz (x) qy (x) qx
-    const V ex = vfma(A, sr, vneg(B * cr));
-    const V ey = vfma(C, cr, D * sr);
-    const V ez = vfma(D, cr, vneg(C * sr));
+    V ew, ex, ey, ez;  // qE = qz (x) qy (x) qx
+    if (ANG == 4) {
+      // |h| <= 0.008: the four components as their series to O(h^4) (dropped terms < 3.5e-9, far below fp32
+      // resolution): e_v = h_i (1 - n/2 + h_i^2/3) -/+ h_j h_k,  e_w = 1 - n/2 + hx hy hz,  n = |h|^2
+      const V sx = h0 * h0, sy = h1 * h1, sz = h2 * h2;
+      const V g = vfma((sx + sy) + sz, S<V>(-0.5f), one);
+      const V third = S<V>(0.333333333f);
+      const V yz = h1 * h2, xz = h0 * h2, xy = h0 * h1;
+      ex = vfma(h0, vfma(sx, third, g), vneg(yz));
+      ey = vfma(h1, vfma(sy, third, g), xz);
+      ez = vfma(h2, vfma(sz, third, g), vneg(xy));
+      ew = vfma(h0, yz, g);
+    } else {
+      V sr, cr, sp, cp, sy, cy;
+      vsincos<ANG>(h0, sr, cr);
+      vsincos<ANG>(h1, sp, cp);
+      vsincos<ANG>(h2, sy, cy);
+      const V A = cy * cp, B = sy * sp, C = cy * sp, D = sy * cp;
+      ew = vfma(A, cr, B * sr);
+      ex = vfma(A, sr, vneg(B * cr));
+      ey = vfma(C, cr, D * sr);
+      ez = vfma(D, cr, vneg(C * sr));
+    }
     // p = conj(qE)^2 = (ew^2 - |ev|^2, -2 ew ev)
     const V pw = vfma(ew, ew, vneg(vfma(ex, ex, vfma(ey, ey, ez * ez))));
     const V m2 = ew * S<V>(-2.f);

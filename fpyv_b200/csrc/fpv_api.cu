@@ -138,7 +138,8 @@ void launch_drone_g(const DroneK& k, const DroneIO& io, bool general, cudaStream
 }
 template <class V>
 void launch_drone_a(const DroneK& k, const DroneIO& io, int ang, bool general, cudaStream_t st) {
-  if (ang == 3) launch_drone_g<V, 3>(k, io, general, st);
+  if (ang == 4) launch_drone_g<V, 4>(k, io, general, st);
+  else if (ang == 3) launch_drone_g<V, 3>(k, io, general, st);
   else if (ang == 2) launch_drone_g<V, 2>(k, io, general, st);
   else if (ang == 1) launch_drone_g<V, 1>(k, io, general, st);
   else launch_drone_g<V, 0>(k, io, general, st);
@@ -271,7 +272,7 @@ int fpv_drone_step(const fpv_drone_params_t* p, const fpv_drone_io_t* io, void* 
   // (see vsincos in vec.cuh), full-range sincosf beyond it.
   const double max_angle = std::fabs((double)p->max_rates) * 0.017453292519943295 * (double)p->dt;
   const double half = 0.5 * max_angle;   // the kernel evaluates sin/cos of the HALF angles (quaternion update)
-  const int ang = half <= 0.03 ? 3 : (half <= 0.05 ? 2 : (half <= 0.25 ? 1 : 0));
+  const int ang = half <= 0.008 ? 4 : (half <= 0.03 ? 3 : (half <= 0.05 ? 2 : (half <= 0.25 ? 1 : 0)));
   // hot kernel = reference configuration (ground plane, undamped contact spring); everything else is general
   const bool general = p->n_objects > 0 || io->override_q != nullptr || p->spring_c != 0.f || !(p->flags & FPV_F_GROUND);
   cudaStream_t st = (cudaStream_t)stream;
