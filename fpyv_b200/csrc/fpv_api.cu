@@ -105,7 +105,9 @@ bool launch_drone_tma(const DroneK& k, const DroneIO& io, cudaStream_t st) {
     occ_smem = smem;
   }
   const long long tiles = (io.n + TILE - 1) / TILE;
-  const long long wave = (long long)sm_count_of_current_device() * occ_cache;
+  static const int occ_cap = tune_env("FPV_TUNE_OCC", 0);
+  const int occ_used = (occ_cap > 0 && occ_cap < occ_cache) ? occ_cap : occ_cache;
+  const long long wave = (long long)sm_count_of_current_device() * occ_used;
   const unsigned grid = (unsigned)(tiles < wave ? tiles : wave);
   static const int no_pdl = tune_env("FPV_TUNE_NOPDL", 0);
   if (no_pdl) {
