@@ -26,6 +26,7 @@ ENVS_PER_GPU = 1 << 20
 SUBSTEPS = 8
 DT = 1e-3
 LUT_N = int(os.environ.get("FPV_BENCH_LUT", "2049"))   # env override: developer tuning only
+CHAINED = os.environ.get("FPV_BENCH_CHAINED", "1") != "0"   # developer A/B: 0 = every launch waits for the previous grid
 # algorithmic work per env (quaternion state, 64 B each way)
 BYTES_PER_ENV_STEP = 64 + 64 + 16 + 1          # state read + state write + action + done flag
 FLOP_PER_ENV_SUBSTEP = 252                     # 245 arithmetic + 6 sin/cos + 1 sqrt
@@ -215,14 +216,16 @@ def run_gpu(args):
         synchronize on both sides).  Step i advances batch i % NB, so its state was evicted from L2 by the other
         batches' traffic (inputs larger than L2)."""
         for i in range(warm):
-            ds[i % len(ds)].step(ring[i % 4], return_obs=False)
+            ds[i % len(ds)].step(ring[i % 4], return_obs=False, chained=CHAINED)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         e0.record()
         for i in range(steps):
-            ds[i % len(ds)].step(ring[i % 4], return_obs=False)
+            # the stick commands of every step exist before the loop starts (open-loop rollout), so consecutive
+            # launches may be chained: launch i+1 starts on the SMs launch i has left (per-chunk ordering of the state)
+            ds[i % len(ds)].step(ring[i % 4], return_obs=False, chained=CHAINED)
         e1.record()
         torch.cuda.synchronize()
         if world > 1:

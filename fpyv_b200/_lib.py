@@ -8,10 +8,10 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 # FPYV_B200_LIB: developer override used to A/B differently tuned builds of the same ABI
 LIB_PATH = os.environ.get("FPYV_B200_LIB") or os.path.join(HERE, "libfpyv_b200.so")
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 # flags (fpv_api.h)
-F_GROUND, F_AUTO_RESET, F_FREEZE_DONE, F_THRUST_LUT, F_SCALAR = 1, 2, 4, 8, 32
+F_GROUND, F_AUTO_RESET, F_FREEZE_DONE, F_THRUST_LUT, F_SCALAR, F_CHAINED = 1, 2, 4, 8, 32, 64
 OBJ_SPHERE, OBJ_CYLINDER = 1, 2
 MAX_OBJECTS = 16
 DRONE_PLANES, RACER_PLANES = 4, 7
@@ -49,7 +49,8 @@ class DroneIO(C.Structure):
                 ("wind_env", C.c_void_p), ("lut", C.c_void_p), ("lut_n", C.c_int32), ("done", C.c_void_p),
                 ("acc_out", C.c_void_p), ("reset_state", C.c_void_p), ("override_q", C.c_void_p),
                 ("override_thrust", C.c_void_p),
-                ("objects", C.POINTER(Object)), ("stats", C.c_void_p), ("work", C.c_void_p), ("trace", C.c_void_p)]
+                ("objects", C.POINTER(Object)), ("stats", C.c_void_p), ("work", C.c_void_p), ("chunk_epoch", C.c_void_p),
+                ("epoch", C.c_uint32), ("reserved0", C.c_uint32), ("trace", C.c_void_p)]
 
 
 class StickCalib(C.Structure):

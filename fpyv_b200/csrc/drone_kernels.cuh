@@ -55,6 +55,8 @@ struct DroneIO {
   const float* override_thrust;  // [n]
   fpv_stats_t* stats;
   unsigned* work;              // [0] next-chunk counter, [1] finished-warp counter (dynamic scheduling), or null
+  unsigned* chunk_epoch;       // [n_chunks] per-chunk step count (chained launches), or null
+  unsigned epoch;              // value chunk_epoch[] holds before this launch; the launch publishes epoch + 1
   unsigned long long* trace;
 };
 
@@ -336,11 +338,17 @@ __device__ __forceinline__ void stats_warp_flush(fpv_stats_t* stats, const TileS
 // One tile worth of work for this thread: unpack L envs from their float4 rows, run the substeps in registers,
 // episode bookkeeping, stores.  q[p][l] = plane p of slot l; slot l is env base + l*SLOT_STRIDE (ei[l] = the same
 // index clamped to n-1, used for the side inputs).
-template <class V, int ANG, bool GENERAL, int SLOT_STRIDE>
+struct NoHook {
+  __device__ __forceinline__ void operator()() const {}
+};
+// `pre_store` runs between the arithmetic and the first store of the tile (used by the ring kernel to publish the
+// PREVIOUS chunk's epoch once its stores have had a whole substep loop to land).
+template <class V, int ANG, bool GENERAL, int SLOT_STRIDE, class PreStore = NoHook>
 __device__ __forceinline__ void drone_tile(const DroneK& k, const DroneIO& io, const float* lut_s,
                                            const float4 (&q)[FPV_DRONE_PLANES][Lane<V>::N],
                                            const float4 (&act)[Lane<V>::N], const long long (&ei)[Lane<V>::N],
-                                           long long base, TileStats& st, const bool wind_on) {
+                                           long long base, TileStats& st, const bool wind_on,
+                                           PreStore pre_store = PreStore()) {
   constexpr int L = Lane<V>::N;
   DroneRegs<V> s;
   s.px = Pack<V>::x(q[0]); s.py = Pack<V>::y(q[0]); s.pz = Pack<V>::z(q[0]); s.pt = Pack<V>::w(q[0]);
@@ -385,6 +393,7 @@ __device__ __forceinline__ void drone_tile(const DroneK& k, const DroneIO& io, c
   if (wind_on) done = drone_substeps<V, ANG, GENERAL, true>(k, s, a0, a1, a2, target, wx, wy, wz, has_ovr, o_thrust, oqw, oqx, oqy, oqz);
   else done = drone_substeps<V, ANG, GENERAL, false>(k, s, a0, a1, a2, target, wx, wy, wz, has_ovr, o_thrust, oqw, oqx, oqy, oqz);
 
+  pre_store();
   // ---- epilogue per env: episode bookkeeping, freeze / auto-reset, stores
 #pragma unroll
   for (int l = 0; l < L; ++l) {
@@ -541,8 +550,12 @@ __global__ void __launch_bounds__(THREADS, MINB) drone_step_tma_kernel(const __g
   // Programmatic dependent launch: let the NEXT launch on the stream become resident as our CTAs retire (its
   // prologue then overlaps our tail), and wait for the PREVIOUS launch -- which may have written this very state --
   // before the first byte of state is touched.  Without the launch attribute both instructions are no-ops.
+  // A CHAINED launch skips the grid-wide wait: the caller vouches for the side inputs, and the state is ordered chunk
+  // by chunk through io.chunk_epoch (acquire before a chunk's TMA loads, release after its stores), so this grid's
+  // first chunks run on the SMs the previous grid has already left while that grid's last chunks are still computing.
+  const bool chained = (k.flags & FPV_F_CHAINED) != 0;
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (!chained) asm volatile("griddepcontrol.wait;" ::: "memory");
 
   const long long n_chunks = (io.n + CHUNK - 1) / CHUNK;
   const long long my_warp = (long long)blockIdx.x * WARPS + warp;
@@ -556,6 +569,16 @@ __global__ void __launch_bounds__(THREADS, MINB) drone_step_tma_kernel(const __g
     const unsigned count = (unsigned)(rem < (long long)CHUNK ? rem : (long long)CHUNK);
     const unsigned bytes = count * (unsigned)sizeof(float4);
     float4* dst = ring + (size_t)slot * ROWS * CHUNK;
+    if (chained) {  // the previous step of THIS chunk must have been stored (possibly by a grid that is still running)
+      const unsigned* f = io.chunk_epoch + chunk;
+      unsigned v;
+      for (;;) {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+        if (v == io.epoch) break;
+        __nanosleep(64);
+      }
+      asm volatile("fence.proxy.async.global;" ::: "memory");  // generic-proxy stores -> async-proxy (TMA) loads
+    }
     mbar_expect_tx(&full[slot], bytes * ROWS);
 #pragma unroll
     for (int p = 0; p < FPV_DRONE_PLANES; ++p) tma_load_1d(dst + p * CHUNK, io.state + p * io.stride + first, bytes, &full[slot]);
@@ -603,6 +626,7 @@ __global__ void __launch_bounds__(THREADS, MINB) drone_step_tma_kernel(const __g
   long long ph_wait = 0, ph_read = 0, ph_tile = 0;
   const long long c_begin = clock64();
 #endif
+  long long pending = -1;   // chunk whose stores are issued but whose epoch is not published yet
   for (int it = 0; cur < n_chunks; ++it) {
     const int slot = it & 1;
 #ifdef FPV_TRACE_PHASES
@@ -633,12 +657,26 @@ __global__ void __launch_bounds__(THREADS, MINB) drone_step_tma_kernel(const __g
 #ifdef FPV_TRACE_PHASES
     const long long c_c = clock64();
 #endif
-    if (base < io.n) drone_tile<V, ANG, false, 32>(k, io, lut_s, q, act, ei, base, st, wind_on);
+    // Publishing a chunk's epoch needs its stores to be performed first (a release waits for them).  Doing that right
+    // after the stores would stall the warp for a full store round trip per chunk, so the flag of chunk i goes out in
+    // the middle of chunk i+1 -- after that chunk's substep loop, when the stores are long done and the release is
+    // free.  Order: all lanes' stores of chunk i -> the __syncwarp() above (iteration i+1) -> the leader's release.
+    auto publish_pending = [&]() {
+      if (pending >= 0 && leader)
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(io.chunk_epoch + pending), "r"(io.epoch + 1u) : "memory");
+    };
+    if (base < io.n) drone_tile<V, ANG, false, 32>(k, io, lut_s, q, act, ei, base, st, wind_on, publish_pending);
+    pending = io.chunk_epoch ? cur : -1;
 #ifdef FPV_TRACE_PHASES
     const long long c_d = clock64();
     ph_wait += c_b - c_a; ph_read += c_c - c_b; ph_tile += c_d - c_c;
 #endif
     cur = nxt;
+  }
+  if (pending >= 0) {  // the warp's last chunk
+    __syncwarp();
+    if (leader)
+      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(io.chunk_epoch + pending), "r"(io.epoch + 1u) : "memory");
   }
   if (dynamic && leader) {
     const unsigned finished = atomicAdd(io.work + 1, 1u);

@@ -110,8 +110,13 @@ bool launch_drone_tma(const DroneK& k, const DroneIO& io, cudaStream_t st) {
   const long long wave = (long long)sm_count_of_current_device() * occ_used;
   const unsigned grid = (unsigned)(tiles < wave ? tiles : wave);
   static const int no_pdl = tune_env("FPV_TUNE_NOPDL", 0);
+  // FPV_F_CHAINED is honoured only by full persistent grids: such a grid cannot become fully resident before the
+  // previous one has left the SMs, so at most two launches ever overlap (which is what the two pull-counter pairs and
+  // the forward-progress argument of the per-chunk waits rely on).  Anything else keeps plain stream order.
+  DroneK kk = k;
+  if ((kk.flags & FPV_F_CHAINED) && (no_pdl || (long long)grid != wave)) kk.flags &= ~FPV_F_CHAINED;
   if (no_pdl) {
-    kern<<<grid, kThreads, smem, st>>>(k, io, lut_bytes);
+    kern<<<grid, kThreads, smem, st>>>(kk, io, lut_bytes);
     return true;
   }
   // programmatic dependent launch: this grid may become resident while the previous one on the stream drains
@@ -125,18 +130,38 @@ bool launch_drone_tma(const DroneK& k, const DroneIO& io, cudaStream_t st) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaLaunchKernelEx(&cfg, kern, k, io, lut_bytes);
+  cudaLaunchKernelEx(&cfg, kern, kk, io, lut_bytes);
   return true;
+}
+
+__global__ void fill_u32_kernel(unsigned* p, long long n, unsigned v) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// Kernels without the per-chunk protocol run in plain stream order and publish all epochs afterwards.
+template <class V, int ANG, bool GENERAL>
+void launch_drone_plain(const DroneK& k, const DroneIO& io, cudaStream_t st) {
+  DroneK kk = k;
+  kk.flags &= ~FPV_F_CHAINED;
+  launch_drone<V, ANG, GENERAL>(kk, io, st);
+  if (io.chunk_epoch) {
+    const long long chunks = (io.n + 63) / 64;
+    fill_u32_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, st>>>(io.chunk_epoch, chunks, io.epoch + 1u);
+  }
 }
 
 template <class V, int ANG>
 void launch_drone_g(const DroneK& k, const DroneIO& io, bool general, cudaStream_t st) {
   static const int no_tma = tune_env("FPV_TUNE_NOTMA", 0);     // developer A/B switches, not part of the ABI
-  if (general) { launch_drone<V, ANG, true>(k, io, st); return; }
-  if (!no_tma) {
+  if (general) { launch_drone_plain<V, ANG, true>(k, io, st); return; }
+  if (!no_tma && fpv::Lane<V>::N == 2) {   // chunk_epoch is indexed by 64-env chunks = the packed kernel's warp-chunk
     if (launch_drone_tma<V, ANG, 2>(k, io, st)) return;
   }
-  launch_drone<V, ANG, false>(k, io, st);
+  if (!no_tma && !io.chunk_epoch) {
+    if (launch_drone_tma<V, ANG, 2>(k, io, st)) return;
+  }
+  launch_drone_plain<V, ANG, false>(k, io, st);
 }
 template <class V>
 void launch_drone_a(const DroneK& k, const DroneIO& io, int ang, bool general, cudaStream_t st) {
@@ -267,6 +292,12 @@ int fpv_drone_step(const fpv_drone_params_t* p, const fpv_drone_io_t* io, void* 
   // pulled chunks pay one atomic round trip per chunk: worth it once a chunk carries enough arithmetic to hide it
   static const int no_dyn = tune_env("FPV_TUNE_STATIC", 0);
   d.work = (no_dyn || p->substeps < 4) ? nullptr : (unsigned*)io->work;
+  d.chunk_epoch = (unsigned*)io->chunk_epoch;
+  d.epoch = io->epoch;
+  // two launches that overlap (FPV_F_CHAINED) must not share the pull counters: one pair per epoch parity
+  if (d.work && d.chunk_epoch) d.work += 2 * (io->epoch & 1u);
+  if ((p->flags & FPV_F_CHAINED) && !io->chunk_epoch)
+    return fail(FPV_EINVAL, "fpv_drone_step: FPV_F_CHAINED needs io.chunk_epoch");
   d.trace = (unsigned long long*)io->trace;
 
   // |rates| <= max_rates is an invariant of action2force (a convex mix of clipped commands), so the

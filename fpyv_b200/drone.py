@@ -96,7 +96,12 @@ class BatchedDrone:
         self._acc = torch.zeros((n, 4), dtype=torch.float32, device=dev)
         self._actions = torch.zeros((n, 4), dtype=torch.float32, device=dev)
         self._stats = torch.zeros(8, dtype=torch.float64, device=dev)
-        self._work = torch.zeros(2, dtype=torch.int32, device=dev)      # dynamic chunk counter (fpv_drone_io_t.work)
+        self._work = torch.zeros(4, dtype=torch.int32, device=dev)      # dynamic chunk counters (fpv_drone_io_t.work)
+        # chained launches (fpv_drone_io_t.chunk_epoch): one step count per 64-env chunk, and the host's copy of it
+        self._chunk_epoch = torch.zeros((n + 63) // 64, dtype=torch.int32, device=dev)
+        self._chunk_epoch_ptr = self._chunk_epoch.data_ptr()
+        self._epoch = 0
+        self._chain_ready = False    # True while the last writer of the state was step() itself
         self._lut = None
         if thrust_lut:
             self._lut = torch.from_numpy(config.thrust_table(c, int(thrust_lut), lut_source)).to(dev)
@@ -168,6 +173,7 @@ class BatchedDrone:
         m = None if mask is None else _as_dev(mask, dev, (n,), torch.uint8)
         _lib.check(self._lib.fpv_drone_set_rotation(_lib.ptr(self._state), n, self._stride, _lib.ptr(R), _lib.ptr(m),
                                                     _lib.current_stream(dev)))
+        self._chain_ready = False
 
     @property
     def prev_rates(self):
@@ -229,19 +235,36 @@ class BatchedDrone:
                 sel = m.bool()
                 self._reset_state[:, :n][:, sel] = self._state[:, :n][:, sel]
         self._is_reset = True
+        self._chain_ready = False
 
     def read_sticks(self):
         """components.py:250-253 on the batched joystick source."""
         return self.rc.read_actions()
 
     def step(self, action, wind_velocity_vector=None, object_list=None, rotation_matrix=None, thrust_force=None,
-             return_obs: bool = True):
+             return_obs: bool = True, chained: bool = False):
         """Drone.step (components.py:220-248) for every env: `substeps` reference steps with `action` held.
         action: [n,4] (roll, pitch, yaw, throttle) in [-1,1], or None to poll the joystick source.
-        Returns (R^T [n,3,3], euler_matrix(*rates) [n,3,3], R @ acc [n,3]) when return_obs."""
+        Returns (R^T [n,3,3], euler_matrix(*rates) [n,3,3], R @ acc [n,3]) when return_obs.
+
+        chained=True (open-loop rollouts: the actions of several steps exist up front) lets this launch start on the
+        SMs the previous launch on the stream has already left instead of waiting for its last chunk
+        (FPV_F_CHAINED, fpv_api.h).  The caller promises that `action` was complete before the PREVIOUS launch on
+        this stream was enqueued and that nothing but step() touched the state since the last step; it is ignored
+        after reset()/set_*() and on the general (obstacle / override) path."""
         if not self._is_reset:
             raise RuntimeError("call reset() before step() (the reference's state is None until reset)")
         n, dev = self.num_envs, self.device
+        # chunk epochs are published only by launches that ask for chaining (the first one of a run is still plain
+        # stream order: it has nothing published to wait on)
+        chain_now = chained and self._chain_ready
+        self._chain_ready = chained
+        if chained:
+            self._io.epoch = self._epoch & 0xFFFFFFFF
+            self._epoch += 1
+            self._io.chunk_epoch = self._chunk_epoch_ptr
+        else:
+            self._io.chunk_epoch = None
         # fast path (the RL inner loop): device float32 actions, nothing else changed since the last full call --
         # one pointer store and one C call, no allocation (so it can be captured in a CUDA graph)
         if (self._fast_ok and wind_velocity_vector is None and object_list is None and rotation_matrix is None
@@ -249,6 +272,7 @@ class BatchedDrone:
                 and action.shape == self._act_shape and action.is_contiguous()):
             self._last_action = action
             self._io.actions = action.data_ptr()
+            self._p.flags = (self._flags | _lib.F_CHAINED) if chain_now else self._flags
             rc = self._step_fn(self._p_ref, self._io_ref, torch.cuda.current_stream(dev).cuda_stream)
             if rc:
                 _lib.check(rc)

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define FPV_ABI_VERSION 8
+#define FPV_ABI_VERSION 9
 
 /* error codes */
 #define FPV_OK 0
@@ -62,6 +62,13 @@ extern "C" {
                                    reference's own behaviour: done is reported, integration goes on */
 #define FPV_F_THRUST_LUT 8u     /* throttle->thrust through io.lut (shared-memory table, linear
                                    interpolation) instead of the cubic                          */
+#define FPV_F_CHAINED 64u       /* this launch may overlap the END of the previous launch on the stream: it does not
+                                   wait for the previous grid (programmatic dependent launch) and orders its accesses
+                                   to `state` chunk by chunk through io.chunk_epoch instead.  The caller promises that
+                                   (1) every input other than `state` (actions, lut, wind, reset_state) is not being
+                                   written by work that may still be running, and (2) the last writer of `state` was a
+                                   fpv_drone_step launch with the same chunk_epoch and epoch - 1.  Ignored (plain stream
+                                   order) whenever the launch cannot honour it.                                   */
 #define FPV_F_SCALAR 32u        /* one env per thread (plain FP32 instructions) instead of the
                                    default two envs per thread on packed f32x2 instructions     */
 
@@ -123,9 +130,14 @@ typedef struct fpv_drone_io {
   const float* override_thrust; /* float[n]: thrust_force of the same call */
   const fpv_object_t* objects; /* HOST pointer, params.n_objects entries, or NULL                  */
   fpv_stats_t* stats;       /* device, may be NULL                                                */
-  void* work;               /* device uint32[2], zeroed ONCE by the caller: chunk counter for dynamic load balancing
+  void* work;               /* device uint32[4], zeroed ONCE by the caller: chunk counter for dynamic load balancing
                                (warps pull the next 64-env chunk with one atomic); every launch leaves it zeroed.
                                NULL = static round-robin distribution.                                     */
+  void* chunk_epoch;        /* device uint32[ceil(n / 64)], zeroed once by the caller, or NULL.  After the launch
+                               every entry holds epoch + 1 (published chunk by chunk as the chunk's state is stored);
+                               with FPV_F_CHAINED chunk c is loaded only once chunk_epoch[c] == epoch.            */
+  uint32_t epoch;           /* number of fpv_drone_step launches already applied to `state` through chunk_epoch  */
+  uint32_t reserved0;
   void* trace;              /* developer profiling hook: device uint64[3 * warps] receiving per-warp
                                (start ns, end ns, SM id) of the hot kernel; NULL in production           */
 } fpv_drone_io_t;

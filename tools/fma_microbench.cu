@@ -6,7 +6,43 @@
 template <int MODE>
 __global__ void __launch_bounds__(256) bench(float* out, int iters, float a, float b) {
   // 8 independent accumulator chains per thread
-  if (MODE == 0) {  // scalar FFMA, 3 register operands
+  if (MODE == 6 || MODE == 7 || MODE == 8) {  // scalar ops with distinct rotating operands (no reuse-cache help)
+    float x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = threadIdx.x * 0.001f + i + a;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (MODE == 6) asm volatile("fma.rn.f32 %0, %1, %2, %0;" : "+f"(x[i]) : "f"(x[(i + 1) & 7]), "f"(x[(i + 2) & 7]));
+        if (MODE == 7) asm volatile("mul.rn.f32 %0, %1, %2;" : "=f"(x[i]) : "f"(x[(i + 1) & 7]), "f"(x[(i + 2) & 7]));
+        if (MODE == 8) asm volatile("fma.rn.f32 %0, %1, %2, %3;" : "=f"(x[i]) : "f"(x[(i + 1) & 7]), "f"(x[(i + 2) & 7]), "f"(x[(i + 3) & 7]));
+      }
+    }
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += x[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+  } else if (MODE == 9) {  // hybrid: one packed 2-operand FMUL2 + two scalar 3-operand FFMA per group
+    unsigned long long x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) asm("mov.b64 %0, {%1, %2};" : "=l"(x[i]) : "f"(threadIdx.x * 0.001f + i), "f"(threadIdx.x * 0.002f + i + a));
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float l0, h0, l1, h1, l2, h2;
+        asm volatile("mov.b64 {%0, %1}, %2;" : "=f"(l0), "=f"(h0) : "l"(x[i]));
+        asm volatile("mov.b64 {%0, %1}, %2;" : "=f"(l1), "=f"(h1) : "l"(x[(i + 1) & 7]));
+        asm volatile("mov.b64 {%0, %1}, %2;" : "=f"(l2), "=f"(h2) : "l"(x[(i + 2) & 7]));
+        asm volatile("fma.rn.f32 %0, %1, %2, %0;" : "+f"(l0) : "f"(l1), "f"(l2));
+        asm volatile("fma.rn.f32 %0, %1, %2, %0;" : "+f"(h0) : "f"(h1), "f"(h2));
+        asm volatile("mov.b64 %0, {%1, %2};" : "=l"(x[i]) : "f"(l0), "f"(h0));
+      }
+    }
+    unsigned long long s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s ^= x[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = (float)(s & 0xffff);
+  } else if (MODE == 0) {  // scalar FFMA, 3 register operands
     float x[8], y = a, z = b;
 #pragma unroll
     for (int i = 0; i < 8; ++i) x[i] = threadIdx.x * 0.001f + i;
@@ -78,5 +114,9 @@ int main() {
   run<3>("FADD2  (packed, 2 reg-pair operands)", 2, d, p.multiProcessorCount, clk);
   run<4>("FFMA2 + LOP3x2 interleaved", 2, d, p.multiProcessorCount, clk);
   run<5>("FFMA2  (3 distinct rotating operands)", 2, d, p.multiProcessorCount, clk);
+  run<6>("FFMA   (scalar, 3 distinct rotating, acc)", 1, d, p.multiProcessorCount, clk);
+  run<7>("FMUL   (scalar, 2 distinct rotating)", 1, d, p.multiProcessorCount, clk);
+  run<8>("FFMA   (scalar, 3 distinct rotating, new dst)", 1, d, p.multiProcessorCount, clk);
+  run<9>("FFMA x2 on halves of rotating pairs (2/grp)", 2, d, p.multiProcessorCount, clk);
   return 0;
 }

@@ -12,7 +12,7 @@ for K in (8, 1, 32):
     fl = torch.ones(64 << 20, dtype=torch.float32, device=dev)
     for _ in range(5): d.step(a, return_obs=False)
     W = 592 * 4
-    d._trace = torch.zeros(4 * W, dtype=torch.int64, device=dev)
+    d._trace = torch.zeros(4 * W, dtype=torch.int64, device=dev); d._fast_ok = False
     fl.sum(); torch.cuda.synchronize()
     d.step(a, return_obs=False); torch.cuda.synchronize()
     t = d._trace.cpu().numpy()

@@ -3,7 +3,7 @@ import sys, torch, numpy as np
 sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 from fpyv_b200 import BatchedDrone
 dev='cuda:0'; n=1<<20
-for K in (8, 1):
+for K in (8,):
     d = BatchedDrone(None, num_envs=n, device=dev, substeps=K, dt=1e-3, auto_reset=True, thrust_lut=2049)
     g = torch.Generator(device=dev).manual_seed(1)
     pos = torch.randn(n, 3, device=dev, generator=g) * 5; pos[:, 2] = 0.05 + torch.rand(n, device=dev, generator=g) * 2.95
@@ -11,7 +11,7 @@ for K in (8, 1):
     a = torch.rand(n, 4, device=dev, generator=g) * 2 - 1
     fl = torch.ones(64 << 20, dtype=torch.float32, device=dev)
     for _ in range(5): d.step(a, return_obs=False)
-    d._trace = torch.zeros(3 * 4 * 1024, dtype=torch.int64, device=dev)
+    d._trace = torch.zeros(3 * 4 * 1024, dtype=torch.int64, device=dev); d._fast_ok = False
     fl.sum(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); d.step(a, return_obs=False); e1.record(); torch.cuda.synchronize()
@@ -25,6 +25,7 @@ for K in (8, 1):
     for s_, e_, m_ in zip(st, en, sm): per.setdefault(int(m_), []).append((s_, e_))
     cnt = np.array([len(v) for v in per.values()])
     print(f"   SMs {len(per)}; warps/SM min {cnt.min()} max {cnt.max()}; per-SM last end: min {min(max(e for _,e in v) for v in per.values()):.1f} max {max(max(e for _,e in v) for v in per.values()):.1f}")
+    print(f"   warp-residency utilisation: {(en-st).sum()/(en.max()*len(t)):.3f} (sum of warp durations / (last end x warps))")
     hist, edges = np.histogram(en, bins=12)
     print("   end histogram:", list(zip(np.round(edges[:-1],1), hist)))
     hist, edges = np.histogram(st, bins=8)
