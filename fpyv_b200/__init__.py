@@ -5,7 +5,7 @@ from . import config
 from ._lib import FpvError
 
 __all__ = ["config", "FpvError", "BatchedDrone", "Drone", "BatchedRacer", "Racer", "Joystick", "Ground",
-           "Cylinder", "Target", "Gate"]
+           "Cylinder", "Target", "Gate", "BatchedCamera", "World", "Autopilot", "PID"]
 
 
 def __getattr__(name):
@@ -21,4 +21,10 @@ def __getattr__(name):
     if name in ("Ground", "Cylinder", "Target", "Gate", "Trail"):
         from . import objects
         return getattr(objects, name)
+    if name in ("BatchedCamera", "World"):
+        from . import camera
+        return getattr(camera, name)
+    if name in ("Autopilot", "PID"):
+        from . import autopilot
+        return getattr(autopilot, name)
     raise AttributeError(name)

@@ -16,7 +16,8 @@ OBJ_SPHERE, OBJ_CYLINDER = 1, 2
 MAX_OBJECTS = 16
 DRONE_PLANES, RACER_PLANES = 4, 7
 EXPORTS = ("fpv_abi_version", "fpv_last_error", "fpv_sizeof", "fpv_device_info", "fpv_drone_reset",
-           "fpv_drone_step", "fpv_drone_observe", "fpv_drone_get_rotation", "fpv_drone_set_rotation", "fpv_matrix_to_quat", "fpv_sticks_to_actions", "fpv_racer_reset", "fpv_racer_step", "fpv_gate_env_reset", "fpv_gate_env_step")
+           "fpv_drone_step", "fpv_drone_observe", "fpv_drone_get_rotation", "fpv_drone_set_rotation", "fpv_matrix_to_quat", "fpv_sticks_to_actions", "fpv_racer_reset", "fpv_racer_step", "fpv_gate_env_reset", "fpv_gate_env_step",
+           "fpv_camera_update", "fpv_camera_render", "fpv_camera_target_pixel", "fpv_camera_rays", "fpv_autopilot")
 
 
 class FpvError(RuntimeError):
@@ -75,7 +76,22 @@ class GateEnvParams(C.Structure):
                 ("w_gate", C.c_float), ("w_progress", C.c_float), ("w_crash", C.c_float), ("gates", Gate * MAX_GATES)]
 
 
-_STRUCTS = (DroneParams, DroneIO, Object, Stats, StickCalib, RacerParams, GateEnvParams)
+CAM_MAX_OBJECTS = 64
+
+
+class CameraParams(C.Structure):
+    _fields_ = [("rel_rot", C.c_double * 9), ("rel_pos", C.c_double * 3), ("fx", C.c_double), ("fy", C.c_double),
+                ("cx", C.c_double), ("cy", C.c_double), ("width", C.c_int32), ("height", C.c_int32)]
+
+
+class AutopilotParams(C.Structure):
+    _fields_ = [(k, C.c_double) for k in ("mass", "dt", "virtual_drag_coef", "virtual_lift_coef", "tof_effective_dist",
+                                          "keep_distance", "uwb_max_range", "kP", "kI", "kD", "integral_clip",
+                                          "min_output", "max_output", "derivative_transition_rate")] + \
+               [("ref_frame", C.c_int32), ("mode", C.c_int32)]
+
+
+_STRUCTS = (DroneParams, DroneIO, Object, Stats, StickCalib, RacerParams, GateEnvParams, CameraParams, AutopilotParams)
 _lib = None
 
 
@@ -112,6 +128,12 @@ def load():
                                        C.c_void_p, C.c_void_p]
     lib.fpv_gate_env_step.argtypes = [C.POINTER(GateEnvParams), C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    P, V, I64, I32, D = C.POINTER, C.c_void_p, C.c_int64, C.c_int32, C.c_double
+    lib.fpv_camera_update.argtypes = [P(CameraParams), V, I64, I64, V, V]
+    lib.fpv_camera_render.argtypes = [P(CameraParams), V, I64, V, I32, V, I32, V, D, V, V, V]
+    lib.fpv_camera_target_pixel.argtypes = [P(CameraParams), V, I64, V, I32, V, I32, V, D, V, V, V]
+    lib.fpv_camera_rays.argtypes = [P(CameraParams), V, I64, V, I32, V, V]
+    lib.fpv_autopilot.argtypes = [P(AutopilotParams), P(CameraParams), V, I64, I64, V, V, V, V, V, V, V, V, V]
     v = lib.fpv_abi_version()
     if v != ABI_VERSION:
         raise ImportError(f"{LIB_PATH} has ABI version {v}, this package needs {ABI_VERSION}; rebuild it")

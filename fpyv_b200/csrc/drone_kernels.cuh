@@ -135,10 +135,12 @@ __device__ __forceinline__ typename Lane<V>::Mask drone_substeps(const DroneK& k
     h0 = vfma(h0, omr, c0); h1 = vfma(h1, omr, c1); h2 = vfma(h2, omr, c2);
     V th = vfma(s.pt, omt, tt);
     s.pt = th;
-    if (GENERAL && has_override) {  // components.py:230-232
+    if (GENERAL && has_override) {  // components.py:230-232; a NaN thrust leaves that env on its stick command
       const V r2 = S<V>(1.41421356237f);
-      s.qw = oqw * r2; s.qx = oqx * r2; s.qy = oqy * r2; s.qz = oqz * r2;
-      th = o_thrust;
+      const M ovr = vle(o_thrust, o_thrust);
+      s.qw = vsel(ovr, oqw * r2, s.qw); s.qx = vsel(ovr, oqx * r2, s.qx);
+      s.qy = vsel(ovr, oqy * r2, s.qy); s.qz = vsel(ovr, oqz * r2, s.qz);
+      th = vsel(ovr, o_thrust, th);
     }
     // ---- the entries of R(q) this step reads: columns 1 and 2 and R[2][0]  (helper_functions.py:100-117).
     //      The loop carries s = sqrt(2) q, so every "2 q_a q_b" of the matrix is the plain product s_a s_b

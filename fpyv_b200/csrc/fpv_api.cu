@@ -10,6 +10,7 @@
 #include "drone_kernels.cuh"
 #include "misc_kernels.cuh"
 #include "env_kernels.cuh"
+#include "chase_kernels.cuh"
 
 namespace {
 
@@ -189,6 +190,8 @@ int fpv_sizeof(int which) {
     case 4: return (int)sizeof(fpv_stick_calib_t);
     case 5: return (int)sizeof(fpv_racer_params_t);
     case 6: return (int)sizeof(fpv_gate_env_params_t);
+    case 7: return (int)sizeof(fpv_camera_params_t);
+    case 8: return (int)sizeof(fpv_autopilot_params_t);
     default: return -1;
   }
 }
@@ -452,6 +455,116 @@ int fpv_gate_env_step(const fpv_gate_env_params_t* p, const void* state, int64_t
       *p, (const float4*)state, n, plane_stride, agent_done, (float2*)prev, progress, agent_reward, env_reward, env_done,
       (float4*)obs, stats);
   return check_launch("fpv_gate_env_step");
+}
+
+namespace {
+int make_cam(const fpv_camera_params_t* c, fpv::CamK& k, const char* who) {
+  if (!c) return fail(FPV_EINVAL, "%s: null camera params", who);
+  if (c->width < 1 || c->height < 1) return fail(FPV_EINVAL, "%s: bad resolution %dx%d", who, c->width, c->height);
+  if (!(c->fx != 0.0) || !(c->fy != 0.0)) return fail(FPV_EINVAL, "%s: focal length must be non-zero", who);
+  for (int i = 0; i < 9; ++i) k.rel_rot[i] = c->rel_rot[i];
+  for (int i = 0; i < 3; ++i) k.rel_pos[i] = c->rel_pos[i];
+  k.fx = c->fx; k.fy = c->fy; k.cx = c->cx; k.cy = c->cy;
+  k.W = c->width; k.H = c->height;
+  return FPV_OK;
+}
+int check_world(const double* pose, int64_t n, const double* points, int32_t n_points, const double* boxes,
+                int32_t n_objects, const char* who) {
+  if (!pose || !points || !boxes) return fail(FPV_EINVAL, "%s: null pointer", who);
+  if (n < 0 || n_points < 0) return fail(FPV_EINVAL, "%s: bad n / n_points", who);
+  if (n_objects < 1 || n_objects > FPV_CAM_MAX_OBJECTS)
+    return fail(FPV_EINVAL, "%s: n_objects=%d out of [1,%d]", who, n_objects, FPV_CAM_MAX_OBJECTS);
+  if (!aligned16(points)) return fail(FPV_EINVAL, "%s: points must be 16-byte aligned", who);
+  return FPV_OK;
+}
+}  // namespace
+
+int fpv_camera_update(const fpv_camera_params_t* cam, const void* state, int64_t n, int64_t plane_stride, double* pose,
+                      void* stream) {
+  fpv::CamK k;
+  if (int rc = make_cam(cam, k, "fpv_camera_update")) return rc;
+  if (!state || !pose) return fail(FPV_EINVAL, "fpv_camera_update: null pointer");
+  if (n < 0 || plane_stride < n || !aligned16(state)) return fail(FPV_EINVAL, "fpv_camera_update: bad n/stride/alignment");
+  if (n == 0) return FPV_OK;
+  fpv::camera_update_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(k, (const float4*)state, n, plane_stride, pose);
+  return check_launch("fpv_camera_update");
+}
+
+int fpv_camera_render(const fpv_camera_params_t* cam, const double* pose, int64_t n, const double* points,
+                      int32_t n_points, const double* boxes, int32_t n_objects, const double* obj_offset, double max_depth,
+                      uint8_t* keep, uint8_t* image, void* stream) {
+  fpv::CamK k;
+  if (int rc = make_cam(cam, k, "fpv_camera_render")) return rc;
+  if (int rc = check_world(pose, n, points, n_points, boxes, n_objects, "fpv_camera_render")) return rc;
+  if (!keep || !image) return fail(FPV_EINVAL, "fpv_camera_render: null keep / image");
+  if (((int64_t)k.W * k.H) % 4 != 0 || (reinterpret_cast<uintptr_t>(image) & 3u))
+    return fail(FPV_EINVAL, "fpv_camera_render: width*height must be a multiple of 4 and the image 4-byte aligned");
+  if (n > 65535) return fail(FPV_EINVAL, "fpv_camera_render: at most 65535 cameras per call (got %lld)", (long long)n);
+  if (n == 0) return FPV_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(image, 0, (size_t)n * k.W * k.H, st);
+  const long long no = (long long)n * n_objects;
+  fpv::camera_prune_kernel<<<(unsigned)((no + 127) / 128), 128, 0, st>>>(k, pose, n, boxes, n_objects, obj_offset, keep);
+  if (n_points > 0) {
+    dim3 grid((unsigned)((n_points + 255) / 256), (unsigned)n);
+    fpv::camera_splat_kernel<<<grid, 256, 0, st>>>(k, pose, (const double4*)points, n_points, n_objects, obj_offset, keep,
+                                                   max_depth, image);
+  }
+  return check_launch("fpv_camera_render");
+}
+
+int fpv_camera_target_pixel(const fpv_camera_params_t* cam, const double* pose, int64_t n, const double* points,
+                            int32_t n_points, const double* boxes, int32_t n_objects, const double* obj_offset,
+                            double max_depth, double* pixel, uint8_t* seen, void* stream) {
+  fpv::CamK k;
+  if (int rc = make_cam(cam, k, "fpv_camera_target_pixel")) return rc;
+  if (int rc = check_world(pose, n, points, n_points, boxes, n_objects, "fpv_camera_target_pixel")) return rc;
+  if (!pixel || !seen) return fail(FPV_EINVAL, "fpv_camera_target_pixel: null pixel / seen");
+  if (!(max_depth > 0.0)) return fail(FPV_EINVAL, "fpv_camera_target_pixel: max_depth must be positive");
+  const size_t smem = (((size_t)k.W * k.H + 31) / 32) * sizeof(unsigned);
+  if (smem > 200 * 1024) return fail(FPV_EINVAL, "fpv_camera_target_pixel: %dx%d frame bitmap does not fit in shared memory", k.W, k.H);
+  if (n == 0) return FPV_OK;
+  static size_t attr_set = 0;
+  if (smem > 48 * 1024 && smem > attr_set) {
+    cudaFuncSetAttribute(fpv::camera_target_pixel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_set = smem;
+  }
+  fpv::camera_target_pixel_kernel<<<(unsigned)n, 256, smem, (cudaStream_t)stream>>>(
+      k, pose, (const double4*)points, n_points, n_objects, boxes, obj_offset, max_depth, pixel, seen);
+  return check_launch("fpv_camera_target_pixel");
+}
+
+int fpv_camera_rays(const fpv_camera_params_t* cam, const double* pose, int64_t n, const double* pixel, int32_t frame,
+                    double* dir, void* stream) {
+  fpv::CamK k;
+  if (int rc = make_cam(cam, k, "fpv_camera_rays")) return rc;
+  if (!pose || !pixel || !dir) return fail(FPV_EINVAL, "fpv_camera_rays: null pointer");
+  if (frame < 0 || frame > 2) return fail(FPV_EINVAL, "fpv_camera_rays: ref_frame must be world, drone or camera");
+  if (n < 0) return fail(FPV_EINVAL, "fpv_camera_rays: bad n");
+  if (n == 0) return FPV_OK;
+  fpv::camera_rays_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(k, pose, n, pixel, frame, dir);
+  return check_launch("fpv_camera_rays");
+}
+
+int fpv_autopilot(const fpv_autopilot_params_t* ap, const fpv_camera_params_t* cam, const void* state, int64_t n,
+                  int64_t plane_stride, const double* pixel, const uint8_t* seen, const double* target_pos,
+                  const double* target_radius, double* pid, float* rot, void* quat, float* force, void* stream) {
+  fpv::CamK k;
+  if (int rc = make_cam(cam, k, "fpv_autopilot")) return rc;
+  if (!ap || !state || !pixel || !target_pos || !target_radius || !pid) return fail(FPV_EINVAL, "fpv_autopilot: null pointer");
+  if (n < 0 || plane_stride < n || !aligned16(state) || !aligned16(quat)) return fail(FPV_EINVAL, "fpv_autopilot: bad n/stride/alignment");
+  if (ap->ref_frame < 0 || ap->ref_frame > 1) return fail(FPV_EINVAL, "fpv_autopilot: Unknown reference frame");
+  if (ap->mode < 0 || ap->mode > 1) return fail(FPV_EINVAL, "fpv_autopilot: Unknown mode");
+  if (!(ap->dt > 0.0)) return fail(FPV_EINVAL, "fpv_autopilot: dt must be positive");
+  fpv::AutopilotK a;
+  a.mass = ap->mass; a.dt = ap->dt; a.vdrag_coef = ap->virtual_drag_coef; a.vlift_coef = ap->virtual_lift_coef;
+  a.tof_dist = ap->tof_effective_dist; a.keep_distance = ap->keep_distance; a.uwb_max = ap->uwb_max_range;
+  a.kP = ap->kP; a.kI = ap->kI; a.kD = ap->kD; a.integral_clip = ap->integral_clip; a.min_out = ap->min_output;
+  a.max_out = ap->max_output; a.dtr = ap->derivative_transition_rate; a.ref_frame = ap->ref_frame; a.mode = ap->mode;
+  if (n == 0) return FPV_OK;
+  fpv::autopilot_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      a, k, (const float4*)state, n, plane_stride, pixel, seen, target_pos, target_radius, pid, rot, (float4*)quat, force);
+  return check_launch("fpv_autopilot");
 }
 
 }  // extern "C"

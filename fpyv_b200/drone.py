@@ -306,9 +306,12 @@ class BatchedDrone:
         if rotation_matrix is not None:
             if thrust_force is None:
                 raise ValueError("rotation_matrix override needs thrust_force (components.py:230-232)")
-            R = _as_dev(rotation_matrix, dev, (n, 3, 3))
-            ovr_q = torch.empty((n, 4), dtype=torch.float32, device=dev)
-            _lib.check(self._lib.fpv_matrix_to_quat(_lib.ptr(R), n, _lib.ptr(ovr_q), _lib.current_stream(dev)))
+            if isinstance(rotation_matrix, torch.Tensor) and rotation_matrix.shape == (n, 4):
+                ovr_q = _as_dev(rotation_matrix, dev, (n, 4))      # already a quaternion (Autopilot(as_quaternion=True))
+            else:
+                R = _as_dev(rotation_matrix, dev, (n, 3, 3))
+                ovr_q = torch.empty((n, 4), dtype=torch.float32, device=dev)
+                _lib.check(self._lib.fpv_matrix_to_quat(_lib.ptr(R), n, _lib.ptr(ovr_q), _lib.current_stream(dev)))
             ovr_t = _as_dev(thrust_force, dev, (n,))
         io.state, io.n, io.plane_stride = self._state.data_ptr(), n, self._stride
         io.actions = act.data_ptr()

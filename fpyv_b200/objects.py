@@ -9,42 +9,137 @@ import numpy as np
 from . import _lib
 
 
-class Ground:
-    """Plane z = 0, normal +z (components.py:674-680)."""
+def _bbox3d(points):
+    """helper_functions.py:120-136: the 8 corners of the tight axis-aligned box around `points`."""
+    lo, hi = points.min(axis=0), points.max(axis=0)
+    box = np.zeros((8, 3))
+    box[:4, 0], box[4:, 0] = lo[0], hi[0]
+    box[::2, 1], box[1::2, 1] = lo[1], hi[1]
+    box[[0, 1, 4, 5], 2], box[[2, 3, 6, 7], 2] = lo[2], hi[2]
+    return box
 
-    def __init__(self, size=None, resolution=None, random=False):
+
+def icosphere_vertices(nu=1):
+    """Vertices of a geodesic icosahedron of subdivision frequency nu (10 nu^2 + 2 points on the unit sphere) -- the
+    shape `icosphere.icosphere(nu)` gives the reference's Target (components.py:761); vertex order is ours."""
+    t = (1.0 + 5.0 ** 0.5) / 2.0
+    v = np.array([[-1, t, 0], [1, t, 0], [-1, -t, 0], [1, -t, 0], [0, -1, t], [0, 1, t], [0, -1, -t], [0, 1, -t],
+                  [t, 0, -1], [t, 0, 1], [-t, 0, -1], [-t, 0, 1]], dtype=np.float64)
+    f = [(0, 11, 5), (0, 5, 1), (0, 1, 7), (0, 7, 10), (0, 10, 11), (1, 5, 9), (5, 11, 4), (11, 10, 2), (10, 7, 6),
+         (7, 1, 8), (3, 9, 4), (3, 4, 2), (3, 2, 6), (3, 6, 8), (3, 8, 9), (4, 9, 5), (2, 4, 11), (6, 2, 10), (8, 6, 7),
+         (9, 8, 1)]
+    pts = []
+    for a, b, c in f:
+        for i in range(nu + 1):
+            for j in range(nu + 1 - i):
+                pts.append((v[a] * (nu - i - j) + v[b] * i + v[c] * j) / nu)
+    pts = np.array(pts)
+    pts /= np.linalg.norm(pts, axis=1, keepdims=True)
+    _, idx = np.unique(np.round(pts, 9), axis=0, return_index=True)
+    return pts[np.sort(idx)]
+
+
+class Ground:
+    """Plane z = 0, normal +z (components.py:674-680), with the point cloud the camera sees (:655-667)."""
+
+    def __init__(self, size=None, resolution=None, random=False, rng=None):
         self.size, self.resolution = size, resolution
+        self.points = None
+        if size is not None and resolution is not None:
+            self.points = self.generate_points(random, rng)
+
+    def generate_points(self, random, rng=None):
+        if random:                                                          # components.py:656-660
+            rng = np.random.default_rng() if rng is None else rng
+            pts = self.size * (2 * rng.random((self.resolution ** 2, 3)) - 1)
+            pts[:, 2] /= self.size
+            pts[:, 2] *= 0.2
+            return pts
+        axis = np.linspace(-self.size / 2, self.size / 2, self.resolution)   # :662-664
+        x, y = np.meshgrid(axis, axis)
+        return np.vstack([x.reshape(-1), y.reshape(-1), np.zeros(x.shape).reshape(-1)]).T
 
     position = property(lambda self: np.zeros(3))
+    bbox3d = property(lambda self: _bbox3d(self.points))
 
 
 class Cylinder:
-    """Upright cylinder: base centre `position`, `radius`, `height` (components.py:685-729)."""
+    """Upright cylinder: base centre `position`, `radius`, `height` (components.py:685-729), with its surface
+    point cloud (:697-708) when the two resolutions are given."""
 
-    def __init__(self, position, radius, height, *_, **__):
+    def __init__(self, position, radius, height, angle_resolution=None, height_resolution=None, random=False, rng=None):
         assert radius > 0, "radius must be positive"
         assert height > 0, "height must be positive"
         self.position = np.asarray(position, dtype=np.float64)
         self.radius, self.height = float(radius), float(height)
+        self.angle_resolution, self.height_resolution = angle_resolution, height_resolution
+        self.points = None
+        if angle_resolution is not None and height_resolution is not None:
+            self.points = self.position + self.generate_points(random, rng)
+
+    def generate_points(self, random, rng=None):
+        if random:                                                          # components.py:698-700
+            rng = np.random.default_rng() if rng is None else rng
+            angles = rng.random((self.height_resolution, self.angle_resolution)) * 2 * np.pi
+            heights = rng.random((self.height_resolution, self.angle_resolution)) * self.height
+        else:                                                               # :702-704
+            angles = np.linspace(0, 2 * np.pi, self.angle_resolution)
+            heights = np.linspace(0, self.height, self.height_resolution)
+            angles, heights = np.meshgrid(angles, heights)
+        return np.vstack([self.radius * np.cos(angles).reshape(-1), self.radius * np.sin(angles).reshape(-1),
+                          heights.reshape(-1)]).T
+
+    bbox3d = property(lambda self: _bbox3d(self.points))
 
 
 class Target:
-    """Sphere: centre `position`, `radius` (components.py:757-777)."""
+    """Sphere: centre `position`, `radius` (components.py:757-777); `vertices` (unit-sphere points scaled by the
+    radius, :761-763) default to the geodesic icosahedron of frequency `nu`."""
 
-    def __init__(self, position, radius, *_, **__):
+    def __init__(self, position, radius, nu=None, path=None, vertices=None):
         self.position = np.asarray(position, dtype=np.float64)
         self.radius = float(radius)
+        self.vertices = None
+        if vertices is not None:
+            self.vertices = np.asarray(vertices, dtype=np.float64) * self.radius
+        elif nu is not None:
+            self.vertices = icosphere_vertices(int(nu)) * self.radius
+
+    @property
+    def points(self):                                                       # components.py:766-768
+        return None if self.vertices is None else self.vertices + self.position
+
+    bbox3d = property(lambda self: _bbox3d(self.points))
+
+    def calculate_distance(self, point):                                    # :773-774
+        return float(np.linalg.norm(np.asarray(point, dtype=np.float64) - self.position) - self.radius)
 
 
 class Gate:
-    """Gate plane (components.py:784-822).  Gates never collide (handle_collisions skips them,
-    components.py:203); the plane is used by the gate-race reward of fpyv_b200.env."""
+    """Gate plane (components.py:784-822) and its outline polygon (:787-805).  Gates never collide
+    (handle_collisions skips them, components.py:203); the plane is used by the gate-race reward of fpyv_b200.env."""
 
     def __init__(self, position, rotation_matrix, size, shape="rectangle", resolution=17):
         self.position = np.asarray(position, dtype=np.float64)
         self.rotation_matrix = np.asarray(rotation_matrix, dtype=np.float64)
         self.size = float(size)
         self.shape = shape
+        size = self.size
+        if shape == "rectangle":
+            corners = np.array([[0, -1, -1], [0, 1, -1], [0, 1, 1], [0, -1, 1]]) * size / 2
+        elif "circle" in shape:
+            coef = 1 if "half" in shape else 2
+            theta = np.linspace(0, coef * np.pi, resolution)
+            corners = np.vstack((np.zeros_like(theta), np.cos(theta) * size / coef, np.sin(theta) * size / coef)).T
+            if "half" in shape:
+                corners = corners - np.array([0, 0, size / 2])
+        else:
+            raise NotImplementedError
+        corners = (self.rotation_matrix @ corners.T).T + self.position
+        self.corners = np.vstack((corners, corners[0]))
+
+    points = property(lambda self: self.corners)
+    bbox3d = property(lambda self: _bbox3d(self.points))
 
     @property
     def normal(self):

@@ -127,7 +127,7 @@ typedef struct fpv_drone_io {
   const void* override_q;   /* float4[n]: rotation override as quaternion (w,x,y,z), see fpv_matrix_to_quat
                                (step(rotation_matrix=, thrust_force=), components.py:230-232); NULL = none.
                                Requires substeps == 1 and override_thrust. */
-  const float* override_thrust; /* float[n]: thrust_force of the same call */
+  const float* override_thrust; /* float[n]: thrust_force of the same call; NaN = no override for that env */
   const fpv_object_t* objects; /* HOST pointer, params.n_objects entries, or NULL                  */
   fpv_stats_t* stats;       /* device, may be NULL                                                */
   void* work;               /* device uint32[4], zeroed ONCE by the caller: chunk counter for dynamic load balancing
@@ -147,7 +147,8 @@ const char* fpv_last_error(void);
 
 /* sizeof() of the ABI structs as this library was compiled, so that a foreign-language binding can
  * verify its own struct layout: which = 0 fpv_drone_params_t, 1 fpv_drone_io_t, 2 fpv_object_t,
- * 3 fpv_stats_t, 4 fpv_stick_calib_t, 5 fpv_racer_params_t; -1 for an unknown index. */
+ * 3 fpv_stats_t, 4 fpv_stick_calib_t, 5 fpv_racer_params_t, 6 fpv_gate_env_params_t, 7 fpv_camera_params_t,
+ * 8 fpv_autopilot_params_t; -1 for an unknown index. */
 int fpv_sizeof(int which);
 
 /* Number of SMs / compute capability of `device`; used by hosts to size persistent launches. */
@@ -269,6 +270,68 @@ int fpv_gate_env_reset(const fpv_gate_env_params_t* params, const void* state, i
 int fpv_gate_env_step(const fpv_gate_env_params_t* params, const void* state, int64_t n_agents, int64_t plane_stride,
                       const uint8_t* agent_done, void* prev, int32_t* progress, float* agent_reward, float* env_reward,
                       uint8_t* env_done, float* obs, fpv_stats_t* stats, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Chase pipeline: the callers on either side of Drone.step in src/core/simulator.py:98-110 --
+ *   target_img = drone.camera.render_depth_image([target], max_depth)      components.py:614-629
+ *   pixel      = mean (x, y) of the non-zero pixels                        simulator.py:104-108
+ *   rot, f     = drone.calculate_needed_force_orientation(pixel, target)   components.py:258-304 (+ PID :43-54)
+ *   drone.step(action, wind, objects, rotation_matrix=rot, thrust_force=f) components.py:230-232
+ * Geometry here is float64 on the device (the splat produces integer pixel indices and bytes by truncation, which
+ * only reproduce the float64 reference if the projection is float64).  All arrays are device pointers.
+ * -------------------------------------------------------------------------------------------*/
+#define FPV_CAM_MAX_OBJECTS 64
+typedef struct fpv_camera_params {   /* Camera.__init__, components.py:450-470 */
+  double rel_rot[9];                 /* relative_rotation_matrix = WORLD2CAM^T Rx(pitch), row-major   :455 */
+  double rel_pos[3];                 /* position_relative_to_frame                                    :452 */
+  double fx, fy, cx, cy;             /* intrinsic_matrix(f, f, W/2, H/2)                              :469-470 */
+  int32_t width, height;             /* resolution [W, H] */
+} fpv_camera_params_t;
+
+typedef struct fpv_autopilot_params { /* Drone.__init__, components.py:96-97, :113-118, :143-145 */
+  double mass, dt;
+  double virtual_drag_coef, virtual_lift_coef, tof_effective_dist;  /* params["point_and_shoot"] */
+  double keep_distance, uwb_max_range;                              /* params["drone"]           */
+  double kP, kI, kD, integral_clip, min_output, max_output, derivative_transition_rate;  /* force_multiplier_pid */
+  int32_t ref_frame;                 /* 0 'world', 1 'drone'            components.py:270-279 */
+  int32_t mode;                      /* 0 'level', 1 'frontarget'       components.py:295-301 */
+} fpv_autopilot_params_t;
+
+/* Camera.update (components.py:501-503) for every env: pose[e] = { R_cam row-major [9], camera position [3] }. */
+int fpv_camera_update(const fpv_camera_params_t* cam, const void* state, int64_t n, int64_t plane_stride, double* pose,
+                      void* stream);
+
+/* Camera.render_depth_image (max_depth > 0, components.py:614-629) or Camera.render_image (max_depth <= 0, :601-612),
+ * including pruned_objects_list (:584-599), for n cameras looking at ONE shared world:
+ *   points: double[n_points][4] = x, y, z, object index; boxes: double[n_objects][6] = min xyz, max xyz of each object's
+ *   points (bbox3d, helper_functions.py:120-136); obj_offset: double[n][n_objects][3] per-env translation of each
+ *   object (moving / per-env targets) or NULL; keep: uint8[n][n_objects] scratch (receives the prune flags);
+ *   image: uint8[n][height][width] out (width*height must be a multiple of 4; zeroed by the call). */
+int fpv_camera_render(const fpv_camera_params_t* cam, const double* pose, int64_t n, const double* points,
+                      int32_t n_points, const double* boxes, int32_t n_objects, const double* obj_offset, double max_depth,
+                      uint8_t* keep, uint8_t* image, void* stream);
+
+/* simulator.py:104-108 fused with the target's depth image: pixel[e] = mean (x, y) over the distinct non-zero pixels
+ * of render_depth_image(objects, max_depth), seen[e] = 0 when there is none (pixel then 0, 0).  The frame lives as a
+ * bitmap in shared memory (width*height bits <= 200 KiB); the byte image is never written. */
+int fpv_camera_target_pixel(const fpv_camera_params_t* cam, const double* pose, int64_t n, const double* points,
+                            int32_t n_points, const double* boxes, int32_t n_objects, const double* obj_offset,
+                            double max_depth, double* pixel, uint8_t* seen, void* stream);
+
+/* Camera.pixel2direction (components.py:505-526): pixel double[n][2] -> unit vectors double[n][3];
+ * frame 0 'world', 1 'drone', 2 'camera'. */
+int fpv_camera_rays(const fpv_camera_params_t* cam, const double* pose, int64_t n, const double* pixel, int32_t frame,
+                    double* dir, void* stream);
+
+/* Drone.calculate_needed_force_orientation (components.py:258-304) for every env, reading position / velocity /
+ * attitude from `state`.  pixel: double[n][2]; seen: uint8[n] or NULL (envs with seen == 0 are skipped: their PID
+ * state is untouched and force = NaN, which fpv_drone_step reads as "no override for this env");
+ * target_pos: double[n][3]; target_radius: double[n]; pid: double[n][4] in/out = integral, prev_derivative,
+ * previous_error, is_first (reset = 0, 0, 0, 1; components.py:35-41).  Outputs (each may be NULL): rot float[n][9]
+ * row-major (columns x, y, force direction), quat float4[n] of the same rotation (for io.override_q), force float[n]. */
+int fpv_autopilot(const fpv_autopilot_params_t* ap, const fpv_camera_params_t* cam, const void* state, int64_t n,
+                  int64_t plane_stride, const double* pixel, const uint8_t* seen, const double* target_pos,
+                  const double* target_radius, double* pid, float* rot, void* quat, float* force, void* stream);
 
 #ifdef __cplusplus
 }
