@@ -5,7 +5,7 @@ from . import config
 from ._lib import FpvError
 
 __all__ = ["config", "FpvError", "BatchedDrone", "Drone", "BatchedRacer", "Racer", "Joystick", "Ground",
-           "Cylinder", "Target", "Gate", "BatchedCamera", "World", "Autopilot", "PID"]
+           "Cylinder", "Target", "Gate", "BatchedCamera", "World", "Autopilot", "PID", "BatchedAcroDrone"]
 
 
 def __getattr__(name):
@@ -27,4 +27,7 @@ def __getattr__(name):
     if name in ("Autopilot", "PID"):
         from . import autopilot
         return getattr(autopilot, name)
+    if name == "BatchedAcroDrone":
+        from .acro import BatchedAcroDrone
+        return BatchedAcroDrone
     raise AttributeError(name)

@@ -17,7 +17,8 @@ MAX_OBJECTS = 16
 DRONE_PLANES, RACER_PLANES = 4, 7
 EXPORTS = ("fpv_abi_version", "fpv_last_error", "fpv_sizeof", "fpv_device_info", "fpv_drone_reset",
            "fpv_drone_step", "fpv_drone_observe", "fpv_drone_get_rotation", "fpv_drone_set_rotation", "fpv_matrix_to_quat", "fpv_sticks_to_actions", "fpv_racer_reset", "fpv_racer_step", "fpv_gate_env_reset", "fpv_gate_env_step",
-           "fpv_camera_update", "fpv_camera_render", "fpv_camera_target_pixel", "fpv_camera_rays", "fpv_autopilot")
+           "fpv_camera_update", "fpv_camera_render", "fpv_camera_target_pixel", "fpv_camera_rays", "fpv_autopilot",
+           "fpv_acro_reset", "fpv_acro_step")
 
 
 class FpvError(RuntimeError):
@@ -91,7 +92,20 @@ class AutopilotParams(C.Structure):
                [("ref_frame", C.c_int32), ("mode", C.c_int32)]
 
 
-_STRUCTS = (DroneParams, DroneIO, Object, Stats, StickCalib, RacerParams, GateEnvParams, CameraParams, AutopilotParams)
+ACRO_PLANES = 7
+
+
+class AcroParams(C.Structure):
+    _fields_ = [("dt", C.c_float), ("substeps", C.c_int32), ("gravity", C.c_float), ("mass", C.c_float),
+                ("max_rates", C.c_float), ("rates_transition_rate", C.c_float), ("thrust_transition_rate", C.c_float),
+                ("k_drag", C.c_float * 3), ("motor_xy", (C.c_float * 2) * 4), ("motor_radius", C.c_float),
+                ("spring_k", C.c_float), ("gains", (C.c_float * 3) * 3), ("integral_limit", C.c_float),
+                ("inertia", C.c_float * 3), ("kappa", C.c_float), ("spin", C.c_float * 4), ("u_min", C.c_float),
+                ("u_max", C.c_float), ("thrust_poly", C.c_float * 4), ("wind", C.c_float * 3), ("flags", C.c_uint32)]
+
+
+_STRUCTS = (DroneParams, DroneIO, Object, Stats, StickCalib, RacerParams, GateEnvParams, CameraParams, AutopilotParams,
+            AcroParams)
 _lib = None
 
 
@@ -134,6 +148,8 @@ def load():
     lib.fpv_camera_target_pixel.argtypes = [P(CameraParams), V, I64, V, I32, V, I32, V, D, V, V, V]
     lib.fpv_camera_rays.argtypes = [P(CameraParams), V, I64, V, I32, V, V]
     lib.fpv_autopilot.argtypes = [P(AutopilotParams), P(CameraParams), V, I64, I64, V, V, V, V, V, V, V, V, V]
+    lib.fpv_acro_reset.argtypes = [V, I64, I64, V, V, V, V, V]
+    lib.fpv_acro_step.argtypes = [P(AcroParams), V, I64, I64, V, V, I32, V, V, V, V, V]
     v = lib.fpv_abi_version()
     if v != ABI_VERSION:
         raise ImportError(f"{LIB_PATH} has ABI version {v}, this package needs {ABI_VERSION}; rebuild it")

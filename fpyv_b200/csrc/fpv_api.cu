@@ -11,6 +11,7 @@
 #include "misc_kernels.cuh"
 #include "env_kernels.cuh"
 #include "chase_kernels.cuh"
+#include "acro_kernels.cuh"
 
 namespace {
 
@@ -192,6 +193,7 @@ int fpv_sizeof(int which) {
     case 6: return (int)sizeof(fpv_gate_env_params_t);
     case 7: return (int)sizeof(fpv_camera_params_t);
     case 8: return (int)sizeof(fpv_autopilot_params_t);
+    case 9: return (int)sizeof(fpv_acro_params_t);
     default: return -1;
   }
 }
@@ -565,6 +567,73 @@ int fpv_autopilot(const fpv_autopilot_params_t* ap, const fpv_camera_params_t* c
   fpv::autopilot_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
       a, k, (const float4*)state, n, plane_stride, pixel, seen, target_pos, target_radius, pid, rot, (float4*)quat, force);
   return check_launch("fpv_autopilot");
+}
+
+int fpv_acro_reset(void* state, int64_t n, int64_t plane_stride, const float* pos, const float* vel,
+                   const float* rpy_deg, const uint8_t* mask, void* stream) {
+  if (!state || !pos || !vel || !rpy_deg) return fail(FPV_EINVAL, "fpv_acro_reset: null pointer");
+  if (n < 0 || plane_stride < n || !aligned16(state)) return fail(FPV_EINVAL, "fpv_acro_reset: bad n/stride/alignment");
+  if (n == 0) return FPV_OK;
+  fpv::acro_reset_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((float4*)state, n, plane_stride, pos, vel, rpy_deg, mask);
+  return check_launch("fpv_acro_reset");
+}
+
+int fpv_acro_step(const fpv_acro_params_t* p, void* state, int64_t n, int64_t plane_stride, const void* actions,
+                  const float* lut, int32_t lut_n, uint8_t* done, void* motor_thrust, const void* reset_state,
+                  fpv_stats_t* stats, void* stream) {
+  if (!p || !state || !actions) return fail(FPV_EINVAL, "fpv_acro_step: null pointer");
+  if (n < 0 || plane_stride < n) return fail(FPV_EINVAL, "fpv_acro_step: bad n/stride");
+  if (!aligned16(state) || !aligned16(actions) || !aligned16(motor_thrust) || !aligned16(reset_state))
+    return fail(FPV_EINVAL, "fpv_acro_step: float4 planes must be 16-byte aligned");
+  if (p->substeps < 1 || !(p->dt > 0.f) || !(p->mass > 0.f)) return fail(FPV_EINVAL, "fpv_acro_step: bad dt/mass/substeps");
+  if ((p->flags & FPV_F_AUTO_RESET) && !reset_state) return fail(FPV_EINVAL, "fpv_acro_step: FPV_F_AUTO_RESET needs reset_state");
+  if (p->flags & FPV_F_THRUST_LUT) {
+    if (!lut || lut_n < 2) return fail(FPV_EINVAL, "fpv_acro_step: FPV_F_THRUST_LUT needs lut with lut_n >= 2");
+    if ((size_t)lut_n * sizeof(float) > 200 * 1024) return fail(FPV_EINVAL, "fpv_acro_step: lut_n=%d does not fit in shared memory", lut_n);
+  }
+  if (!(p->u_min < p->u_max)) return fail(FPV_EINVAL, "fpv_acro_step: u_min must be below u_max");
+  fpv::AcroK k;
+  std::memset(&k, 0, sizeof(k));
+  k.dt = p->dt; k.inv_dt = (float)(1.0 / (double)p->dt); k.substeps = p->substeps;
+  k.max_rates = p->max_rates;
+  k.rtr = p->rates_transition_rate; k.one_minus_rtr = (float)(1.0 - (double)p->rates_transition_rate);
+  k.ttr = p->thrust_transition_rate; k.one_minus_ttr = (float)(1.0 - (double)p->thrust_transition_rate);
+  k.deg2rad = (float)0.017453292519943295;
+  for (int i = 0; i < 3; ++i) {
+    if (!(p->inertia[i] > 0.f)) return fail(FPV_EINVAL, "fpv_acro_step: inertia must be positive");
+    for (int j = 0; j < 3; ++j) k.gains[i][j] = p->gains[i][j];
+    const double ki = p->gains[i][1] > 1e-12f ? (double)p->gains[i][1] : 1e-12;
+    k.i_lim[i] = (float)((double)p->integral_limit / ki);
+    k.inertia[i] = p->inertia[i]; k.inv_inertia[i] = (float)(1.0 / (double)p->inertia[i]);
+    k.kd[i] = p->k_drag[i]; k.wind[i] = p->wind[i];
+  }
+  for (int m = 0; m < 4; ++m) {
+    const float x = p->motor_xy[m][0], y = p->motor_xy[m][1];
+    k.motor_xy[m][0] = x; k.motor_xy[m][1] = y;
+    k.mix[m][0] = y > 0.f ? 1.f : (y < 0.f ? -1.f : 0.f);
+    k.mix[m][1] = x > 0.f ? -1.f : (x < 0.f ? 1.f : 0.f);
+    k.mix[m][2] = p->spin[m];
+    k.spin_kappa[m] = p->spin[m] * p->kappa;
+  }
+  k.u_min = p->u_min; k.u_max = p->u_max;
+  for (int i = 0; i < 4; ++i) k.poly[i] = p->thrust_poly[i];
+  k.lut_n = (p->flags & FPV_F_THRUST_LUT) ? lut_n : 0;
+  k.lut_scale = (float)((lut_n - 1) * 0.5);
+  k.grav_z = (float)(-(double)p->gravity * (double)p->mass);
+  k.inv_mass = (float)(1.0 / (double)p->mass);
+  k.motor_radius = p->motor_radius; k.spring_k = p->spring_k;
+  k.flags = p->flags;
+  if (n == 0) return FPV_OK;
+  const size_t smem = (p->flags & FPV_F_THRUST_LUT) ? sizeof(float) * (size_t)lut_n : 0;
+  auto kern = fpv::acro_step_kernel<kThreads>;
+  static size_t attr_set = 0;
+  if (smem > 48 * 1024 && smem > attr_set) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_set = smem;
+  }
+  kern<<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, smem, (cudaStream_t)stream>>>(
+      k, (float4*)state, n, plane_stride, (const float4*)actions, lut, done, (float4*)motor_thrust, (const float4*)reset_state, stats);
+  return check_launch("fpv_acro_step");
 }
 
 }  // extern "C"

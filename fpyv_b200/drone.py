@@ -335,6 +335,40 @@ class BatchedDrone:
             return self.observe()
         return None
 
+    def rollout(self, actions, done_out=None):
+        """Open-loop rollout: T control steps with the stick commands of all steps given up front
+        (actions [T,n,4] float32 on the device -- random exploration, MPC shooting, or recorded sticks replayed through
+        `Joystick.replay`, the sim-to-real check of SURVEY section 8f row 4).  One launch per control step, chained
+        (FPV_F_CHAINED): each launch starts on the SMs the previous one has already left.
+        done_out: optional uint8 [T,n] receiving every step's done flags.  Returns done_out (or the last flags)."""
+        if not (isinstance(actions, torch.Tensor) and actions.is_cuda and actions.dtype is torch.float32
+                and actions.dim() == 3 and tuple(actions.shape[1:]) == (self.num_envs, 4) and actions.is_contiguous()):
+            raise ValueError("rollout expects a contiguous float32 CUDA tensor [T, num_envs, 4]")
+        if done_out is not None and tuple(done_out.shape) != (actions.shape[0], self.num_envs):
+            raise ValueError("done_out must be uint8 [T, num_envs]")
+        if done_out is not None and not (done_out.is_cuda and done_out.dtype is torch.uint8 and done_out.is_contiguous()):
+            raise ValueError("done_out must be a contiguous uint8 CUDA tensor")
+        T = int(actions.shape[0])
+        if T == 0:
+            return done_out if done_out is not None else self._done
+        if not self._fast_ok:       # the first call configures the io block; the rest ride the allocation-free path
+            self.step(actions[0], return_obs=False, chained=True)
+            if done_out is not None:
+                done_out[0].copy_(self._done, non_blocking=True)
+            first = 1
+        else:
+            first = 0
+        try:
+            for t in range(first, T):
+                if done_out is not None:     # every step's flags land directly in their row: nothing between the launches
+                    self._io.done = done_out[t].data_ptr()
+                self.step(actions[t], return_obs=False, chained=True)
+        finally:
+            self._io.done = self._done.data_ptr()
+        if done_out is not None and T > first:
+            self._done.copy_(done_out[T - 1], non_blocking=True)
+        return done_out if done_out is not None else self._done
+
     def observe(self):
         """The tuple Drone.step returns (components.py:247-248)."""
         n, dev = self.num_envs, self.device

@@ -80,6 +80,24 @@ class Joystick:
                                              _lib.current_stream(self.device)))
         return actions, cal
 
+    def replay(self, raw_log):
+        """Recorded raw stick readings [T,n,6] (or [T,6] for one radio) -> actions [T,n,4] in ONE launch: the
+        `calib_read` + `read_sticks` maps (get_sticks.py:254-265, components.py:250-253) applied to every logged frame,
+        ready for `BatchedDrone.rollout`."""
+        if self._c is None:
+            raise RuntimeError("Joystick is not calibrated: call calibrate(path) first")
+        t = raw_log if isinstance(raw_log, torch.Tensor) else torch.as_tensor(np.asarray(raw_log))
+        if t.dim() == 2:
+            t = t[:, None, :]
+        if t.dim() != 3 or t.shape[2] != 6:
+            raise ValueError("raw_log must be [T, n, 6] or [T, 6]")
+        T, n = int(t.shape[0]), int(t.shape[1])
+        raw = t.to(self.device, torch.int32).reshape(T * n, 6).contiguous()
+        actions = torch.empty((T * n, 4), dtype=torch.float32, device=self.device)
+        _lib.check(_lib.load().fpv_sticks_to_actions(C.byref(self._c), _lib.ptr(raw), T * n, _lib.ptr(actions), None,
+                                                    _lib.current_stream(self.device)))
+        return actions.reshape(T, n, 4)
+
     def calib_read(self):
         """[n,6] calibrated axes (get_sticks.py:254-265)."""
         _, cal = self._run(True)

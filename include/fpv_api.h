@@ -148,7 +148,7 @@ const char* fpv_last_error(void);
 /* sizeof() of the ABI structs as this library was compiled, so that a foreign-language binding can
  * verify its own struct layout: which = 0 fpv_drone_params_t, 1 fpv_drone_io_t, 2 fpv_object_t,
  * 3 fpv_stats_t, 4 fpv_stick_calib_t, 5 fpv_racer_params_t, 6 fpv_gate_env_params_t, 7 fpv_camera_params_t,
- * 8 fpv_autopilot_params_t; -1 for an unknown index. */
+ * 8 fpv_autopilot_params_t, 9 fpv_acro_params_t; -1 for an unknown index. */
 int fpv_sizeof(int which);
 
 /* Number of SMs / compute capability of `device`; used by hosts to size persistent launches. */
@@ -332,6 +332,51 @@ int fpv_camera_rays(const fpv_camera_params_t* cam, const double* pose, int64_t 
 int fpv_autopilot(const fpv_autopilot_params_t* ap, const fpv_camera_params_t* cam, const void* state, int64_t n,
                   int64_t plane_stride, const double* pixel, const uint8_t* seen, const double* target_pos,
                   const double* target_radius, double* pid, float* rot, void* quat, float* force, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Mode C ("acro"): stick -> rate set-point -> acro rate PID -> motor mixer -> per-motor thrust / torque from the
+ * T-Motor F80 bench curve (shared-memory LUT) -> rigid-body rotation, feeding the reference's translational model.
+ * PARITY UNPINNED: the reference has no such model (its Drone applies the commanded rates kinematically,
+ * components.py:216-218, and has ONE scalar thrust, :133-137).  Definition and only oracle: oracle/acro_oracle.py.
+ * Reused reference pieces: action2force's maps and low-passes (components.py:185-194), the PID form of
+ * tests/racer_drone_test.py:22-32, the motor layout (components.py:120-125), the bench curve (:133-136), drag /
+ * gravity / ground spring / crash (:233-243) and the translation order of kinematics.py:21-22.
+ * State: float4[FPV_ACRO_PLANES][plane_stride]
+ *   0 position xyz, filtered collective throttle   1 velocity xyz, episode counter (int bits)   2 quaternion wxyz
+ *   3 filtered rate set-point xyz [deg/s], PID first-call flag   4 body rates xyz [rad/s]   5 PID integral xyz
+ *   6 previous rate error xyz
+ * -------------------------------------------------------------------------------------------*/
+#define FPV_ACRO_PLANES 7
+typedef struct fpv_acro_params {
+  float dt;
+  int32_t substeps;
+  float gravity, mass;
+  float max_rates, rates_transition_rate, thrust_transition_rate;   /* components.py:85, :105-106 */
+  float k_drag[3];              /* -0.5 Cd rho A                                  kinematics.py:36 */
+  float motor_xy[4][2];         /* body-frame motor offsets                      components.py:123-125 */
+  float motor_radius, spring_k; /* components.py:121, :198 */
+  float gains[3][3];            /* rows roll, pitch, yaw; columns P, I, D; output in throttle units */
+  float integral_limit;         /* clamp on |kI * integral| (throttle units) */
+  float inertia[3];             /* diagonal body inertia [kg m^2] */
+  float kappa;                  /* rotor reaction torque per thrust [m] */
+  float spin[4];                /* +1 / -1 spin direction of motor k */
+  float u_min, u_max;           /* motor throttle limits in [-1, 1] (idle = 5 %: -0.9, components.py:138-139) */
+  float thrust_poly[4];         /* 4-motor bench cubic in throttle percent        components.py:136 */
+  float wind[3];
+  uint32_t flags;               /* FPV_F_GROUND | FPV_F_AUTO_RESET | FPV_F_THRUST_LUT */
+} fpv_acro_params_t;
+
+/* pos, vel, rpy_deg: float[n][3]; motors off (throttle -1), zero rates, fresh PID.  mask as in fpv_drone_reset. */
+int fpv_acro_reset(void* state, int64_t n, int64_t plane_stride, const float* pos, const float* vel,
+                   const float* rpy_deg, const uint8_t* mask, void* stream);
+
+/* params->substeps model steps with the action [roll, pitch, yaw, throttle] in [-1,1]^4 held.  lut: float[lut_n]
+ * 4-motor thrust [N] sampled uniformly at throttle -1..1 (FPV_F_THRUST_LUT) or NULL; done: uint8[n] or NULL;
+ * motor_thrust: float4[n] out (per-motor thrust of the last substep) or NULL; reset_state: snapshot for
+ * FPV_F_AUTO_RESET; stats: crashes / episodes / episode_len_sum, may be NULL. */
+int fpv_acro_step(const fpv_acro_params_t* params, void* state, int64_t n, int64_t plane_stride, const void* actions,
+                  const float* lut, int32_t lut_n, uint8_t* done, void* motor_thrust, const void* reset_state,
+                  fpv_stats_t* stats, void* stream);
 
 #ifdef __cplusplus
 }

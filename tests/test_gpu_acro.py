@@ -1,0 +1,141 @@
+"""Mode C ("acro": rate PID -> mixer -> per-motor bench-curve thrust -> rigid body, on the reference's translational
+model) on the GPU against its float64 model oracle/acro_oracle.py.  PARITY UNPINNED: there is no reference
+implementation of this model; the tolerance is the path's own: <= 1e-5 relative per step."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import CONFIG
+from oracle import acro_oracle as ao
+from oracle import fpv_oracle as fo
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def consts(dt):
+    import yaml
+    with open(os.path.join(CONFIG, "params.yaml")) as f:
+        params = yaml.safe_load(f)
+    return ao.default_consts(fo.derive_consts(params, os.path.join(CONFIG, "t_motos_f80_motor_test.csv"), dt=dt))
+
+
+def state_err(d, s):
+    g = lambda a, b: np.max(np.abs(a - b), axis=1) / np.maximum(1.0, np.max(np.abs(b), axis=1))
+    f = lambda t: t.double().cpu().numpy()
+    q = f(d.quaternion)
+    q = q * np.where(np.sum(q * s.q, axis=1, keepdims=True) < 0, -1.0, 1.0)
+    return np.max(np.stack([g(f(d.position), s.pos), g(f(d.velocity), s.vel), g(q, s.q), g(f(d.angular_velocity), s.omega),
+                            g(f(d.rate_setpoint), s.rate_sp), g(f(d.throttle)[:, None], s.throttle[:, None]),
+                            g(f(d.pid_integral), s.integral)]), axis=0)
+
+
+def seeded(n, seed, z_lo=2.0, z_hi=12.0):
+    rng = np.random.default_rng(seed)
+    pos = np.stack([rng.normal(0, 5, n), rng.normal(0, 5, n), rng.uniform(z_lo, z_hi, n)], axis=1)
+    return rng, pos, rng.normal(0, 1, (n, 3)), rng.uniform(-30, 30, (n, 3))
+
+
+@pytest.mark.parametrize("lut", [2049, 0])
+@pytest.mark.parametrize("dt,K", [(1e-3, 1), (1e-3, 8), (1 / 60, 1)])
+def test_single_control_steps_vs_model(dt, K, lut):
+    """Every control step restarts from the model's own float64 state (rounded to float32), so the error is one
+    step's worth: <= 1e-5 relative."""
+    from fpyv_b200 import BatchedAcroDrone
+    n, T = 256, 25
+    rng, pos, vel, rpy = seeded(n, 11)
+    c = consts(dt)
+    table = None
+    d = BatchedAcroDrone(None, num_envs=n, device=DEV, substeps=K, dt=dt, thrust_lut=lut)
+    if lut:
+        table = d._lut.double().cpu().numpy()
+    s = ao.acro_reset(c, pos, vel, rpy)
+    d.reset(pos, vel, rpy)
+    worst = 0.0
+    f32 = lambda x: torch.as_tensor(np.asarray(x), dtype=torch.float32, device=DEV)
+    for t in range(T):
+        act = rng.uniform(-1, 1, (n, 4))
+        # restart the device from the model's state
+        d.position.copy_(f32(s.pos)); d.velocity.copy_(f32(s.vel)); d.quaternion.copy_(f32(s.q))
+        d.throttle.copy_(f32(s.throttle)); d.rate_setpoint.copy_(f32(s.rate_sp)); d.angular_velocity.copy_(f32(s.omega))
+        d.pid_integral.copy_(f32(s.integral)); d._state[6, :n, :3].copy_(f32(s.e_prev))
+        d._state[3, :n, 3].copy_(f32(s.first.astype(np.float64)))
+        # ... and the model from the device's float32 rounding of it
+        f = lambda x: x.double().cpu().numpy()
+        s.pos, s.vel, s.q, s.throttle = f(d.position), f(d.velocity), f(d.quaternion), f(d.throttle)
+        s.rate_sp, s.omega, s.integral, s.e_prev = f(d.rate_setpoint), f(d.angular_velocity), f(d.pid_integral), f(d._state[6, :n, :3])
+        ao.acro_step(c, s, act, substeps=K, lut=table)
+        done = d.step(act).cpu().numpy().astype(bool)
+        assert np.array_equal(done, s.done)
+        worst = max(worst, state_err(d, s).max())
+        np.testing.assert_allclose(d.motor_thrust.double().cpu().numpy(), s.motor_thrust, rtol=2e-5, atol=2e-5)
+    print(f"acro dt={dt:.4g} K={K} lut={lut}: max single-step rel err {worst:.2e}")
+    assert worst < 1e-5
+
+
+def test_free_running_1s_divergence_and_physics():
+    """1 s horizon (125 control steps x 8 substeps of 1 ms) free-running vs the model, then physical sanity: zero
+    sticks at hover throttle hold attitude; a held roll stick converges to the commanded rate (-stick * max_rates, the
+    reference's sign, components.py:185); saturated motors stay inside the bench curve's range."""
+    from fpyv_b200 import BatchedAcroDrone
+    n, dt, K = 128, 1e-3, 8
+    rng, pos, vel, rpy = seeded(n, 12, z_lo=20, z_hi=40)
+    c = consts(dt)
+    d = BatchedAcroDrone(None, num_envs=n, device=DEV, substeps=K, dt=dt, thrust_lut=0)
+    d.reset(pos, vel, rpy)
+    s = ao.acro_reset(c, pos, vel, rpy)
+    curve = []
+    for t in range(125):
+        act = rng.uniform(-1, 1, (n, 4)) if t % 10 == 0 else act
+        ao.acro_step(c, s, act, substeps=K)
+        d.step(act)
+        if t + 1 in (1, 2, 5, 10, 30, 60, 125):
+            curve.append((t + 1, float(np.median(state_err(d, s))), float(state_err(d, s).max())))
+    print("acro divergence vs float64 model (control step: median, max):", " ".join(f"@{t}:{m:.1e},{x:.1e}" for t, m, x in curve))
+    assert curve[0][2] < 1e-5 and curve[-1][1] < 1e-3
+    # hover: level, zero sticks
+    d = BatchedAcroDrone(None, num_envs=4, device=DEV, substeps=K, dt=dt)
+    uh = d.hover_throttle()
+    d.reset(np.tile([0, 0, 10.0], (4, 1)), np.zeros((4, 3)), np.zeros((4, 3)))
+    d.throttle.fill_(uh)
+    for _ in range(125):
+        d.step(np.tile([0, 0, 0, uh], (4, 1)))
+    assert torch.allclose(d.quaternion[:, 0], torch.ones(4, device=DEV), atol=1e-6)
+    assert float(d.position[:, 2].sub(10).abs().max()) < 0.05 and float(d.angular_velocity.abs().max()) < 1e-4
+    assert abs(float(d.motor_thrust.sum(1)[0]) - d.mass * d.gravity) < 0.02
+    # roll stick 0.5 -> -100 deg/s
+    for _ in range(60):
+        d.step(np.tile([0.5, 0, 0, uh], (4, 1)))
+    rate = np.rad2deg(d.angular_velocity.cpu().numpy()[0])
+    assert abs(rate[0] + 100.0) < 5.0 and abs(rate[1]) < 1.0 and abs(rate[2]) < 1.0
+    # full deflection on every axis at full throttle: motors clipped to the curve's range
+    for _ in range(20):
+        d.step(np.tile([1.0, -1.0, 1.0, 1.0], (4, 1)))
+    mt = d.motor_thrust.cpu().numpy()
+    top = float(d.constants.throttle2thrust(1.0)) / 4
+    idle = float(d.constants.throttle2thrust(-0.9)) / 4
+    assert (mt <= top * (1 + 1e-5)).all() and (mt >= idle * (1 - 1e-4)).all()
+
+
+def test_ground_crash_auto_reset_and_errors():
+    from fpyv_b200 import BatchedAcroDrone, FpvError
+    n = 512
+    rng, pos, vel, rpy = seeded(n, 13, z_lo=0.15, z_hi=1.0)
+    d = BatchedAcroDrone(None, num_envs=n, device=DEV, substeps=8, dt=1e-3, auto_reset=True)
+    d.reset(pos, vel, rpy)
+    snap = d._state.clone()
+    crashed = torch.zeros(n, dtype=torch.bool, device=DEV)
+    for _ in range(80):                      # motors at idle: everything falls
+        done = d.step(np.tile([0, 0, 0, -1.0], (n, 1))).bool()
+        just = done & ~crashed
+        if just.any():                       # a crashed env restarts from the reset snapshot
+            assert torch.equal(d._state[:, :n][:, just][..., :3], snap[:, :n][:, just][..., :3])
+        crashed |= done
+    assert crashed.float().mean() > 0.5
+    assert float(d._stats[1]) == float(d._stats[2]) > 0          # crashes == episodes under auto-reset
+    with pytest.raises(FpvError):
+        bad = BatchedAcroDrone(None, num_envs=4, device=DEV, inertia=[0.0, 1e-3, 1e-3])
+        bad.reset(np.zeros((4, 3)), np.zeros((4, 3)), np.zeros((4, 3)))
+        bad.step(np.zeros((4, 4)))

@@ -551,3 +551,34 @@ def test_chained_launches_are_bit_identical(n, K):
     assert int(e0.max()) == 0                                     # plain launches publish nothing
     assert int(e1.min()) == steps and int(e1.max()) == steps       # every chunk saw every chained launch
     assert st0["crashes"] > 0
+
+
+def test_rollout_and_stick_replay_match_stepwise():
+    """BatchedDrone.rollout (chained launches) and Joystick.replay (whole log in one launch) reproduce the step-by-step
+    joystick path -- checked against the golden joystick-driven reference run (drone_sticks.npz) and bit-for-bit
+    against step(None) on the same raw log."""
+    from fpyv_b200 import Joystick
+    g = load("drone_sticks")
+    raw = g["raw"][:, 0]                                    # [T,6]
+    T = len(raw)
+    calib = os.path.join(os.path.dirname(GOLDEN), "..", "fpyv_b200", "config", "frsky.json")
+    rc = Joystick(device=DEV)
+    rc.calibrate(calib, load_calibration_file=True)
+    acts = rc.replay(raw)                                   # [T,1,4]
+    np.testing.assert_allclose(acts[:, 0].double().cpu().numpy(), g["actions"][:, 0], rtol=0, atol=2e-6)
+    d = make(1)
+    d.reset(g["pos0"], g["vel0"], g["rpy0"])
+    dones = torch.zeros((T, 1), dtype=torch.uint8, device=DEV)
+    d.rollout(acts.contiguous(), done_out=dones)
+    err = drone_err(d, g["state"][-1], g["R"][-1], g["prev_rates"][-1], g["prev_thrust"][-1])
+    assert err.max() < 2e-5, err.max()                      # 30 free-running steps
+    assert np.array_equal(dones.cpu().numpy().astype(bool), g["done"].astype(bool))
+    # bit-for-bit against the stepwise joystick path
+    d2 = make(1)
+    d2.reset(g["pos0"], g["vel0"], g["rpy0"])
+    for t in range(T):
+        d2.rc.feed(raw[t][None])
+        d2.step(None, return_obs=False)
+    assert torch.equal(d._state, d2._state)
+    with pytest.raises(ValueError):
+        d.rollout(acts[:, :, :3])
