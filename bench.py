@@ -339,7 +339,7 @@ def run_gpu(args):
             "env_substeps_per_sec": value * SUBSTEPS,
             "e2e": {"value": total_envs * K / (ms_e2e * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": 16 * n * world,
                     "d2h_bytes_per_step": n * world, "ms_per_step": ms_e2e / K,
-                    "api": "BatchedDrone.step_host(pinned actions) -> pinned done flags; host waits every step"},
+                    "api": "BatchedDrone.step_host(pinned actions) -> pinned done flags, 4 env slices pipelined over H2D / step / D2H streams; host waits every step"},
             "ms_per_step_flushed": ms_flushed_per_step,
             "gpu_launches": K, "roofline": roof,
             "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},

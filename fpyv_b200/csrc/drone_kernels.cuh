@@ -628,7 +628,11 @@ __global__ void __launch_bounds__(THREADS, MINB) drone_step_tma_kernel(const __g
   long long ph_wait = 0, ph_read = 0, ph_tile = 0;
   const long long c_begin = clock64();
 #endif
-  long long pending = -1;   // chunk whose stores are issued but whose epoch is not published yet
+#ifndef FPV_PUBLISH_BATCH
+#define FPV_PUBLISH_BATCH 4
+#endif
+  unsigned pend[FPV_PUBLISH_BATCH + 1];   // chunks whose stores are issued but whose epochs are not published yet
+  int n_pend = 0;
   for (int it = 0; cur < n_chunks; ++it) {
     const int slot = it & 1;
 #ifdef FPV_TRACE_PHASES
@@ -659,26 +663,37 @@ __global__ void __launch_bounds__(THREADS, MINB) drone_step_tma_kernel(const __g
 #ifdef FPV_TRACE_PHASES
     const long long c_c = clock64();
 #endif
-    // Publishing a chunk's epoch needs its stores to be performed first (a release waits for them).  Doing that right
-    // after the stores would stall the warp for a full store round trip per chunk, so the flag of chunk i goes out in
-    // the middle of chunk i+1 -- after that chunk's substep loop, when the stores are long done and the release is
-    // free.  Order: all lanes' stores of chunk i -> the __syncwarp() above (iteration i+1) -> the leader's release.
+    // Publishing a chunk's epoch needs its stores to be performed first: a release is MEMBAR.GPU + ERRBAR, which
+    // drains the warp's memory pipeline.  Two things keep that off the critical path: the flags go out in the MIDDLE of
+    // a later chunk (after that chunk's substep loop, when the stores are long done), and they go out in batches of
+    // FPV_PUBLISH_BATCH chunks under ONE fence -- a consumer launch only gets onto the SMs when this launch's first
+    // CTAs retire, tens of microseconds after the early chunks were stored, so a few chunks of publication lag are
+    // invisible to it.  Order: all lanes' stores of chunk i -> the __syncwarp() of a later iteration -> the leader's
+    // fence -> the flag stores.
+    const bool flush_now = n_pend >= FPV_PUBLISH_BATCH;   // warp-uniform
     auto publish_pending = [&]() {
-      if (pending >= 0 && leader)
-        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(io.chunk_epoch + pending), "r"(io.epoch + 1u) : "memory");
+      if (flush_now && leader) {
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        for (int j = 0; j < n_pend; ++j)
+          asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(io.chunk_epoch + pend[j]), "r"(io.epoch + 1u) : "memory");
+      }
     };
     if (base < io.n) drone_tile<V, ANG, false, 32>(k, io, lut_s, q, act, ei, base, st, wind_on, publish_pending);
-    pending = io.chunk_epoch ? cur : -1;
+    if (flush_now) n_pend = 0;
+    if (io.chunk_epoch) pend[n_pend++] = (unsigned)cur;
 #ifdef FPV_TRACE_PHASES
     const long long c_d = clock64();
     ph_wait += c_b - c_a; ph_read += c_c - c_b; ph_tile += c_d - c_c;
 #endif
     cur = nxt;
   }
-  if (pending >= 0) {  // the warp's last chunk
+  if (n_pend > 0) {  // whatever is still unpublished, the warp's last chunk included
     __syncwarp();
-    if (leader)
-      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(io.chunk_epoch + pending), "r"(io.epoch + 1u) : "memory");
+    if (leader) {
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
+      for (int j = 0; j < n_pend; ++j)
+        asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(io.chunk_epoch + pend[j]), "r"(io.epoch + 1u) : "memory");
+    }
   }
   if (dynamic && leader) {
     const unsigned finished = atomicAdd(io.work + 1, 1u);
