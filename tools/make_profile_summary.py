@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Turn gpurun_out/{launches_r1.csv, prof_*.ncu-rep, bench_full.json, bench_ref.json} into the tracked profiles/ files.
-usage: python tools/make_profile_summary.py gpurun_out/prof_r1e.ncu-rep"""
+usage: python tools/make_profile_summary.py gpurun_out/prof_r1f.ncu-rep"""
 import collections, csv, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rep = sys.argv[1]
@@ -45,15 +45,19 @@ md = f"""# Round 1 ncu evidence (B200, sm_100a) -- `python bench.py --steps 3 --
 Commands (B200_PROFILING.md recipe; the plain run exited 0 first, in the same gpurun call):
 ```
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_r1.csv python bench.py --steps 3 --warmup 3 --profile
-ncu --set full --clock-control none --import-source on -k regex:drone_step -s 6 -c 4 -o gpurun_out/prof_r1e python bench.py --steps 3 --warmup 3 --profile
+ncu --set full --clock-control none --import-source on -k regex:drone_step -s 6 -c 4 -o gpurun_out/prof_r1f python bench.py --steps 3 --warmup 3 --profile
 ```
 Files here: `r1_launches.csv` (every launch of the profile run), `r1_ncu_drone_step.json` (raw-page metrics of the
 captured `drone_step_tma_kernel` launches, all K = 8), `r1_bench_n1.json` / `r1_bench_reference_arm.json` (bench lines of
 the same build taken WITHOUT a profiler), `r1_fp32_pipe_microbench.txt` (tools/fma_microbench.cu),
-`r1_warp_timeline_static.txt` (per-warp start/end with the static chunk split, the motivation for pulled chunks).
+`r1_warp_timeline_static.txt` (per-warp start/end with the static chunk split, the motivation for pulled chunks),
+`r1_chain_timeline.txt` (per-warp start/end of three chained launches), `r1_batch_size_sweep.txt` (step time vs batch size:
+steady-state cost and fixed cost), `r1_chase_bench.json` / `r1_chase_launches.csv` / `r1_ncu_camera_splat.json` (chase pipeline).
 
 ## Launch list (ncu serialises and flushes caches: compare shares, not absolutes)
 Inside a timed step there is exactly ONE launch, `drone_step_tma_kernel` (share of the step: 100 %; `gpu_launches` = steps).
+In the timed rotation the launches are CHAINED (DESIGN.md section 4.1): launch i+1 starts on the SMs launch i has left, which a
+serialising profiler cannot show -- `r1_chain_timeline.txt` (tools/tune_chain_trace.py, %globaltimer per warp) does.
 The rest of the profile run is set-up (synthetic init) and the L2-flush kernels of the cross-check loop.
 
 {chr(10).join(lines)}
