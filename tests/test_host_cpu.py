@@ -195,3 +195,59 @@ def test_gate_env_model_basics():
     p1 = p0 + [1.5, 0, 0]
     r, re, de, prev, g, laps = go.step(gates, p1, np.array([False, False]), prev, g, laps, 2, 10.0, 1.0, 5.0, 0)
     assert g.tolist() == [1, 0] and r[0] > 10 and r[1] < 10 and re[0] == r.sum() and not de[0]
+
+
+def test_header_is_plain_c():
+    """The drop-in boundary is a C ABI: the header must compile as C (no C++-isms, no CUDA types)."""
+    import subprocess
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c",
+                        os.path.join(ROOT, "include", "fpv_api.h")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_object_point_clouds_match_the_reference_shapes():
+    """Ground / Cylinder / Gate point clouds (components.py:655-667, :697-708, :787-805) against the arrays the
+    reference itself produced for the golden world (oracle/make_golden_chase.py)."""
+    from fpyv_b200 import Cylinder, Gate, Ground, Target
+    from fpyv_b200.objects import icosphere_vertices
+    g = np.load(os.path.join(GOLDEN, "chase_camera.npz"))
+    np.testing.assert_allclose(Ground(40, 24, random=False).points, g["obj4"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(Cylinder(np.array([6.0, 2.0, 0.0]), 1.5, 8.0, 10, 12).points, g["obj1"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(Cylinder(np.array([-4.0, -7.0, 0.0]), 2.0, 5.0, 8, 9).points, g["obj2"], rtol=0, atol=1e-12)
+    yaw = 0.7
+    rot = np.array([[np.cos(yaw), -np.sin(yaw), 0], [np.sin(yaw), np.cos(yaw), 0], [0, 0, 1.0]])
+    np.testing.assert_allclose(Gate(np.array([3.0, -5.0, 2.5]), rot, 5.0, shape="circle", resolution=17).points, g["obj3"],
+                               rtol=0, atol=1e-12)
+    for nu in (1, 2, 5):
+        v = icosphere_vertices(nu)
+        assert v.shape == (10 * nu * nu + 2, 3)
+        np.testing.assert_allclose(np.linalg.norm(v, axis=1), 1.0, rtol=0, atol=1e-12)
+    t = Target(np.array([1.0, 2.0, 3.0]), 0.5, nu=2)
+    np.testing.assert_allclose(np.linalg.norm(t.points - t.position, axis=1), 0.5, rtol=0, atol=1e-12)
+    assert t.calculate_distance(np.array([1.0, 2.0, 5.0])) == pytest.approx(1.5)
+    box = Ground(40, 24).bbox3d
+    assert box.shape == (8, 3) and box[:, 0].min() == -20 and box[:, 0].max() == 20
+    rg = Ground(60, 50, random=True, rng=np.random.default_rng(0)).points
+    assert rg.shape == (2500, 3) and np.abs(rg[:, :2]).max() <= 60 and np.abs(rg[:, 2]).max() <= 0.2
+
+
+def test_new_entry_points_validate_without_a_gpu(lib):
+    from fpyv_b200 import _lib
+    cam, ap, ac = _lib.CameraParams(), _lib.AutopilotParams(), _lib.AcroParams()
+    assert lib.fpv_camera_update(None, None, 0, 0, None, None) == -22
+    assert lib.fpv_camera_update(C.byref(cam), None, 0, 0, None, None) == -22 and b"resolution" in lib.fpv_last_error()
+    cam.width, cam.height, cam.fx, cam.fy = 641, 481, 100.0, 100.0
+    dummy = (C.c_double * 64)()
+    img = (C.c_uint8 * 64)()
+    assert lib.fpv_camera_render(C.byref(cam), dummy, 1, dummy, 1, dummy, 1, None, 10.0, img, img, None) == -22
+    assert b"multiple of 4" in lib.fpv_last_error()
+    cam.width, cam.height = 640, 480
+    assert lib.fpv_camera_render(C.byref(cam), dummy, 1, dummy, 1, dummy, 65, None, 10.0, img, img, None) == -22
+    assert lib.fpv_camera_target_pixel(C.byref(cam), dummy, 1, dummy, 1, dummy, 1, None, 0.0, dummy, img, None) == -22
+    assert lib.fpv_camera_rays(C.byref(cam), dummy, 1, dummy, 7, dummy, None) == -22 and b"world, drone or camera" in lib.fpv_last_error()
+    ap.ref_frame = 5
+    ap.dt = 0.01
+    assert lib.fpv_autopilot(C.byref(ap), C.byref(cam), dummy, 0, 0, dummy, None, dummy, dummy, dummy, None, None, None, None) == -22
+    assert b"Unknown reference frame" in lib.fpv_last_error()
+    assert lib.fpv_acro_step(C.byref(ac), dummy, 0, 0, dummy, None, 0, None, None, None, None, None) == -22
+    assert lib.fpv_acro_reset(None, 0, 0, None, None, None, None, None) == -22
