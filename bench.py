@@ -183,6 +183,11 @@ def run_gpu(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line: native libraries (NCCL prints its version banner to fd 1 when NCCL_DEBUG is
+    # set by the environment or an nccl.conf) are sent to stderr for the duration of the run
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -270,6 +275,7 @@ def run_gpu(args):
         ms_k1_fl = timed_loop(d1s[0], K_fl, W)
         if rank == 0:
             p = timed_loop.last
+            os.dup2(real_stdout, 1)
             print(json.dumps({"profile_run": True, "ms_per_step_k8": ms / K, "ms_per_step_k1": ms_k1 / K,
                               "flushed_k8": ms_flushed / K_fl, "flushed_k1": ms_k1_fl / K_fl,
                               "k1_fl_min_med_max": [p[0], p[len(p) // 2], p[-1]], "k8_fl_sorted": k8_sorted[:3] + k8_sorted[-3:]}))
@@ -345,7 +351,7 @@ def run_gpu(args):
             "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "clocks": clocks, "episode_stats": stats}
     sys.stdout.flush()
-    print(json.dumps(line), flush=True)
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

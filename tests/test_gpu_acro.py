@@ -139,3 +139,34 @@ def test_ground_crash_auto_reset_and_errors():
         bad = BatchedAcroDrone(None, num_envs=4, device=DEV, inertia=[0.0, 1e-3, 1e-3])
         bad.reset(np.zeros((4, 3)), np.zeros((4, 3)), np.zeros((4, 3)))
         bad.step(np.zeros((4, 4)))
+
+
+@pytest.mark.parametrize("n", [1, 127, 129, 1000])
+def test_ragged_sizes_leave_padding_and_guards_untouched(n):
+    """Envs beyond n (the padding up to plane_stride) and sentinel rows around the done / motor outputs stay as they
+    were; the first n envs match a larger batch stepped with the same inputs."""
+    import ctypes as C
+    from fpyv_b200 import BatchedAcroDrone, _lib
+    rng, pos, vel, rpy = seeded(1024, 21)
+    big = BatchedAcroDrone(None, num_envs=1024, device=DEV, substeps=4, dt=1e-3)
+    big.reset(pos, vel, rpy)
+    act = rng.uniform(-1, 1, (1024, 4))
+    d = BatchedAcroDrone(None, num_envs=n, device=DEV, substeps=4, dt=1e-3)
+    d.reset(pos[:n], vel[:n], rpy[:n])
+    d._state[:, n:] = 123.0                                      # padding envs
+    lib = _lib.load()
+    G = 256
+    done = torch.full((G + n + G,), 0xAB, dtype=torch.uint8, device=DEV)
+    motor = torch.full((G + n + G, 4), -7.0, dtype=torch.float32, device=DEV)
+    a = torch.as_tensor(act[:n], dtype=torch.float32, device=DEV).contiguous()
+    for _ in range(3):
+        big.step(act)
+        _lib.check(lib.fpv_acro_step(C.byref(d._p), _lib.ptr(d._state), n, d._stride, _lib.ptr(a), _lib.ptr(d._lut),
+                                     d._lut.numel(), C.c_void_p(done.data_ptr() + G), C.c_void_p(motor.data_ptr() + 16 * G),
+                                     None, None, _lib.current_stream(torch.device(DEV))))
+    torch.cuda.synchronize()
+    assert bool((d._state[:, n:] == 123.0).all())
+    assert bool((done[:G] == 0xAB).all()) and bool((done[G + n:] == 0xAB).all())
+    assert bool((motor[:G] == -7.0).all()) and bool((motor[G + n:] == -7.0).all())
+    assert torch.equal(d._state[:, :n], big._state[:, :n])
+    assert torch.equal(motor[G:G + n], big.motor_thrust[:n])

@@ -248,3 +248,58 @@ def test_full_frame_batch_against_oracle():
     un = ~seen.bool()
     assert torch.equal(d.position[un], d2.position[un]) and torch.equal(d.quaternion[un], d2.quaternion[un])
     assert not torch.equal(d.quaternion[seen.bool()], d2.quaternion[seen.bool()])
+
+
+def test_guard_cells_around_every_output_of_the_chase_kernels():
+    """Raw C-ABI calls on ragged sizes with sentinel bytes on both sides of every output buffer (compute-sanitizer is
+    not available on the GPU pool: out-of-bounds writes are caught by guard cells instead)."""
+    import ctypes as C
+    from fpyv_b200 import BatchedDrone, _lib
+    lib = _lib.load()
+    g = load("chase_camera")
+    n = 7
+    cam = make_cam(n)
+    p = cam._params()
+    W, H = int(cam.resolution[0]), int(cam.resolution[1])
+    d = BatchedDrone(None, num_envs=n, device=DEV)
+    d.reset(g["pos"][:n], np.ones((n, 3)), g["rpy"][:n])
+    st = _lib.current_stream(torch.device(DEV))
+    G = 4096
+
+    def guarded(nbytes, dtype):
+        buf = torch.full((G + nbytes + G,), 0xAB, dtype=torch.uint8, device=DEV)
+        return buf, buf[G:G + nbytes].view(dtype)
+
+    pose_b, pose = guarded(n * 12 * 8, torch.float64)
+    _lib.check(lib.fpv_camera_update(p, _lib.ptr(d._state), n, d._stride, _lib.ptr(pose), st))
+    from fpyv_b200 import World
+    w = World(world_objects(g), DEV)
+    img_b, img = guarded(n * W * H, torch.uint8)
+    keep_b, keep = guarded(n * w.n_objects, torch.uint8)
+    _lib.check(lib.fpv_camera_render(p, _lib.ptr(pose), n, _lib.ptr(w.points), w.n_points, _lib.ptr(w.boxes), w.n_objects, None,
+                                     15.0, _lib.ptr(keep), _lib.ptr(img), st))
+    px_b, px = guarded(n * 2 * 8, torch.float64)
+    seen_b, seen = guarded(n, torch.uint8)
+    _lib.check(lib.fpv_camera_target_pixel(p, _lib.ptr(pose), n, _lib.ptr(w.points), w.n_points, _lib.ptr(w.boxes), w.n_objects,
+                                           None, 15.0, _lib.ptr(px), _lib.ptr(seen), st))
+    ray_b, ray = guarded(n * 3 * 8, torch.float64)
+    _lib.check(lib.fpv_camera_rays(p, _lib.ptr(pose), n, _lib.ptr(px), 0, _lib.ptr(ray), st))
+    from fpyv_b200 import Autopilot
+    ap = Autopilot(d, cam)
+    pid_b, pid = guarded(n * 4 * 8, torch.float64)
+    pid.copy_(torch.tensor([0.0, 0, 0, 1], dtype=torch.float64, device=DEV).repeat(n))
+    rot_b, rot = guarded(n * 9 * 4, torch.float32)
+    q_b, q = guarded(n * 16, torch.float32)
+    f_b, f = guarded(n * 4, torch.float32)
+    tp = torch.as_tensor(np.tile(g["target_pos"], (n, 1)), dtype=torch.float64, device=DEV).contiguous()
+    tr = torch.ones(n, dtype=torch.float64, device=DEV)
+    _lib.check(lib.fpv_autopilot(ap._params("world", "level"), p, _lib.ptr(d._state), n, d._stride, _lib.ptr(px), _lib.ptr(seen),
+                                 _lib.ptr(tp), _lib.ptr(tr), _lib.ptr(pid), _lib.ptr(rot), _lib.ptr(q), _lib.ptr(f), st))
+    torch.cuda.synchronize()
+    for name, b in (("pose", pose_b), ("image", img_b), ("keep", keep_b), ("pixel", px_b), ("seen", seen_b), ("rays", ray_b),
+                    ("pid", pid_b), ("rot", rot_b), ("quat", q_b), ("force", f_b)):
+        assert bool((b[:G] == 0xAB).all()) and bool((b[-G:] == 0xAB).all()), name
+    # and the guarded outputs are the API's outputs
+    cam.update_from(d)
+    assert torch.equal(pose.view(n, 12), cam._pose)
+    assert torch.equal(img.view(n, H, W), cam.render_depth_image(w, 15))

@@ -1,5 +1,5 @@
 """dev helper: per-warp start/end timeline of the hot kernel"""
-import sys, torch, numpy as np
+import os, sys, torch, numpy as np
 sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 from fpyv_b200 import BatchedDrone
 dev='cuda:0'; n=1<<20
@@ -16,6 +16,7 @@ for K in (8,):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); d.step(a, return_obs=False); e1.record(); torch.cuda.synchronize()
     t = d._trace.cpu().numpy().reshape(-1, 3); t = t[t[:, 0] > 0]
+    np.save(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", f"trace_k{K}.npy"), t)
     t0 = t[:, 0].min()
     st, en, sm = (t[:, 0] - t0) / 1e3, (t[:, 1] - t0) / 1e3, t[:, 2]
     print(f"K={K}: event time {e0.elapsed_time(e1)*1e3:.1f} us; warps {len(t)}; start us: min {st.min():.1f} p50 {np.median(st):.1f} p90 {np.percentile(st,90):.1f} max {st.max():.1f}")
