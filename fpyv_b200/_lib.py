@@ -8,7 +8,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 # FPYV_B200_LIB: developer override used to A/B differently tuned builds of the same ABI
 LIB_PATH = os.environ.get("FPYV_B200_LIB") or os.path.join(HERE, "libfpyv_b200.so")
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 # flags (fpv_api.h)
 F_GROUND, F_AUTO_RESET, F_FREEZE_DONE, F_THRUST_LUT, F_SCALAR, F_CHAINED = 1, 2, 4, 8, 32, 64
@@ -17,7 +17,7 @@ MAX_OBJECTS = 16
 DRONE_PLANES, RACER_PLANES = 4, 7
 EXPORTS = ("fpv_abi_version", "fpv_last_error", "fpv_sizeof", "fpv_device_info", "fpv_drone_reset",
            "fpv_drone_step", "fpv_drone_observe", "fpv_drone_get_rotation", "fpv_drone_set_rotation", "fpv_matrix_to_quat", "fpv_sticks_to_actions", "fpv_racer_reset", "fpv_racer_step", "fpv_gate_env_reset", "fpv_gate_env_step",
-           "fpv_camera_update", "fpv_camera_render", "fpv_camera_target_pixel", "fpv_camera_rays", "fpv_autopilot",
+           "fpv_camera_update", "fpv_camera_render", "fpv_camera_target_pixel", "fpv_camera_rays", "fpv_autopilot", "fpv_point_and_shoot",
            "fpv_acro_reset", "fpv_acro_step")
 
 
@@ -89,7 +89,8 @@ class AutopilotParams(C.Structure):
     _fields_ = [(k, C.c_double) for k in ("mass", "dt", "virtual_drag_coef", "virtual_lift_coef", "tof_effective_dist",
                                           "keep_distance", "uwb_max_range", "kP", "kI", "kD", "integral_clip",
                                           "min_output", "max_output", "derivative_transition_rate")] + \
-               [("ref_frame", C.c_int32), ("mode", C.c_int32)]
+               [("ref_frame", C.c_int32), ("mode", C.c_int32), ("max_throttle_force", C.c_double),
+                ("max_limit_iterations", C.c_int32), ("reserved", C.c_int32)]
 
 
 ACRO_PLANES = 7
@@ -148,6 +149,7 @@ def load():
     lib.fpv_camera_target_pixel.argtypes = [P(CameraParams), V, I64, V, I32, V, I32, V, D, V, V, V]
     lib.fpv_camera_rays.argtypes = [P(CameraParams), V, I64, V, I32, V, V]
     lib.fpv_autopilot.argtypes = [P(AutopilotParams), P(CameraParams), V, I64, I64, V, V, V, V, V, V, V, V, V]
+    lib.fpv_point_and_shoot.argtypes = [P(AutopilotParams), P(CameraParams), V, I64, I64, V, V, V, V, V, V, V, V, V]
     lib.fpv_acro_reset.argtypes = [V, I64, I64, V, V, V, V, V]
     lib.fpv_acro_step.argtypes = [P(AcroParams), V, I64, I64, V, V, I32, V, V, V, V, V]
     v = lib.fpv_abi_version()

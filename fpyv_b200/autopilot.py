@@ -61,10 +61,15 @@ class Autopilot:
         self.UWB_sensor_max_range = dr["UWB_sensor_max_range"]
         # Drone.__init__ overwrites the PID's output limits with the thrust limits (components.py:143-145)
         self.force_multiplier_pid = PID(**dr["force_multiplier_pid"], dt=drone.dt, num_envs=n, device=dev)
+        self.prev_pixel = None                                            # components.py:146-147
+        self.pixel_velocity = torch.zeros((n, 2), dtype=torch.float64, device=dev)
 
     def reset(self, mask=None):
-        """The autopilot part of Drone.reset, components.py:166."""
+        """The autopilot part of Drone.reset, components.py:166-168."""
         self.force_multiplier_pid.reset(mask)
+        if mask is None or self.prev_pixel is None:
+            self.prev_pixel = None
+            self.pixel_velocity = torch.zeros((self.drone.num_envs, 2), dtype=torch.float64, device=self.drone.device)
 
     def _params(self, ref_frame, mode) -> _lib.AutopilotParams:
         if ref_frame not in _FRAMES:
@@ -80,6 +85,8 @@ class Autopilot:
         p.min_output, p.max_output = pid.min_output, pid.max_output
         p.derivative_transition_rate = pid.derivative_transition_rate
         p.ref_frame, p.mode = _FRAMES[ref_frame], _MODES[mode]
+        p.max_throttle_force = float(self.drone.max_throttle_in_force)
+        p.max_limit_iterations = 64
         return p
 
     def calculate_needed_force_orientation(self, pixel, target_position, target_radius=0.0, ref_frame="world",
@@ -101,4 +108,34 @@ class Autopilot:
                                            d._stride, _lib.ptr(px), _lib.ptr(sn), _lib.ptr(tp), _lib.ptr(tr),
                                            _lib.ptr(self.force_multiplier_pid.state), _lib.ptr(rot), _lib.ptr(quat),
                                            _lib.ptr(force), _lib.current_stream(dev)))
+        return (quat if as_quaternion else rot), force
+
+    def convert_action2position(self, action):
+        """components.py:383-387: on-screen target position in pixels, truncated to int."""
+        a = torch.as_tensor(action, dtype=torch.float64, device=self.drone.device).reshape(-1, 4)
+        res = torch.as_tensor(np.asarray(self.camera.resolution, dtype=np.float64), device=a.device)
+        return (res / 2 * (1 + a[:, :2])).to(torch.int64)
+
+    def point_and_shoot(self, pixel, action, ref_frame="world", mode="level", seen=None, as_quaternion=False):
+        """components.py:312-381.  pixel [n,2]; action [n,4] = (target column, target row on the screen, virtual-target
+        x / y offset) in [-1,1].  Updates `prev_pixel` / `pixel_velocity` like :325-330.
+        Returns (rotation_to_apply_force float32 [n,3,3] or its quaternion [n,4], force float32 [n])."""
+        d = self.drone
+        n, dev = d.num_envs, d.device
+        f64 = lambda x, shape: torch.broadcast_to(torch.as_tensor(x, dtype=torch.float64, device=dev), shape).contiguous()
+        px, act = f64(pixel, (n, 2)), f64(action, (n, 4))
+        sn = None if seen is None else torch.as_tensor(seen, device=dev).to(torch.uint8).contiguous()
+        rot = None if as_quaternion else torch.empty((n, 3, 3), dtype=torch.float32, device=dev)
+        quat = torch.empty((n, 4), dtype=torch.float32, device=dev) if as_quaternion else None
+        force = torch.empty(n, dtype=torch.float32, device=dev)
+        shifted = torch.empty((n, 2), dtype=torch.float64, device=dev)
+        _lib.check(self._lib.fpv_point_and_shoot(self._params(ref_frame, mode), self.camera._params(), _lib.ptr(d._state), n,
+                                                 d._stride, _lib.ptr(px), _lib.ptr(act), _lib.ptr(sn),
+                                                 _lib.ptr(self.force_multiplier_pid.state), _lib.ptr(rot), _lib.ptr(quat),
+                                                 _lib.ptr(force), _lib.ptr(shifted), _lib.current_stream(dev)))
+        if self.prev_pixel is None:                                       # :325-330
+            self.pixel_velocity = torch.zeros_like(shifted)
+        else:
+            self.pixel_velocity = (shifted - self.prev_pixel) / self.force_multiplier_pid.dt
+        self.prev_pixel = shifted
         return (quat if as_quaternion else rot), force

@@ -226,6 +226,8 @@ struct AutopilotK {
   double kP, kI, kD, integral_clip, min_out, max_out, dtr;
   int ref_frame;  // 0 world, 1 drone
   int mode;       // 0 level, 1 frontarget
+  double max_force;  // max_throttle_in_force: the limit of point_and_shoot's loop (components.py:355)
+  int max_iter;
 };
 
 __device__ __forceinline__ void cross3(const double (&a)[3], const double (&b)[3], double (&c)[3]) {
@@ -234,10 +236,16 @@ __device__ __forceinline__ void cross3(const double (&a)[3], const double (&b)[3
   c[2] = a[0] * b[1] - a[1] * b[0];
 }
 
+// VARIANT 0: calculate_needed_force_orientation (:258-304).  VARIANT 1: point_and_shoot (:312-381) -- the pixel is
+// shifted by the virtual-target part of `action` (:322-323), the PID regulates the pixel ROW against the on-screen
+// target row (:348-350), the virtual lift scales with the sink rate (:345), and the multiplier is walked down until the
+// force fits max_throttle_in_force (:355-363; the reference's loop has no exit when drag + lift + gravity alone exceed the
+// limit -- capped at max_iter passes here).
+template <int VARIANT>
 __global__ void autopilot_kernel(const __grid_constant__ AutopilotK a, const __grid_constant__ CamK k, const float4* state,
                                  long long n, long long stride, const double* pixel, const unsigned char* seen,
-                                 const double* target_pos, const double* target_radius, double* pid, float* rot_out,
-                                 float4* quat_out, float* force_out) {
+                                 const double* target_pos, const double* target_radius, const double* action, double* pid,
+                                 float* rot_out, float4* quat_out, float* force_out, double* pixel_out) {
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n) return;
   if (seen && !seen[e]) {
@@ -260,7 +268,13 @@ __global__ void autopilot_kernel(const __grid_constant__ AutopilotK a, const __g
   const double pos[3] = {(double)pf.x, (double)pf.y, (double)pf.z};
   const double vel[3] = {(double)vf.x, (double)vf.y, (double)vf.z};
   double dir[3];
-  pixel_ray(k, camR, pixel[2 * e], pixel[2 * e + 1], 0, dir);  // :268 (always the world-frame ray)
+  double pu = pixel[2 * e], pv = pixel[2 * e + 1];
+  if (VARIANT == 1) {  // virtual target relative to the real one, :322-323
+    pu += action[4 * e + 2] * (0.5 * k.W);
+    pv += action[4 * e + 3] * (0.5 * k.H);
+    if (pixel_out) { pixel_out[2 * e] = pu; pixel_out[2 * e + 1] = pv; }
+  }
+  pixel_ray(k, camR, pu, pv, 0, dir);  // :268 / :332 (always the world-frame ray)
   const double speed = sqrt(vel[0] * vel[0] + vel[1] * vel[1] + vel[2] * vel[2]);
   double grav[3] = {0.0, 0.0, -9.81 * a.mass};  // kinematics.gravity_vector(mass, g=9.81), :271
   double v[3] = {vel[0], vel[1], vel[2]};
@@ -275,22 +289,42 @@ __global__ void autopilot_kernel(const __grid_constant__ AutopilotK a, const __g
   const double cosang = (v[0] / speed) * dir[0] + (v[1] / speed) * dir[1] + (v[2] / speed) * dir[2];
   const double dscale = -(cosang - 1.0) / 2.0;
   const bool low = pos[2] < a.tof_dist;  // virtual lift near the ground, :287
-  const double lift = low ? -(a.tof_dist - pos[2]) * a.vlift_coef * (1.0 + fabs(vel[2])) : 0.0;
-  // measured distance and the force-multiplier PID, :288-291 (+ Target.calculate_distance :770-771)
-  const double tx = pos[0] - target_pos[3 * e], ty = pos[1] - target_pos[3 * e + 1], tz = pos[2] - target_pos[3 * e + 2];
-  const double dist = fmin(sqrt(tx * tx + ty * ty + tz * tz) - target_radius[e], a.uwb_max);
+  const double lift_gain = VARIANT == 1 ? -fmin(vel[2], 0.0) : 1.0 + fabs(vel[2]);  // :345 / :287
+  const double lift = low ? -(a.tof_dist - pos[2]) * a.vlift_coef * lift_gain : 0.0;
   double* ps = pid + 4 * e;
-  const double err = dist - a.keep_distance;
+  double err;
+  if (VARIANT == 1) {
+    // on-screen target row, convert_action2position :383-387 (astype(int): truncation), PID on the pixel row :350
+    const double row = (double)(long long)(0.5 * k.H * (1.0 + action[4 * e + 1]));
+    err = pv - row;
+  } else {
+    // measured distance and the force-multiplier PID, :288-291 (+ Target.calculate_distance :770-771)
+    const double tx = pos[0] - target_pos[3 * e], ty = pos[1] - target_pos[3 * e + 1], tz = pos[2] - target_pos[3 * e + 2];
+    const double dist = fmin(sqrt(tx * tx + ty * ty + tz * tz) - target_radius[e], a.uwb_max);
+    err = dist - a.keep_distance;
+  }
   const double integ = fmin(fmax(0.99 * ps[0] + err * a.dt, -a.integral_clip), a.integral_clip);
   double der = fmin(fmax((ps[3] != 0.0 ? 0.0 : 1.0) * (err - ps[2]) / a.dt, -1.0), 1.0);
   der = (1.0 - a.dtr) * ps[1] + a.dtr * der;
   ps[0] = integ; ps[1] = der; ps[2] = err; ps[3] = 0.0;
-  const double mult = fmin(fmax(a.kP * err + a.kI * integ + a.kD * der, a.min_out), a.max_out);
-  double f[3];
+  double mult = fmin(fmax(a.kP * err + a.kI * integ + a.kD * der, a.min_out), a.max_out);
+  double rest[3], f[3];
 #pragma unroll
-  for (int i = 0; i < 3; ++i)  // :293
-    f[i] = mult * dir[i] + a.vdrag_coef * (dscale * -v[i] * speed) + lift * grav[i] - grav[i];
-  const double fn = sqrt(f[0] * f[0] + f[1] * f[1] + f[2] * f[2]);
+  for (int i = 0; i < 3; ++i) {  // :293 / :352
+    rest[i] = a.vdrag_coef * (dscale * -v[i] * speed) + lift * grav[i] - grav[i];
+    f[i] = mult * dir[i] + rest[i];
+  }
+  double fn = sqrt(f[0] * f[0] + f[1] * f[1] + f[2] * f[2]);
+  if (VARIANT == 1) {  // :353-363
+    double crit = 0.9999;
+    for (int it = 0; it < a.max_iter && fn > a.max_force; ++it) {
+      mult = fmin(fmax(mult * crit, a.min_out), a.max_out);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) f[i] = mult * dir[i] + rest[i];
+      fn = sqrt(f[0] * f[0] + f[1] * f[1] + f[2] * f[2]);
+      crit = a.max_force / fn;
+    }
+  }
   double yv[3], xv[3];
   if (a.mode == 0) cross3(f, grav, yv); else cross3(f, dir, yv);  // :295-300
   cross3(yv, f, xv);

@@ -548,25 +548,51 @@ int fpv_camera_rays(const fpv_camera_params_t* cam, const double* pose, int64_t 
   return check_launch("fpv_camera_rays");
 }
 
-int fpv_autopilot(const fpv_autopilot_params_t* ap, const fpv_camera_params_t* cam, const void* state, int64_t n,
-                  int64_t plane_stride, const double* pixel, const uint8_t* seen, const double* target_pos,
-                  const double* target_radius, double* pid, float* rot, void* quat, float* force, void* stream) {
-  fpv::CamK k;
-  if (int rc = make_cam(cam, k, "fpv_autopilot")) return rc;
-  if (!ap || !state || !pixel || !target_pos || !target_radius || !pid) return fail(FPV_EINVAL, "fpv_autopilot: null pointer");
-  if (n < 0 || plane_stride < n || !aligned16(state) || !aligned16(quat)) return fail(FPV_EINVAL, "fpv_autopilot: bad n/stride/alignment");
-  if (ap->ref_frame < 0 || ap->ref_frame > 1) return fail(FPV_EINVAL, "fpv_autopilot: Unknown reference frame");
-  if (ap->mode < 0 || ap->mode > 1) return fail(FPV_EINVAL, "fpv_autopilot: Unknown mode");
-  if (!(ap->dt > 0.0)) return fail(FPV_EINVAL, "fpv_autopilot: dt must be positive");
-  fpv::AutopilotK a;
+namespace {
+int make_autopilot(const fpv_autopilot_params_t* ap, fpv::AutopilotK& a, const char* who) {
+  if (!ap) return fail(FPV_EINVAL, "%s: null params", who);
+  if (ap->ref_frame < 0 || ap->ref_frame > 1) return fail(FPV_EINVAL, "%s: Unknown reference frame", who);
+  if (ap->mode < 0 || ap->mode > 1) return fail(FPV_EINVAL, "%s: Unknown mode", who);
+  if (!(ap->dt > 0.0)) return fail(FPV_EINVAL, "%s: dt must be positive", who);
   a.mass = ap->mass; a.dt = ap->dt; a.vdrag_coef = ap->virtual_drag_coef; a.vlift_coef = ap->virtual_lift_coef;
   a.tof_dist = ap->tof_effective_dist; a.keep_distance = ap->keep_distance; a.uwb_max = ap->uwb_max_range;
   a.kP = ap->kP; a.kI = ap->kI; a.kD = ap->kD; a.integral_clip = ap->integral_clip; a.min_out = ap->min_output;
   a.max_out = ap->max_output; a.dtr = ap->derivative_transition_rate; a.ref_frame = ap->ref_frame; a.mode = ap->mode;
+  a.max_force = ap->max_throttle_force;
+  a.max_iter = ap->max_limit_iterations > 0 ? ap->max_limit_iterations : 64;
+  return FPV_OK;
+}
+}  // namespace
+
+int fpv_autopilot(const fpv_autopilot_params_t* ap, const fpv_camera_params_t* cam, const void* state, int64_t n,
+                  int64_t plane_stride, const double* pixel, const uint8_t* seen, const double* target_pos,
+                  const double* target_radius, double* pid, float* rot, void* quat, float* force, void* stream) {
+  fpv::CamK k;
+  fpv::AutopilotK a;
+  if (int rc = make_cam(cam, k, "fpv_autopilot")) return rc;
+  if (int rc = make_autopilot(ap, a, "fpv_autopilot")) return rc;
+  if (!state || !pixel || !target_pos || !target_radius || !pid) return fail(FPV_EINVAL, "fpv_autopilot: null pointer");
+  if (n < 0 || plane_stride < n || !aligned16(state) || !aligned16(quat)) return fail(FPV_EINVAL, "fpv_autopilot: bad n/stride/alignment");
   if (n == 0) return FPV_OK;
-  fpv::autopilot_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
-      a, k, (const float4*)state, n, plane_stride, pixel, seen, target_pos, target_radius, pid, rot, (float4*)quat, force);
+  fpv::autopilot_kernel<0><<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      a, k, (const float4*)state, n, plane_stride, pixel, seen, target_pos, target_radius, nullptr, pid, rot, (float4*)quat, force, nullptr);
   return check_launch("fpv_autopilot");
+}
+
+int fpv_point_and_shoot(const fpv_autopilot_params_t* ap, const fpv_camera_params_t* cam, const void* state, int64_t n,
+                        int64_t plane_stride, const double* pixel, const double* action, const uint8_t* seen, double* pid,
+                        float* rot, void* quat, float* force, double* shifted_pixel, void* stream) {
+  fpv::CamK k;
+  fpv::AutopilotK a;
+  if (int rc = make_cam(cam, k, "fpv_point_and_shoot")) return rc;
+  if (int rc = make_autopilot(ap, a, "fpv_point_and_shoot")) return rc;
+  if (!state || !pixel || !action || !pid) return fail(FPV_EINVAL, "fpv_point_and_shoot: null pointer");
+  if (n < 0 || plane_stride < n || !aligned16(state) || !aligned16(quat)) return fail(FPV_EINVAL, "fpv_point_and_shoot: bad n/stride/alignment");
+  if (!(ap->max_throttle_force > 0.0)) return fail(FPV_EINVAL, "fpv_point_and_shoot: max_throttle_force must be positive");
+  if (n == 0) return FPV_OK;
+  fpv::autopilot_kernel<1><<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      a, k, (const float4*)state, n, plane_stride, pixel, seen, nullptr, nullptr, action, pid, rot, (float4*)quat, force, shifted_pixel);
+  return check_launch("fpv_point_and_shoot");
 }
 
 int fpv_acro_reset(void* state, int64_t n, int64_t plane_stride, const float* pos, const float* vel,

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define FPV_ABI_VERSION 9
+#define FPV_ABI_VERSION 10
 
 /* error codes */
 #define FPV_OK 0
@@ -295,6 +295,9 @@ typedef struct fpv_autopilot_params { /* Drone.__init__, components.py:96-97, :1
   double kP, kI, kD, integral_clip, min_output, max_output, derivative_transition_rate;  /* force_multiplier_pid */
   int32_t ref_frame;                 /* 0 'world', 1 'drone'            components.py:270-279 */
   int32_t mode;                      /* 0 'level', 1 'frontarget'       components.py:295-301 */
+  double max_throttle_force;         /* Drone.max_throttle_in_force (components.py:142): limit of point_and_shoot's loop */
+  int32_t max_limit_iterations;      /* cap on that loop (the reference's has none and can spin forever); <= 0: 64 */
+  int32_t reserved;
 } fpv_autopilot_params_t;
 
 /* Camera.update (components.py:501-503) for every env: pose[e] = { R_cam row-major [9], camera position [3] }. */
@@ -332,6 +335,14 @@ int fpv_camera_rays(const fpv_camera_params_t* cam, const double* pose, int64_t 
 int fpv_autopilot(const fpv_autopilot_params_t* ap, const fpv_camera_params_t* cam, const void* state, int64_t n,
                   int64_t plane_stride, const double* pixel, const uint8_t* seen, const double* target_pos,
                   const double* target_radius, double* pid, float* rot, void* quat, float* force, void* stream);
+
+/* Drone.point_and_shoot (components.py:312-381) for every env.  pixel: double[n][2]; action: double[n][4] =
+ * (target column, target row on the screen, virtual-target x / y offset), each in [-1, 1] (:316, :322-323, :383-387);
+ * seen / pid / rot / quat / force as in fpv_autopilot; shifted_pixel: double[n][2] out (pixel + virtual target, the
+ * value the reference stores in prev_pixel, :325-330) or NULL. */
+int fpv_point_and_shoot(const fpv_autopilot_params_t* ap, const fpv_camera_params_t* cam, const void* state, int64_t n,
+                        int64_t plane_stride, const double* pixel, const double* action, const uint8_t* seen, double* pid,
+                        float* rot, void* quat, float* force, double* shifted_pixel, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Mode C ("acro"): stick -> rate set-point -> acro rate PID -> motor mixer -> per-motor thrust / torque from the

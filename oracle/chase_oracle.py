@@ -264,3 +264,63 @@ def needed_force_orientation(a: AutopilotConsts, cam: CameraConsts, pid: PIDStat
     rot = np.stack([xv, yv, force], axis=2)                                      # columns, :303
     rot = rot / np.linalg.norm(rot, axis=1, keepdims=True)                       # :304 (column norms)
     return rot, fnorm
+
+
+# --------------------------------------------------------------------------------------
+# Drone.point_and_shoot (src/utils/components.py:312-381) and convert_action2position (:383-387)
+# --------------------------------------------------------------------------------------
+def convert_action2position(cam: CameraConsts, action):
+    """components.py:383-387: (resolution[i] / 2 * (1 + action[i])).astype(int), i = 0, 1."""
+    return (cam.resolution[None, :] / 2 * (1 + np.asarray(action, dtype=np.float64)[:, :2])).astype(int)
+
+
+def point_and_shoot(a: AutopilotConsts, cam: CameraConsts, pid: PIDState, pixel, action, pos, vel, R, max_force,
+                    ref_frame="world", mode="level", max_iter=64):
+    """components.py:312-381 for n envs.  pixel [n,2], action [n,4] = (target row/column on screen in [-1,1]^2,
+    virtual-target offset in [-1,1]^2).  Returns (rotation_to_apply_force [n,3,3], force_vector_norm [n], shifted
+    pixel [n,2]).  The reference's `while force_vector_norm > max_throttle_in_force` loop (:350-358) does not terminate
+    when the drag / lift / gravity terms alone exceed the limit; it is capped at `max_iter` passes here."""
+    action = np.asarray(action, dtype=np.float64)
+    pixel = np.asarray(pixel, dtype=np.float64) + action[:, 2:] * cam.resolution / 2          # :322-323
+    _, cam_R = camera_update(cam, pos, R)
+    dir2t = pixel2direction(cam, pixel, cam_R)                                                 # :332
+    speed = np.linalg.norm(vel, axis=1, keepdims=True)
+    if ref_frame == "world":
+        gravity = np.tile([0.0, 0.0, -9.81 * a.mass], (len(pos), 1))
+        cosang = np.einsum("ni,ni->n", vel / speed, dir2t)[:, None]
+        vdrag = -(cosang - 1) / 2 * -vel * speed
+    elif ref_frame == "drone":
+        gravity = np.einsum("nij,j->ni", R, np.array([0.0, 0.0, -9.81 * a.mass]))
+        rv = np.einsum("nij,nj->ni", R, vel)
+        cosang = np.einsum("ni,ni->n", rv / speed, dir2t)[:, None]
+        vdrag = -(cosang - 1) / 2 * -rv * speed
+    else:
+        raise ValueError("Unknown reference frame")
+    vdrag_force = a.virtual_drag_coef * vdrag
+    z = pos[:, 2:3]
+    vlift = (z < a.tof_effective_dist) * -(a.tof_effective_dist - z) * a.virtual_lift_coef * gravity * -np.minimum(vel[:, 2:3], 0.0)  # :345
+    position = convert_action2position(cam, action)                                            # :348
+    mult = pid_call(pid, pixel[:, 1], position[:, 1].astype(np.float64), a.kP, a.kI, a.kD, a.dt, a.integral_clip,
+                    a.min_output, a.max_output, a.dtr)                                         # :350
+    rest = vdrag_force + vlift - gravity
+    force = mult[:, None] * dir2t + rest
+    fnorm = np.linalg.norm(force, axis=1)
+    crit = np.full(len(pos), 0.9999)
+    for _ in range(max_iter):                                                                  # :355-363
+        over = fnorm > max_force
+        if not over.any():
+            break
+        mult = np.where(over, np.clip(mult * crit, a.min_output, a.max_output), mult)
+        force = np.where(over[:, None], mult[:, None] * dir2t + rest, force)
+        fnorm = np.where(over, np.linalg.norm(force, axis=1), fnorm)
+        crit = np.where(over, max_force / fnorm, crit)
+    if mode == "level":
+        yv = np.cross(force, gravity)
+    elif mode == "frontarget":
+        yv = np.cross(force, dir2t)
+    else:
+        raise ValueError("Unknown mode")
+    xv = np.cross(yv, force)
+    rot = np.stack([xv, yv, force], axis=2)
+    rot = rot / np.linalg.norm(rot, axis=1, keepdims=True)
+    return rot, fnorm, pixel

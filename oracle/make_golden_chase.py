@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import copy
 import os
+import signal
 import sys
 
 import numpy as np
@@ -113,6 +114,45 @@ def main():
     np.savez_compressed(os.path.join(OUT, "chase_autopilot.npz"), pos=pos, vel=vel, rpy=rpy, target_pos=tpos,
                         target_radius=trad, pixel=pixel, min_force=dr.min_throttle_in_force,
                         max_force=dr.max_throttle_in_force, **out)
+
+    # ------------------------------------------------------------------ point_and_shoot (components.py:312-381)
+    n = 24
+    rng = np.random.default_rng(24)
+    pos = np.stack([rng.uniform(-6, 6, n), rng.uniform(-6, 6, n), rng.uniform(0.5, 8, n)], axis=1)
+    vel = rng.normal(0, 3, (n, 3))
+    # (|v| is kept moderate: the reference's force-limit loop :355-363 never terminates once drag + lift + gravity
+    #  alone exceed max_throttle_in_force; every call below runs under a watchdog for that reason)
+    rpy = rng.uniform(-30, 30, (n, 3))
+    pixel = rng.uniform(0.2, 0.8, (n, 2)) * np.array(params["camera"]["resolution"])
+    action = rng.uniform(-0.6, 0.6, (n, 4))
+    out = {}
+    for frame in ("world", "drone"):
+        for mode in ("level", "frontarget"):
+            rots, forces, pid_state, pv = [], [], [], []
+            for e in range(n):
+                dr = rs.make_drone(params)
+                with rs.quiet():
+                    dr.reset(pos[e], vel[e], rpy[e])
+                    calls = []
+                    for k in range(10):     # the PID integrates the pixel error: later calls saturate the multiplier
+                        signal.alarm(10)
+                        rot, f = dr.point_and_shoot(pixel[e] + 3.0 * k, action[e], ref_frame=frame, mode=mode)
+                        signal.alarm(0)
+                        calls.append((np.array(rot), float(f)))
+                rots.append([c[0] for c in calls])
+                forces.append([c[1] for c in calls])
+                p = dr.force_multiplier_pid
+                pid_state.append([p.integral, p.prev_derivative, p.previous_error, float(p.is_first)])
+                pv.append(np.concatenate([dr.pixel_velocity, dr.prev_pixel]))
+            out[f"rot_{frame}_{mode}"] = np.array(rots)
+            out[f"force_{frame}_{mode}"] = np.array(forces)
+            out[f"pid_{frame}_{mode}"] = np.array(pid_state)
+            out[f"pixvel_{frame}_{mode}"] = np.array(pv)
+    np.savez_compressed(os.path.join(OUT, "chase_point_and_shoot.npz"), pos=pos, vel=vel, rpy=rpy, pixel=pixel, action=action,
+                        max_force=dr.max_throttle_in_force, min_force=dr.min_throttle_in_force,
+                        position=np.array([dr.convert_action2position(a_) for a_ in action]), **out)
+    print("chase_point_and_shoot: (env, call) pairs held at the force limit:",
+          int((out["force_world_level"] >= dr.max_throttle_in_force * (1 - 1e-6)).sum()), "of", out["force_world_level"].size)
 
     # ------------------------------------------------------------------ the closed loop of simulator.py:98-110 (dim == 3)
     n, T = 8, 40

@@ -111,3 +111,30 @@ def test_closed_loop_matches_reference():
             np.testing.assert_allclose(np.concatenate([s.pos[0], s.vel[0]]), g["state"][t, e], rtol=1e-9, atol=1e-9)
             np.testing.assert_allclose(s.R[0], g["R"][t, e], rtol=0, atol=1e-9)
             assert bool(s.done[0]) == bool(g["done"][t, e])
+
+
+@pytest.mark.parametrize("frame", ["world", "drone"])
+@pytest.mark.parametrize("mode", ["level", "frontarget"])
+def test_point_and_shoot(frame, mode):
+    """Drone.point_and_shoot (components.py:312-381) incl. its force-limit loop, 10 consecutive calls per env."""
+    g = load("chase_point_and_shoot")
+    p = params()
+    c = co.camera_consts(p)
+    a = co.autopilot_consts(p, float(g["min_force"]), float(g["max_force"]))
+    n = len(g["pos"])
+    ang = np.deg2rad(g["rpy"])
+    R = fo.euler_matrix(ang[:, 0], ang[:, 1], ang[:, 2])
+    assert np.array_equal(co.convert_action2position(c, g["action"]), g["position"])
+    pid = co.pid_reset(n)
+    prev = None
+    for call in range(g[f"force_{frame}_{mode}"].shape[1]):
+        rot, f, shifted = co.point_and_shoot(a, c, pid, g["pixel"] + 3.0 * call, g["action"], g["pos"], g["vel"], R,
+                                             float(g["max_force"]), ref_frame=frame, mode=mode)
+        np.testing.assert_allclose(rot, g[f"rot_{frame}_{mode}"][:, call], rtol=0, atol=1e-9)
+        np.testing.assert_allclose(f, g[f"force_{frame}_{mode}"][:, call], rtol=1e-10)
+        pv = np.zeros_like(shifted) if prev is None else (shifted - prev) / a.dt          # components.py:325-330
+        prev = shifted
+    np.testing.assert_allclose(np.concatenate([pv, prev], axis=1), g[f"pixvel_{frame}_{mode}"], rtol=1e-10, atol=1e-9)
+    st = np.stack([pid.integral, pid.prev_derivative, pid.previous_error, pid.is_first.astype(float)], axis=1)
+    np.testing.assert_allclose(st, g[f"pid_{frame}_{mode}"], rtol=1e-11, atol=1e-13)
+    assert (g[f"force_{frame}_{mode}"] >= float(g["max_force"]) * (1 - 1e-6)).any()       # the limit loop ran

@@ -303,3 +303,29 @@ def test_guard_cells_around_every_output_of_the_chase_kernels():
     cam.update_from(d)
     assert torch.equal(pose.view(n, 12), cam._pose)
     assert torch.equal(img.view(n, H, W), cam.render_depth_image(w, 15))
+
+
+@pytest.mark.parametrize("frame", ["world", "drone"])
+@pytest.mark.parametrize("mode", ["level", "frontarget"])
+def test_point_and_shoot_vs_reference(frame, mode):
+    """Drone.point_and_shoot (components.py:312-381): 10 consecutive calls per env against the reference's outputs,
+    including the calls where the force-limit loop (:355-363) holds the force at max_throttle_in_force."""
+    from fpyv_b200 import Autopilot
+    g = load("chase_point_and_shoot")
+    d = _drone_from(g["pos"], g["vel"], g["rpy"])
+    ap = Autopilot(d)
+    assert np.array_equal(ap.convert_action2position(g["action"]).cpu().numpy(), g["position"])
+    calls = g[f"force_{frame}_{mode}"].shape[1]
+    limited = 0
+    for call in range(calls):
+        rot, f = ap.point_and_shoot(g["pixel"] + 3.0 * call, g["action"], ref_frame=frame, mode=mode)
+        np.testing.assert_allclose(rot.double().cpu().numpy(), g[f"rot_{frame}_{mode}"][:, call], rtol=0, atol=1e-5)
+        np.testing.assert_allclose(f.double().cpu().numpy(), g[f"force_{frame}_{mode}"][:, call], rtol=1e-5)
+        limited += int((g[f"force_{frame}_{mode}"][:, call] >= float(g["max_force"]) * (1 - 1e-6)).sum())
+    assert limited > 0
+    np.testing.assert_allclose(ap.force_multiplier_pid.state.cpu().numpy(), g[f"pid_{frame}_{mode}"], rtol=1e-5, atol=1e-6)
+    pv = torch.cat([ap.pixel_velocity, ap.prev_pixel], dim=1).cpu().numpy()
+    np.testing.assert_allclose(pv, g[f"pixvel_{frame}_{mode}"], rtol=1e-9, atol=1e-9)
+    q, f2 = ap.point_and_shoot(g["pixel"], g["action"], ref_frame=frame, mode=mode, as_quaternion=True,
+                               seen=np.arange(len(g["pos"])) % 2)
+    assert torch.isnan(f2[::2]).all() and torch.isfinite(f2[1::2]).all()

@@ -607,3 +607,45 @@ def test_step_host_pipelined_slices_match_plain_step():
         assert torch.equal(done_h, b.done.cpu()), i
     assert torch.equal(a._state, b._state)
     assert a.episode_stats() == b.episode_stats()
+
+
+def test_baseline_config0_single_drone_10k_steps():
+    """BASELINE.json configs[0]: ONE drone, dt = 1 ms, 10,000 steps (the CPU-runnable case of the reference), both
+    dynamics modes, free-running against the float64 oracle.  The single-step bound is the north_star's 1e-5; the
+    divergence curve over the 10 s horizon is reported (acro dynamics are chaotic) and bounded loosely."""
+    from fpyv_b200 import BatchedDrone, BatchedRacer
+    rng = np.random.default_rng(31)
+    # --- mode A: Drone.step with sticks changing every 50 ms
+    c = fo_consts(1e-3)
+    d = BatchedDrone(None, num_envs=1, device=DEV, dt=1e-3)
+    pos, vel, rpy = np.array([[0.0, 0, 10]]), np.array([[1.0, 0, 0]]), np.zeros((1, 3))       # params.yaml initial state
+    d.reset(pos, vel, rpy)
+    s = fo.drone_reset(c, pos, vel, rpy)
+    curve = {}
+    act = None
+    for t in range(10_000):
+        if t % 50 == 0:
+            act = rng.uniform(-1, 1, (1, 4)) * np.array([0.3, 0.3, 0.3, 1.0]) + np.array([0, 0, 0, -0.3])
+        fo.drone_step(c, s, act)
+        d.step(act, return_obs=False)
+        if t + 1 in (1, 10, 100, 1000, 10_000):
+            curve[t + 1] = float(drone_err(d, np.concatenate([s.pos, s.vel], 1), s.R, s.prev_rates, s.prev_thrust).max())
+    print("\nconfigs[0] Drone, 1 env, dt 1 ms: divergence " + " ".join(f"@{k}:{v:.1e}" for k, v in curve.items()))
+    assert curve[1] <= TOL_STEP and curve[1000] <= 1e-4 and curve[10_000] <= 5e-2
+    # --- mode B: the Racer of tests/racer_drone_test.py, its own demo gains and set-point switch, 10,000 steps
+    gains = {"roll": [2, 0, 0], "pitch": [2, 0, 0], "yaw": [0.1, 0, 0]}
+    rc = fo.RacerConsts(gains=np.array(list(gains.values()), dtype=np.float64))
+    rs = fo.RacerState(1)
+    r = BatchedRacer(5, gains, num_envs=1, device=DEV)
+    r.reset()
+    curve = {}
+    for t in range(10_000):
+        a = np.array([[80.0, 10, 0, 0]]) if t <= 20 else np.array([[-30.0, -50, 0, 0]])
+        fo.racer_step(rc, rs, a)
+        r.step(a)
+        if t + 1 in (1, 10, 100, 1000, 10_000):
+            curve[t + 1] = float(max(group_err(r.angular_velocity.cpu().numpy(), rs.omega).max(),
+                                     group_err(r.orientation.cpu().numpy(), rs.R).max(),
+                                     group_err(r.linear_velocity.cpu().numpy(), rs.vel).max()))
+    print("configs[0] Racer, 1 env, dt 1 ms: divergence " + " ".join(f"@{k}:{v:.1e}" for k, v in curve.items()))
+    assert curve[1] <= TOL_STEP and curve[10_000] <= 5e-2
