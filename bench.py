@@ -300,16 +300,34 @@ def run_gpu(args):
     torch.cuda.synchronize()
     ms_e2e = e0.elapsed_time(e1)
 
+    # ---- the same workload as an open-loop rollout in ONE launch per 16 control steps (fpv_drone_rollout: state in
+    #      registers across the steps).  Reported next to the headline, never as it: the headline keeps one launch and
+    #      one HBM round trip of the state per control step.  4 batches x 16 steps x 16 MiB of actions >> L2.
+    T_ro = 16
+    ro_actions = (torch.rand(T_ro, n, 4, device=dev, generator=gen) * 2 - 1).contiguous()
+    reps = max(1, K // T_ro)
+    for j in range(len(drones)):
+        drones[j].rollout(ro_actions, fused=True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(reps):
+        drones[i % len(drones)].rollout(ro_actions, fused=True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_rollout = e0.elapsed_time(e1) / (reps * T_ro)
+    del ro_actions
+
     # ---- HBM-bound variant of the same kernel (K = 1) for the memory-roofline placement
     d1s = [make(1, seed_off=j)[0] for j in range(NB)]
     ms_k1 = timed_rotation(d1s, K, W)
 
     t1 = time.time()
     clocks = sampler.stop(t0, t1) if sampler else None      # covers the K=8 loop, the e2e loop and the K=1 loop
-    t = torch.tensor([ms, ms_e2e, ms_k1], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, ms_e2e, ms_k1, ms_rollout], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e, ms_k1 = t.tolist()
+    ms, ms_e2e, ms_k1, ms_rollout = t.tolist()
     stats = drone.episode_stats(all_reduce=world > 1)      # the engine's only collective (NCCL), outside the timed loop
     ms_flushed_per_step = ms_flushed / K_fl
     if rank != 0:
@@ -347,6 +365,10 @@ def run_gpu(args):
                     "d2h_bytes_per_step": n * world, "ms_per_step": ms_e2e / K,
                     "api": "BatchedDrone.step_host(pinned actions) -> pinned done flags, 4 env slices pipelined over H2D / step / D2H streams; host waits every step"},
             "ms_per_step_flushed": ms_flushed_per_step,
+            "rollout_fused": {"ms_per_step": ms_rollout, "env_steps_per_sec": total_envs / (ms_rollout * 1e-3),
+                              "steps_per_launch": T_ro, "fp32_frac": FLOP_PER_ENV_SUBSTEP * SUBSTEPS * n / (ms_rollout * 1e-3) / 1e12 / (sm_count * FP32_LANES_PER_SM * 2 * pk["sm_max_mhz"] * 1e6 / 1e12),
+                              "api": "BatchedDrone.rollout(actions[16, n, 4]): fpv_drone_rollout, bit-identical to 16 step() calls; "
+                                     "extra metric, not the headline (the state stays in registers between control steps)"},
             "gpu_launches": K, "roofline": roof,
             "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "clocks": clocks, "episode_stats": stats}

@@ -714,4 +714,145 @@ __global__ void __launch_bounds__(THREADS, MINB) drone_step_tma_kernel(const __g
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Kernel 3 (open-loop rollouts): T control steps per launch with the state held in REGISTERS across the steps.
+// Every env's state is read once and written once per launch; per control step only its 16-byte action is read and
+// its done byte written (17 B/env/step instead of 145).  Arithmetic per control step is drone_substeps() exactly as in
+// the step kernels -- the values pass through the same float32 registers they would pass through in memory -- so a
+// rollout is BIT-IDENTICAL to T launches of fpv_drone_step, episode bookkeeping, auto-reset and statistics included.
+// Warp-chunks of 32*L envs are pulled dynamically; the next step's actions are fetched while the current step computes.
+// ---------------------------------------------------------------------------------------------------------------
+template <class V> __device__ __forceinline__ V lane_set(V v, int l, float x);
+template <> __device__ __forceinline__ float lane_set<float>(float, int, float x) { return x; }
+template <> __device__ __forceinline__ F2 lane_set<F2>(F2 v, int l, float x) {
+  float a, b;
+  f2_unpack(v, a, b);
+  return l ? f2_pack(a, x) : f2_pack(x, b);
+}
+
+template <class V, int ANG, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) drone_rollout_kernel(const __grid_constant__ DroneK k, const DroneIO io,
+                                                                      const float4* actions_seq, const long long act_stride,
+                                                                      const int T, unsigned char* done_seq,
+                                                                      const long long done_stride) {
+  constexpr int L = Lane<V>::N;
+  constexpr int CHUNK = 32 * L;
+  constexpr int WARPS = THREADS / 32;
+  extern __shared__ __align__(16) float lut_dyn[];
+  if (k.flags & FPV_F_THRUST_LUT) {
+    for (int i = threadIdx.x; i < k.lut_n; i += THREADS) lut_dyn[i] = io.lut[i];
+    __syncthreads();
+  }
+  const int lane = threadIdx.x & 31;
+  const long long n_chunks = (io.n + CHUNK - 1) / CHUNK;
+  const long long total_warps = (long long)gridDim.x * WARPS;
+  const bool wind_on = k.wind[0] != 0.f || k.wind[1] != 0.f || k.wind[2] != 0.f;
+  const V wx = S<V>(k.wind[0]), wy = S<V>(k.wind[1]), wz = S<V>(k.wind[2]);
+  const V zero = S<V>(0.f);
+  if (io.stats && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&io.stats->env_steps, (double)io.n * (double)T);
+  TileStats st = {0.f, 0.f, 0.f, 0.f, 0.f};
+  long long cur = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5);   // first chunk static, the rest pulled
+  while (cur < n_chunks) {
+    const long long base = cur * CHUNK + lane;
+    long long ei[L];
+    bool live[L];
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+      live[l] = base + (long long)l * 32 < io.n;
+      ei[l] = min(base + (long long)l * 32, io.n - 1);   // a slot past the end recomputes env n-1 and is never stored
+    }
+    float4 q[FPV_DRONE_PLANES][L];
+#pragma unroll
+    for (int p = 0; p < FPV_DRONE_PLANES; ++p)
+#pragma unroll
+      for (int l = 0; l < L; ++l) q[p][l] = ldg_stream(io.state + p * io.stride + ei[l]);
+    float4 act[L], act_next[L];
+#pragma unroll
+    for (int l = 0; l < L; ++l) act[l] = ldg_stream(actions_seq + ei[l]);
+    DroneRegs<V> s;
+    s.px = Pack<V>::x(q[0]); s.py = Pack<V>::y(q[0]); s.pz = Pack<V>::z(q[0]); s.pt = Pack<V>::w(q[0]);
+    s.vx = Pack<V>::x(q[1]); s.vy = Pack<V>::y(q[1]); s.vz = Pack<V>::z(q[1]);
+    s.qw = Pack<V>::x(q[2]); s.qx = Pack<V>::y(q[2]); s.qy = Pack<V>::z(q[2]); s.qz = Pack<V>::w(q[2]);
+    s.pr0 = Pack<V>::x(q[3]); s.pr1 = Pack<V>::y(q[3]); s.pr2 = Pack<V>::z(q[3]);
+    s.ax = zero; s.ay = zero; s.az = zero;
+    int epi[L];
+    float spare[L];
+#pragma unroll
+    for (int l = 0; l < L; ++l) { epi[l] = __float_as_int(q[1][l].w); spare[l] = q[3][l].w; }
+
+    for (int t = 0; t < T; ++t) {
+      if (t + 1 < T) {   // next step's sticks travel while this step computes
+#pragma unroll
+        for (int l = 0; l < L; ++l) act_next[l] = ldg_stream(actions_seq + (long long)(t + 1) * act_stride + ei[l]);
+      }
+      const V a0 = Pack<V>::x(act), a1 = Pack<V>::y(act), a2 = Pack<V>::z(act), a3 = Pack<V>::w(act);
+      V target;
+      if (k.flags & FPV_F_THRUST_LUT) {
+        float tt[2];
+#pragma unroll
+        for (int l = 0; l < L; ++l) tt[l] = thrust_lut1(k, lut_dyn, act[l].w);
+        target = Lane<V>::make(tt[0], tt[L - 1]);
+      } else {
+        target = thrust_poly<V>(k, a3);
+      }
+      typename Lane<V>::Mask done;
+      if (wind_on) done = drone_substeps<V, ANG, false, true>(k, s, a0, a1, a2, target, wx, wy, wz, false, zero, zero, zero, zero, zero);
+      else done = drone_substeps<V, ANG, false, false>(k, s, a0, a1, a2, target, wx, wy, wz, false, zero, zero, zero, zero, zero);
+      // ---- per-step bookkeeping, exactly drone_tile's epilogue but on registers
+#pragma unroll
+      for (int l = 0; l < L; ++l) {
+        if (!live[l]) continue;
+        const bool d = mask_get(done, l);
+        if (done_seq) done_seq[(long long)t * done_stride + ei[l]] = d ? 1 : 0;
+        if (io.done && t == T - 1) io.done[ei[l]] = d ? 1 : 0;
+        epi[l] += 1;
+        if (d) {
+          st.crash += 1.f;
+          if (k.flags & FPV_F_AUTO_RESET) {   // restart from the reset snapshot: the registers take its rows
+            st.epi += 1.f; st.len += (float)epi[l];
+            float4 v[FPV_DRONE_PLANES];
+#pragma unroll
+            for (int p = 0; p < FPV_DRONE_PLANES; ++p) v[p] = ldg_stream(io.reset_state + p * io.stride + ei[l]);
+            s.px = lane_set<V>(s.px, l, v[0].x); s.py = lane_set<V>(s.py, l, v[0].y); s.pz = lane_set<V>(s.pz, l, v[0].z);
+            s.pt = lane_set<V>(s.pt, l, v[0].w);
+            s.vx = lane_set<V>(s.vx, l, v[1].x); s.vy = lane_set<V>(s.vy, l, v[1].y); s.vz = lane_set<V>(s.vz, l, v[1].z);
+            s.qw = lane_set<V>(s.qw, l, v[2].x); s.qx = lane_set<V>(s.qx, l, v[2].y); s.qy = lane_set<V>(s.qy, l, v[2].z);
+            s.qz = lane_set<V>(s.qz, l, v[2].w);
+            s.pr0 = lane_set<V>(s.pr0, l, v[3].x); s.pr1 = lane_set<V>(s.pr1, l, v[3].y); s.pr2 = lane_set<V>(s.pr2, l, v[3].z);
+            spare[l] = v[3].w;
+            epi[l] = 0;
+            continue;
+          }
+        }
+        if (!(fabsf((Lane<V>::get(s.px, l) + Lane<V>::get(s.py, l)) + Lane<V>::get(s.pz, l)) <= 3.0e38f)) st.nf += 1.f;
+      }
+#pragma unroll
+      for (int l = 0; l < L; ++l) act[l] = act_next[l];
+    }
+    // ---- the state goes back once
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+      if (!live[l]) continue;
+      const long long e = base + (long long)l * 32;
+      float4* const dst = io.state + e;
+      if (io.acc_out)
+        stg_stream(io.acc_out + e, make_float4(Lane<V>::get(s.ax, l), Lane<V>::get(s.ay, l), Lane<V>::get(s.az, l), 0.f));
+      stg_stream(dst, make_float4(Lane<V>::get(s.px, l), Lane<V>::get(s.py, l), Lane<V>::get(s.pz, l), Lane<V>::get(s.pt, l)));
+      stg_stream(dst + io.stride, make_float4(Lane<V>::get(s.vx, l), Lane<V>::get(s.vy, l), Lane<V>::get(s.vz, l), __int_as_float(epi[l])));
+      stg_stream(dst + 2 * io.stride, make_float4(Lane<V>::get(s.qw, l), Lane<V>::get(s.qx, l), Lane<V>::get(s.qy, l), Lane<V>::get(s.qz, l)));
+      stg_stream(dst + 3 * io.stride, make_float4(Lane<V>::get(s.pr0, l), Lane<V>::get(s.pr1, l), Lane<V>::get(s.pr2, l), spare[l]));
+    }
+    // next chunk
+    unsigned v = 0;
+    if (lane == 0) v = atomicAdd(io.work, 1u);
+    v = __shfl_sync(0xffffffffu, v, 0);
+    cur = total_warps + (long long)v;
+  }
+  if (lane == 0) {   // the last warp to finish puts the counters back
+    const unsigned finished = atomicAdd(io.work + 1, 1u);
+    if (finished == (unsigned)total_warps - 1u) { io.work[0] = 0u; io.work[1] = 0u; }
+  }
+  if (io.stats) stats_warp_flush(io.stats, st);
+}
+
 }  // namespace fpv

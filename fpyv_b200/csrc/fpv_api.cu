@@ -219,12 +219,16 @@ int fpv_drone_reset(void* state, int64_t n, int64_t plane_stride, const float* p
   return check_launch("fpv_drone_reset");
 }
 
-int fpv_drone_step(const fpv_drone_params_t* p, const fpv_drone_io_t* io, void* stream) {
+namespace {
+// Validation and the double-precision derivation of the launch constants shared by fpv_drone_step and
+// fpv_drone_rollout.  Returns FPV_OK, a negative error, or 1 for an empty batch.
+int prepare_drone(const fpv_drone_params_t* p, const fpv_drone_io_t* io, bool need_actions, DroneK& k, DroneIO& d,
+                  int& ang, bool& general) {
   if (!p || !io) return fail(FPV_EINVAL, "fpv_drone_step: null params/io");
   if (io->n < 0 || io->plane_stride < io->n)
     return fail(FPV_EINVAL, "fpv_drone_step: bad n=%lld stride=%lld", (long long)io->n, (long long)io->plane_stride);
-  if (io->n == 0) return FPV_OK;
-  if (!io->state || !io->actions) return fail(FPV_EINVAL, "fpv_drone_step: state/actions must not be null");
+  if (io->n == 0) return 1;   /* empty batch: nothing to launch */
+  if (!io->state || (need_actions && !io->actions)) return fail(FPV_EINVAL, "fpv_drone_step: state/actions must not be null");
   if (!aligned16(io->state) || !aligned16(io->actions) || !aligned16(io->wind_env) || !aligned16(io->acc_out) ||
       !aligned16(io->reset_state) || !aligned16(io->override_q))
     return fail(FPV_EINVAL, "fpv_drone_step: float4 planes must be 16-byte aligned");
@@ -246,7 +250,6 @@ int fpv_drone_step(const fpv_drone_params_t* p, const fpv_drone_io_t* io, void* 
     if ((size_t)io->lut_n * sizeof(float) > 200 * 1024) return fail(FPV_EINVAL, "fpv_drone_step: lut_n=%d does not fit in shared memory", io->lut_n);
   }
 
-  DroneK k;
   std::memset(&k, 0, sizeof(k));
   const double rtr = p->rates_transition_rate, ttr = p->thrust_transition_rate;
   k.dt = p->dt;
@@ -281,7 +284,6 @@ int fpv_drone_step(const fpv_drone_params_t* p, const fpv_drone_io_t* io, void* 
       return fail(FPV_EINVAL, "fpv_drone_step: object %d has unknown kind %d", i, k.objects[i].kind);
   }
 
-  DroneIO d;
   d.state = (float4*)io->state;
   d.n = io->n;
   d.stride = io->plane_stride;
@@ -310,13 +312,70 @@ int fpv_drone_step(const fpv_drone_params_t* p, const fpv_drone_io_t* io, void* 
   // (see vsincos in vec.cuh), full-range sincosf beyond it.
   const double max_angle = std::fabs((double)p->max_rates) * 0.017453292519943295 * (double)p->dt;
   const double half = 0.5 * max_angle;   // the kernel evaluates sin/cos of the HALF angles (quaternion update)
-  const int ang = half <= 0.008 ? 4 : (half <= 0.03 ? 3 : (half <= 0.05 ? 2 : (half <= 0.25 ? 1 : 0)));
+  ang = half <= 0.008 ? 4 : (half <= 0.03 ? 3 : (half <= 0.05 ? 2 : (half <= 0.25 ? 1 : 0)));
   // hot kernel = reference configuration (ground plane, undamped contact spring); everything else is general
-  const bool general = p->n_objects > 0 || io->override_q != nullptr || p->spring_c != 0.f || !(p->flags & FPV_F_GROUND);
+  general = p->n_objects > 0 || io->override_q != nullptr || p->spring_c != 0.f || !(p->flags & FPV_F_GROUND);
+  return FPV_OK;
+}
+}  // namespace
+
+int fpv_drone_step(const fpv_drone_params_t* p, const fpv_drone_io_t* io, void* stream) {
+  DroneK k;
+  DroneIO d;
+  int ang = 0;
+  bool general = false;
+  const int rc = prepare_drone(p, io, true, k, d, ang, general);
+  if (rc != FPV_OK) return rc > 0 ? FPV_OK : rc;
   cudaStream_t st = (cudaStream_t)stream;
   if (p->flags & FPV_F_SCALAR) launch_drone_a<float>(k, d, ang, general, st);
   else launch_drone_a<F2>(k, d, ang, general, st);
   return check_launch("fpv_drone_step");
+}
+
+
+int fpv_drone_rollout(const fpv_drone_params_t* p, const fpv_drone_io_t* io, const void* actions_seq,
+                      int64_t action_stride, int32_t n_steps, uint8_t* done_seq, int64_t done_stride, void* stream) {
+  DroneK k;
+  DroneIO d;
+  int ang = 0;
+  bool general = false;
+  const int rc = prepare_drone(p, io, false, k, d, ang, general);
+  if (rc != FPV_OK) return rc > 0 ? FPV_OK : rc;
+  if (n_steps < 0) return fail(FPV_EINVAL, "fpv_drone_rollout: n_steps must be >= 0");
+  if (n_steps == 0) return FPV_OK;
+  if (!actions_seq || !aligned16(actions_seq) || action_stride < io->n)
+    return fail(FPV_EINVAL, "fpv_drone_rollout: actions_seq must be a 16-byte aligned float4[T][action_stride >= n]");
+  if (done_seq && done_stride < io->n) return fail(FPV_EINVAL, "fpv_drone_rollout: done_stride must be >= n");
+  if (general || io->wind_env || (p->flags & (FPV_F_SCALAR | FPV_F_FREEZE_DONE)) || io->chunk_epoch)
+    return fail(FPV_EINVAL, "fpv_drone_rollout: only the hot-path configuration is supported (no obstacles, overrides, "
+                            "per-env wind, FPV_F_SCALAR, FPV_F_FREEZE_DONE or chunk_epoch); step instead");
+  if (!io->work) return fail(FPV_EINVAL, "fpv_drone_rollout: io.work is required");
+  d.work = (unsigned*)io->work;
+  d.chunk_epoch = nullptr;
+  const size_t smem = (k.flags & FPV_F_THRUST_LUT) ? sizeof(float) * (size_t)k.lut_n : 0;
+  auto launch = [&](auto kern) {
+    static size_t attr_set = 0;
+    if (smem > 48 * 1024 && smem > attr_set) {
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      attr_set = smem;
+    }
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem);
+    if (occ < 1) occ = 1;
+    const long long chunks = (io->n + 63) / 64;
+    const long long warps_needed = chunks;                       // one warp-chunk at a time per warp
+    const long long wave = (long long)sm_count_of_current_device() * occ;
+    const long long ctas = (warps_needed + kThreads / 32 - 1) / (kThreads / 32);
+    const unsigned grid = (unsigned)(ctas < wave ? ctas : wave);
+    kern<<<grid, kThreads, smem, (cudaStream_t)stream>>>(k, d, (const float4*)actions_seq, (long long)action_stride, (int)n_steps,
+                                                        done_seq, (long long)done_stride);
+  };
+  if (ang == 4) launch(fpv::drone_rollout_kernel<F2, 4, kThreads, FPV_MINB>);
+  else if (ang == 3) launch(fpv::drone_rollout_kernel<F2, 3, kThreads, FPV_MINB>);
+  else if (ang == 2) launch(fpv::drone_rollout_kernel<F2, 2, kThreads, FPV_MINB>);
+  else if (ang == 1) launch(fpv::drone_rollout_kernel<F2, 1, kThreads, FPV_MINB>);
+  else launch(fpv::drone_rollout_kernel<F2, 0, kThreads, FPV_MINB>);
+  return check_launch("fpv_drone_rollout");
 }
 
 int fpv_drone_get_rotation(const void* state, int64_t n, int64_t plane_stride, float* R, void* stream) {

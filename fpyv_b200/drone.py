@@ -337,11 +337,15 @@ class BatchedDrone:
             return self.observe()
         return None
 
-    def rollout(self, actions, done_out=None):
+    def rollout(self, actions, done_out=None, fused=True):
         """Open-loop rollout: T control steps with the stick commands of all steps given up front
         (actions [T,n,4] float32 on the device -- random exploration, MPC shooting, or recorded sticks replayed through
-        `Joystick.replay`, the sim-to-real check of SURVEY section 8f row 4).  One launch per control step, chained
-        (FPV_F_CHAINED): each launch starts on the SMs the previous one has already left.
+        `Joystick.replay`, the sim-to-real check of SURVEY section 8f row 4).
+        fused=True (default): ONE launch for all T steps (fpv_drone_rollout) -- every env's state stays in registers from
+        the first step to the last, so per control step only its action is read and its done flag written.
+        fused=False (or a configuration the fused kernel does not cover: scalar kernel, freeze_done): one launch per
+        control step, chained (FPV_F_CHAINED), each starting on the SMs the previous one has already left.
+        Both are bit-identical to calling step() T times.
         done_out: optional uint8 [T,n] receiving every step's done flags.  Returns done_out (or the last flags)."""
         if not (isinstance(actions, torch.Tensor) and actions.is_cuda and actions.dtype is torch.float32
                 and actions.dim() == 3 and tuple(actions.shape[1:]) == (self.num_envs, 4) and actions.is_contiguous()):
@@ -360,6 +364,18 @@ class BatchedDrone:
             first = 1
         else:
             first = 0
+        if fused and first < T and not (self._flags & (_lib.F_SCALAR | _lib.F_FREEZE_DONE)):
+            if not self._is_reset:
+                raise RuntimeError("call reset() before step() (the reference's state is None until reset)")
+            self._p.flags = self._flags
+            self._io.chunk_epoch = None
+            self._chain_ready = False
+            self._last_action = actions[T - 1]
+            n = self.num_envs
+            _lib.check(self._lib.fpv_drone_rollout(self._p_ref, self._io_ref, actions[first].data_ptr(), n, T - first,
+                                                   None if done_out is None else done_out[first].data_ptr(), n,
+                                                   torch.cuda.current_stream(self.device).cuda_stream))
+            return done_out if done_out is not None else self._done
         try:
             for t in range(first, T):
                 if done_out is not None:     # every step's flags land directly in their row: nothing between the launches

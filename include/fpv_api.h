@@ -168,6 +168,19 @@ int fpv_drone_reset(void* state, int64_t n, int64_t plane_stride, const float* p
  * Runs params->substeps reference steps per env with the state held in registers. */
 int fpv_drone_step(const fpv_drone_params_t* params, const fpv_drone_io_t* io, void* stream);
 
+/* Open-loop rollout: T consecutive calls of Drone.step (components.py:220-248, params->substeps reference steps each)
+ * in ONE launch, with every env's state held in registers from the first step to the last: the state planes are read
+ * once and written once, per control step only the env's action is read and its done flag written (17 B/env/step instead
+ * of 145).  Bit-identical to T calls of fpv_drone_step on the same inputs (episode counters, FPV_F_AUTO_RESET restarts
+ * and statistics included).
+ *   actions_seq: float4[T][action_stride] (step t of env e at t*action_stride + e; action_stride >= n);
+ *   done_seq:    uint8[T][done_stride] out, or NULL; io->done (if set) receives the LAST step's flags;
+ *   io->actions is ignored; io->work (uint32[4], zeroed once) is required.
+ * Supported configuration: the hot path of fpv_drone_step (ground plane, no obstacles / overrides / per-env wind, packed
+ * kernel) without FPV_F_FREEZE_DONE and without io->chunk_epoch; anything else returns FPV_EINVAL and the caller steps. */
+int fpv_drone_rollout(const fpv_drone_params_t* params, const fpv_drone_io_t* io, const void* actions_seq,
+                      int64_t action_stride, int32_t n_steps, uint8_t* done_seq, int64_t done_stride, void* stream);
+
 /* Drone.rotation_matrix (components.py:154) read / write: R is float[n][9] row-major, body->world.
  * set: robust matrix->quaternion (all four Shepperd branches), normalised; mask as in fpv_drone_reset. */
 int fpv_drone_get_rotation(const void* state, int64_t n, int64_t plane_stride, float* R, void* stream);

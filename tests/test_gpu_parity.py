@@ -649,3 +649,39 @@ def test_baseline_config0_single_drone_10k_steps():
                                      group_err(r.linear_velocity.cpu().numpy(), rs.vel).max()))
     print("configs[0] Racer, 1 env, dt 1 ms: divergence " + " ".join(f"@{k}:{v:.1e}" for k, v in curve.items()))
     assert curve[1] <= TOL_STEP and curve[10_000] <= 5e-2
+
+
+@pytest.mark.parametrize("n,K,T,auto_reset", [(1 << 18, 8, 6, True), (100_003, 1, 17, True), (5000, 4, 9, False), (63, 2, 5, True)])
+def test_fused_rollout_is_bit_identical_to_steps(n, K, T, auto_reset):
+    """fpv_drone_rollout (T control steps per launch, state in registers across the steps) against T plain steps:
+    state, every step's done flags, the last acceleration and the episode statistics, bit for bit -- with crashes and
+    auto-reset restarts happening inside the rollout."""
+    g = torch.Generator(device=DEV).manual_seed(17)
+    pos = torch.randn(n, 3, device=DEV, generator=g) * 5
+    pos[:, 2] = 0.05 + torch.rand(n, device=DEV, generator=g) * 1.5
+    vel = torch.randn(n, 3, device=DEV, generator=g)
+    rpy = (torch.rand(n, 3, device=DEV, generator=g) * 2 - 1) * 30
+    acts = (torch.rand(T, n, 4, device=DEV, generator=g) * 2 - 1).contiguous()
+    a = make(n, substeps=K, dt=1e-3, auto_reset=auto_reset, thrust_lut=2049)
+    b = make(n, substeps=K, dt=1e-3, auto_reset=auto_reset, thrust_lut=2049)
+    a.reset(pos, vel, rpy)
+    b.reset(pos, vel, rpy)
+    a._state[:, n:] = 77.0                       # padding up to the plane stride must stay untouched
+    done_a = torch.full((T + 2, n), 0xAB, dtype=torch.uint8, device=DEV)      # guard rows around the flags
+    a.rollout(acts, done_out=done_a[1:T + 1], fused=True)
+    done_b = torch.empty((T, n), dtype=torch.uint8, device=DEV)
+    for t in range(T):
+        b.step(acts[t], return_obs=False)
+        done_b[t] = b.done
+    torch.cuda.synchronize()
+    assert torch.equal(a._state[:, :n].view(torch.int32), b._state[:, :n].view(torch.int32))
+    assert bool((a._state[:, n:] == 77.0).all())
+    assert torch.equal(done_a[1:T + 1], done_b) and bool((done_a[0] == 0xAB).all()) and bool((done_a[T + 1] == 0xAB).all())
+    assert torch.equal(a.done, b.done) and torch.equal(a._acc, b._acc)
+    sa, sb = a.episode_stats(), b.episode_stats()
+    assert all(sa[k] == sb[k] or (sa[k] != sa[k] and sb[k] != sb[k]) for k in sa), (sa, sb)
+    assert n < 5000 or int(done_b.sum()) > 0
+    # a second rollout continues from the first one's state; chained per-step rollout agrees too
+    a.rollout(acts, fused=True)
+    b.rollout(acts, fused=False)
+    assert torch.equal(a._state[:, :n].view(torch.int32), b._state[:, :n].view(torch.int32))
