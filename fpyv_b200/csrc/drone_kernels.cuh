@@ -574,10 +574,13 @@ __global__ void __launch_bounds__(THREADS, MINB) drone_step_tma_kernel(const __g
     if (chained) {  // the previous step of THIS chunk must have been stored (possibly by a grid that is still running)
       const unsigned* f = io.chunk_epoch + chunk;
       unsigned v;
-      for (;;) {
+      for (unsigned spins = 0;; ++spins) {
         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
         if (v == io.epoch) break;
         __nanosleep(64);
+        // a chunk that never reaches this epoch means the caller broke the FPV_F_CHAINED contract (e.g. replayed a
+        // captured launch with a stale epoch): fail the launch after ~1 s instead of hanging the device
+        if (spins > (1u << 23)) __trap();
       }
       asm volatile("fence.proxy.async.global;" ::: "memory");  // generic-proxy stores -> async-proxy (TMA) loads
     }

@@ -259,6 +259,8 @@ class BatchedDrone:
         n, dev = self.num_envs, self.device
         # chunk epochs are published only by launches that ask for chaining (the first one of a run is still plain
         # stream order: it has nothing published to wait on)
+        if chained and torch.cuda.is_current_stream_capturing():
+            chained = False      # a captured launch would replay a stale epoch: graphs use plain stream order
         chain_now = chained and self._chain_ready
         self._chain_ready = chained
         if chained:

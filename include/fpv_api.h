@@ -68,7 +68,9 @@ extern "C" {
                                    (1) every input other than `state` (actions, lut, wind, reset_state) is not being
                                    written by work that may still be running, and (2) the last writer of `state` was a
                                    fpv_drone_step launch with the same chunk_epoch and epoch - 1.  Ignored (plain stream
-                                   order) whenever the launch cannot honour it.                                   */
+                                   order) whenever the launch cannot honour it.  Do not capture a chained launch in a
+                                   CUDA graph (the replay would carry a stale epoch); a chunk that never reaches the
+                                   expected epoch traps the launch after about a second instead of hanging.        */
 #define FPV_F_SCALAR 32u        /* one env per thread (plain FP32 instructions) instead of the
                                    default two envs per thread on packed f32x2 instructions     */
 
