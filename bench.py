@@ -27,6 +27,7 @@ SUBSTEPS = 8
 DT = 1e-3
 LUT_N = int(os.environ.get("FPV_BENCH_LUT", "2049"))   # env override: developer tuning only
 CHAINED = os.environ.get("FPV_BENCH_CHAINED", "1") != "0"   # developer A/B: 0 = every launch waits for the previous grid
+CTA_SLOTS = int(os.environ.get("FPV_BENCH_CTA_SLOTS", "2"))  # CTA slots per SM one launch takes in the primary loop (0 = all)
 # algorithmic work per env (quaternion state, 64 B each way)
 BYTES_PER_ENV_STEP = 64 + 64 + 16 + 1          # state read + state write + action + done flag
 FLOP_PER_ENV_SUBSTEP = 252                     # 245 arithmetic + 6 sin/cos + 1 sqrt
@@ -167,7 +168,12 @@ def workload_config(n_gpus, **extra):
                "= one control step of ONE batch; 4 x (64 MiB state + 16 MiB actions) read + 4 x 64 MiB written per "
                "rotation > 126 MB L2), steps back to back in one CUDA-event bracket; ms_per_step_flushed is the "
                "cross-check with ONE batch and an explicit L2 flush (256 MiB write + 256 MiB read) before every step, "
-               "per-step event intervals summed"}
+               "per-step event intervals summed",
+         "launches": f"one launch per control step; the stick commands of all steps exist before the loop, so launches are "
+                     f"chained (FPV_F_CHAINED: no grid-wide wait, state ordered per 64-env chunk) and each takes {CTA_SLOTS or 'all'} "
+                     f"of the 4 CTA slots per SM, so launches of consecutive (independent) batches overlap; "
+                     f"ms_per_step_chained_full_grid = chained with all slots, ms_per_step_unchained = every launch waits "
+                     f"for the previous grid, ms_per_step_flushed = one isolated launch"}
     c.update(extra)
     return c
 
@@ -216,12 +222,16 @@ def run_gpu(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     flush_r = torch.ones(64 << 20, dtype=torch.float32, device=dev)
 
-    def timed_rotation(ds, steps, warm):
+    def timed_rotation(ds, steps, warm, chained=CHAINED, cta_slots=CTA_SLOTS):
         """The contract's timed region: `steps` control steps back to back inside ONE CUDA-event bracket (barrier +
         synchronize on both sides).  Step i advances batch i % NB, so its state was evicted from L2 by the other
-        batches' traffic (inputs larger than L2)."""
+        batches' traffic (inputs larger than L2).  The NB batches are independent, so with `cta_slots` = 2 every launch
+        takes two of the four CTA slots of each SM and two consecutive launches are resident side by side: the idle
+        tail and the start-up of one launch are covered by the bulk of its neighbour."""
+        for d_ in ds:
+            d_._io.max_ctas_per_sm = cta_slots if chained else 0
         for i in range(warm):
-            ds[i % len(ds)].step(ring[i % 4], return_obs=False, chained=CHAINED)
+            ds[i % len(ds)].step(ring[i % 4], return_obs=False, chained=chained)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         if world > 1:
             dist.barrier()
@@ -230,11 +240,13 @@ def run_gpu(args):
         for i in range(steps):
             # the stick commands of every step exist before the loop starts (open-loop rollout), so consecutive
             # launches may be chained: launch i+1 starts on the SMs launch i has left (per-chunk ordering of the state)
-            ds[i % len(ds)].step(ring[i % 4], return_obs=False, chained=CHAINED)
+            ds[i % len(ds)].step(ring[i % 4], return_obs=False, chained=chained)
         e1.record()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
+        for d_ in ds:
+            d_._io.max_ctas_per_sm = 0
         return e0.elapsed_time(e1)
 
     def timed_loop(d, steps, warm):
@@ -263,6 +275,8 @@ def run_gpu(args):
         time.sleep(0.3)
     t0 = time.time()
     ms = timed_rotation(drones, K, W)
+    ms_full_grid = timed_rotation(drones, K, W, chained=True, cta_slots=0)     # chained, every launch takes all CTA slots
+    ms_unchained = timed_rotation(drones, K, W, chained=False)                 # every launch waits for the previous grid
     ms_flushed = timed_loop(drone, min(K, 200), W)
     K_fl = min(K, 200)
 
@@ -324,10 +338,10 @@ def run_gpu(args):
 
     t1 = time.time()
     clocks = sampler.stop(t0, t1) if sampler else None      # covers the K=8 loop, the e2e loop and the K=1 loop
-    t = torch.tensor([ms, ms_e2e, ms_k1, ms_rollout], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, ms_e2e, ms_k1, ms_rollout, ms_full_grid, ms_unchained], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e, ms_k1, ms_rollout = t.tolist()
+    ms, ms_e2e, ms_k1, ms_rollout, ms_full_grid, ms_unchained = t.tolist()
     stats = drone.episode_stats(all_reduce=world > 1)      # the engine's only collective (NCCL), outside the timed loop
     ms_flushed_per_step = ms_flushed / K_fl
     if rank != 0:
@@ -365,6 +379,7 @@ def run_gpu(args):
                     "d2h_bytes_per_step": n * world, "ms_per_step": ms_e2e / K,
                     "api": "BatchedDrone.step_host(pinned actions) -> pinned done flags, 4 env slices pipelined over H2D / step / D2H streams; host waits every step"},
             "ms_per_step_flushed": ms_flushed_per_step,
+            "ms_per_step_chained_full_grid": ms_full_grid / K, "ms_per_step_unchained": ms_unchained / K,
             "rollout_fused": {"ms_per_step": ms_rollout, "env_steps_per_sec": total_envs / (ms_rollout * 1e-3),
                               "steps_per_launch": T_ro, "fp32_frac": FLOP_PER_ENV_SUBSTEP * SUBSTEPS * n / (ms_rollout * 1e-3) / 1e12 / (sm_count * FP32_LANES_PER_SM * 2 * pk["sm_max_mhz"] * 1e6 / 1e12),
                               "api": "BatchedDrone.rollout(actions[16, n, 4]): fpv_drone_rollout, bit-identical to 16 step() calls; "

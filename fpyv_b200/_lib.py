@@ -52,7 +52,7 @@ class DroneIO(C.Structure):
                 ("acc_out", C.c_void_p), ("reset_state", C.c_void_p), ("override_q", C.c_void_p),
                 ("override_thrust", C.c_void_p),
                 ("objects", C.POINTER(Object)), ("stats", C.c_void_p), ("work", C.c_void_p), ("chunk_epoch", C.c_void_p),
-                ("epoch", C.c_uint32), ("reserved0", C.c_uint32), ("trace", C.c_void_p)]
+                ("epoch", C.c_uint32), ("max_ctas_per_sm", C.c_uint32), ("trace", C.c_void_p)]
 
 
 class StickCalib(C.Structure):

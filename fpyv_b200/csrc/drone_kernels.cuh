@@ -57,6 +57,7 @@ struct DroneIO {
   unsigned* work;              // [0] next-chunk counter, [1] finished-warp counter (dynamic scheduling), or null
   unsigned* chunk_epoch;       // [n_chunks] per-chunk step count (chained launches), or null
   unsigned epoch;              // value chunk_epoch[] holds before this launch; the launch publishes epoch + 1
+  unsigned cta_cap;            // host only: cap on resident CTAs per SM (0 = none)
   unsigned long long* trace;
 };
 

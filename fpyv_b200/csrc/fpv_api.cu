@@ -107,7 +107,8 @@ bool launch_drone_tma(const DroneK& k, const DroneIO& io, cudaStream_t st) {
     occ_smem = smem;
   }
   const long long tiles = (io.n + TILE - 1) / TILE;
-  static const int occ_cap = tune_env("FPV_TUNE_OCC", 0);
+  static const int occ_env = tune_env("FPV_TUNE_OCC", 0);
+  const int occ_cap = io.cta_cap > 0 ? (int)io.cta_cap : occ_env;
   const int occ_used = (occ_cap > 0 && occ_cap < occ_cache) ? occ_cap : occ_cache;
   const long long wave = (long long)sm_count_of_current_device() * occ_used;
   const unsigned grid = (unsigned)(tiles < wave ? tiles : wave);
@@ -301,6 +302,7 @@ int prepare_drone(const fpv_drone_params_t* p, const fpv_drone_io_t* io, bool ne
   d.work = (no_dyn || p->substeps < 4) ? nullptr : (unsigned*)io->work;
   d.chunk_epoch = (unsigned*)io->chunk_epoch;
   d.epoch = io->epoch;
+  d.cta_cap = io->max_ctas_per_sm;
   // two launches that overlap (FPV_F_CHAINED) must not share the pull counters: one pair per epoch parity
   if (d.work && d.chunk_epoch) d.work += 2 * (io->epoch & 1u);
   if ((p->flags & FPV_F_CHAINED) && !io->chunk_epoch)

@@ -38,7 +38,7 @@ def _as_dev(x, device, shape=None, dtype=torch.float32):
 class BatchedDrone:
     def __init__(self, params=None, num_envs: int = 1, device="cuda:0", substeps: int = 1, dt: float | None = None,
                  auto_reset: bool = False, freeze_done: bool = False, thrust_lut: int = 0, lut_source: str = "poly",
-                 packed: bool = True, ground: bool = True, joystick=None):
+                 packed: bool = True, ground: bool = True, joystick=None, cta_slots: int = 0):
         self._lib = _lib.load()
         if isinstance(params, str) or params is None:
             params = config.load_params(params)
@@ -110,6 +110,9 @@ class BatchedDrone:
                        (0 if packed else _lib.F_SCALAR))
         self._p = self._make_params()
         self._io = _lib.DroneIO()
+        # cta_slots > 0: the step kernel takes at most that many CTA slots per SM, so that chained launches of
+        # INDEPENDENT batches stepped round-robin run side by side (fpv_drone_io_t.max_ctas_per_sm)
+        self._io.max_ctas_per_sm = int(cta_slots)
         self._host_actions = None
         self._host_done = None
         self._pipe = None

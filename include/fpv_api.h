@@ -139,7 +139,11 @@ typedef struct fpv_drone_io {
                                every entry holds epoch + 1 (published chunk by chunk as the chunk's state is stored);
                                with FPV_F_CHAINED chunk c is loaded only once chunk_epoch[c] == epoch.            */
   uint32_t epoch;           /* number of fpv_drone_step launches already applied to `state` through chunk_epoch  */
-  uint32_t reserved0;
+  uint32_t max_ctas_per_sm; /* 0 = every CTA slot of every SM (default).  k > 0: the persistent grid takes at most k slots
+                               per SM, so that CHAINED launches of INDEPENDENT batches stepped round-robin are resident
+                               side by side (the idle tail and start-up of one launch are covered by the others' bulk);
+                               do not combine with chaining consecutive steps of the SAME batch -- the trailing launch
+                               would hold its slots while it waits for the leading one chunk by chunk.            */
   void* trace;              /* developer profiling hook: device uint64[3 * warps] receiving per-warp
                                (start ns, end ns, SM id) of the hot kernel; NULL in production           */
 } fpv_drone_io_t;

@@ -1,1 +1,1 @@
-for o in 1 2 3 4; do echo "occ=$o"; FPV_TUNE_OCC=$o FPV_BENCH_CHAINED=0 python bench.py --profile --steps 20 --warmup 5 --envs 4194304 2>&1 | tail -1 | cut -c1-150; done
+for o in 4 3 2 1; do echo "occ=$o chained"; FPV_TUNE_OCC=$o python bench.py --profile --steps 100 --warmup 10 2>&1 | tail -1 | cut -c1-110; done
