@@ -25,7 +25,7 @@ class BatchedAcroDrone:
     def __init__(self, params=None, num_envs: int = 1, device="cuda:0", substeps: int = 1, dt: float | None = None,
                  gains=None, inertia=None, kappa: float = 0.016, spin=(1.0, -1.0, 1.0, -1.0), u_min: float = -0.9,
                  u_max: float = 1.0, integral_limit: float = 0.5, thrust_lut: int = 2049, auto_reset: bool = False,
-                 ground: bool = True):
+                 ground: bool = True, packed: bool = True):
         self._lib = _lib.load()
         if isinstance(params, str) or params is None:
             params = config.load_params(params)
@@ -51,7 +51,7 @@ class BatchedAcroDrone:
         self._stats = torch.zeros(8, dtype=torch.float64, device=dev)
         self._lut = torch.from_numpy(config.thrust_table(c, int(thrust_lut), "poly")).to(dev) if thrust_lut else None
         self._flags = ((_lib.F_GROUND if ground else 0) | (_lib.F_AUTO_RESET if auto_reset else 0) |
-                       (_lib.F_THRUST_LUT if thrust_lut else 0))
+                       (_lib.F_THRUST_LUT if thrust_lut else 0) | (0 if packed else _lib.F_SCALAR))
         p = self._p = _lib.AcroParams()
         p.dt, p.substeps, p.gravity, p.mass, p.max_rates = c.dt, self.substeps, c.gravity, c.mass, c.max_rates
         p.rates_transition_rate, p.thrust_transition_rate = c.rates_transition_rate, c.thrust_transition_rate

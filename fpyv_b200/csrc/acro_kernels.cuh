@@ -8,6 +8,7 @@
 #pragma once
 #include "../../include/fpv_api.h"
 #include "vec.cuh"
+#include "drone_kernels.cuh"
 
 namespace fpv {
 
@@ -72,142 +73,216 @@ __global__ void acro_reset_kernel(float4* state, long long n, long long stride, 
   state[6 * stride + e] = zero;
 }
 
-template <int THREADS>
+template <class V> __device__ __forceinline__ V acro_motor_thrust_v(const AcroK& k, const float* lut_s, V u);
+template <> __device__ __forceinline__ float acro_motor_thrust_v<float>(const AcroK& k, const float* lut_s, float u) {
+  return acro_motor_thrust(k, lut_s, u);
+}
+template <> __device__ __forceinline__ F2 acro_motor_thrust_v<F2>(const AcroK& k, const float* lut_s, F2 u) {
+  if (k.flags & FPV_F_THRUST_LUT) {   // table lookups are per lane
+    float a, b;
+    f2_unpack(u, a, b);
+    return f2_pack(acro_motor_thrust(k, lut_s, a), acro_motor_thrust(k, lut_s, b));
+  }
+  const F2 pct = vfma(u, S<F2>(50.f), S<F2>(50.f));
+  F2 p = vfma(S<F2>(k.poly[0]), pct, S<F2>(k.poly[1]));
+  p = vfma(p, pct, S<F2>(k.poly[2]));
+  return vfma(p, pct, S<F2>(k.poly[3])) * S<F2>(0.25f);
+}
+
+// sin(a)/a and cos(a) of the half rotation angle from a^2.  |a| < 0.1 (|omega| < 200 rad/s at dt = 1 ms): series to a^6
+// (truncation < 3e-13); beyond that the accurate functions, chosen PER LANE so that an env's result never depends on
+// which other env shares its thread.
+__device__ __forceinline__ void sinc_cos_small(float a2, float& sinc, float& cs) {
+  sinc = fmaf(a2, fmaf(a2, fmaf(a2, -1.f / 5040.f, 1.f / 120.f), -1.f / 6.f), 1.f);
+  cs = fmaf(a2, fmaf(a2, fmaf(a2, -1.f / 720.f, 1.f / 24.f), -0.5f), 1.f);
+}
+__device__ __forceinline__ void sinc_cos_any(float a2, float& sinc, float& cs) {
+  if (a2 < 0.01f) { sinc_cos_small(a2, sinc, cs); return; }
+  const float a = sqrtf(a2);
+  float sn;
+  sincosf(a, &sn, &cs);
+  sinc = sn / a;
+}
+template <class V> __device__ __forceinline__ void sinc_cos(V a2, V& sinc, V& cs);
+template <> __device__ __forceinline__ void sinc_cos<float>(float a2, float& sinc, float& cs) { sinc_cos_any(a2, sinc, cs); }
+template <> __device__ __forceinline__ void sinc_cos<F2>(F2 a2, F2& sinc, F2& cs) {
+  if (!vany(vle(S<F2>(0.01f), a2))) {   // common case: both lanes small -> packed series
+    const F2 ps = vfma(a2, vfma(a2, S<F2>(-1.f / 5040.f), S<F2>(1.f / 120.f)), S<F2>(-1.f / 6.f));
+    sinc = vfma(a2, ps, S<F2>(1.f));
+    const F2 pc = vfma(a2, vfma(a2, S<F2>(-1.f / 720.f), S<F2>(1.f / 24.f)), S<F2>(-0.5f));
+    cs = vfma(a2, pc, S<F2>(1.f));
+    return;
+  }
+  float x, y, s0, c0, s1, c1;
+  f2_unpack(a2, x, y);
+  sinc_cos_any(x, s0, c0);
+  sinc_cos_any(y, s1, c1);
+  sinc = f2_pack(s0, s1);
+  cs = f2_pack(c0, c1);
+}
+
+// One thread owns L envs (1 = float, 2 = packed F2: FFMA2/FMUL2/FADD2); CTA tile = THREADS*L envs, slot l of thread t
+// is env tile*TILE + l*THREADS + t (every 128-bit access of a warp is one contiguous 512 B run).
+template <class V, int THREADS>
 __global__ void __launch_bounds__(THREADS) acro_step_kernel(const __grid_constant__ AcroK k, float4* state, long long n,
                                                             long long stride, const float4* actions, const float* lut,
                                                             unsigned char* done_out, float4* motor_out,
                                                             const float4* reset_state, fpv_stats_t* stats) {
+  constexpr int L = Lane<V>::N;
+  constexpr int TILE = THREADS * L;
+  using M = typename Lane<V>::Mask;
   extern __shared__ float lut_s[];
   if (k.flags & FPV_F_THRUST_LUT) {
     for (int i = threadIdx.x; i < k.lut_n; i += THREADS) lut_s[i] = lut[i];
     __syncthreads();
   }
-  const long long e = (long long)blockIdx.x * THREADS + threadIdx.x;
-  if (e >= n) return;
-  float4 p0 = ldg_stream(state + e), p1 = ldg_stream(state + stride + e), q = ldg_stream(state + 2 * stride + e);
-  float4 p3 = ldg_stream(state + 3 * stride + e), p4 = ldg_stream(state + 4 * stride + e);
-  float4 p5 = ldg_stream(state + 5 * stride + e), p6 = ldg_stream(state + 6 * stride + e);
-  const float4 a = ldg_stream(actions + e);
-  float sp_deg[3] = {p3.x, p3.y, p3.z};
-  float w[3] = {p4.x, p4.y, p4.z}, ie[3] = {p5.x, p5.y, p5.z}, le[3] = {p6.x, p6.y, p6.z};
-  bool first = p3.w != 0.f;
-  float thr = p0.w;
-  const float act[3] = {a.x, a.y, a.z};
-  float cmd[3];
+  const long long base = (long long)blockIdx.x * TILE + threadIdx.x;
+  if (base >= n) return;
+  long long ei[L];
 #pragma unroll
-  for (int i = 0; i < 3; ++i) cmd[i] = fminf(fmaxf(-act[i] * k.max_rates, -k.max_rates), k.max_rates) * k.rtr;
-  const float thr_in = a.w * k.ttr;
-  bool done = false;
-  float fm[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int l = 0; l < L; ++l) ei[l] = min(base + (long long)l * THREADS, n - 1);   // a slot past the end is never stored
+  float4 q[FPV_ACRO_PLANES][L], act[L];
+#pragma unroll
+  for (int p = 0; p < FPV_ACRO_PLANES; ++p)
+#pragma unroll
+    for (int l = 0; l < L; ++l) q[p][l] = ldg_stream(state + p * stride + ei[l]);
+#pragma unroll
+  for (int l = 0; l < L; ++l) act[l] = ldg_stream(actions + ei[l]);
+  V px = Pack<V>::x(q[0]), py = Pack<V>::y(q[0]), pz = Pack<V>::z(q[0]), thr = Pack<V>::w(q[0]);
+  V vx = Pack<V>::x(q[1]), vy = Pack<V>::y(q[1]), vz = Pack<V>::z(q[1]);
+  V qw = Pack<V>::x(q[2]), qx = Pack<V>::y(q[2]), qy = Pack<V>::z(q[2]), qz = Pack<V>::w(q[2]);
+  V sp[3] = {Pack<V>::x(q[3]), Pack<V>::y(q[3]), Pack<V>::z(q[3])};
+  V w[3] = {Pack<V>::x(q[4]), Pack<V>::y(q[4]), Pack<V>::z(q[4])};
+  V ie[3] = {Pack<V>::x(q[5]), Pack<V>::y(q[5]), Pack<V>::z(q[5])};
+  V le[3] = {Pack<V>::x(q[6]), Pack<V>::y(q[6]), Pack<V>::z(q[6])};
+  int epi[L];
+  float nf_[2];
+#pragma unroll
+  for (int l = 0; l < L; ++l) { epi[l] = __float_as_int(q[1][l].w); nf_[l] = q[3][l].w != 0.f ? 0.f : 1.f; }
+  V notfirst = Lane<V>::make(nf_[0], nf_[L - 1]);   // 0 on a PID's first call: no derivative term (racer_drone_test.py:28)
+  const V zero = S<V>(0.f), one = S<V>(1.f);
+  const V mr = S<V>(k.max_rates), rtr = S<V>(k.rtr);
+  V cmd[3];
+  {
+    const V a3[3] = {Pack<V>::x(act), Pack<V>::y(act), Pack<V>::z(act)};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) cmd[i] = vmin(vmax(vneg(a3[i]) * mr, vneg(mr)), mr) * rtr;   // components.py:185
+  }
+  const V thr_in = Pack<V>::w(act) * S<V>(k.ttr);
+  const V omr = S<V>(k.one_minus_rtr), omt = S<V>(k.one_minus_ttr), dt = S<V>(k.dt), inv_dt = S<V>(k.inv_dt);
+  const V d2r = S<V>(k.deg2rad), hdt = S<V>(0.5f * k.dt), s_m = S<V>(k.inv_mass * k.dt);
+  M done = vlt(one, zero);
+  V fm[4] = {zero, zero, zero, zero};
 #pragma unroll 1
   for (int it = 0; it < k.substeps; ++it) {
     // ---- stick -> rate set-point / collective throttle, low-passed (components.py:185-194)
-    thr = fmaf(thr, k.one_minus_ttr, thr_in);
-    float pid[3];
+    thr = vfma(thr, omt, thr_in);
+    V pid[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-      sp_deg[i] = fmaf(sp_deg[i], k.one_minus_rtr, cmd[i]);
+      sp[i] = vfma(sp[i], omr, cmd[i]);
       // ---- rate PID (racer_drone_test.py:22-32) with an integrator clamp
-      const float err = fmaf(sp_deg[i], k.deg2rad, -w[i]);
-      ie[i] = fminf(fmaxf(fmaf(err, k.dt, ie[i]), -k.i_lim[i]), k.i_lim[i]);
-      const float de = first ? 0.f : (err - le[i]) * k.inv_dt;
+      const V err = vfma(sp[i], d2r, vneg(w[i]));
+      ie[i] = vmin(vmax(vfma(err, dt, ie[i]), S<V>(-k.i_lim[i])), S<V>(k.i_lim[i]));
+      const V de = ((err - le[i]) * inv_dt) * notfirst;
       le[i] = err;
-      pid[i] = fmaf(k.gains[i][0], err, fmaf(k.gains[i][1], ie[i], k.gains[i][2] * de));
+      pid[i] = vfma(S<V>(k.gains[i][0]), err, vfma(S<V>(k.gains[i][1]), ie[i], S<V>(k.gains[i][2]) * de));
     }
-    first = false;
+    notfirst = one;
     // ---- mixer in throttle units, per-motor saturation, bench curve (shared-memory LUT) -> per-motor thrust
-    float tx = 0.f, ty = 0.f, tz = 0.f, fsum = 0.f;
+    V tx = zero, ty = zero, tz = zero, fsum = zero;
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
-      float u = fmaf(k.mix[m][0], pid[0], fmaf(k.mix[m][1], pid[1], fmaf(k.mix[m][2], pid[2], thr)));
-      u = fminf(fmaxf(u, k.u_min), k.u_max);
-      const float f = acro_motor_thrust(k, lut_s, u);
+      V u = vfma(S<V>(k.mix[m][0]), pid[0], vfma(S<V>(k.mix[m][1]), pid[1], vfma(S<V>(k.mix[m][2]), pid[2], thr)));
+      u = vmin(vmax(u, S<V>(k.u_min)), S<V>(k.u_max));
+      const V f = acro_motor_thrust_v<V>(k, lut_s, u);
       fm[m] = f;
-      fsum += f;
-      tx = fmaf(k.motor_xy[m][1], f, tx);        // arm x thrust: roll torque  =  sum y_m f_m
-      ty = fmaf(-k.motor_xy[m][0], f, ty);       //               pitch torque = -sum x_m f_m
-      tz = fmaf(k.spin_kappa[m], f, tz);         // rotor reaction torque
+      fsum = fsum + f;
+      tx = vfma(S<V>(k.motor_xy[m][1]), f, tx);     // arm x thrust: roll torque  =  sum y_m f_m
+      ty = vfma(S<V>(-k.motor_xy[m][0]), f, ty);    //               pitch torque = -sum x_m f_m
+      tz = vfma(S<V>(k.spin_kappa[m]), f, tz);      // rotor reaction torque
     }
     // ---- Euler's rigid-body equation, diagonal inertia
-    const float Iw0 = k.inertia[0] * w[0], Iw1 = k.inertia[1] * w[1], Iw2 = k.inertia[2] * w[2];
-    const float wd0 = (tx - (w[1] * Iw2 - w[2] * Iw1)) * k.inv_inertia[0];
-    const float wd1 = (ty - (w[2] * Iw0 - w[0] * Iw2)) * k.inv_inertia[1];
-    const float wd2 = (tz - (w[0] * Iw1 - w[1] * Iw0)) * k.inv_inertia[2];
+    const V Iw0 = S<V>(k.inertia[0]) * w[0], Iw1 = S<V>(k.inertia[1]) * w[1], Iw2 = S<V>(k.inertia[2]) * w[2];
+    const V wd0 = (tx - vfma(w[1], Iw2, vneg(w[2] * Iw1))) * S<V>(k.inv_inertia[0]);
+    const V wd1 = (ty - vfma(w[2], Iw0, vneg(w[0] * Iw2))) * S<V>(k.inv_inertia[1]);
+    const V wd2 = (tz - vfma(w[0], Iw1, vneg(w[1] * Iw0))) * S<V>(k.inv_inertia[2]);
     // ---- the reference's force model on the current attitude (components.py:233-243)
-    float R[9];
-    {
-      const float qw = q.x, qx = q.y, qy = q.z, qz = q.w;
-      R[0] = 1.f - 2.f * (qy * qy + qz * qz); R[1] = 2.f * (qx * qy - qz * qw); R[2] = 2.f * (qx * qz + qy * qw);
-      R[3] = 2.f * (qx * qy + qz * qw); R[4] = 1.f - 2.f * (qx * qx + qz * qz); R[5] = 2.f * (qy * qz - qx * qw);
-      R[6] = 2.f * (qx * qz - qy * qw); R[7] = 2.f * (qy * qz + qx * qw); R[8] = 1.f - 2.f * (qx * qx + qy * qy);
-    }
-    const float ux = p1.x + k.wind[0], uy = p1.y + k.wind[1], uz = p1.z + k.wind[2];   // kinematics.py:34 (PLUS wind)
-    const float nrm = sqrtf(fmaf(ux, ux, fmaf(uy, uy, uz * uz)));
-    const float b0 = k.kd[0] * nrm * fmaf(R[0], ux, fmaf(R[3], uy, R[6] * uz));
-    const float b1 = k.kd[1] * nrm * fmaf(R[1], ux, fmaf(R[4], uy, R[7] * uz));
-    const float b2 = k.kd[2] * nrm * fmaf(R[2], ux, fmaf(R[5], uy, R[8] * uz)) + fsum;  // thrust rides on body z
-    float Fx = fmaf(R[0], b0, fmaf(R[1], b1, R[2] * b2));
-    float Fy = fmaf(R[3], b0, fmaf(R[4], b1, R[5] * b2));
-    float Fz = fmaf(R[6], b0, fmaf(R[7], b1, R[8] * b2)) + k.grav_z;
+    const V two = S<V>(2.f);
+    const V xx = qx * qx, yy = qy * qy, zz = qz * qz, xy = qx * qy, xz = qx * qz, yz = qy * qz;
+    const V wx_ = qw * qx, wy_ = qw * qy, wz_ = qw * qz;
+    const V R0 = vfma(vneg(two), yy + zz, one), R1 = two * (xy - wz_), R2 = two * (xz + wy_);
+    const V R3 = two * (xy + wz_), R4 = vfma(vneg(two), xx + zz, one), R5 = two * (yz - wx_);
+    const V R6 = two * (xz - wy_), R7 = two * (yz + wx_), R8 = vfma(vneg(two), xx + yy, one);
+    const V ux = vx + S<V>(k.wind[0]), uy = vy + S<V>(k.wind[1]), uz = vz + S<V>(k.wind[2]);   // kinematics.py:34 (PLUS wind)
+    const V nrm = vsqrt_fast(vfma(ux, ux, vfma(uy, uy, uz * uz)));
+    const V b0 = (S<V>(k.kd[0]) * nrm) * vfma(R0, ux, vfma(R3, uy, R6 * uz));
+    const V b1 = (S<V>(k.kd[1]) * nrm) * vfma(R1, ux, vfma(R4, uy, R7 * uz));
+    const V b2 = vfma(S<V>(k.kd[2]) * nrm, vfma(R2, ux, vfma(R5, uy, R8 * uz)), fsum);   // thrust rides on body z
+    const V Fx = vfma(R0, b0, vfma(R1, b1, R2 * b2));
+    const V Fy = vfma(R3, b0, vfma(R4, b1, R5 * b2));
+    V Fz = vfma(R6, b0, vfma(R7, b1, vfma(R8, b2, S<V>(k.grav_z))));
     if (k.flags & FPV_F_GROUND) {   // components.py:198-214, :239 with the plane z = 0
-      bool crashed = false;
-      float spring = 0.f;
+      M crashed = vlt(one, zero);
+      V comp = zero;
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
-        const float mz = fmaf(k.motor_xy[m][0], R[6], fmaf(k.motor_xy[m][1], R[7], p0.z));
-        crashed |= mz < 0.f;
-        const float pen = mz - k.motor_radius;
-        spring += pen < 0.f ? -k.spring_k * pen : 0.f;
+        const V mz = vfma(S<V>(k.motor_xy[m][0]), R6, vfma(S<V>(k.motor_xy[m][1]), R7, pz));
+        crashed = vor(crashed, vlt(mz, zero));
+        comp = comp + vmax(S<V>(k.motor_radius) - mz, zero);   // spring compression of motor m
       }
-      Fz += crashed ? 0.f : spring;
-      done |= crashed;
+      Fz = vfma(S<V>(k.spring_k), vsel(crashed, zero, comp), Fz);
+      done = vor(done, crashed);
     }
     // ---- translation, kinematics.py:21-22 (old velocity first)
-    p0.x = fmaf(p1.x, k.dt, p0.x); p0.y = fmaf(p1.y, k.dt, p0.y); p0.z = fmaf(p1.z, k.dt, p0.z);
-    const float s = k.inv_mass * k.dt;
-    p1.x = fmaf(Fx, s, p1.x); p1.y = fmaf(Fy, s, p1.y); p1.z = fmaf(Fz, s, p1.z);
+    px = vfma(vx, dt, px); py = vfma(vy, dt, py); pz = vfma(vz, dt, pz);
+    vx = vfma(Fx, s_m, vx); vy = vfma(Fy, s_m, vy); vz = vfma(Fz, s_m, vz);
     // ---- rotation: omega first, then q <- q (x) exp(omega dt / 2)
-    w[0] = fmaf(wd0, k.dt, w[0]); w[1] = fmaf(wd1, k.dt, w[1]); w[2] = fmaf(wd2, k.dt, w[2]);
-    const float hx = 0.5f * k.dt * w[0], hy = 0.5f * k.dt * w[1], hz = 0.5f * k.dt * w[2];
-    const float ang2 = fmaf(hx, hx, fmaf(hy, hy, hz * hz));
-    float sn, cs;
-    const float ang = sqrtf(ang2);
-    sincosf(ang, &sn, &cs);
-    const float sinc = ang > 1e-6f ? sn / ang : 1.f - ang2 * (1.f / 6.f);
-    const float dw = cs, dx = hx * sinc, dy = hy * sinc, dz = hz * sinc;
-    const float qw = q.x, qx = q.y, qy = q.z, qz = q.w;
-    float nw = qw * dw - qx * dx - qy * dy - qz * dz;
-    float nx = qw * dx + qx * dw + qy * dz - qz * dy;
-    float ny = qw * dy - qx * dz + qy * dw + qz * dx;
-    float nz = qw * dz + qx * dy - qy * dx + qz * dw;
-    const float inv = rsqrtf(fmaf(nw, nw, fmaf(nx, nx, fmaf(ny, ny, nz * nz))));
-    q = make_float4(nw * inv, nx * inv, ny * inv, nz * inv);
+    w[0] = vfma(wd0, dt, w[0]); w[1] = vfma(wd1, dt, w[1]); w[2] = vfma(wd2, dt, w[2]);
+    const V hx = hdt * w[0], hy = hdt * w[1], hz = hdt * w[2];
+    const V ang2 = vfma(hx, hx, vfma(hy, hy, hz * hz));
+    V sinc, cs;
+    sinc_cos<V>(ang2, sinc, cs);
+    const V dx = hx * sinc, dy = hy * sinc, dz = hz * sinc;
+    const V nw = vfma(qw, cs, vneg(vfma(qx, dx, vfma(qy, dy, qz * dz))));
+    const V nx = vfma(qw, dx, vfma(qx, cs, vfma(qy, dz, vneg(qz * dy))));
+    const V ny = vfma(qw, dy, vfma(qy, cs, vfma(qz, dx, vneg(qx * dz))));
+    const V nz = vfma(qw, dz, vfma(qz, cs, vfma(qx, dy, vneg(qy * dx))));
+    const V inv = vrsqrt_fast(vfma(nw, nw, vfma(nx, nx, vfma(ny, ny, nz * nz))));
+    qw = nw * inv; qx = nx * inv; qy = ny * inv; qz = nz * inv;
   }
-  int ep = __float_as_int(p1.w) + 1;
-  if (done_out) done_out[e] = done ? 1 : 0;
-  if (motor_out) stg_stream(motor_out + e, make_float4(fm[0], fm[1], fm[2], fm[3]));
-  if (done && stats) {
-    atomicAdd(&stats->crashes, 1.0);
-    if (k.flags & FPV_F_AUTO_RESET) { atomicAdd(&stats->episodes, 1.0); atomicAdd(&stats->episode_len_sum, (double)ep); }
-  }
-  if (done && (k.flags & FPV_F_AUTO_RESET)) {
-    float4 v[FPV_ACRO_PLANES];
+  // ---- epilogue per env
 #pragma unroll
-    for (int p = 0; p < FPV_ACRO_PLANES; ++p) v[p] = ldg_stream(reset_state + p * stride + e);
-    v[1].w = __int_as_float(0);
+  for (int l = 0; l < L; ++l) {
+    const long long e = base + (long long)l * THREADS;
+    if (e >= n) break;
+    const bool d = mask_get(done, l);
+    const int ep = epi[l] + 1;
+    if (done_out) done_out[e] = d ? 1 : 0;
+    if (motor_out)
+      stg_stream(motor_out + e, make_float4(Lane<V>::get(fm[0], l), Lane<V>::get(fm[1], l), Lane<V>::get(fm[2], l), Lane<V>::get(fm[3], l)));
+    if (d && stats) {
+      atomicAdd(&stats->crashes, 1.0);
+      if (k.flags & FPV_F_AUTO_RESET) { atomicAdd(&stats->episodes, 1.0); atomicAdd(&stats->episode_len_sum, (double)ep); }
+    }
+    if (d && (k.flags & FPV_F_AUTO_RESET)) {
+      float4 v[FPV_ACRO_PLANES];
 #pragma unroll
-    for (int p = 0; p < FPV_ACRO_PLANES; ++p) stg_stream(state + p * stride + e, v[p]);
-    return;
+      for (int p = 0; p < FPV_ACRO_PLANES; ++p) v[p] = ldg_stream(reset_state + p * stride + e);
+      v[1].w = __int_as_float(0);
+#pragma unroll
+      for (int p = 0; p < FPV_ACRO_PLANES; ++p) stg_stream(state + p * stride + e, v[p]);
+      continue;
+    }
+    const auto g = [&](V v) { return Lane<V>::get(v, l); };
+    stg_stream(state + e, make_float4(g(px), g(py), g(pz), g(thr)));
+    stg_stream(state + stride + e, make_float4(g(vx), g(vy), g(vz), __int_as_float(ep)));
+    stg_stream(state + 2 * stride + e, make_float4(g(qw), g(qx), g(qy), g(qz)));
+    stg_stream(state + 3 * stride + e, make_float4(g(sp[0]), g(sp[1]), g(sp[2]), 0.f));   // .w: PID has been called
+    stg_stream(state + 4 * stride + e, make_float4(g(w[0]), g(w[1]), g(w[2]), 0.f));
+    stg_stream(state + 5 * stride + e, make_float4(g(ie[0]), g(ie[1]), g(ie[2]), 0.f));
+    stg_stream(state + 6 * stride + e, make_float4(g(le[0]), g(le[1]), g(le[2]), 0.f));
   }
-  p0.w = thr;
-  p1.w = __int_as_float(ep);
-  stg_stream(state + e, p0);
-  stg_stream(state + stride + e, p1);
-  stg_stream(state + 2 * stride + e, q);
-  stg_stream(state + 3 * stride + e, make_float4(sp_deg[0], sp_deg[1], sp_deg[2], first ? 1.f : 0.f));
-  stg_stream(state + 4 * stride + e, make_float4(w[0], w[1], w[2], 0.f));
-  stg_stream(state + 5 * stride + e, make_float4(ie[0], ie[1], ie[2], 0.f));
-  stg_stream(state + 6 * stride + e, make_float4(le[0], le[1], le[2], 0.f));
 }
 
 }  // namespace fpv

@@ -712,14 +712,18 @@ int fpv_acro_step(const fpv_acro_params_t* p, void* state, int64_t n, int64_t pl
   k.flags = p->flags;
   if (n == 0) return FPV_OK;
   const size_t smem = (p->flags & FPV_F_THRUST_LUT) ? sizeof(float) * (size_t)lut_n : 0;
-  auto kern = fpv::acro_step_kernel<kThreads>;
-  static size_t attr_set = 0;
-  if (smem > 48 * 1024 && smem > attr_set) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_set = smem;
-  }
-  kern<<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, smem, (cudaStream_t)stream>>>(
-      k, (float4*)state, n, plane_stride, (const float4*)actions, lut, done, (float4*)motor_thrust, (const float4*)reset_state, stats);
+  auto launch = [&](auto kern, int envs_per_thread) {
+    static size_t attr_set = 0;
+    if (smem > 48 * 1024 && smem > attr_set) {
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      attr_set = smem;
+    }
+    const long long tile = (long long)kThreads * envs_per_thread;
+    kern<<<(unsigned)((n + tile - 1) / tile), kThreads, smem, (cudaStream_t)stream>>>(
+        k, (float4*)state, n, plane_stride, (const float4*)actions, lut, done, (float4*)motor_thrust, (const float4*)reset_state, stats);
+  };
+  if (p->flags & FPV_F_SCALAR) launch(fpv::acro_step_kernel<float, kThreads>, 1);
+  else launch(fpv::acro_step_kernel<F2, kThreads>, 2);
   return check_launch("fpv_acro_step");
 }
 

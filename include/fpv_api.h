@@ -393,7 +393,7 @@ typedef struct fpv_acro_params {
   float u_min, u_max;           /* motor throttle limits in [-1, 1] (idle = 5 %: -0.9, components.py:138-139) */
   float thrust_poly[4];         /* 4-motor bench cubic in throttle percent        components.py:136 */
   float wind[3];
-  uint32_t flags;               /* FPV_F_GROUND | FPV_F_AUTO_RESET | FPV_F_THRUST_LUT */
+  uint32_t flags;               /* FPV_F_GROUND | FPV_F_AUTO_RESET | FPV_F_THRUST_LUT | FPV_F_SCALAR (one env per thread) */
 } fpv_acro_params_t;
 
 /* pos, vel, rpy_deg: float[n][3]; motors off (throttle -1), zero rates, fresh PID.  mask as in fpv_drone_reset. */

@@ -38,9 +38,10 @@ def seeded(n, seed, z_lo=2.0, z_hi=12.0):
     return rng, pos, rng.normal(0, 1, (n, 3)), rng.uniform(-30, 30, (n, 3))
 
 
+@pytest.mark.parametrize("packed", [True, False])
 @pytest.mark.parametrize("lut", [2049, 0])
 @pytest.mark.parametrize("dt,K", [(1e-3, 1), (1e-3, 8), (1 / 60, 1)])
-def test_single_control_steps_vs_model(dt, K, lut):
+def test_single_control_steps_vs_model(dt, K, lut, packed):
     """Every control step restarts from the model's own float64 state (rounded to float32), so the error is one
     step's worth: <= 1e-5 relative."""
     from fpyv_b200 import BatchedAcroDrone
@@ -48,7 +49,7 @@ def test_single_control_steps_vs_model(dt, K, lut):
     rng, pos, vel, rpy = seeded(n, 11)
     c = consts(dt)
     table = None
-    d = BatchedAcroDrone(None, num_envs=n, device=DEV, substeps=K, dt=dt, thrust_lut=lut)
+    d = BatchedAcroDrone(None, num_envs=n, device=DEV, substeps=K, dt=dt, thrust_lut=lut, packed=packed)
     if lut:
         table = d._lut.double().cpu().numpy()
     s = ao.acro_reset(c, pos, vel, rpy)
@@ -71,7 +72,7 @@ def test_single_control_steps_vs_model(dt, K, lut):
         assert np.array_equal(done, s.done)
         worst = max(worst, state_err(d, s).max())
         np.testing.assert_allclose(d.motor_thrust.double().cpu().numpy(), s.motor_thrust, rtol=2e-5, atol=2e-5)
-    print(f"acro dt={dt:.4g} K={K} lut={lut}: max single-step rel err {worst:.2e}")
+    print(f"acro dt={dt:.4g} K={K} lut={lut} packed={packed}: max single-step rel err {worst:.2e}")
     assert worst < 1e-5
 
 
@@ -170,3 +171,25 @@ def test_ragged_sizes_leave_padding_and_guards_untouched(n):
     assert bool((motor[:G] == -7.0).all()) and bool((motor[G + n:] == -7.0).all())
     assert torch.equal(d._state[:, :n], big._state[:, :n])
     assert torch.equal(motor[G:G + n], big.motor_thrust[:n])
+
+
+def test_tumbling_envs_take_the_accurate_rotation_path():
+    """|omega| dt / 2 >= 0.1 rad switches a lane from the series to sincosf; mixed pairs (one tumbling, one calm env in
+    the same thread) must both stay within tolerance of the model."""
+    from fpyv_b200 import BatchedAcroDrone
+    n, dt = 512, 1e-3
+    rng, pos, vel, rpy = seeded(n, 14, z_lo=30, z_hi=60)
+    c = consts(dt)
+    d = BatchedAcroDrone(None, num_envs=n, device=DEV, substeps=4, dt=dt, thrust_lut=0)
+    d.reset(pos, vel, rpy)
+    s = ao.acro_reset(c, pos, vel, rpy)
+    omega = rng.normal(0, 1, (n, 3))
+    omega[::3] *= 400.0                                   # every third env tumbles at hundreds of rad/s
+    d.angular_velocity.copy_(torch.as_tensor(omega, dtype=torch.float32, device=DEV))
+    s.omega = d.angular_velocity.double().cpu().numpy()
+    act = rng.uniform(-1, 1, (n, 4))
+    ao.acro_step(c, s, act, substeps=4)
+    d.step(act)
+    err = state_err(d, s)
+    print(f"acro tumbling: max rel err {err.max():.2e} (tumbling envs {err[::3].max():.2e}, calm {np.delete(err, np.s_[::3]).max():.2e})")
+    assert err.max() < 1e-5
