@@ -229,7 +229,7 @@ def run_gpu(args):
         takes two of the four CTA slots of each SM and two consecutive launches are resident side by side: the idle
         tail and the start-up of one launch are covered by the bulk of its neighbour."""
         for d_ in ds:
-            d_._io.max_ctas_per_sm = cta_slots if chained else 0
+            d_.cta_slots = cta_slots if chained else 0
         for i in range(warm):
             ds[i % len(ds)].step(ring[i % 4], return_obs=False, chained=chained)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -246,7 +246,7 @@ def run_gpu(args):
         if world > 1:
             dist.barrier()
         for d_ in ds:
-            d_._io.max_ctas_per_sm = 0
+            d_.cta_slots = 0
         return e0.elapsed_time(e1)
 
     def timed_loop(d, steps, warm):

@@ -342,6 +342,16 @@ class BatchedDrone:
             return self.observe()
         return None
 
+    @property
+    def cta_slots(self) -> int:
+        """CTA slots per SM one step launch takes (0 = all); see fpv_drone_io_t.max_ctas_per_sm."""
+        return int(self._io.max_ctas_per_sm)
+
+    @cta_slots.setter
+    def cta_slots(self, k: int):
+        self._io.max_ctas_per_sm = int(k)
+        self._slice_cache = None
+
     def rollout(self, actions, done_out=None, fused=True):
         """Open-loop rollout: T control steps with the stick commands of all steps given up front
         (actions [T,n,4] float32 on the device -- random exploration, MPC shooting, or recorded sticks replayed through
