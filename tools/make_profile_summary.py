@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Turn gpurun_out/{launches_r1.csv, prof_*.ncu-rep, bench_full.json, bench_ref.json} into the tracked profiles/ files.
-usage: python tools/make_profile_summary.py gpurun_out/prof_r1f.ncu-rep"""
+usage: python tools/make_profile_summary.py gpurun_out/prof_r1g.ncu-rep"""
 import collections, csv, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rep = sys.argv[1]
@@ -45,7 +45,7 @@ md = f"""# Round 1 ncu evidence (B200, sm_100a) -- `python bench.py --steps 3 --
 Commands (B200_PROFILING.md recipe; the plain run exited 0 first, in the same gpurun call):
 ```
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_r1.csv python bench.py --steps 3 --warmup 3 --profile
-ncu --set full --clock-control none --import-source on -k regex:drone_step -s 6 -c 4 -o gpurun_out/prof_r1f python bench.py --steps 3 --warmup 3 --profile
+ncu --set full --clock-control none --import-source on -k regex:drone_step -s 6 -c 4 -o gpurun_out/prof_r1g python bench.py --steps 3 --warmup 3 --profile
 ```
 Files here: `r1_launches.csv` (every launch of the profile run), `r1_ncu_drone_step.json` (raw-page metrics of the
 captured `drone_step_tma_kernel` launches, all K = 8), `r1_bench_n1.json` / `r1_bench_reference_arm.json` (bench lines of
@@ -63,7 +63,9 @@ The rest of the profile run is set-up (synthetic init) and the L2-flush kernels 
 {chr(10).join(lines)}
 
 Per-launch durations of `drone_step_tma_kernel` in launch order (us): {', '.join(f'{x:.1f}' for x in step)}
-(order: K=8 rotation 3 warm-up + 3 timed, K=8 flushed 3 + 3, K=1 rotation 3 + 3, K=1 flushed 3 + 3).
+(order, each 3 warm-up + 3 timed: K=8 rotation chained on 2 of 4 CTA slots [grid 296: under ncu's serialisation a half-size
+grid simply takes longer -- side by side they overlap], K=8 rotation chained full grid, K=8 rotation unchained, K=8 flushed,
+then the same three rotations and the flushed loop at K=1; the full capture below is of the full-grid launches).
 
 ## `fpv::drone_step_tma_kernel<F2, ANG=4, 128, 4, 2>` -- K = 8, 1,048,576 envs
 
