@@ -27,6 +27,7 @@ SUBSTEPS = 8
 DT = 1e-3
 LUT_N = int(os.environ.get("FPV_BENCH_LUT", "2049"))   # env override: developer tuning only
 CHAINED = os.environ.get("FPV_BENCH_CHAINED", "1") != "0"   # developer A/B: 0 = every launch waits for the previous grid
+E2E_SLICES = int(os.environ.get("FPV_BENCH_E2E_SLICES", "4"))
 CTA_SLOTS = int(os.environ.get("FPV_BENCH_CTA_SLOTS", "2"))  # CTA slots per SM one launch takes in the primary loop (0 = all)
 # algorithmic work per env (quaternion state, 64 B each way)
 BYTES_PER_ENV_STEP = 64 + 64 + 16 + 1          # state read + state write + action + done flag
@@ -299,7 +300,7 @@ def run_gpu(args):
     host_actions = [torch.empty(n, 4, dtype=torch.float32, pin_memory=True).uniform_(-1, 1) for _ in range(2)]
     host_done = torch.empty(n, dtype=torch.uint8, pin_memory=True)
     for i in range(max(3, W)):
-        drone.step_host(host_actions[i % 2], host_done)
+        drone.step_host(host_actions[i % 2], host_done, slices=E2E_SLICES)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -307,7 +308,7 @@ def run_gpu(args):
     e0.record()
     crashed = 0
     for i in range(K):
-        drone.step_host(host_actions[i % 2], host_done)
+        drone.step_host(host_actions[i % 2], host_done, slices=E2E_SLICES)
         torch.cuda.current_stream().synchronize()      # the caller consumes the done flags every step
         crashed += int(host_done[:64].sum())
     e1.record()
@@ -377,7 +378,7 @@ def run_gpu(args):
             "env_substeps_per_sec": value * SUBSTEPS,
             "e2e": {"value": total_envs * K / (ms_e2e * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": 16 * n * world,
                     "d2h_bytes_per_step": n * world, "ms_per_step": ms_e2e / K,
-                    "api": "BatchedDrone.step_host(pinned actions) -> pinned done flags, 4 env slices pipelined over H2D / step / D2H streams; host waits every step"},
+                    "api": "BatchedDrone.step_host(pinned actions) -> pinned done flags = fpv_drone_step_host: 4 env slices pipelined over H2D / step / D2H streams inside the library; host waits every step"},
             "ms_per_step_flushed": ms_flushed_per_step,
             "ms_per_step_chained_full_grid": ms_full_grid / K, "ms_per_step_unchained": ms_unchained / K,
             "rollout_fused": {"ms_per_step": ms_rollout, "env_steps_per_sec": total_envs / (ms_rollout * 1e-3),

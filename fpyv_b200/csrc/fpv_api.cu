@@ -335,6 +335,83 @@ int fpv_drone_step(const fpv_drone_params_t* p, const fpv_drone_io_t* io, void* 
 }
 
 
+namespace {
+struct HostPipe {
+  cudaStream_t in = nullptr, out = nullptr;
+  cudaEvent_t ready = nullptr, joined = nullptr;
+  cudaEvent_t h2d[16] = {}, stepped[16] = {};
+  bool ok = false;
+};
+HostPipe& host_pipe_of_current_device() {
+  static HostPipe pipes[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  HostPipe& p = pipes[dev];
+  if (!p.ok) {
+    cudaStreamCreateWithFlags(&p.in, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&p.out, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&p.ready, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&p.joined, cudaEventDisableTiming);
+    for (int i = 0; i < 16; ++i) {
+      cudaEventCreateWithFlags(&p.h2d[i], cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&p.stepped[i], cudaEventDisableTiming);
+    }
+    p.ok = cudaGetLastError() == cudaSuccess;
+  }
+  return p;
+}
+}  // namespace
+
+int fpv_drone_step_host(const fpv_drone_params_t* p, const fpv_drone_io_t* io, const float* actions_host,
+                        uint8_t* done_host, int32_t slices, void* stream) {
+  if (!p || !io) return fail(FPV_EINVAL, "fpv_drone_step_host: null params/io");
+  if (!actions_host || !done_host) return fail(FPV_EINVAL, "fpv_drone_step_host: null host buffer");
+  if (!io->actions || !io->done) return fail(FPV_EINVAL, "fpv_drone_step_host: io.actions / io.done must be device staging buffers");
+  if (io->n < 0 || io->plane_stride < io->n) return fail(FPV_EINVAL, "fpv_drone_step_host: bad n/stride");
+  if (io->n == 0) return FPV_OK;
+  if (slices <= 0) slices = 4;
+  if (slices > 16) slices = 16;
+  const long long n = io->n;
+  long long per = (n + slices - 1) / slices;
+  per = (per + 63) / 64 * 64;
+  if (per < 65536) per = 65536;   // below this a slice is launch-latency bound
+  HostPipe& hp = host_pipe_of_current_device();
+  if (!hp.ok) return fail(FPV_ECUDA, "fpv_drone_step_host: could not create the copy streams");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaEventRecord(hp.ready, st);            // everything queued so far (the previous step reads the staging buffer) ...
+  cudaStreamWaitEvent(hp.in, hp.ready, 0);  // ... precedes the first byte of the new actions
+  cudaStreamWaitEvent(hp.out, hp.ready, 0);
+  fpv_drone_params_t pp = *p;
+  pp.flags &= ~FPV_F_CHAINED;
+  int c = 0;
+  for (long long a = 0; a < n; a += per, ++c) {
+    const long long b = a + per < n ? a + per : n;
+    cudaMemcpyAsync((char*)io->actions + 16 * a, (const char*)actions_host + 16 * a, (size_t)(16 * (b - a)), cudaMemcpyHostToDevice, hp.in);
+    cudaEventRecord(hp.h2d[c], hp.in);
+    cudaStreamWaitEvent(st, hp.h2d[c], 0);
+    fpv_drone_io_t s = *io;
+    s.state = (char*)io->state + 16 * a;
+    s.n = b - a;
+    s.actions = (const char*)io->actions + 16 * a;
+    s.done = io->done + a;
+    if (io->wind_env) s.wind_env = (const char*)io->wind_env + 16 * a;
+    if (io->acc_out) s.acc_out = (char*)io->acc_out + 16 * a;
+    if (io->reset_state) s.reset_state = (const char*)io->reset_state + 16 * a;
+    if (io->override_q) s.override_q = (const char*)io->override_q + 16 * a;
+    if (io->override_thrust) s.override_thrust = io->override_thrust + a;
+    s.chunk_epoch = nullptr;
+    s.trace = nullptr;
+    if (int rc = fpv_drone_step(&pp, &s, stream)) return rc;
+    cudaEventRecord(hp.stepped[c], st);
+    cudaStreamWaitEvent(hp.out, hp.stepped[c], 0);
+    cudaMemcpyAsync(done_host + a, io->done + a, (size_t)(b - a), cudaMemcpyDeviceToHost, hp.out);
+  }
+  cudaEventRecord(hp.joined, hp.out);
+  cudaStreamWaitEvent(st, hp.joined, 0);
+  return check_launch("fpv_drone_step_host");
+}
+
 int fpv_drone_rollout(const fpv_drone_params_t* p, const fpv_drone_io_t* io, const void* actions_seq,
                       int64_t action_stride, int32_t n_steps, uint8_t* done_seq, int64_t done_stride, void* stream) {
   DroneK k;

@@ -115,7 +115,6 @@ class BatchedDrone:
         self._io.max_ctas_per_sm = int(cta_slots)
         self._host_actions = None
         self._host_done = None
-        self._pipe = None
         self._slice_cache = None
         self._last_action = None
         self._is_reset = False
@@ -414,13 +413,12 @@ class BatchedDrone:
 
     # ------------------------------------------------------------------ host-buffer entry (end-to-end path)
     def step_host(self, actions_host: torch.Tensor, done_host: torch.Tensor | None = None, slices: int = 4):
-        """One control step with HOST buffers: pinned actions [n,4] -> device, step, done flags -> pinned host.
-        This is the call timed as `e2e` in bench.py (H2D 16 B/env, D2H 1 B/env per step).
+        """One control step with HOST buffers: pinned actions [n,4] -> device, step, done flags -> pinned host
+        (fpv_drone_step_host).  This is the call timed as `e2e` in bench.py (H2D 16 B/env, D2H 1 B/env per step).
 
-        The step is PCIe-bound, so the batch is cut into `slices` env ranges and pipelined over three streams: the
-        H2D copy of slice c+1 runs while slice c is stepped and slice c-1's flags travel back.  Each slice is an
-        ordinary fpv_drone_step launch on its own env range (pointers offset, same plane stride).  The caller's
-        current stream is joined to the last D2H copy, so synchronising it means the flags are on the host."""
+        The step is PCIe-bound, so the library cuts the batch into `slices` env ranges and pipelines them over three
+        streams: the H2D copy of slice c+1 runs while slice c is stepped and slice c-1's flags travel back.  The
+        caller's current stream is joined to the last D2H copy, so synchronising it means the flags are on the host."""
         n, dev = self.num_envs, self.device
         if done_host is None:
             if self._host_done is None:
@@ -428,67 +426,28 @@ class BatchedDrone:
             done_host = self._host_done
         if not self._is_reset:
             raise RuntimeError("call reset() before step() (the reference's state is None until reset)")
-        bounds = self._slice_bounds(slices)
-        if len(bounds) < 2 or not self._fast_ok:
-            self._actions.copy_(actions_host, non_blocking=True)
+        if (not self._fast_ok or actions_host.is_cuda or actions_host.dtype is not torch.float32
+                or not actions_host.is_contiguous() or tuple(actions_host.shape) != (n, 4)
+                or done_host.dtype is not torch.uint8 or not done_host.is_contiguous()):
+            self._actions.copy_(actions_host, non_blocking=True)      # first call / odd inputs: the plain path
             self.step(self._actions, return_obs=False)
             done_host.copy_(self._done, non_blocking=True)
             return done_host
-        cur = torch.cuda.current_stream(dev)
-        if self._pipe is None:
-            self._pipe = (torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Event(), torch.cuda.Event())
-        s_in, s_out, ev_free, ev_done = self._pipe
-        ev_free.record(cur)               # everything queued so far (the previous step reads self._actions) ...
-        s_in.wait_event(ev_free)          # ... precedes the first byte of the new actions
-        s_out.wait_event(ev_free)
-        ios = self._slice_ios(bounds)
         self._last_action = self._actions
         self._chain_ready = False
         self._p.flags = self._flags
-        for (a, b), io_ref in zip(bounds, ios):
-            with torch.cuda.stream(s_in):
-                self._actions[a:b].copy_(actions_host[a:b], non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(s_in)
-            cur.wait_event(ev)
-            rc = self._step_fn(self._p_ref, io_ref, cur.cuda_stream)
-            if rc:
-                _lib.check(rc)
-            ev2 = torch.cuda.Event()
-            ev2.record(cur)
-            s_out.wait_event(ev2)
-            with torch.cuda.stream(s_out):
-                done_host[a:b].copy_(self._done[a:b], non_blocking=True)
-        ev_done.record(s_out)
-        cur.wait_event(ev_done)
+        self._io.actions = self._actions.data_ptr()
+        self._io.chunk_epoch = None
+        _lib.check(self._lib.fpv_drone_step_host(self._p_ref, self._io_ref, actions_host.data_ptr(), done_host.data_ptr(),
+                                                 int(slices), torch.cuda.current_stream(dev).cuda_stream))
         return done_host
 
     def _slice_bounds(self, slices):
-        """Env ranges of a sliced step: multiples of 64 envs (the kernel's chunk), at least 64K envs each."""
+        """Env ranges of a sliced step as the library cuts them: multiples of 64 envs, at least 64K envs each."""
         n = self.num_envs
-        k = max(1, min(int(slices), n // 65536))
-        per = -(-n // k)
-        per = -(-per // 64) * 64
+        per = -(-n // max(1, int(slices)))
+        per = max(65536, -(-per // 64) * 64)
         return [(a, min(n, a + per)) for a in range(0, n, per)]
-
-    def _slice_ios(self, bounds):
-        key = tuple(bounds)
-        if self._slice_cache is None or self._slice_cache[0] != key:
-            ios = []
-            for a, b in bounds:
-                io = _lib.DroneIO()
-                C.memmove(C.byref(io), C.byref(self._io), C.sizeof(io))
-                off4 = lambda t: None if t is None else t.data_ptr() + 16 * a
-                io.state, io.n = self._state.data_ptr() + 16 * a, b - a
-                io.actions = self._actions.data_ptr() + 16 * a
-                io.done = self._done.data_ptr() + a
-                io.acc_out = off4(self._acc)
-                io.reset_state = off4(self._reset_state)
-                io.chunk_epoch = None
-                io.trace = None
-                ios.append(io)
-            self._slice_cache = (key, ios, [C.byref(x) for x in ios])
-        return self._slice_cache[2]
 
     # ------------------------------------------------------------------ episode statistics
     def episode_stats(self, all_reduce: bool = False, reset: bool = False) -> dict:

@@ -174,6 +174,17 @@ int fpv_drone_reset(void* state, int64_t n, int64_t plane_stride, const float* p
  * Runs params->substeps reference steps per env with the state held in registers. */
 int fpv_drone_step(const fpv_drone_params_t* params, const fpv_drone_io_t* io, void* stream);
 
+/* Drone.step with HOST buffers (the call a CPU-side caller of the reference makes: NumPy in, flags out):
+ * actions_host float[n][4] and done_host uint8[n] are host pointers (page-locked memory for full speed); io->actions
+ * must point at a device staging buffer float4[n], io->done at a device uint8[n].  The batch is cut into `slices` env
+ * ranges (multiples of 64 envs) pipelined over three streams -- H2D copy of slice c+1 | step of slice c | D2H copy of
+ * slice c-1 -- because the call is PCIe-bound (16 B/env in, 1 B/env out).  Everything is ordered after the work already
+ * queued on `stream`, and `stream` is joined to the last copy: synchronising it means done_host is valid.  The two
+ * extra streams and the events are created once per device and cached inside the library (the only state it keeps).
+ * io->chunk_epoch / FPV_F_CHAINED are ignored.  slices <= 0: 4. */
+int fpv_drone_step_host(const fpv_drone_params_t* params, const fpv_drone_io_t* io, const float* actions_host,
+                        uint8_t* done_host, int32_t slices, void* stream);
+
 /* Open-loop rollout: T consecutive calls of Drone.step (components.py:220-248, params->substeps reference steps each)
  * in ONE launch, with every env's state held in registers from the first step to the last: the state planes are read
  * once and written once, per control step only the env's action is read and its done flag written (17 B/env/step instead
