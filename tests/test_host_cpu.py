@@ -251,3 +251,43 @@ def test_new_entry_points_validate_without_a_gpu(lib):
     assert b"Unknown reference frame" in lib.fpv_last_error()
     assert lib.fpv_acro_step(C.byref(ac), dummy, 0, 0, dummy, None, 0, None, None, None, None, None) == -22
     assert lib.fpv_acro_reset(None, 0, 0, None, None, None, None, None) == -22
+
+
+def test_host_and_rollout_entry_points_validate_without_a_gpu(lib):
+    from fpyv_b200 import _lib
+    p, io = _lib.DroneParams(), _lib.DroneIO()
+    buf = (C.c_float * 64)()
+    assert lib.fpv_drone_step_host(None, None, None, None, 4, None) == -22
+    assert lib.fpv_drone_step_host(C.byref(p), C.byref(io), None, None, 4, None) == -22 and b"host buffer" in lib.fpv_last_error()
+    assert lib.fpv_drone_step_host(C.byref(p), C.byref(io), buf, buf, 4, None) == -22 and b"staging" in lib.fpv_last_error()
+    assert lib.fpv_drone_rollout(None, None, None, 0, 1, None, 0, None) == -22
+    io.n = io.plane_stride = 0
+    assert lib.fpv_drone_rollout(C.byref(p), C.byref(io), None, 0, 4, None, 0, None) == 0      # empty batch: no-op
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("slots", [1, 2, 3])
+def test_cta_slots_do_not_change_results(slots):
+    """max_ctas_per_sm only changes how much of each SM a launch occupies: results are bit-identical."""
+    import torch
+    from fpyv_b200 import BatchedDrone
+    n, dev = 1 << 19, "cuda:0"
+    g = torch.Generator(device=dev).manual_seed(4)
+    pos = torch.randn(n, 3, device=dev, generator=g) * 5
+    pos[:, 2] = 0.05 + torch.rand(n, device=dev, generator=g) * 2.95
+    vel = torch.randn(n, 3, device=dev, generator=g)
+    rpy = (torch.rand(n, 3, device=dev, generator=g) * 2 - 1) * 30
+    acts = [torch.rand(n, 4, device=dev, generator=g) * 2 - 1 for _ in range(6)]
+    ref = BatchedDrone(None, num_envs=n, device=dev, substeps=8, dt=1e-3, auto_reset=True, thrust_lut=2049)
+    a = BatchedDrone(None, num_envs=n, device=dev, substeps=8, dt=1e-3, auto_reset=True, thrust_lut=2049, cta_slots=slots)
+    b = BatchedDrone(None, num_envs=n, device=dev, substeps=8, dt=1e-3, auto_reset=True, thrust_lut=2049, cta_slots=slots)
+    for d in (ref, a, b):
+        d.reset(pos, vel, rpy)
+    assert a.cta_slots == slots
+    for t in range(6):      # a and b alternate, chained: their launches run side by side
+        ref.step(acts[t], return_obs=False)
+        a.step(acts[t], return_obs=False, chained=True)
+        b.step(acts[t], return_obs=False, chained=True)
+    torch.cuda.synchronize()
+    assert torch.equal(a._state, ref._state) and torch.equal(b._state, ref._state)
+    assert torch.equal(a.done, ref.done) and a.episode_stats()["crashes"] == ref.episode_stats()["crashes"]
