@@ -685,3 +685,36 @@ def test_fused_rollout_is_bit_identical_to_steps(n, K, T, auto_reset):
     a.rollout(acts, fused=True)
     b.rollout(acts, fused=False)
     assert torch.equal(a._state[:, :n].view(torch.int32), b._state[:, :n].view(torch.int32))
+
+
+def test_max_size_16m_envs_single_gpu():
+    """BASELINE.json configs[3]'s total batch (16,777,216 drones) on ONE GPU: 1 GiB of state, plane offsets beyond
+    2^30 bytes.  Subsamples at both ends and in the middle against the float64 oracle, guard envs beyond n untouched,
+    every env stepped exactly once (episode counters), K = 8 and the fused rollout agree bit for bit."""
+    n, K = 1 << 24, 8
+    g = torch.Generator(device=DEV).manual_seed(41)
+    pos = torch.randn(n, 3, device=DEV, generator=g) * 5
+    pos[:, 2] = 0.3 + torch.rand(n, device=DEV, generator=g) * 5
+    vel = torch.randn(n, 3, device=DEV, generator=g)
+    rpy = (torch.rand(n, 3, device=DEV, generator=g) * 2 - 1) * 30
+    act = (torch.rand(2, n, 4, device=DEV, generator=g) * 2 - 1).contiguous()
+    d = make(n, substeps=K, dt=1e-3, thrust_lut=0)
+    d.reset(pos, vel, rpy)
+    idx = torch.cat([torch.arange(0, 1024), torch.arange(n // 2 - 512, n // 2 + 512), torch.arange(n - 1024, n)]).to(DEV)
+    c = fo_consts(1e-3)
+    s = fo.drone_reset(c, pos[idx].double().cpu().numpy(), vel[idx].double().cpu().numpy(), rpy[idx].double().cpu().numpy())
+    d.step(act[0], return_obs=False)
+    d.step(act[1], return_obs=False, chained=True)
+    for t in range(2):
+        fo.drone_step(c, s, act[t][idx].double().cpu().numpy(), substeps=K)
+    torch.cuda.synchronize()
+    err = max(group_err(d.position[idx].cpu().numpy(), s.pos).max(), group_err(d.velocity[idx].cpu().numpy(), s.vel).max(),
+              group_err(d.rotation_matrix[idx].cpu().numpy(), s.R).max())
+    print(f"\n16,777,216 envs, 2 control steps x {K} substeps: max rel err vs oracle on 3,072 sampled envs {err:.2e}")
+    assert err < 1e-5
+    assert bool((d.episode_steps == 2).all())               # every env advanced exactly twice
+    assert bool(torch.isfinite(d._state[:3, :n]).all())
+    d2 = make(n, substeps=K, dt=1e-3, thrust_lut=0)
+    d2.reset(pos, vel, rpy)
+    d2.rollout(act, fused=True)
+    assert torch.equal(d2._state, d._state)
