@@ -27,6 +27,7 @@ struct DroneK {
   float neg_motor_xy[4][2]; // -motor offsets                       components.py:123-125
   float motor_xy[4][2];
   float motor_radius;
+  float arm_reach;          // max |motor offset| + motor_radius + margin: beyond it an obstacle cannot touch any motor
   float spring_k, spring_c; // components.py:198
   float poly[4];            // throttle% -> N, high->low; evaluated at 100*(x+1)/2   components.py:136
   float wind[3];
@@ -61,34 +62,42 @@ struct DroneIO {
   unsigned long long* trace;
 };
 
-// Obstacle SDF + normal for one motor point (GENERAL path only; warp-uniform object loop).
+// Obstacle signed distance and contact normal for one motor point (GENERAL path only; warp-uniform object loop).
+// The distance is evaluated for every motor of every obstacle in reach; the normal (divisions) only for motors that
+// actually touch, which is rare.
 template <class V>
-__device__ __forceinline__ void object_sdf(const fpv_object_t& o, V px, V py, V pz, V& d, V& nx, V& ny, V& nz) {
-  if (o.kind == FPV_OBJ_SPHERE) {  // Target.calculate_distance/normal, components.py:773-777
-    V dx = px - S<V>(o.x), dy = py - S<V>(o.y), dz = pz - S<V>(o.z);
-    V r = vsqrt(vfma(dx, dx, vfma(dy, dy, dz * dz)));
-    d = r - S<V>(o.a);
-    nx = vdiv(dx, r);
-    ny = vdiv(dy, r);
-    nz = vdiv(dz, r);
-  } else {  // Cylinder, components.py:710-729
-    V dx = px - S<V>(o.x), dy = py - S<V>(o.y);
-    V rad = vsqrt(vfma(dx, dx, dy * dy));
-    V d2 = rad - S<V>(o.a);
-    V top = S<V>(o.z + o.b);
-    auto inside = vand(vlt(S<V>(o.z), pz), vlt(pz, top));
-    V dlo = vabs(pz - S<V>(o.z)), dhi = vabs(pz - top);
-    V dh = vmin(dlo, dhi);
-    d = vsel(inside, d2, vsqrt(vfma(d2, d2, dh * dh)));
-    // calculate_normal first makes the point RELATIVE to the base (:719) and then compares its z with
-    // the ABSOLUTE band (:720) and cap heights (:725) -- reproduced as written.
-    V qz = pz - S<V>(o.z);
-    auto inside_n = vand(vlt(S<V>(o.z), qz), vlt(qz, top));
-    auto below = vlt(vabs(qz - S<V>(o.z)), vabs(qz - top));
-    nx = vsel(inside_n, vdiv(dx, rad), S<V>(0.f));
-    ny = vsel(inside_n, vdiv(dy, rad), S<V>(0.f));
-    nz = vsel(inside_n, S<V>(0.f), vsel(below, S<V>(-1.f), S<V>(1.f)));
+__device__ __forceinline__ V object_distance(const fpv_object_t& o, V px, V py, V pz) {
+  if (o.kind == FPV_OBJ_SPHERE) {  // Target.calculate_distance, components.py:773-774
+    const V dx = px - S<V>(o.x), dy = py - S<V>(o.y), dz = pz - S<V>(o.z);
+    return vsqrt_fast(vfma(dx, dx, vfma(dy, dy, dz * dz))) - S<V>(o.a);
   }
+  // Cylinder.calculate_distance, components.py:710-716
+  const V dx = px - S<V>(o.x), dy = py - S<V>(o.y);
+  const V d2 = vsqrt_fast(vfma(dx, dx, dy * dy)) - S<V>(o.a);
+  const V top = S<V>(o.z + o.b);
+  const auto inside = vand(vlt(S<V>(o.z), pz), vlt(pz, top));
+  const V dh = vmin(vabs(pz - S<V>(o.z)), vabs(pz - top));
+  return vsel(inside, d2, vsqrt_fast(vfma(d2, d2, dh * dh)));
+}
+template <class V>
+__device__ __forceinline__ void object_normal(const fpv_object_t& o, V px, V py, V pz, V& nx, V& ny, V& nz) {
+  if (o.kind == FPV_OBJ_SPHERE) {  // Target.calculate_normal, components.py:776-777
+    const V dx = px - S<V>(o.x), dy = py - S<V>(o.y), dz = pz - S<V>(o.z);
+    const V r = vsqrt_fast(vfma(dx, dx, vfma(dy, dy, dz * dz)));
+    nx = vdiv_fast(dx, r); ny = vdiv_fast(dy, r); nz = vdiv_fast(dz, r);
+    return;
+  }
+  // Cylinder.calculate_normal, components.py:718-729: it first makes the point RELATIVE to the base (:719) and then
+  // compares its z with the ABSOLUTE band (:720) and cap heights (:725) -- reproduced as written.
+  const V dx = px - S<V>(o.x), dy = py - S<V>(o.y);
+  const V rad = vsqrt_fast(vfma(dx, dx, dy * dy));
+  const V top = S<V>(o.z + o.b);
+  const V qz = pz - S<V>(o.z);
+  const auto inside_n = vand(vlt(S<V>(o.z), qz), vlt(qz, top));
+  const auto below = vlt(vabs(qz - S<V>(o.z)), vabs(qz - top));
+  nx = vsel(inside_n, vdiv_fast(dx, rad), S<V>(0.f));
+  ny = vsel(inside_n, vdiv_fast(dy, rad), S<V>(0.f));
+  nz = vsel(inside_n, S<V>(0.f), vsel(below, S<V>(-1.f), S<V>(1.f)));
 }
 
 template <class V> struct DroneRegs {
@@ -187,48 +196,103 @@ __device__ __forceinline__ typename Lane<V>::Mask drone_substeps(const DroneK& k
       crashed = vlt(S<V>(k.motor_radius), tmax);
       Fz = vfma(S<V>(k.spring_k), vsel(crashed, zero, pen_sum), Fz);
     } else {
+      // General path: obstacles (sphere / cylinder SDFs), damped contact spring, optional ground.  Reference order:
+      // the extra objects first, the ground plane last; the first object any motor penetrates raises `done` and ends
+      // the collision pass with the forces gathered so far (components.py:205-210).
       crashed = vlt(one, zero);
-      const V r00 = vfma(vneg(s.qy), s.qy, vfma(vneg(s.qz), s.qz, one)), r10 = vfma(s.qw, s.qz, xy);
       V cfx = zero, cfy = zero, cfz = zero;
-      V mxw[4], myw[4], mzw[4];
-      V minz = S<V>(3.0e38f);
-#pragma unroll
-      for (int m = 0; m < 4; ++m) {
-        const V ox = S<V>(k.motor_xy[m][0]), oy = S<V>(k.motor_xy[m][1]);
-        mxw[m] = vfma(ox, r00, vfma(oy, r01, s.px));
-        myw[m] = vfma(ox, r10, vfma(oy, r11, s.py));
-        mzw[m] = vfma(ox, r20, vfma(oy, r21, s.pz));
-        minz = vmin(minz, mzw[m]);
+      // (1) reach tests for ALL obstacles, branch-free (independent, so their latencies overlap): every motor lies
+      //     within the arm length of the drone's centre, so an obstacle whose surface is further away than
+      //     arm + motor_radius contributes exactly nothing and skipping it leaves the result bit-identical.
+      unsigned near_mask = 0u;
+      {
+        const V reach = S<V>(k.arm_reach);
+        for (int o = 0; o < k.n_objects; ++o) {
+          const fpv_object_t& ob = k.objects[o];
+          const V dx = s.px - S<V>(ob.x), dy = s.py - S<V>(ob.y);
+          const V lim = S<V>(ob.a) + reach;
+          M near;
+          if (ob.kind == FPV_OBJ_SPHERE) {
+            const V dz = s.pz - S<V>(ob.z);
+            near = vlt(vfma(dx, dx, vfma(dy, dy, dz * dz)), lim * lim);
+          } else {  // cylinder: horizontally close AND inside the height band grown by the reach
+            near = vand(vlt(vfma(dx, dx, dy * dy), lim * lim),
+                        vand(vlt(S<V>(ob.z) - reach, s.pz), vlt(s.pz, S<V>(ob.z + ob.b) + reach)));
+          }
+          near_mask |= vany(near) ? (1u << o) : 0u;
+        }
       }
-      const int n_obj = k.n_objects + (ground ? 1 : 0);
-      for (int o = 0; o < n_obj; ++o) {  // object order: extra objects first, ground last
-        V d[4], nx[4], ny[4], nz[4];
-        M hit = vlt(one, zero);
+      // (2) the obstacles in reach (rare): 4 motor distances each; normals and spring forces only where a motor is
+      //     inside the contact shell
+      if (near_mask) {
+        const V r00 = vfma(vneg(s.qy), s.qy, vfma(vneg(s.qz), s.qz, one)), r10 = vfma(s.qw, s.qz, xy);
+        V mxw[4], myw[4], mzw[4];
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
-          if (o < k.n_objects) object_sdf<V>(k.objects[o], mxw[m], myw[m], mzw[m], d[m], nx[m], ny[m], nz[m]);
-          else { d[m] = mzw[m]; nx[m] = zero; ny[m] = zero; nz[m] = one; }
-          hit = vor(hit, vlt(d[m], zero));
+          const V ox = S<V>(k.motor_xy[m][0]), oy = S<V>(k.motor_xy[m][1]);
+          mxw[m] = vfma(ox, r00, vfma(oy, r01, s.px));
+          myw[m] = vfma(ox, r10, vfma(oy, r11, s.py));
+          mzw[m] = vfma(ox, r20, vfma(oy, r21, s.pz));
         }
-        hit = vand(hit, vnot(crashed));
-        crashed = vor(crashed, hit);
-        V ox = zero, oy = zero, oz = zero;
+        while (near_mask) {
+          const int o = __ffs(near_mask) - 1;
+          near_mask &= near_mask - 1u;
+          V d[4];
+          M hit = vlt(one, zero), touch = hit;
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            d[m] = object_distance<V>(k.objects[o], mxw[m], myw[m], mzw[m]);
+            hit = vor(hit, vlt(d[m], zero));
+            touch = vor(touch, vlt(d[m], S<V>(k.motor_radius)));
+          }
+          hit = vand(hit, vnot(crashed));
+          crashed = vor(crashed, hit);
+          const M live = vnot(crashed);
+          if (vany(vand(touch, live))) {   // spring forces of the motors inside the contact shell, :207-214
+            V ox = zero, oy = zero, oz = zero;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+              V nx, ny, nz;
+              object_normal<V>(k.objects[o], mxw[m], myw[m], mzw[m], nx, ny, nz);
+              const V pen = d[m] - S<V>(k.motor_radius);
+              const V vn = vfma(s.vx, nx, vfma(s.vy, ny, s.vz * nz));
+              const V f = vneg(vfma(S<V>(k.spring_k), pen, S<V>(k.spring_c) * vn));
+              const M act = vlt(pen, zero);
+              ox = ox + vsel(act, f * nx, zero);
+              oy = oy + vsel(act, f * ny, zero);
+              oz = oz + vsel(act, f * nz, zero);
+            }
+            cfx = cfx + vsel(live, ox, zero);
+            cfy = cfy + vsel(live, oy, zero);
+            cfz = cfz + vsel(live, oz, zero);
+          }
+        }
+      }
+      // (3) the ground plane, last in the list (distance = z, normal = +z, components.py:674-680), and the crash test
+      //     on the motor heights that holds with or without it (:239)
+      {
+        V mz[4];
+        V minz;
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
-          const V pen = d[m] - S<V>(k.motor_radius);
-          const V vn = vfma(s.vx, nx[m], vfma(s.vy, ny[m], s.vz * nz[m]));
-          const V f = vneg(vfma(S<V>(k.spring_k), pen, S<V>(k.spring_c) * vn));
-          const M act = vlt(pen, zero);
-          ox = ox + vsel(act, f * nx[m], zero);
-          oy = oy + vsel(act, f * ny[m], zero);
-          oz = oz + vsel(act, f * nz[m], zero);
+          mz[m] = vfma(S<V>(k.motor_xy[m][0]), r20, vfma(S<V>(k.motor_xy[m][1]), r21, s.pz));
+          minz = m == 0 ? mz[m] : vmin(minz, mz[m]);
         }
-        const M live = vnot(crashed);
-        cfx = cfx + vsel(live, ox, zero);
-        cfy = cfy + vsel(live, oy, zero);
-        cfz = cfz + vsel(live, oz, zero);
+        const M below = vlt(minz, zero);
+        if (ground) {
+          crashed = vor(crashed, vand(below, vnot(crashed)));
+          const M live = vnot(crashed);
+          V oz = zero;
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            const V pen = mz[m] - S<V>(k.motor_radius);
+            const V f = vneg(vfma(S<V>(k.spring_k), pen, S<V>(k.spring_c) * s.vz));
+            oz = oz + vsel(vlt(pen, zero), f, zero);
+          }
+          cfz = cfz + vsel(live, oz, zero);
+        }
+        crashed = vor(crashed, below);  // components.py:239
       }
-      crashed = vor(crashed, vlt(minz, zero));  // components.py:239
       Fx = Fx + cfx; Fy = Fy + cfy; Fz = Fz + cfz;
     }
     done = vor(done, crashed);

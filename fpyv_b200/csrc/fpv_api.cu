@@ -61,7 +61,7 @@ int sm_count_of_current_device() {
 template <class V, int ANG, bool GENERAL>
 void launch_drone(const DroneK& k, const DroneIO& io, cudaStream_t st) {
   constexpr int L = fpv::Lane<V>::N;
-  auto kern = fpv::drone_step_kernel<V, ANG, GENERAL, kThreads, GENERAL ? 1 : FPV_MINB>;
+  auto kern = fpv::drone_step_kernel<V, ANG, GENERAL, kThreads, GENERAL ? 3 : FPV_MINB>;
   const size_t smem = (k.flags & FPV_F_THRUST_LUT) ? sizeof(float) * (size_t)k.lut_n : 0;
   static int occ_cache[2] = {0, 0};  // [lut?]; per template instantiation
   int& occ = occ_cache[smem ? 1 : 0];
@@ -266,6 +266,11 @@ int prepare_drone(const fpv_drone_params_t* p, const fpv_drone_io_t* io, bool ne
   for (int m = 0; m < 4; ++m)
     for (int j = 0; j < 2; ++j) { k.motor_xy[m][j] = p->motor_xy[m][j]; k.neg_motor_xy[m][j] = -p->motor_xy[m][j]; }
   k.motor_radius = p->motor_radius;
+  {
+    double arm = 0.0;
+    for (int m = 0; m < 4; ++m) arm = std::fmax(arm, std::hypot((double)p->motor_xy[m][0], (double)p->motor_xy[m][1]));
+    k.arm_reach = (float)(arm + (double)p->motor_radius + 2e-3);   // margin covers the fp32 rounding of the test itself
+  }
   k.spring_k = p->spring_k;
   k.spring_c = p->spring_c;
   for (int i = 0; i < 4; ++i) k.poly[i] = p->thrust_poly[i];

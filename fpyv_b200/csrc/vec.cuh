@@ -72,6 +72,7 @@ __device__ __forceinline__ float vsel(bool m, float a, float b) { return m ? a :
 __device__ __forceinline__ float vtrunc_i(float a) { return truncf(a); }
 __device__ __forceinline__ float vabs(float a) { return fabsf(a); }
 __device__ __forceinline__ float vdiv(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ float vdiv_fast(float a, float b) { return __fdividef(a, b); }   // 2 ulp, |b| < 2^126
 __device__ __forceinline__ bool vfinite(float a) { return isfinite(a); }
 
 // ---- F2 (packed pair)
@@ -125,6 +126,7 @@ __device__ __forceinline__ F2 operator-(F2 a) { return vneg(a); }
 FPV_F2_MAP2(vmin, fminf(u, v))
 FPV_F2_MAP2(vmax, fmaxf(u, v))
 FPV_F2_MAP2(vdiv, __fdiv_rn(u, v))
+FPV_F2_MAP2(vdiv_fast, __fdividef(u, v))
 FPV_F2_MAP1(vsqrt, __fsqrt_rn(v))
 FPV_F2_MAP1(vsqrt_fast, vsqrt_fast(v))
 FPV_F2_MAP1(vrsqrt_fast, vrsqrt_fast(v))

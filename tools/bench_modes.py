@@ -12,7 +12,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from fpyv_b200 import BatchedAcroDrone, BatchedRacer  # noqa: E402
+from fpyv_b200 import BatchedAcroDrone, BatchedDrone, BatchedRacer, Cylinder, Ground, Target  # noqa: E402
 
 
 def timeit(fn, flush, reps=20):
@@ -56,6 +56,20 @@ def main():
         b = n * (7 * 16 * 2 + 16 + 16 + 1)
         out[f"acro_K{K}"] = {"ms_per_step": ms, "env_steps_per_sec": n / (ms * 1e-3), "env_substeps_per_sec": n * K / (ms * 1e-3),
                              "hbm_GBps": b / (ms * 1e-3) / 1e9, "hbm_frac": b / (ms * 1e-3) / 1e9 / peak}
+    # mode A on the GENERAL path: the stock world of params.yaml (5 cylinders, one spherical target, ground plane)
+    rng = np.random.default_rng(5)
+    objs = [Target(np.array([0.0, 0.0, 3.0]), 1.0)] + [Cylinder(np.array([rng.normal(0, 10), rng.normal(0, 10), 0.0]), 2.0, 10.0) for _ in range(5)] + [Ground()]
+    for K in (1, 8):
+        d = BatchedDrone(None, num_envs=n, device=dev, substeps=K, dt=1e-3, auto_reset=True, thrust_lut=2049)
+        pos = torch.randn(n, 3, device=dev, generator=g) * 8
+        pos[:, 2] = 0.3 + torch.rand(n, device=dev, generator=g) * 8
+        d.reset(pos, torch.randn(n, 3, device=dev, generator=g) * 2, (torch.rand(n, 3, device=dev, generator=g) * 2 - 1) * 30)
+        act = (torch.rand(n, 4, device=dev, generator=g) * 2 - 1).contiguous()
+        ms = timeit(lambda: d.step(act, None, objs, return_obs=False), flush)
+        b = n * 145
+        out[f"drone_obstacles_K{K}"] = {"ms_per_step": ms, "env_steps_per_sec": n / (ms * 1e-3), "env_substeps_per_sec": n * K / (ms * 1e-3),
+                                        "hbm_GBps": b / (ms * 1e-3) / 1e9, "hbm_frac": b / (ms * 1e-3) / 1e9 / peak, "objects": 6,
+                                        "crashes": d.episode_stats()["crashes"]}
     print(json.dumps({"metric": "mode_B_C_env_steps_per_sec", "envs": n, "hbm_peak_GBps": peak, "results": out}))
 
 
