@@ -11,11 +11,16 @@
  *   - Every function returns 0 on success and a negative FPV_E* code otherwise; nothing throws
  *     across the ABI.  fpv_last_error() returns a thread-local message for the last failure.
  *   - All data pointers are DEVICE pointers owned by the caller (PyTorch owns the memory; the
- *     library only borrows them for the launch).  Parameter structs are HOST pointers to PODs
- *     that are copied by value into the launch (kernel-parameter constant bank): the library
- *     keeps no per-device state, so it is re-entrant and usable from one host thread per GPU.
+ *     library only borrows them for the launch) unless an argument is named *_host.  Parameter
+ *     structs are HOST pointers to PODs that are copied by value into the launch (kernel-parameter
+ *     constant bank).  The library keeps no state about the simulation, so it is re-entrant and
+ *     usable from one host thread per GPU; the only things it caches are occupancy numbers per
+ *     kernel and, for fpv_drone_step_host, two copy streams + events per device.
  *   - Launches are asynchronous and ordered on `stream` (a cudaStream_t / CUstream handle; 0 =
- *     legacy default stream).  No hidden synchronisation, no allocation.
+ *     legacy default stream).  No hidden synchronisation, no allocation.  Two documented
+ *     relaxations of plain stream order exist, both opt-in: FPV_F_CHAINED (a launch may overlap the
+ *     end of the previous one; the state is ordered per 64-env chunk instead) and
+ *     fpv_drone_step_host (internal copy streams, joined back to `stream`).
  *   - "float4 plane" = an array of n 16-byte elements, 16-byte aligned.  Env i lives at
  *     element i of every plane.  Planes of one state buffer are `plane_stride` ELEMENTS apart.
  *   - Arithmetic is FP32 (the reference is float64 NumPy); parity tolerance is stated in
