@@ -366,6 +366,9 @@ def run_gpu(args):
             "peak_source": f"{sm_count} SMs x {FP32_LANES_PER_SM} FP32 lanes x 2 x {pk['sm_max_mhz']:.0f} MHz (clocks.max.sm); "
                            "tensor cores unused by design (no dense contraction on this path)",
             "algorithmic": f"{FLOP_PER_ENV_SUBSTEP} flop/env/substep x {SUBSTEPS} substeps x {n} envs per launch",
+            "frac_chained_full_grid": FLOP_PER_ENV_SUBSTEP * SUBSTEPS * n / (ms_full_grid * 1e-3 / K) / 1e12 / fp32_peak,
+            "frac_unchained": FLOP_PER_ENV_SUBSTEP * SUBSTEPS * n / (ms_unchained * 1e-3 / K) / 1e12 / fp32_peak,
+            "frac_isolated_launch": FLOP_PER_ENV_SUBSTEP * SUBSTEPS * n / (ms_flushed_per_step * 1e-3) / 1e12 / fp32_peak,
             "hbm": {"achieved": hbm_ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": hbm_ach / pk["hbm_gbs"],
                     "algorithmic": f"{BYTES_PER_ENV_STEP} B/env/control-step x {n} envs per launch", "peak_source": pk["source"]},
             "hbm_bound_variant_k1": {"bound": "hbm", "achieved": hbm_k1, "peak": pk["hbm_gbs"], "unit": "GB/s",

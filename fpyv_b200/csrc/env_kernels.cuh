@@ -32,6 +32,15 @@ __global__ void __launch_bounds__(THREADS) gate_env_step_kernel(const __grid_con
                                                                 const unsigned char* agent_done, float2* prev,
                                                                 int* progress, float* agent_reward, float* env_reward,
                                                                 unsigned char* env_done, float4* obs, fpv_stats_t* stats) {
+  // The gate table is indexed PER AGENT (every agent is at its own gate): from the kernel-parameter constant bank a warp
+  // with 8 different gates would serialise every field load 8 times, so the table is staged in shared memory first.
+  __shared__ fpv_gate_t gates[FPV_MAX_GATES];
+  {
+    const float* src = reinterpret_cast<const float*>(k.gates);
+    float* dst = reinterpret_cast<float*>(gates);
+    for (int j = threadIdx.x; j < k.n_gates * (int)(sizeof(fpv_gate_t) / sizeof(float)); j += THREADS) dst[j] = src[j];
+    __syncthreads();
+  }
   const long long i = (long long)blockIdx.x * THREADS + threadIdx.x;
   const int A = k.agents_per_env;
   const bool live = i < n;  // n is a multiple of A (checked by the host), so groups are all-live or all-dead
@@ -44,10 +53,10 @@ __global__ void __launch_bounds__(THREADS) gate_env_step_kernel(const __grid_con
     int g = prog & 0xffff, laps = prog >> 16;
     crashed = agent_done[i] != 0;
     float d, r;
-    gate_metrics(k.gates[g], p.x, p.y, p.z, d, r);
+    gate_metrics(gates[g], p.x, p.y, p.z, d, r);
     bool passed = false;
     if (!crashed) {
-      passed = pr.x < 0.f && d >= 0.f && (r * r - d * d) <= k.gates[g].half_size * k.gates[g].half_size;
+      passed = pr.x < 0.f && d >= 0.f && (r * r - d * d) <= gates[g].half_size * gates[g].half_size;
       reward = k.w_progress * (pr.y - r) + (passed ? k.w_gate : 0.f);
     } else {
       reward = -k.w_crash;
@@ -58,14 +67,14 @@ __global__ void __launch_bounds__(THREADS) gate_env_step_kernel(const __grid_con
     }
     if (crashed) { g = 0; laps = 0; }
     finished = k.laps_to_finish > 0 && laps >= k.laps_to_finish;
-    if (passed || crashed) gate_metrics(k.gates[g], p.x, p.y, p.z, d, r);  // re-base on the agent's next gate
+    if (passed || crashed) gate_metrics(gates[g], p.x, p.y, p.z, d, r);  // re-base on the agent's next gate
     prev[i] = make_float2(d, r);
     progress[i] = (laps << 16) | g;
     if (agent_reward) agent_reward[i] = reward;
     if (obs) {
       float R[9];
       quat_to_matrix(q, R);
-      const fpv_gate_t& gt = k.gates[g];
+      const fpv_gate_t& gt = gates[g];
       const float dx = gt.cx - p.x, dy = gt.cy - p.y, dz = gt.cz - p.z;
       float4* o = obs + 4 * i;
       // R^T x = columns of R dotted with x
