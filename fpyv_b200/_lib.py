@@ -8,10 +8,10 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 # FPYV_B200_LIB: developer override used to A/B differently tuned builds of the same ABI
 LIB_PATH = os.environ.get("FPYV_B200_LIB") or os.path.join(HERE, "libfpyv_b200.so")
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 # flags (fpv_api.h)
-F_GROUND, F_AUTO_RESET, F_FREEZE_DONE, F_THRUST_LUT, F_SCALAR, F_CHAINED = 1, 2, 4, 8, 32, 64
+F_GROUND, F_AUTO_RESET, F_FREEZE_DONE, F_THRUST_LUT, F_SCALAR, F_CHAINED, F_RATE_CURVE = 1, 2, 4, 8, 32, 64, 128
 OBJ_SPHERE, OBJ_CYLINDER = 1, 2
 MAX_OBJECTS = 16
 DRONE_PLANES, RACER_PLANES = 4, 7
@@ -102,7 +102,8 @@ class AcroParams(C.Structure):
                 ("k_drag", C.c_float * 3), ("motor_xy", (C.c_float * 2) * 4), ("motor_radius", C.c_float),
                 ("spring_k", C.c_float), ("gains", (C.c_float * 3) * 3), ("integral_limit", C.c_float),
                 ("inertia", C.c_float * 3), ("kappa", C.c_float), ("spin", C.c_float * 4), ("u_min", C.c_float),
-                ("u_max", C.c_float), ("thrust_poly", C.c_float * 4), ("wind", C.c_float * 3), ("flags", C.c_uint32)]
+                ("u_max", C.c_float), ("thrust_poly", C.c_float * 4), ("wind", C.c_float * 3), ("flags", C.c_uint32),
+                ("rate_curve", (C.c_float * 3) * 3)]
 
 
 _STRUCTS = (DroneParams, DroneIO, Object, Stats, StickCalib, RacerParams, GateEnvParams, CameraParams, AutopilotParams,

@@ -25,7 +25,7 @@ class BatchedAcroDrone:
     def __init__(self, params=None, num_envs: int = 1, device="cuda:0", substeps: int = 1, dt: float | None = None,
                  gains=None, inertia=None, kappa: float = 0.016, spin=(1.0, -1.0, 1.0, -1.0), u_min: float = -0.9,
                  u_max: float = 1.0, integral_limit: float = 0.5, thrust_lut: int = 2049, auto_reset: bool = False,
-                 ground: bool = True, packed: bool = True):
+                 ground: bool = True, packed: bool = True, rate_curve=None):
         self._lib = _lib.load()
         if isinstance(params, str) or params is None:
             params = config.load_params(params)
@@ -66,6 +66,16 @@ class BatchedAcroDrone:
         p.integral_limit, p.kappa, p.u_min, p.u_max = self.integral_limit, self.kappa, self.u_min, self.u_max
         for i in range(4):
             p.thrust_poly[i] = float(c.thrust_poly.coeffs[i])
+        # stick -> rate curve: None = the reference's linear map (components.py:185); else (centre sensitivity, max rate,
+        # expo) in deg/s, one triple for all axes or one per axis -- the flight-controller "actual rates" curve
+        self.rate_curve = None
+        if rate_curve is not None:
+            rc = np.broadcast_to(np.asarray(rate_curve, dtype=np.float64), (3, 3))
+            self.rate_curve = rc.copy()
+            for i in range(3):
+                for j in range(3):
+                    p.rate_curve[i][j] = float(rc[i, j])
+            self._flags |= _lib.F_RATE_CURVE
         p.flags = self._flags
 
     # ------------------------------------------------------------------ state views (leading env axis)

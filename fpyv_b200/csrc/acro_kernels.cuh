@@ -27,6 +27,7 @@ struct AcroK {
   float poly[4];          // 4-motor bench cubic (components.py:136); per motor = / 4
   float lut_scale;
   int lut_n;
+  float rc_cen[3], rc_span[3], rc_expo[3];   // stick curve: centre sensitivity, max(0, max - centre), expo (FPV_F_RATE_CURVE)
   float kd[3];            // k_drag, kinematics.py:36
   float wind[3];
   float grav_z;           // -g m
@@ -166,7 +167,18 @@ __global__ void __launch_bounds__(THREADS) acro_step_kernel(const __grid_constan
   {
     const V a3[3] = {Pack<V>::x(act), Pack<V>::y(act), Pack<V>::z(act)};
 #pragma unroll
-    for (int i = 0; i < 3; ++i) cmd[i] = vmin(vmax(vneg(a3[i]) * mr, vneg(mr)), mr) * rtr;   // components.py:185
+    for (int i = 0; i < 3; ++i) {
+      if (k.flags & FPV_F_RATE_CURVE) {   // "actual rates": s c + span |s| (s^5 e + s (1 - e)),  s = -stick in [-1, 1]
+        const V sx = vmin(vmax(vneg(a3[i]), S<V>(-1.f)), one);
+        const V s2 = sx * sx;
+        const V s5 = (s2 * s2) * sx;
+        const V e = S<V>(k.rc_expo[i]);
+        const V ex = vabs(sx) * vfma(s5, e, sx * (one - e));
+        cmd[i] = vfma(S<V>(k.rc_span[i]), ex, sx * S<V>(k.rc_cen[i])) * rtr;
+      } else {
+        cmd[i] = vmin(vmax(vneg(a3[i]) * mr, vneg(mr)), mr) * rtr;   // components.py:185
+      }
+    }
   }
   const V thr_in = Pack<V>::w(act) * S<V>(k.ttr);
   const V omr = S<V>(k.one_minus_rtr), omt = S<V>(k.one_minus_ttr), dt = S<V>(k.dt), inv_dt = S<V>(k.inv_dt);

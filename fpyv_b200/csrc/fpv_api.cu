@@ -775,6 +775,11 @@ int fpv_acro_step(const fpv_acro_params_t* p, void* state, int64_t n, int64_t pl
     k.i_lim[i] = (float)((double)p->integral_limit / ki);
     k.inertia[i] = p->inertia[i]; k.inv_inertia[i] = (float)(1.0 / (double)p->inertia[i]);
     k.kd[i] = p->k_drag[i]; k.wind[i] = p->wind[i];
+    k.rc_cen[i] = p->rate_curve[i][0];
+    k.rc_span[i] = (float)std::fmax(0.0, (double)p->rate_curve[i][1] - (double)p->rate_curve[i][0]);
+    k.rc_expo[i] = p->rate_curve[i][2];
+    if ((p->flags & FPV_F_RATE_CURVE) && !(p->rate_curve[i][2] >= 0.f && p->rate_curve[i][2] <= 1.f))
+      return fail(FPV_EINVAL, "fpv_acro_step: rate_curve expo must be in [0,1]");
   }
   for (int m = 0; m < 4; ++m) {
     const float x = p->motor_xy[m][0], y = p->motor_xy[m][1];

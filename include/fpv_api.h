@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define FPV_ABI_VERSION 10
+#define FPV_ABI_VERSION 11
 
 /* error codes */
 #define FPV_OK 0
@@ -76,6 +76,7 @@ extern "C" {
                                    order) whenever the launch cannot honour it.  Do not capture a chained launch in a
                                    CUDA graph (the replay would carry a stale epoch); a chunk that never reaches the
                                    expected epoch traps the launch after about a second instead of hanging.        */
+#define FPV_F_RATE_CURVE 128u    /* fpv_acro_params_t.rate_curve is used (mode C only)                            */
 #define FPV_F_SCALAR 32u        /* one env per thread (plain FP32 instructions) instead of the
                                    default two envs per thread on packed f32x2 instructions     */
 
@@ -409,7 +410,12 @@ typedef struct fpv_acro_params {
   float u_min, u_max;           /* motor throttle limits in [-1, 1] (idle = 5 %: -0.9, components.py:138-139) */
   float thrust_poly[4];         /* 4-motor bench cubic in throttle percent        components.py:136 */
   float wind[3];
-  uint32_t flags;               /* FPV_F_GROUND | FPV_F_AUTO_RESET | FPV_F_THRUST_LUT | FPV_F_SCALAR (one env per thread) */
+  uint32_t flags;               /* FPV_F_GROUND | FPV_F_AUTO_RESET | FPV_F_THRUST_LUT | FPV_F_SCALAR (one env per thread)
+                                   | FPV_F_RATE_CURVE */
+  float rate_curve[3][3];       /* FPV_F_RATE_CURVE: per axis (centre sensitivity [deg/s], maximum rate [deg/s], expo in
+                                   [0,1]) of the flight-controller "actual rates" stick curve
+                                     rate(s) = s c + max(0, m - c) |s| (s^5 e + s (1 - e)),   s = -stick clipped to [-1,1];
+                                   without the flag the reference's linear map clip(-stick * max_rates) (components.py:185) */
 } fpv_acro_params_t;
 
 /* pos, vel, rpy_deg: float[n][3]; motors off (throttle -1), zero rates, fresh PID.  mask as in fpv_drone_reset. */

@@ -36,6 +36,10 @@ class AcroConsts:
     u_min: float = -0.9                    # 5 % throttle, the reference's motor idle (components.py:138-139)
     u_max: float = 1.0
     integral_limit: float = 0.5            # anti-windup clamp on the PID's I term contribution (throttle units)
+    # stick -> rate curve.  None = the reference's linear map (components.py:185).  Otherwise per axis
+    # (centre sensitivity [deg/s], maximum rate [deg/s], expo in [0,1]) of the flight-controller "actual rates" curve:
+    #   rate(s) = s c + max(0, m - c) |s| (s^5 e + s (1 - e)),  s = -stick (the reference's sign, components.py:185)
+    rate_curve: np.ndarray | None = None
 
     @property
     def mix(self):
@@ -88,6 +92,18 @@ def _quat_mul(a, b):
                      w1 * y2 - x1 * z2 + y1 * w2 + z1 * x2, w1 * z2 + x1 * y2 - y1 * x2 + z1 * w2], axis=1)
 
 
+def stick_to_rate(c: AcroConsts, sticks):
+    """Rate set-point [deg/s] from the three rate sticks [n,3]."""
+    b = c.base
+    if c.rate_curve is None:
+        return np.clip(-sticks * b.max_rates, -b.max_rates, b.max_rates)          # components.py:185
+    rc = np.asarray(c.rate_curve, dtype=np.float64).reshape(3, 3)
+    sx = np.clip(-sticks, -1.0, 1.0)
+    cen, mx, ex = rc[:, 0], rc[:, 1], rc[:, 2]
+    expo = np.abs(sx) * (sx ** 5 * ex + sx * (1 - ex))
+    return sx * cen + np.maximum(0.0, mx - cen) * expo
+
+
 def motor_thrust_curve(c: AcroConsts, u, lut=None):
     """Single-motor thrust [N] at throttle u in [-1,1]: the 4-motor bench cubic / 4, or linear interpolation in a table
     sampled uniformly on [-1,1] (the device's shared-memory LUT)."""
@@ -107,7 +123,7 @@ def acro_substep(c: AcroConsts, s: AcroState, action, wind=None, dt=None, lut=No
     action = np.broadcast_to(np.asarray(action, dtype=np.float64), (n, 4))
     wind = np.zeros(3) if wind is None else np.asarray(wind, dtype=np.float64)
     # --- stick -> rate set-point and collective throttle, low-passed like action2force (components.py:185-194)
-    cmd = np.clip(-action[:, :3] * b.max_rates, -b.max_rates, b.max_rates)
+    cmd = stick_to_rate(c, action[:, :3])
     s.rate_sp = cmd * b.rtr + s.rate_sp * (1 - b.rtr)
     s.throttle = action[:, 3] * b.ttr + s.throttle * (1 - b.ttr)
     sp = np.deg2rad(s.rate_sp)

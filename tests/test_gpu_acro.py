@@ -193,3 +193,44 @@ def test_tumbling_envs_take_the_accurate_rotation_path():
     err = state_err(d, s)
     print(f"acro tumbling: max rel err {err.max():.2e} (tumbling envs {err[::3].max():.2e}, calm {np.delete(err, np.s_[::3]).max():.2e})")
     assert err.max() < 1e-5
+
+
+def test_stick_rate_curve_vs_model_and_shape():
+    """FPV_F_RATE_CURVE: the flight-controller 'actual rates' stick curve (centre sensitivity, max rate, expo) in place
+    of the reference's linear stick map.  Checked against the float64 model, and for its defining properties: full stick
+    gives the maximum rate, small sticks the centre sensitivity, expo 0 and centre = max is the reference's linear map."""
+    from fpyv_b200 import BatchedAcroDrone
+    n, dt, K = 512, 1e-3, 4
+    rng, pos, vel, rpy = seeded(n, 15, z_lo=20, z_hi=40)
+    curve = np.array([[70.0, 670.0, 0.4], [70.0, 670.0, 0.4], [90.0, 400.0, 0.0]])
+    c = consts(dt)
+    c.rate_curve = curve
+    d = BatchedAcroDrone(None, num_envs=n, device=DEV, substeps=K, dt=dt, thrust_lut=0, rate_curve=curve)
+    d.reset(pos, vel, rpy)
+    s = ao.acro_reset(c, pos, vel, rpy)
+    worst = 0.0
+    for t in range(12):
+        act = rng.uniform(-1.2, 1.2, (n, 4))             # beyond +-1: the curve clips the stick
+        ao.acro_step(c, s, act, substeps=K)
+        d.step(act)
+        worst = max(worst, float(state_err(d, s).max()))
+    print(f"acro with stick rate curve: max rel err over 12 free-running control steps {worst:.2e}")
+    assert worst < 1e-5
+    # shape of the curve through the filtered set-point (hold the stick long enough for the low-pass to settle)
+    e = BatchedAcroDrone(None, num_envs=4, device=DEV, substeps=50, dt=dt, thrust_lut=0, rate_curve=curve)
+    e.reset(np.tile([0, 0, 50.0], (4, 1)), np.zeros((4, 3)), np.zeros((4, 3)))
+    sticks = np.array([[1.0, -1.0, 1.0, 0.0], [0.01, 0.01, 0.01, 0.0], [-0.5, 0.5, 0.0, 0.0], [3.0, 0.0, -2.0, 0.0]])
+    e.step(sticks)
+    sp = e.rate_setpoint.cpu().numpy()
+    np.testing.assert_allclose(sp[0], [-670.0, 670.0, -400.0], rtol=1e-5)
+    rate = lambda s_, cen, mx, ex: s_ * cen + (mx - cen) * abs(s_) * (s_ ** 5 * ex + s_ * (1 - ex))
+    np.testing.assert_allclose(sp[1], [rate(-0.01, 70, 670, 0.4), rate(-0.01, 70, 670, 0.4), rate(-0.01, 90, 400, 0.0)], rtol=1e-5)
+    assert abs(sp[1][0] / -0.01 - 70.0) < 4.0                     # slope at the centre ~ the centre sensitivity
+    np.testing.assert_allclose(sp[2], [rate(0.5, 70, 670, 0.4), rate(-0.5, 70, 670, 0.4), 0.0], rtol=1e-5, atol=1e-4)
+    np.testing.assert_allclose(sp[3], [-670.0, 0.0, 400.0], rtol=1e-5, atol=1e-4)
+    lin = BatchedAcroDrone(None, num_envs=4, device=DEV, substeps=50, dt=dt, thrust_lut=0, rate_curve=[200.0, 200.0, 0.0])
+    ref = BatchedAcroDrone(None, num_envs=4, device=DEV, substeps=50, dt=dt, thrust_lut=0)
+    for x in (lin, ref):
+        x.reset(np.tile([0, 0, 50.0], (4, 1)), np.zeros((4, 3)), np.zeros((4, 3)))
+        x.step(sticks)
+    np.testing.assert_allclose(lin.rate_setpoint.cpu().numpy(), ref.rate_setpoint.cpu().numpy(), rtol=1e-6, atol=1e-4)
