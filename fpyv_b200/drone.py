@@ -113,9 +113,7 @@ class BatchedDrone:
         # cta_slots > 0: the step kernel takes at most that many CTA slots per SM, so that chained launches of
         # INDEPENDENT batches stepped round-robin run side by side (fpv_drone_io_t.max_ctas_per_sm)
         self._io.max_ctas_per_sm = int(cta_slots)
-        self._host_actions = None
         self._host_done = None
-        self._slice_cache = None
         self._last_action = None
         self._is_reset = False
         self._fast_ok = False
@@ -349,7 +347,6 @@ class BatchedDrone:
     @cta_slots.setter
     def cta_slots(self, k: int):
         self._io.max_ctas_per_sm = int(k)
-        self._slice_cache = None
 
     def rollout(self, actions, done_out=None, fused=True):
         """Open-loop rollout: T control steps with the stick commands of all steps given up front
