@@ -291,3 +291,16 @@ def test_cta_slots_do_not_change_results(slots):
     torch.cuda.synchronize()
     assert torch.equal(a._state, ref._state) and torch.equal(b._state, ref._state)
     assert torch.equal(a.done, ref.done) and a.episode_stats()["crashes"] == ref.episode_stats()["crashes"]
+
+
+def test_plain_c_consumer_of_the_abi(lib, tmp_path):
+    """A C99 program (tests/c/abi_smoke.c) dlopens the library, compares sizeof() of every ABI struct as the C compiler
+    lays it out with what the library was built with, and drives the argument validation."""
+    import subprocess
+    exe = tmp_path / "abi_smoke"
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "tests", "c", "abi_smoke.c"), "-ldl", "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe), os.path.join(ROOT, "fpyv_b200", "libfpyv_b200.so")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "10 struct layouts agree" in r.stdout
