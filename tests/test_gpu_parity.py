@@ -760,3 +760,86 @@ def test_obstacle_reach_test_is_exact_against_oracle(packed):
           f"{int((np.abs(s.acc).max(1) > 30).sum())}, flag mismatches {int(mism.sum())}")
     assert err[~mism].max() <= TOL_STEP and mism.sum() <= 3
     assert s.done.sum() > 500 and (~s.done).sum() > 5000
+
+
+@pytest.mark.parametrize("packed", [True, False])
+@pytest.mark.parametrize("max_rates,dt,K,ang", [(200.0, 1 / 40, 1, 2), (600.0, 1 / 60, 2, 1), (900.0, 1e-3, 8, 4),
+                                                (2000.0, 1 / 30, 1, 0), (1200.0, 1 / 60, 3, 1)])
+def test_every_angle_kernel_variant_vs_oracle(max_rates, dt, K, ang, packed):
+    """The host picks the sin/cos evaluation of the per-substep half Euler angles from the bound max_rates*dt/2:
+    series (<= 0.008 rad), degree-3/2 (<= 0.03), degree-5/4 (<= 0.05), degree-7/8 minimax (<= 0.25), sincosf beyond.
+    Stock params.yaml only reaches two of them; racing rates (600-1200 deg/s) and coarse steps reach the others.
+    Each variant: hot kernel, obstacle kernel and fused rollout against the float64 oracle, single steps and 20 free-running."""
+    from fpyv_b200 import BatchedDrone, Cylinder, Ground, config
+    half = 0.5 * np.deg2rad(max_rates) * dt
+    want = 4 if half <= 0.008 else 3 if half <= 0.03 else 2 if half <= 0.05 else 1 if half <= 0.25 else 0
+    assert want == ang, (half, want)
+    params = config.load_params(None)
+    params["drone"]["max_rates"] = max_rates
+    c = fo.derive_consts(params, os.path.join(os.path.dirname(GOLDEN), "..", "fpyv_b200", "config", "t_motos_f80_motor_test.csv"), dt=dt)
+    n = 2048
+    rng = np.random.default_rng(int(max_rates))
+    pos = np.stack([rng.normal(0, 5, n), rng.normal(0, 5, n), rng.uniform(0.05, 6, n)], 1)
+    vel, rpy = rng.normal(0, 1, (n, 3)), rng.uniform(-40, 40, (n, 3))
+    acts = rng.uniform(-1, 1, (20, n, 4))
+    far = Cylinder(np.array([300.0, 0.0, 0.0]), 1.0, 5.0)
+    for objs in (None, [far, Ground()]):                       # hot kernel / general kernel
+        d = BatchedDrone(params, num_envs=n, device=DEV, substeps=K, dt=dt, packed=packed)
+        d.reset(pos, vel, rpy)
+        s = fo.drone_reset(c, pos, vel, rpy)
+        worst1 = 0.0
+        for t in range(20):
+            if t < 6:                                          # teacher-forced single steps first
+                set_state(d, np.concatenate([s.pos, s.vel], 1), s.R, s.prev_rates, s.prev_thrust)
+                s.pos, s.vel = d.position.double().cpu().numpy(), d.velocity.double().cpu().numpy()
+                s.R = fo.quaternion_to_matrix(d.quaternion.double().cpu().numpy())
+                s.prev_rates, s.prev_thrust = d.prev_rates.double().cpu().numpy(), d.prev_thrust.double().cpu().numpy()
+            fo.drone_step(c, s, acts[t], substeps=K)
+            d.step(acts[t], None, objs, return_obs=False)
+            e = drone_err(d, np.concatenate([s.pos, s.vel], 1), s.R, s.prev_rates, s.prev_thrust)
+            if t < 6:
+                assert np.array_equal(d.done.cpu().numpy(), s.done)
+                worst1 = max(worst1, float(e.max()))
+        flying = ~s.done & (s.pos[:, 2] > 0.5)
+        assert worst1 <= TOL_STEP, (worst1, objs is not None)
+        assert float(e[flying].max()) <= 2e-4, float(e[flying].max())      # 14 free-running steps
+    if packed:                                                 # the fused rollout uses the same angle kernels
+        a = BatchedDrone(params, num_envs=n, device=DEV, substeps=K, dt=dt)
+        b = BatchedDrone(params, num_envs=n, device=DEV, substeps=K, dt=dt)
+        a.reset(pos, vel, rpy)
+        b.reset(pos, vel, rpy)
+        A = torch.as_tensor(acts[:8], dtype=torch.float32, device=DEV).contiguous()
+        a.rollout(A, fused=True)
+        for t in range(8):
+            b.step(A[t], return_obs=False)
+        assert torch.equal(a._state, b._state)
+
+
+@pytest.mark.parametrize("packed", [True, False])
+def test_general_path_without_ground_and_with_damped_spring(packed):
+    """Two configurations only the general kernel serves: no ground plane in the object list (the crash test on the
+    motor heights, components.py:239, still applies) and a damped contact spring (handle_collisions' damping_constant,
+    components.py:198, is 0 in the reference's call but a parameter of its spring_force, kinematics.py:56-59)."""
+    n = 4096
+    rng = np.random.default_rng(91)
+    pos = np.stack([rng.normal(0, 3, n), rng.normal(0, 3, n), rng.uniform(-0.05, 0.6, n)], 1)
+    vel, rpy = rng.normal(0, 1.5, (n, 3)), rng.uniform(-30, 30, (n, 3))
+    act = rng.uniform(-1, 1, (n, 4))
+    for ground, damping in ((False, 0.0), (True, 7.5)):
+        c = fo_consts()
+        c.ground, c.spring_c = ground, damping
+        d = make(n, packed=packed, ground=ground)
+        d._p.spring_c = damping
+        d.reset(pos, vel, rpy)
+        s = fo.drone_reset(c, pos, vel, rpy)
+        s.pos, s.vel = d.position.double().cpu().numpy(), d.velocity.double().cpu().numpy()
+        s.R = fo.quaternion_to_matrix(d.quaternion.double().cpu().numpy())
+        fo.drone_step(c, s, act)
+        d.step(act, return_obs=False)
+        err = drone_err(d, np.concatenate([s.pos, s.vel], 1), s.R, s.prev_rates, s.prev_thrust)
+        done = d.done.cpu().numpy()
+        mism = done != s.done
+        assert err[~mism].max() <= TOL_STEP, (ground, damping, err.max())
+        assert mism.sum() <= 2 and s.done.sum() > 100 and (~s.done).sum() > 100
+        if damping:
+            assert np.abs(s.acc[~s.done & (s.pos[:, 2] < 0.15)]).max() > 15       # springs engaged
