@@ -234,3 +234,41 @@ def test_stick_rate_curve_vs_model_and_shape():
         x.reset(np.tile([0, 0, 50.0], (4, 1)), np.zeros((4, 3)), np.zeros((4, 3)))
         x.step(sticks)
     np.testing.assert_allclose(lin.rate_setpoint.cpu().numpy(), ref.rate_setpoint.cpu().numpy(), rtol=1e-6, atol=1e-4)
+
+
+@pytest.mark.parametrize("packed", [True, False])
+def test_substeps_compose_bit_exactly(packed):
+    """Mode B and mode C carry no per-control-step work besides the substeps themselves, so one call with K substeps is
+    bit-identical to K calls with one substep and the same sticks."""
+    from fpyv_b200 import BatchedAcroDrone, BatchedRacer
+    n, K = 3000, 6
+    rng, pos, vel, rpy = seeded(n, 16, z_lo=0.3, z_hi=6)
+    act = rng.uniform(-1, 1, (n, 4))
+    a = BatchedAcroDrone(None, num_envs=n, device=DEV, substeps=K, dt=1e-3, packed=packed)
+    b = BatchedAcroDrone(None, num_envs=n, device=DEV, substeps=1, dt=1e-3, packed=packed)
+    a.reset(pos, vel, rpy)
+    b.reset(pos, vel, rpy)
+    any_done = torch.zeros(n, dtype=torch.bool, device=DEV)
+    for _ in range(3):
+        da = a.step(act).bool().clone()
+        db = torch.zeros(n, dtype=torch.bool, device=DEV)
+        for _ in range(K):
+            db |= b.step(act).bool()
+        assert torch.equal(da, db)
+        any_done |= da
+    keep = ~any_done                     # (the episode counter counts control steps, so compare the physical planes)
+    for p in (0, 2, 3, 4, 5, 6):
+        assert torch.equal(a._state[p, :n][keep], b._state[p, :n][keep]), p
+    assert torch.equal(a._state[1, :n, :3][keep], b._state[1, :n, :3][keep])
+    if packed:
+        gains = {"roll": [2, 0.1, 1e-4], "pitch": [1.5, 0.2, 0], "yaw": [0.1, 0, 0]}
+        ra = BatchedRacer(5, gains, num_envs=n, device=DEV, dt=1e-3, substeps=K)
+        rb = BatchedRacer(5, gains, num_envs=n, device=DEV, dt=1e-3, substeps=1)
+        ra.reset()
+        rb.reset()
+        sp = torch.as_tensor(np.concatenate([rng.uniform(-4, 4, (n, 3)), rng.uniform(0, 10, (n, 1))], 1), dtype=torch.float32, device=DEV)
+        for _ in range(3):
+            ra.step(sp)
+            for _ in range(K):
+                rb.step(sp)
+        assert torch.equal(ra._state, rb._state)
