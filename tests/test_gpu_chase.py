@@ -329,3 +329,35 @@ def test_point_and_shoot_vs_reference(frame, mode):
     q, f2 = ap.point_and_shoot(g["pixel"], g["action"], ref_frame=frame, mode=mode, as_quaternion=True,
                                seen=np.arange(len(g["pos"])) % 2)
     assert torch.isnan(f2[::2]).all() and torch.isfinite(f2[1::2]).all()
+
+
+@pytest.mark.parametrize("res,fov,pitch", [([160, 120], 90.0, 10.0), ([320, 200], 150.0, 0.0), ([64, 48], 60.0, 55.0)])
+def test_other_cameras_bit_exact_against_oracle(res, fov, pitch):
+    """Resolutions, fields of view and camera pitches other than params.yaml's: frames, binary image and target pixel
+    bit-exact against the float64 oracle (which is pinned to the reference on the stock camera)."""
+    import copy
+    from fpyv_b200 import BatchedCamera
+    g = load("chase_camera")
+    p = copy.deepcopy(params())
+    p["camera"].update(resolution=res, fov=fov, camera_angle=pitch)
+    n = len(g["pos"])
+    cam = BatchedCamera.from_params(p, n, DEV)
+    cam.update(g["pos"], g["R"])
+    c = co.camera_consts(p)
+    cp, cR = co.camera_update(c, g["pos"], g["R"])
+    np.testing.assert_allclose(cam.position.cpu().numpy(), cp, rtol=0, atol=1e-12)
+    objs = world_objects(g)
+    img = cam.render_depth_image(objs, 20).cpu().numpy()
+    binimg = cam.render_image(objs).cpu().numpy()
+    px, seen = cam.target_pixel([g["obj0"]], 20)
+    lit = 0
+    for e in range(n):
+        ref = co.render_depth_image(c, cp[e], cR[e], objs, 20).astype(np.uint8)
+        assert np.array_equal(img[e], ref), e
+        assert np.array_equal(binimg[e], co.render_image(c, cp[e], cR[e], objs).astype(np.uint8)), e
+        tp = co.target_pixel(co.render_depth_image(c, cp[e], cR[e], [g["obj0"]], 20))
+        assert bool(seen[e]) == (tp is not None)
+        if tp is not None:
+            assert np.array_equal(px[e].cpu().numpy(), tp)
+        lit += int((ref > 0).sum())
+    assert lit > 50
