@@ -843,3 +843,37 @@ def test_general_path_without_ground_and_with_damped_spring(packed):
         assert mism.sum() <= 2 and s.done.sum() > 100 and (~s.done).sum() > 100
         if damping:
             assert np.abs(s.acc[~s.done & (s.pos[:, 2] < 0.15)]).max() > 15       # springs engaged
+
+
+def test_two_batches_on_two_streams_concurrently():
+    """Independent batches stepped from two CUDA streams at once (their persistent grids compete for the SMs): every
+    launch is ordered on the caller's current stream only, results are those of the serial run, bit for bit."""
+    n, K = 400_000, 8
+    g = torch.Generator(device=DEV).manual_seed(23)
+    mk = lambda: (torch.randn(n, 3, device=DEV, generator=g) * 5 + torch.tensor([0.0, 0.0, 12.0], device=DEV),
+                  torch.randn(n, 3, device=DEV, generator=g), (torch.rand(n, 3, device=DEV, generator=g) * 2 - 1) * 30)
+    inits = [mk(), mk()]
+    acts = [torch.rand(n, 4, device=DEV, generator=g) * 2 - 1 for _ in range(10)]
+    ref = []
+    for init in inits:
+        d = make(n, substeps=K, dt=1e-3, thrust_lut=2049)
+        d.reset(*init)
+        for a in acts:
+            d.step(a, return_obs=False)
+        ref.append(d._state.clone())
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    ds = []
+    for init, st in zip(inits, streams):
+        with torch.cuda.stream(st):
+            d = make(n, substeps=K, dt=1e-3, thrust_lut=2049)
+            d.reset(*init)
+        ds.append(d)
+    torch.cuda.synchronize()
+    for a in acts:
+        for d, st in zip(ds, streams):
+            with torch.cuda.stream(st):
+                d.step(a, return_obs=False, chained=True)
+    torch.cuda.synchronize()
+    for d, r in zip(ds, ref):
+        assert torch.equal(d._state, r)
