@@ -113,9 +113,10 @@ bool launch_drone_tma(const DroneK& k, const DroneIO& io, cudaStream_t st) {
   const long long wave = (long long)sm_count_of_current_device() * occ_used;
   const unsigned grid = (unsigned)(tiles < wave ? tiles : wave);
   static const int no_pdl = tune_env("FPV_TUNE_NOPDL", 0);
-  // FPV_F_CHAINED is honoured only by full persistent grids: such a grid cannot become fully resident before the
-  // previous one has left the SMs, so at most two launches ever overlap (which is what the two pull-counter pairs and
-  // the forward-progress argument of the per-chunk waits rely on).  Anything else keeps plain stream order.
+  // FPV_F_CHAINED is honoured only by full persistent grids (every CTA slot a launch may use, on every SM): launch i+1
+  // cannot become fully resident before launch i has left the slots it needs, which bounds the number of launches alive
+  // at once (4 / slots-per-launch + 1) -- what the eight pull-counter pairs and the forward-progress argument of the
+  // per-chunk waits rely on (the producer of an awaited chunk is always resident).  Anything else keeps plain stream order.
   DroneK kk = k;
   if ((kk.flags & FPV_F_CHAINED) && (no_pdl || (long long)grid != wave)) kk.flags &= ~FPV_F_CHAINED;
   if (no_pdl) {
@@ -308,8 +309,10 @@ int prepare_drone(const fpv_drone_params_t* p, const fpv_drone_io_t* io, bool ne
   d.chunk_epoch = (unsigned*)io->chunk_epoch;
   d.epoch = io->epoch;
   d.cta_cap = io->max_ctas_per_sm;
-  // two launches that overlap (FPV_F_CHAINED) must not share the pull counters: one pair per epoch parity
-  if (d.work && d.chunk_epoch) d.work += 2 * (io->epoch & 1u);
+  // launches that overlap (FPV_F_CHAINED) must not share the pull counters.  A chained launch is honoured only as a full
+  // persistent grid of k CTA slots per SM, so at most 4/k + 1 <= 5 launches are ever resident together: eight counter
+  // pairs indexed by the epoch are never shared by two live launches.
+  if (d.work && d.chunk_epoch) d.work += 2 * (io->epoch & 7u);
   if ((p->flags & FPV_F_CHAINED) && !io->chunk_epoch)
     return fail(FPV_EINVAL, "fpv_drone_step: FPV_F_CHAINED needs io.chunk_epoch");
   d.trace = (unsigned long long*)io->trace;

@@ -96,7 +96,7 @@ class BatchedDrone:
         self._acc = torch.zeros((n, 4), dtype=torch.float32, device=dev)
         self._actions = torch.zeros((n, 4), dtype=torch.float32, device=dev)
         self._stats = torch.zeros(8, dtype=torch.float64, device=dev)
-        self._work = torch.zeros(4, dtype=torch.int32, device=dev)      # dynamic chunk counters (fpv_drone_io_t.work)
+        self._work = torch.zeros(16, dtype=torch.int32, device=dev)      # dynamic chunk counters (fpv_drone_io_t.work)
         # chained launches (fpv_drone_io_t.chunk_epoch): one step count per 64-env chunk, and the host's copy of it
         self._chunk_epoch = torch.zeros((n + 63) // 64, dtype=torch.int32, device=dev)
         self._chunk_epoch_ptr = self._chunk_epoch.data_ptr()

@@ -138,7 +138,7 @@ typedef struct fpv_drone_io {
   const float* override_thrust; /* float[n]: thrust_force of the same call; NaN = no override for that env */
   const fpv_object_t* objects; /* HOST pointer, params.n_objects entries, or NULL                  */
   fpv_stats_t* stats;       /* device, may be NULL                                                */
-  void* work;               /* device uint32[4], zeroed ONCE by the caller: chunk counter for dynamic load balancing
+  void* work;               /* device uint32[16], zeroed ONCE by the caller: chunk counter for dynamic load balancing
                                (warps pull the next 64-env chunk with one atomic); every launch leaves it zeroed.
                                NULL = static round-robin distribution.                                     */
   void* chunk_epoch;        /* device uint32[ceil(n / 64)], zeroed once by the caller, or NULL.  After the launch
@@ -198,7 +198,7 @@ int fpv_drone_step_host(const fpv_drone_params_t* params, const fpv_drone_io_t* 
  * and statistics included).
  *   actions_seq: float4[T][action_stride] (step t of env e at t*action_stride + e; action_stride >= n);
  *   done_seq:    uint8[T][done_stride] out, or NULL; io->done (if set) receives the LAST step's flags;
- *   io->actions is ignored; io->work (uint32[4], zeroed once) is required.
+ *   io->actions is ignored; io->work (uint32[16], zeroed once) is required.
  * Supported configuration: the hot path of fpv_drone_step (ground plane, no obstacles / overrides / per-env wind, packed
  * kernel) without FPV_F_FREEZE_DONE and without io->chunk_epoch; anything else returns FPV_EINVAL and the caller steps. */
 int fpv_drone_rollout(const fpv_drone_params_t* params, const fpv_drone_io_t* io, const void* actions_seq,

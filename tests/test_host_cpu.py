@@ -304,3 +304,33 @@ def test_plain_c_consumer_of_the_abi(lib, tmp_path):
     r = subprocess.run([str(exe), os.path.join(ROOT, "fpyv_b200", "libfpyv_b200.so")], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "10 struct layouts agree" in r.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("slots,K", [(1, 8), (2, 8), (2, 1), (3, 4)])
+def test_same_batch_chained_on_partial_grids_stays_correct(slots, K):
+    """Chaining consecutive steps of ONE batch on grids that take only some CTA slots lets up to five launches be alive
+    at once, each waiting chunk by chunk on its predecessor (slow, but it must be right): 60 chained steps bit-identical
+    to plain steps, crossing the uint32 wrap of the epoch counter on the way."""
+    import torch
+    from fpyv_b200 import BatchedDrone
+    n, dev = 1 << 19, "cuda:0"
+    g = torch.Generator(device=dev).manual_seed(5)
+    pos = torch.randn(n, 3, device=dev, generator=g) * 5
+    pos[:, 2] = 0.05 + torch.rand(n, device=dev, generator=g) * 2.95
+    vel = torch.randn(n, 3, device=dev, generator=g)
+    rpy = (torch.rand(n, 3, device=dev, generator=g) * 2 - 1) * 30
+    acts = [torch.rand(n, 4, device=dev, generator=g) * 2 - 1 for _ in range(4)]
+    ref = BatchedDrone(None, num_envs=n, device=dev, substeps=K, dt=1e-3, auto_reset=True, thrust_lut=2049)
+    d = BatchedDrone(None, num_envs=n, device=dev, substeps=K, dt=1e-3, auto_reset=True, thrust_lut=2049, cta_slots=slots)
+    ref.reset(pos, vel, rpy)
+    d.reset(pos, vel, rpy)
+    d._epoch = 0xFFFFFFE0
+    d._chunk_epoch.fill_(-32)
+    for t in range(60):
+        ref.step(acts[t % 4], return_obs=False)
+        d.step(acts[t % 4], return_obs=False, chained=True)
+    torch.cuda.synchronize()
+    assert torch.equal(d._state, ref._state)
+    assert d.episode_stats()["crashes"] == ref.episode_stats()["crashes"]
+    assert int(d._chunk_epoch[0]) & 0xFFFFFFFF == (0xFFFFFFE0 + 60) & 0xFFFFFFFF
