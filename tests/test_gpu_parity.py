@@ -877,3 +877,61 @@ def test_two_batches_on_two_streams_concurrently():
     torch.cuda.synchronize()
     for d, r in zip(ds, ref):
         assert torch.equal(d._state, r)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_api_fuzz_all_step_forms_agree(seed):
+    """A random interleaving of every way to advance a batch -- plain steps, chained steps, fused rollouts, per-step
+    chained rollouts, host-buffer steps, masked resets, a step with obstacles, a change of CTA slots -- against a twin
+    advanced with plain steps only: bit-identical state, flags and statistics at the end."""
+    from fpyv_b200 import Cylinder, Ground
+    n, K = 300_001, 4
+    rng = np.random.default_rng(seed)
+    g = torch.Generator(device=DEV).manual_seed(100 + seed)
+    pos = torch.randn(n, 3, device=DEV, generator=g) * 5
+    pos[:, 2] = 0.05 + torch.rand(n, device=DEV, generator=g) * 2.95
+    vel = torch.randn(n, 3, device=DEV, generator=g)
+    rpy = (torch.rand(n, 3, device=DEV, generator=g) * 2 - 1) * 30
+    a = make(n, substeps=K, dt=1e-3, auto_reset=True, thrust_lut=2049)
+    b = make(n, substeps=K, dt=1e-3, auto_reset=True, thrust_lut=2049)
+    a.reset(pos, vel, rpy)
+    b.reset(pos, vel, rpy)
+    host = torch.empty(n, 4, dtype=torch.float32, pin_memory=True)
+    host_done = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    objs = [Cylinder(np.array([2.0, 1.0, 0.0]), 1.0, 4.0), Ground()]
+    new_act = lambda: (torch.rand(n, 4, device=DEV, generator=g) * 2 - 1).contiguous()
+    log = []
+    for it in range(40):
+        op = rng.choice(["plain", "chained", "chained", "fused", "unfused", "host", "reset", "objects", "slots"])
+        log.append(op)
+        if op in ("plain", "chained"):
+            x = new_act()
+            a.step(x, return_obs=False, chained=(op == "chained"))
+            b.step(x, return_obs=False)
+        elif op in ("fused", "unfused"):
+            T = int(rng.integers(1, 5))
+            xs = torch.stack([new_act() for _ in range(T)]).contiguous()
+            a.rollout(xs, fused=(op == "fused"))
+            for t in range(T):
+                b.step(xs[t], return_obs=False)
+        elif op == "host":
+            host.copy_(new_act().cpu())
+            a.step_host(host, host_done)
+            torch.cuda.current_stream().synchronize()
+            b.step(host.to(DEV), return_obs=False)
+            assert torch.equal(host_done, b.done.to(torch.uint8).cpu())
+        elif op == "reset":
+            mask = torch.rand(n, device=DEV, generator=g) < 0.1
+            for d in (a, b):
+                d.reset(pos, vel, rpy, mask=mask)
+        elif op == "objects":
+            x = new_act()
+            for d in (a, b):
+                d.step(x, None, objs, return_obs=False)
+        elif op == "slots":
+            a.cta_slots = int(rng.choice([0, 1, 2, 3]))
+    torch.cuda.synchronize()
+    assert torch.equal(a._state.view(torch.int32), b._state.view(torch.int32)), log
+    assert torch.equal(a.done, b.done), log
+    sa, sb = a.episode_stats(), b.episode_stats()
+    assert all(sa[k] == sb[k] or (sa[k] != sa[k] and sb[k] != sb[k]) for k in sa), (sa, sb, log)
