@@ -935,3 +935,34 @@ def test_api_fuzz_all_step_forms_agree(seed):
     assert torch.equal(a.done, b.done), log
     sa, sb = a.episode_stats(), b.episode_stats()
     assert all(sa[k] == sb[k] or (sa[k] != sa[k] and sb[k] != sb[k]) for k in sa), (sa, sb, log)
+
+
+def test_non_finite_inputs_stay_contained():
+    """NaN / Inf stick commands poison only their own env: the others match a clean run bit for bit, the table lookup and
+    the stores stay in bounds, and the statistics count the non-finite envs."""
+    n, K = 100_000, 8
+    g = torch.Generator(device=DEV).manual_seed(31)
+    pos = torch.randn(n, 3, device=DEV, generator=g) * 5
+    pos[:, 2] = 5 + torch.rand(n, device=DEV, generator=g) * 5
+    vel = torch.randn(n, 3, device=DEV, generator=g)
+    rpy = (torch.rand(n, 3, device=DEV, generator=g) * 2 - 1) * 30
+    act = (torch.rand(n, 4, device=DEV, generator=g) * 2 - 1).contiguous()
+    bad = act.clone()
+    idx = torch.arange(0, n, 97, device=DEV)
+    bad[idx[0::3], 3] = float("nan")
+    bad[idx[1::3], 0] = float("inf")
+    bad[idx[2::3], 3] = -float("inf")
+    clean = make(n, substeps=K, dt=1e-3, thrust_lut=2049)
+    dirty = make(n, substeps=K, dt=1e-3, thrust_lut=2049)
+    for d in (clean, dirty):
+        d.reset(pos, vel, rpy)
+    for _ in range(3):
+        clean.step(act, return_obs=False)
+        dirty.step(bad, return_obs=False)
+    torch.cuda.synchronize()
+    ok = torch.ones(n, dtype=torch.bool, device=DEV)
+    ok[idx] = False
+    assert torch.equal(clean._state[:, :n][:, ok], dirty._state[:, :n][:, ok])
+    assert not bool(torch.isfinite(dirty.position[idx[0::3]]).all(dim=1).any())       # NaN throttle -> NaN state
+    st = dirty.episode_stats()
+    assert st["nonfinite"] > 0 and clean.episode_stats()["nonfinite"] == 0
