@@ -315,6 +315,25 @@ def run_gpu(args):
     torch.cuda.synchronize()
     ms_e2e = e0.elapsed_time(e1)
 
+    # ---- the same end-to-end step fed the way the reference's simulator feeds it (step(action=None): raw joystick axes,
+    #      components.py:227-228, :250-253) in compact transport form: uint16[n][4] raw sticks, calibrated on the device.
+    #      Extra metric next to `e2e` (8 B/env instead of 16 over PCIe); `e2e` itself stays on float32 actions.
+    host_sticks = [torch.randint(0, 65536, (n, 4), dtype=torch.int32).to(torch.uint16).pin_memory() for _ in range(2)]
+    for i in range(max(3, W)):
+        drone.step_host_sticks(host_sticks[i % 2], host_done, slices=E2E_SLICES)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        drone.step_host_sticks(host_sticks[i % 2], host_done, slices=E2E_SLICES)
+        torch.cuda.current_stream().synchronize()
+        crashed += int(host_done[:64].sum())
+    e1.record()
+    torch.cuda.synchronize()
+    ms_e2e_sticks = e0.elapsed_time(e1)
+
     # ---- the same workload as an open-loop rollout in ONE launch per 16 control steps (fpv_drone_rollout: state in
     #      registers across the steps).  Reported next to the headline, never as it: the headline keeps one launch and
     #      one HBM round trip of the state per control step.  4 batches x 16 steps x 16 MiB of actions >> L2.
@@ -339,10 +358,10 @@ def run_gpu(args):
 
     t1 = time.time()
     clocks = sampler.stop(t0, t1) if sampler else None      # covers the K=8 loop, the e2e loop and the K=1 loop
-    t = torch.tensor([ms, ms_e2e, ms_k1, ms_rollout, ms_full_grid, ms_unchained], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, ms_e2e, ms_k1, ms_rollout, ms_full_grid, ms_unchained, ms_e2e_sticks], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e, ms_k1, ms_rollout, ms_full_grid, ms_unchained = t.tolist()
+    ms, ms_e2e, ms_k1, ms_rollout, ms_full_grid, ms_unchained, ms_e2e_sticks = t.tolist()
     stats = drone.episode_stats(all_reduce=world > 1)      # the engine's only collective (NCCL), outside the timed loop
     ms_flushed_per_step = ms_flushed / K_fl
     if rank != 0:
@@ -382,6 +401,10 @@ def run_gpu(args):
             "e2e": {"value": total_envs * K / (ms_e2e * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": 16 * n * world,
                     "d2h_bytes_per_step": n * world, "ms_per_step": ms_e2e / K,
                     "api": "BatchedDrone.step_host(pinned actions) -> pinned done flags = fpv_drone_step_host: 4 env slices pipelined over H2D / step / D2H streams inside the library; host waits every step"},
+            "e2e_raw_sticks": {"value": total_envs * K / (ms_e2e_sticks * 1e-3), "unit": "env-steps/s", "ms_per_step": ms_e2e_sticks / K,
+                               "h2d_bytes_per_step": 8 * n * world, "d2h_bytes_per_step": n * world,
+                               "api": "BatchedDrone.step_host_sticks(pinned uint16 raw sticks [n,4]) = fpv_drone_step_host_sticks: the "
+                                      "reference's step(action=None) joystick path, calibration on the device; extra metric"},
             "ms_per_step_flushed": ms_flushed_per_step,
             "ms_per_step_chained_full_grid": ms_full_grid / K, "ms_per_step_unchained": ms_unchained / K,
             "rollout_fused": {"ms_per_step": ms_rollout, "env_steps_per_sec": total_envs / (ms_rollout * 1e-3),

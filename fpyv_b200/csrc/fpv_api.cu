@@ -505,32 +505,95 @@ int fpv_drone_observe(const void* state, int64_t n, int64_t plane_stride, const 
   return check_launch("fpv_drone_observe");
 }
 
+namespace {
+int make_sticks(const fpv_stick_calib_t* c, fpv::StickK& k, const char* who) {
+  if (!c) return fail(FPV_EINVAL, "%s: null calibration", who);
+  for (int i = 0; i < 6; ++i) {
+    const double span = (double)c->max_vals[i] - (double)c->min_vals[i];
+    if (span == 0.0) return fail(FPV_EINVAL, "%s: axis %d has max == min", who, i);
+    k.min_v[i] = c->min_vals[i];
+    k.inv_span2[i] = (float)(2.0 / span);
+    k.sign[i] = c->sign_reverse[i];
+  }
+  for (int s = 0; s < 4; ++s) {
+    if (c->stick_idx[s] < 0 || c->stick_idx[s] > 5) return fail(FPV_EINVAL, "%s: stick idx out of range", who);
+    const double ctr = c->stick_center[s];
+    if (ctr <= -1.0 || ctr >= 1.0) return fail(FPV_EINVAL, "%s: stick centre must be inside (-1,1)", who);
+    k.idx[s] = c->stick_idx[s];
+    k.center[s] = c->stick_center[s];
+    k.inv_lo[s] = (float)(1.0 / (ctr + 1.0));
+    k.inv_hi[s] = (float)(1.0 / (1.0 - ctr));
+  }
+  return FPV_OK;
+}
+}  // namespace
+
 int fpv_sticks_to_actions(const fpv_stick_calib_t* c, const int32_t* raw, int64_t n, void* actions, float* calibrated,
                           void* stream) {
   if (!c || !raw || !actions) return fail(FPV_EINVAL, "fpv_sticks_to_actions: null pointer");
   if (n < 0) return fail(FPV_EINVAL, "fpv_sticks_to_actions: bad n");
   if (!aligned16(actions)) return fail(FPV_EINVAL, "fpv_sticks_to_actions: actions must be 16-byte aligned");
   fpv::StickK k;
-  for (int i = 0; i < 6; ++i) {
-    const double span = (double)c->max_vals[i] - (double)c->min_vals[i];
-    if (span == 0.0) return fail(FPV_EINVAL, "fpv_sticks_to_actions: axis %d has max == min", i);
-    k.min_v[i] = c->min_vals[i];
-    k.inv_span2[i] = (float)(2.0 / span);
-    k.sign[i] = c->sign_reverse[i];
-  }
-  for (int s = 0; s < 4; ++s) {
-    if (c->stick_idx[s] < 0 || c->stick_idx[s] > 5) return fail(FPV_EINVAL, "fpv_sticks_to_actions: stick idx out of range");
-    const double ctr = c->stick_center[s];
-    if (ctr <= -1.0 || ctr >= 1.0) return fail(FPV_EINVAL, "fpv_sticks_to_actions: stick centre must be inside (-1,1)");
-    k.idx[s] = c->stick_idx[s];
-    k.center[s] = c->stick_center[s];
-    k.inv_lo[s] = (float)(1.0 / (ctr + 1.0));
-    k.inv_hi[s] = (float)(1.0 / (1.0 - ctr));
-  }
+  if (int rc = make_sticks(c, k, "fpv_sticks_to_actions")) return rc;
   if (n == 0) return FPV_OK;
   const unsigned grid = (unsigned)((n + 255) / 256);
   fpv::sticks_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(k, raw, n, (float4*)actions, calibrated);
   return check_launch("fpv_sticks_to_actions");
+}
+
+int fpv_drone_step_host_sticks(const fpv_drone_params_t* p, const fpv_drone_io_t* io, const fpv_stick_calib_t* calib,
+                               const uint16_t* sticks_host, void* sticks_dev, uint8_t* done_host, int32_t slices,
+                               void* stream) {
+  if (!p || !io) return fail(FPV_EINVAL, "fpv_drone_step_host_sticks: null params/io");
+  if (!sticks_host || !sticks_dev || !done_host) return fail(FPV_EINVAL, "fpv_drone_step_host_sticks: null buffer");
+  if (!io->actions || !io->done) return fail(FPV_EINVAL, "fpv_drone_step_host_sticks: io.actions / io.done must be device buffers");
+  if (reinterpret_cast<uintptr_t>(sticks_dev) & 7u) return fail(FPV_EINVAL, "fpv_drone_step_host_sticks: sticks_dev must be 8-byte aligned");
+  if (io->n < 0 || io->plane_stride < io->n) return fail(FPV_EINVAL, "fpv_drone_step_host_sticks: bad n/stride");
+  fpv::StickK k;
+  if (int rc = make_sticks(calib, k, "fpv_drone_step_host_sticks")) return rc;
+  if (io->n == 0) return FPV_OK;
+  if (slices <= 0) slices = 4;
+  if (slices > 16) slices = 16;
+  const long long n = io->n;
+  long long per = (n + slices - 1) / slices;
+  per = (per + 63) / 64 * 64;
+  if (per < 65536) per = 65536;
+  HostPipe& hp = host_pipe_of_current_device();
+  if (!hp.ok) return fail(FPV_ECUDA, "fpv_drone_step_host_sticks: could not create the copy streams");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaEventRecord(hp.ready, st);
+  cudaStreamWaitEvent(hp.in, hp.ready, 0);
+  cudaStreamWaitEvent(hp.out, hp.ready, 0);
+  fpv_drone_params_t pp = *p;
+  pp.flags &= ~FPV_F_CHAINED;
+  int c = 0;
+  for (long long a = 0; a < n; a += per, ++c) {
+    const long long b = a + per < n ? a + per : n;
+    cudaMemcpyAsync((char*)sticks_dev + 8 * a, (const char*)sticks_host + 8 * a, (size_t)(8 * (b - a)), cudaMemcpyHostToDevice, hp.in);
+    cudaEventRecord(hp.h2d[c], hp.in);
+    cudaStreamWaitEvent(st, hp.h2d[c], 0);
+    fpv::sticks4_u16_kernel<<<(unsigned)((b - a + 255) / 256), 256, 0, st>>>(k, (const ushort4*)sticks_dev + a, b - a,
+                                                                             (float4*)io->actions + a);
+    fpv_drone_io_t s = *io;
+    s.state = (char*)io->state + 16 * a;
+    s.n = b - a;
+    s.actions = (const char*)io->actions + 16 * a;
+    s.done = io->done + a;
+    if (io->wind_env) s.wind_env = (const char*)io->wind_env + 16 * a;
+    if (io->acc_out) s.acc_out = (char*)io->acc_out + 16 * a;
+    if (io->reset_state) s.reset_state = (const char*)io->reset_state + 16 * a;
+    s.override_q = nullptr;
+    s.override_thrust = nullptr;
+    s.chunk_epoch = nullptr;
+    s.trace = nullptr;
+    if (int rc = fpv_drone_step(&pp, &s, stream)) return rc;
+    cudaEventRecord(hp.stepped[c], st);
+    cudaStreamWaitEvent(hp.out, hp.stepped[c], 0);
+    cudaMemcpyAsync(done_host + a, io->done + a, (size_t)(b - a), cudaMemcpyDeviceToHost, hp.out);
+  }
+  cudaEventRecord(hp.joined, hp.out);
+  cudaStreamWaitEvent(st, hp.joined, 0);
+  return check_launch("fpv_drone_step_host_sticks");
 }
 
 int fpv_racer_reset(void* state, int64_t n, int64_t plane_stride, const uint8_t* mask, void* stream) {

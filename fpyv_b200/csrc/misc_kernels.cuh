@@ -158,6 +158,34 @@ __global__ void sticks_kernel(const __grid_constant__ StickK k, const int* raw, 
   }
 }
 
+// The same map for the compact transport format of fpv_drone_step_host_sticks: uint16[n][4] = the raw readings of
+// axes 0, 1, 2 and 5 -- the four values Drone.read_sticks keeps of calib_read's six (components.py:251-252) -- as the
+// joystick driver reports them (0..65535).  Identical arithmetic per axis, so the actions are bit-identical.
+__global__ void sticks4_u16_kernel(const __grid_constant__ StickK k, const ushort4* raw, long long n, float4* actions) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const ushort4 r = raw[e];
+  const int axis[4] = {0, 1, 2, 5};
+  const float in[4] = {(float)r.x, (float)r.y, (float)r.z, (float)r.w};
+  float v[4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int i = axis[a];
+    v[a] = fmaf(in[a] - k.min_v[i], k.inv_span2[i], -1.f) * k.sign[i];
+  }
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      if (axis[a] == k.idx[s]) {
+        const float x = v[a], c = k.center[s];
+        v[a] = (x <= c) ? fmaf(x + 1.f, k.inv_lo[s], -1.f) : (x - c) * k.inv_hi[s];
+      }
+    }
+  }
+  actions[e] = make_float4(-v[1], v[2], v[3], v[0]);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Mode B: Racer (tests/racer_drone_test.py)
 // ---------------------------------------------------------------------------------------------

@@ -114,6 +114,7 @@ class BatchedDrone:
         # INDEPENDENT batches stepped round-robin run side by side (fpv_drone_io_t.max_ctas_per_sm)
         self._io.max_ctas_per_sm = int(cta_slots)
         self._host_done = None
+        self._sticks_dev = None
         self._last_action = None
         self._is_reset = False
         self._fast_ok = False
@@ -437,6 +438,40 @@ class BatchedDrone:
         self._io.chunk_epoch = None
         _lib.check(self._lib.fpv_drone_step_host(self._p_ref, self._io_ref, actions_host.data_ptr(), done_host.data_ptr(),
                                                  int(slices), torch.cuda.current_stream(dev).cuda_stream))
+        return done_host
+
+    def step_host_sticks(self, sticks_host: torch.Tensor, done_host: torch.Tensor | None = None, slices: int = 4):
+        """`step(action=None)` -- the reference's joystick path (components.py:227-228, :250-253) -- with HOST buffers in
+        the compact transport form: sticks_host uint16 [n,4] (pinned) = raw readings 0..65535 of axes 0, 1, 2, 5
+        (throttle, roll, pitch, yaw), calibrated on the device by this drone's `rc` calibration (bit-identical to
+        `rc.feed(raw); step(None)`), stepped, flags back to pinned host memory.  8 B/env in, 1 B/env out."""
+        n, dev = self.num_envs, self.device
+        if self.rc._c is None:
+            raise RuntimeError("Joystick is not calibrated: call calibrate(path) first")
+        if done_host is None:
+            if self._host_done is None:
+                self._host_done = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+            done_host = self._host_done
+        if not self._fast_ok:      # configure the io block once through the plain path
+            raw6 = torch.zeros((n, 6), dtype=torch.int32)
+            raw6[:, [0, 1, 2, 5]] = sticks_host.to(torch.int32)
+            self.rc.feed(raw6)
+            self.step(None, return_obs=False)
+            done_host.copy_(self._done, non_blocking=True)
+            return done_host
+        if (sticks_host.is_cuda or sticks_host.dtype is not torch.uint16 or not sticks_host.is_contiguous()
+                or tuple(sticks_host.shape) != (n, 4)):
+            raise ValueError("step_host_sticks expects a contiguous uint16 host tensor [num_envs, 4]")
+        if self._sticks_dev is None:
+            self._sticks_dev = torch.empty((n, 4), dtype=torch.uint16, device=dev)
+        self._last_action = self._actions
+        self._chain_ready = False
+        self._p.flags = self._flags
+        self._io.actions = self._actions.data_ptr()
+        self._io.chunk_epoch = None
+        _lib.check(self._lib.fpv_drone_step_host_sticks(self._p_ref, self._io_ref, C.byref(self.rc._c), sticks_host.data_ptr(),
+                                                        self._sticks_dev.data_ptr(), done_host.data_ptr(), int(slices),
+                                                        torch.cuda.current_stream(dev).cuda_stream))
         return done_host
 
     def _slice_bounds(self, slices):

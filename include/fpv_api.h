@@ -232,6 +232,16 @@ typedef struct fpv_stick_calib {
 int fpv_sticks_to_actions(const fpv_stick_calib_t* calib, const int32_t* raw, int64_t n, void* actions,
                           float* calibrated, void* stream);
 
+/* Drone.step(action=None, ...) with HOST buffers: the joystick path of the reference (components.py:227-228, :250-253 ->
+ * get_sticks.py:254-265) in the compact transport form of a radio link.  sticks_host: uint16[n][4] = the raw readings of
+ * axes 0, 1, 2 and 5 (throttle, roll, pitch, yaw of the stock calibrations -- the four of calib_read's six values that
+ * read_sticks keeps), 0..65535 as the joystick driver reports them; sticks_dev: device staging uint16[n][4]; the
+ * calibrated actions are written to io->actions (float4[n]) by the same per-axis arithmetic as fpv_sticks_to_actions
+ * (bit-identical), then the step runs and the flags return like in fpv_drone_step_host.  8 B/env in, 1 B/env out. */
+int fpv_drone_step_host_sticks(const fpv_drone_params_t* params, const fpv_drone_io_t* io, const fpv_stick_calib_t* calib,
+                               const uint16_t* sticks_host, void* sticks_dev, uint8_t* done_host, int32_t slices,
+                               void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Mode B: the acro rate-PID drone of tests/racer_drone_test.py (`PID` :11-32, `Racer` :68-103).
  * State: 7 float4 planes

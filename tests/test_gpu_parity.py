@@ -966,3 +966,34 @@ def test_non_finite_inputs_stay_contained():
     assert not bool(torch.isfinite(dirty.position[idx[0::3]]).all(dim=1).any())       # NaN throttle -> NaN state
     st = dirty.episode_stats()
     assert st["nonfinite"] > 0 and clean.episode_stats()["nonfinite"] == 0
+
+
+def test_step_host_sticks_matches_the_joystick_path():
+    """fpv_drone_step_host_sticks (uint16 raw sticks from pinned host memory, calibration on the device, sliced pipeline)
+    against `rc.feed(raw); step(None)` -- the reference's joystick path -- bit for bit, several steps in a row."""
+    n = 300_000
+    g = torch.Generator(device=DEV).manual_seed(12)
+    pos = torch.randn(n, 3, device=DEV, generator=g) * 5
+    pos[:, 2] = 0.05 + torch.rand(n, device=DEV, generator=g) * 2.95
+    vel = torch.randn(n, 3, device=DEV, generator=g)
+    rpy = (torch.rand(n, 3, device=DEV, generator=g) * 2 - 1) * 30
+    a = make(n, substeps=8, dt=1e-3, auto_reset=True, thrust_lut=2049)
+    b = make(n, substeps=8, dt=1e-3, auto_reset=True, thrust_lut=2049)
+    a.reset(pos, vel, rpy)
+    b.reset(pos, vel, rpy)
+    rng = np.random.default_rng(3)
+    done_h = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    for i in range(5):
+        raw4 = rng.integers(0, 65536, (n, 4), dtype=np.uint16)
+        host = torch.from_numpy(raw4).pin_memory()
+        a.step_host_sticks(host, done_h)
+        torch.cuda.current_stream().synchronize()
+        raw6 = np.zeros((n, 6), dtype=np.int32)
+        raw6[:, [0, 1, 2, 5]] = raw4
+        b.rc.feed(raw6)
+        b.step(None, return_obs=False)
+        assert torch.equal(done_h, b.done.to(torch.uint8).cpu()), i
+        assert torch.equal(a._last_action, b._last_action), i
+    assert torch.equal(a._state, b._state)
+    with pytest.raises(ValueError):
+        a.step_host_sticks(torch.zeros((n, 4), dtype=torch.int32), done_h)
