@@ -18,7 +18,7 @@ DRONE_PLANES, RACER_PLANES = 4, 7
 EXPORTS = ("fpv_abi_version", "fpv_last_error", "fpv_sizeof", "fpv_device_info", "fpv_drone_reset",
            "fpv_drone_step", "fpv_drone_step_host", "fpv_drone_step_host_sticks", "fpv_drone_rollout", "fpv_drone_observe", "fpv_drone_get_rotation", "fpv_drone_set_rotation", "fpv_matrix_to_quat", "fpv_sticks_to_actions", "fpv_racer_reset", "fpv_racer_step", "fpv_gate_env_reset", "fpv_gate_env_step",
            "fpv_camera_update", "fpv_camera_render", "fpv_camera_target_pixel", "fpv_camera_rays", "fpv_autopilot", "fpv_point_and_shoot",
-           "fpv_acro_reset", "fpv_acro_step")
+           "fpv_acro_reset", "fpv_acro_step", "fpv_acro_rollout")
 
 
 class FpvError(RuntimeError):
@@ -159,6 +159,7 @@ def load():
     lib.fpv_point_and_shoot.argtypes = [P(AutopilotParams), P(CameraParams), V, I64, I64, V, V, V, V, V, V, V, V, V]
     lib.fpv_acro_reset.argtypes = [V, I64, I64, V, V, V, V, V]
     lib.fpv_acro_step.argtypes = [P(AcroParams), V, I64, I64, V, V, I32, V, V, V, V, V]
+    lib.fpv_acro_rollout.argtypes = [P(AcroParams), V, I64, I64, V, I64, I32, V, I32, V, I64, V, V, V, V, V]
     v = lib.fpv_abi_version()
     if v != ABI_VERSION:
         raise ImportError(f"{LIB_PATH} has ABI version {v}, this package needs {ABI_VERSION}; rebuild it")

@@ -116,6 +116,24 @@ class BatchedAcroDrone:
                                            _lib.ptr(self._stats), _lib.current_stream(dev)))
         return self._done
 
+    def rollout(self, actions, done_out=None):
+        """Open-loop rollout: actions [T,n,4] float32 on the device, all T control steps in ONE launch with the state in
+        registers (fpv_acro_rollout); bit-identical to T step() calls.  done_out: optional uint8 [T,n]."""
+        n, dev = self.num_envs, self.device
+        if not (isinstance(actions, torch.Tensor) and actions.is_cuda and actions.dtype is torch.float32 and actions.dim() == 3
+                and tuple(actions.shape[1:]) == (n, 4) and actions.is_contiguous()):
+            raise ValueError("rollout expects a contiguous float32 CUDA tensor [T, num_envs, 4]")
+        if done_out is not None and not (done_out.is_cuda and done_out.dtype is torch.uint8 and done_out.is_contiguous()
+                                         and tuple(done_out.shape) == (actions.shape[0], n)):
+            raise ValueError("done_out must be a contiguous uint8 CUDA tensor [T, num_envs]")
+        for i in range(3):
+            self._p.wind[i] = 0.0
+        _lib.check(self._lib.fpv_acro_rollout(C.byref(self._p), _lib.ptr(self._state), n, self._stride, _lib.ptr(actions), n,
+                                              int(actions.shape[0]), _lib.ptr(self._lut), 0 if self._lut is None else self._lut.numel(),
+                                              _lib.ptr(done_out), n, _lib.ptr(self._done), _lib.ptr(self._motor),
+                                              _lib.ptr(self._reset_state), _lib.ptr(self._stats), _lib.current_stream(dev)))
+        return done_out if done_out is not None else self._done
+
     def hover_throttle(self):
         """Stick throttle in [-1,1] at which the four motors carry the weight (bench cubic, components.py:136)."""
         lo, hi = -1.0, 1.0

@@ -128,7 +128,13 @@ template <class V, int THREADS>
 __global__ void __launch_bounds__(THREADS) acro_step_kernel(const __grid_constant__ AcroK k, float4* state, long long n,
                                                             long long stride, const float4* actions, const float* lut,
                                                             unsigned char* done_out, float4* motor_out,
-                                                            const float4* reset_state, fpv_stats_t* stats) {
+                                                            const float4* reset_state, fpv_stats_t* stats, const int T,
+                                                            const long long act_stride, unsigned char* done_seq,
+                                                            const long long done_stride) {
+  // T control steps per launch (T = 1: fpv_acro_step; T > 1: fpv_acro_rollout, the open-loop form -- the state stays in
+  // registers from the first step to the last, step t reads actions[t * act_stride + env] and writes
+  // done_seq[t * done_stride + env]; crashes restart from the snapshot IN REGISTERS, so the result is bit-identical to
+  // T launches with T = 1).
   constexpr int L = Lane<V>::N;
   constexpr int TILE = THREADS * L;
   using M = typename Lane<V>::Mask;
@@ -142,7 +148,7 @@ __global__ void __launch_bounds__(THREADS) acro_step_kernel(const __grid_constan
   long long ei[L];
 #pragma unroll
   for (int l = 0; l < L; ++l) ei[l] = min(base + (long long)l * THREADS, n - 1);   // a slot past the end is never stored
-  float4 q[FPV_ACRO_PLANES][L], act[L];
+  float4 q[FPV_ACRO_PLANES][L], act[L], act_next[L];
 #pragma unroll
   for (int p = 0; p < FPV_ACRO_PLANES; ++p)
 #pragma unroll
@@ -157,12 +163,20 @@ __global__ void __launch_bounds__(THREADS) acro_step_kernel(const __grid_constan
   V ie[3] = {Pack<V>::x(q[5]), Pack<V>::y(q[5]), Pack<V>::z(q[5])};
   V le[3] = {Pack<V>::x(q[6]), Pack<V>::y(q[6]), Pack<V>::z(q[6])};
   int epi[L];
-  float nf_[2];
+  float nf_[2], first_flag[2];
 #pragma unroll
-  for (int l = 0; l < L; ++l) { epi[l] = __float_as_int(q[1][l].w); nf_[l] = q[3][l].w != 0.f ? 0.f : 1.f; }
+  for (int l = 0; l < L; ++l) { epi[l] = __float_as_int(q[1][l].w); nf_[l] = q[3][l].w != 0.f ? 0.f : 1.f; first_flag[l] = q[3][l].w; }
   V notfirst = Lane<V>::make(nf_[0], nf_[L - 1]);   // 0 on a PID's first call: no derivative term (racer_drone_test.py:28)
   const V zero = S<V>(0.f), one = S<V>(1.f);
   const V mr = S<V>(k.max_rates), rtr = S<V>(k.rtr);
+  const V omr = S<V>(k.one_minus_rtr), omt = S<V>(k.one_minus_ttr), dt = S<V>(k.dt), inv_dt = S<V>(k.inv_dt);
+  const V d2r = S<V>(k.deg2rad), hdt = S<V>(0.5f * k.dt), s_m = S<V>(k.inv_mass * k.dt);
+  V fm[4] = {zero, zero, zero, zero};
+  for (int t = 0; t < T; ++t) {
+  if (t + 1 < T) {   // next step's sticks travel while this step computes
+#pragma unroll
+    for (int l = 0; l < L; ++l) act_next[l] = ldg_stream(actions + (long long)(t + 1) * act_stride + ei[l]);
+  }
   V cmd[3];
   {
     const V a3[3] = {Pack<V>::x(act), Pack<V>::y(act), Pack<V>::z(act)};
@@ -181,10 +195,7 @@ __global__ void __launch_bounds__(THREADS) acro_step_kernel(const __grid_constan
     }
   }
   const V thr_in = Pack<V>::w(act) * S<V>(k.ttr);
-  const V omr = S<V>(k.one_minus_rtr), omt = S<V>(k.one_minus_ttr), dt = S<V>(k.dt), inv_dt = S<V>(k.inv_dt);
-  const V d2r = S<V>(k.deg2rad), hdt = S<V>(0.5f * k.dt), s_m = S<V>(k.inv_mass * k.dt);
   M done = vlt(one, zero);
-  V fm[4] = {zero, zero, zero, zero};
 #pragma unroll 1
   for (int it = 0; it < k.substeps; ++it) {
     // ---- stick -> rate set-point / collective throttle, low-passed (components.py:185-194)
@@ -263,34 +274,51 @@ __global__ void __launch_bounds__(THREADS) acro_step_kernel(const __grid_constan
     const V inv = vrsqrt_fast(vfma(nw, nw, vfma(nx, nx, vfma(ny, ny, nz * nz))));
     qw = nw * inv; qx = nx * inv; qy = ny * inv; qz = nz * inv;
   }
-  // ---- epilogue per env
+  // ---- per-step bookkeeping on registers: flags, statistics, restart from the snapshot
 #pragma unroll
   for (int l = 0; l < L; ++l) {
     const long long e = base + (long long)l * THREADS;
     if (e >= n) break;
     const bool d = mask_get(done, l);
-    const int ep = epi[l] + 1;
-    if (done_out) done_out[e] = d ? 1 : 0;
-    if (motor_out)
-      stg_stream(motor_out + e, make_float4(Lane<V>::get(fm[0], l), Lane<V>::get(fm[1], l), Lane<V>::get(fm[2], l), Lane<V>::get(fm[3], l)));
+    epi[l] += 1;
+    first_flag[l] = 0.f;   // the PIDs have been called
+    if (done_seq) done_seq[(long long)t * done_stride + e] = d ? 1 : 0;
+    if (done_out && t == T - 1) done_out[e] = d ? 1 : 0;
     if (d && stats) {
       atomicAdd(&stats->crashes, 1.0);
-      if (k.flags & FPV_F_AUTO_RESET) { atomicAdd(&stats->episodes, 1.0); atomicAdd(&stats->episode_len_sum, (double)ep); }
+      if (k.flags & FPV_F_AUTO_RESET) { atomicAdd(&stats->episodes, 1.0); atomicAdd(&stats->episode_len_sum, (double)epi[l]); }
     }
     if (d && (k.flags & FPV_F_AUTO_RESET)) {
       float4 v[FPV_ACRO_PLANES];
 #pragma unroll
       for (int p = 0; p < FPV_ACRO_PLANES; ++p) v[p] = ldg_stream(reset_state + p * stride + e);
-      v[1].w = __int_as_float(0);
-#pragma unroll
-      for (int p = 0; p < FPV_ACRO_PLANES; ++p) stg_stream(state + p * stride + e, v[p]);
-      continue;
+      px = lane_set<V>(px, l, v[0].x); py = lane_set<V>(py, l, v[0].y); pz = lane_set<V>(pz, l, v[0].z); thr = lane_set<V>(thr, l, v[0].w);
+      vx = lane_set<V>(vx, l, v[1].x); vy = lane_set<V>(vy, l, v[1].y); vz = lane_set<V>(vz, l, v[1].z);
+      qw = lane_set<V>(qw, l, v[2].x); qx = lane_set<V>(qx, l, v[2].y); qy = lane_set<V>(qy, l, v[2].z); qz = lane_set<V>(qz, l, v[2].w);
+      sp[0] = lane_set<V>(sp[0], l, v[3].x); sp[1] = lane_set<V>(sp[1], l, v[3].y); sp[2] = lane_set<V>(sp[2], l, v[3].z);
+      w[0] = lane_set<V>(w[0], l, v[4].x); w[1] = lane_set<V>(w[1], l, v[4].y); w[2] = lane_set<V>(w[2], l, v[4].z);
+      ie[0] = lane_set<V>(ie[0], l, v[5].x); ie[1] = lane_set<V>(ie[1], l, v[5].y); ie[2] = lane_set<V>(ie[2], l, v[5].z);
+      le[0] = lane_set<V>(le[0], l, v[6].x); le[1] = lane_set<V>(le[1], l, v[6].y); le[2] = lane_set<V>(le[2], l, v[6].z);
+      first_flag[l] = v[3].w;
+      notfirst = lane_set<V>(notfirst, l, v[3].w != 0.f ? 0.f : 1.f);
+      epi[l] = 0;
     }
+  }
+#pragma unroll
+  for (int l = 0; l < L; ++l) act[l] = act_next[l];
+  }  // control steps
+  // ---- the state goes back once
+#pragma unroll
+  for (int l = 0; l < L; ++l) {
+    const long long e = base + (long long)l * THREADS;
+    if (e >= n) break;
+    if (motor_out)
+      stg_stream(motor_out + e, make_float4(Lane<V>::get(fm[0], l), Lane<V>::get(fm[1], l), Lane<V>::get(fm[2], l), Lane<V>::get(fm[3], l)));
     const auto g = [&](V v) { return Lane<V>::get(v, l); };
     stg_stream(state + e, make_float4(g(px), g(py), g(pz), g(thr)));
-    stg_stream(state + stride + e, make_float4(g(vx), g(vy), g(vz), __int_as_float(ep)));
+    stg_stream(state + stride + e, make_float4(g(vx), g(vy), g(vz), __int_as_float(epi[l])));
     stg_stream(state + 2 * stride + e, make_float4(g(qw), g(qx), g(qy), g(qz)));
-    stg_stream(state + 3 * stride + e, make_float4(g(sp[0]), g(sp[1]), g(sp[2]), 0.f));   // .w: PID has been called
+    stg_stream(state + 3 * stride + e, make_float4(g(sp[0]), g(sp[1]), g(sp[2]), first_flag[l]));   // .w: PID first-call flag
     stg_stream(state + 4 * stride + e, make_float4(g(w[0]), g(w[1]), g(w[2]), 0.f));
     stg_stream(state + 5 * stride + e, make_float4(g(ie[0]), g(ie[1]), g(ie[2]), 0.f));
     stg_stream(state + 6 * stride + e, make_float4(g(le[0]), g(le[1]), g(le[2]), 0.f));

@@ -813,9 +813,10 @@ int fpv_acro_reset(void* state, int64_t n, int64_t plane_stride, const float* po
   return check_launch("fpv_acro_reset");
 }
 
-int fpv_acro_step(const fpv_acro_params_t* p, void* state, int64_t n, int64_t plane_stride, const void* actions,
-                  const float* lut, int32_t lut_n, uint8_t* done, void* motor_thrust, const void* reset_state,
-                  fpv_stats_t* stats, void* stream) {
+namespace {
+int acro_launch(const fpv_acro_params_t* p, void* state, int64_t n, int64_t plane_stride, const void* actions,
+                const float* lut, int32_t lut_n, uint8_t* done, void* motor_thrust, const void* reset_state,
+                fpv_stats_t* stats, int32_t T, int64_t act_stride, uint8_t* done_seq, int64_t done_stride, void* stream) {
   if (!p || !state || !actions) return fail(FPV_EINVAL, "fpv_acro_step: null pointer");
   if (n < 0 || plane_stride < n) return fail(FPV_EINVAL, "fpv_acro_step: bad n/stride");
   if (!aligned16(state) || !aligned16(actions) || !aligned16(motor_thrust) || !aligned16(reset_state))
@@ -873,11 +874,31 @@ int fpv_acro_step(const fpv_acro_params_t* p, void* state, int64_t n, int64_t pl
     }
     const long long tile = (long long)kThreads * envs_per_thread;
     kern<<<(unsigned)((n + tile - 1) / tile), kThreads, smem, (cudaStream_t)stream>>>(
-        k, (float4*)state, n, plane_stride, (const float4*)actions, lut, done, (float4*)motor_thrust, (const float4*)reset_state, stats);
+        k, (float4*)state, n, plane_stride, (const float4*)actions, lut, done, (float4*)motor_thrust, (const float4*)reset_state, stats,
+        (int)T, (long long)act_stride, done_seq, (long long)done_stride);
   };
   if (p->flags & FPV_F_SCALAR) launch(fpv::acro_step_kernel<float, kThreads>, 1);
   else launch(fpv::acro_step_kernel<F2, kThreads>, 2);
   return check_launch("fpv_acro_step");
+}
+}  // namespace
+
+int fpv_acro_step(const fpv_acro_params_t* p, void* state, int64_t n, int64_t plane_stride, const void* actions,
+                  const float* lut, int32_t lut_n, uint8_t* done, void* motor_thrust, const void* reset_state,
+                  fpv_stats_t* stats, void* stream) {
+  return acro_launch(p, state, n, plane_stride, actions, lut, lut_n, done, motor_thrust, reset_state, stats, 1, 0, nullptr, 0, stream);
+}
+
+int fpv_acro_rollout(const fpv_acro_params_t* p, void* state, int64_t n, int64_t plane_stride, const void* actions_seq,
+                     int64_t action_stride, int32_t n_steps, const float* lut, int32_t lut_n, uint8_t* done_seq,
+                     int64_t done_stride, uint8_t* done_last, void* motor_thrust, const void* reset_state, fpv_stats_t* stats,
+                     void* stream) {
+  if (n_steps < 0) return fail(FPV_EINVAL, "fpv_acro_rollout: n_steps must be >= 0");
+  if (n_steps == 0) return FPV_OK;
+  if (action_stride < n) return fail(FPV_EINVAL, "fpv_acro_rollout: action_stride must be >= n");
+  if (done_seq && done_stride < n) return fail(FPV_EINVAL, "fpv_acro_rollout: done_stride must be >= n");
+  return acro_launch(p, state, n, plane_stride, actions_seq, lut, lut_n, done_last, motor_thrust, reset_state, stats, n_steps,
+                     action_stride, done_seq, done_stride, stream);
 }
 
 }  // extern "C"

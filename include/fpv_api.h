@@ -440,6 +440,14 @@ int fpv_acro_step(const fpv_acro_params_t* params, void* state, int64_t n, int64
                   const float* lut, int32_t lut_n, uint8_t* done, void* motor_thrust, const void* reset_state,
                   fpv_stats_t* stats, void* stream);
 
+/* Open-loop rollout of mode C: n_steps control steps in one launch, state in registers across them, bit-identical to
+ * n_steps calls of fpv_acro_step (restarts from the snapshot included).  actions_seq: float4[n_steps][action_stride];
+ * done_seq: uint8[n_steps][done_stride] or NULL; done_last: uint8[n] (flags of the last step) or NULL. */
+int fpv_acro_rollout(const fpv_acro_params_t* params, void* state, int64_t n, int64_t plane_stride, const void* actions_seq,
+                     int64_t action_stride, int32_t n_steps, const float* lut, int32_t lut_n, uint8_t* done_seq,
+                     int64_t done_stride, uint8_t* done_last, void* motor_thrust, const void* reset_state, fpv_stats_t* stats,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -272,3 +272,31 @@ def test_substeps_compose_bit_exactly(packed):
             for _ in range(K):
                 rb.step(sp)
         assert torch.equal(ra._state, rb._state)
+
+
+@pytest.mark.parametrize("packed", [True, False])
+@pytest.mark.parametrize("n,K,T", [(100_003, 4, 7), (300, 1, 12)])
+def test_acro_rollout_is_bit_identical_to_steps(n, K, T, packed):
+    """fpv_acro_rollout (T control steps per launch, state in registers, restarts from the snapshot in registers) against
+    T calls of step(): state, every step's flags, motor thrusts and statistics, bit for bit, with crashes inside."""
+    from fpyv_b200 import BatchedAcroDrone
+    rng, pos, vel, rpy = seeded(n, 18, z_lo=0.12, z_hi=1.5)
+    a = BatchedAcroDrone(None, num_envs=n, device=DEV, substeps=K, dt=1e-3, auto_reset=True, packed=packed)
+    b = BatchedAcroDrone(None, num_envs=n, device=DEV, substeps=K, dt=1e-3, auto_reset=True, packed=packed)
+    a.reset(pos, vel, rpy)
+    b.reset(pos, vel, rpy)
+    a._state[:, n:] = 55.0
+    acts = torch.as_tensor(rng.uniform(-1, 1, (T, n, 4)), dtype=torch.float32, device=DEV).contiguous()
+    acts[..., 3] = acts[..., 3] * 0.3 - 0.8                     # low throttle: many envs reach the ground within the rollout
+    flags = torch.full((T + 2, n), 0xAB, dtype=torch.uint8, device=DEV)
+    a.rollout(acts, done_out=flags[1:T + 1])
+    ref = torch.empty((T, n), dtype=torch.uint8, device=DEV)
+    for t in range(T):
+        ref[t] = b.step(acts[t])
+    torch.cuda.synchronize()
+    assert torch.equal(a._state[:, :n].view(torch.int32), b._state[:, :n].view(torch.int32))
+    assert bool((a._state[:, n:] == 55.0).all())
+    assert torch.equal(flags[1:T + 1], ref) and bool((flags[0] == 0xAB).all()) and bool((flags[T + 1] == 0xAB).all())
+    assert torch.equal(a.done, b.done) and torch.equal(a.motor_thrust, b.motor_thrust)
+    assert torch.equal(a._stats, b._stats)
+    assert n < 1000 or int(ref.sum()) > 0
