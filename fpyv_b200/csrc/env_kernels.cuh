@@ -5,13 +5,29 @@
 #pragma once
 #include "../../include/fpv_api.h"
 #include "misc_kernels.cuh"
+#include "drone_kernels.cuh"
 
 namespace fpv {
 
+// (explicit fused multiply-adds in a fixed order: the same source must give the same bits in every kernel it is inlined in)
 __device__ __forceinline__ void gate_metrics(const fpv_gate_t& g, float px, float py, float pz, float& d, float& r) {
   const float dx = px - g.cx, dy = py - g.cy, dz = pz - g.cz;
-  d = g.nx * dx + g.ny * dy + g.nz * dz;  // Gate.calculate_distance, components.py:819-822
-  r = sqrtf(dx * dx + dy * dy + dz * dz);
+  d = __fmaf_rn(g.nx, dx, __fmaf_rn(g.ny, dy, g.nz * dz));  // Gate.calculate_distance, components.py:819-822
+  r = sqrtf(__fmaf_rn(dx, dx, __fmaf_rn(dy, dy, dz * dz)));
+}
+
+// Observation of one agent: [0:3] R^T (c_g - p)  [3:6] R^T n_g  [6:9] R^T v  [9:12] R^T e_z  [12:15] rates  [15] prev_thrust
+__device__ __forceinline__ void gate_observation(const float4 p, const float4 v, const float4 q, const float4 w,
+                                                 const fpv_gate_t& gt, float4* o) {
+  float R[9];
+  quat_to_matrix(q, R);
+  const float dx = gt.cx - p.x, dy = gt.cy - p.y, dz = gt.cz - p.z;
+  // R^T x = columns of R dotted with x
+  auto col = [&](int c, float x, float y, float z) { return __fmaf_rn(R[c], x, __fmaf_rn(R[3 + c], y, R[6 + c] * z)); };
+  o[0] = make_float4(col(0, dx, dy, dz), col(1, dx, dy, dz), col(2, dx, dy, dz), col(0, gt.nx, gt.ny, gt.nz));
+  o[1] = make_float4(col(1, gt.nx, gt.ny, gt.nz), col(2, gt.nx, gt.ny, gt.nz), col(0, v.x, v.y, v.z), col(1, v.x, v.y, v.z));
+  o[2] = make_float4(col(2, v.x, v.y, v.z), R[6], R[7], R[8]);
+  o[3] = make_float4(w.x, w.y, w.z, p.w);
 }
 
 __global__ void gate_env_reset_kernel(const __grid_constant__ fpv_gate_env_params_t k, const float4* state, long long n,
@@ -56,8 +72,8 @@ __global__ void __launch_bounds__(THREADS) gate_env_step_kernel(const __grid_con
     gate_metrics(gates[g], p.x, p.y, p.z, d, r);
     bool passed = false;
     if (!crashed) {
-      passed = pr.x < 0.f && d >= 0.f && (r * r - d * d) <= gates[g].half_size * gates[g].half_size;
-      reward = k.w_progress * (pr.y - r) + (passed ? k.w_gate : 0.f);
+      passed = pr.x < 0.f && d >= 0.f && __fmaf_rn(r, r, -(d * d)) <= gates[g].half_size * gates[g].half_size;
+      reward = __fmaf_rn(k.w_progress, pr.y - r, passed ? k.w_gate : 0.f);
     } else {
       reward = -k.w_crash;
     }
@@ -71,20 +87,7 @@ __global__ void __launch_bounds__(THREADS) gate_env_step_kernel(const __grid_con
     prev[i] = make_float2(d, r);
     progress[i] = (laps << 16) | g;
     if (agent_reward) agent_reward[i] = reward;
-    if (obs) {
-      float R[9];
-      quat_to_matrix(q, R);
-      const fpv_gate_t& gt = gates[g];
-      const float dx = gt.cx - p.x, dy = gt.cy - p.y, dz = gt.cz - p.z;
-      float4* o = obs + 4 * i;
-      // R^T x = columns of R dotted with x
-      o[0] = make_float4(R[0] * dx + R[3] * dy + R[6] * dz, R[1] * dx + R[4] * dy + R[7] * dz,
-                         R[2] * dx + R[5] * dy + R[8] * dz, R[0] * gt.nx + R[3] * gt.ny + R[6] * gt.nz);
-      o[1] = make_float4(R[1] * gt.nx + R[4] * gt.ny + R[7] * gt.nz, R[2] * gt.nx + R[5] * gt.ny + R[8] * gt.nz,
-                         R[0] * v.x + R[3] * v.y + R[6] * v.z, R[1] * v.x + R[4] * v.y + R[7] * v.z);
-      o[2] = make_float4(R[2] * v.x + R[5] * v.y + R[8] * v.z, R[6], R[7], R[8]);
-      o[3] = make_float4(w.x, w.y, w.z, p.w);
-    }
+    if (obs) gate_observation(p, v, q, w, gates[g], obs + 4 * i);
   }
   // ---- per-env reductions inside the aligned A-lane group: reward sum (xor shuffles), any crashed / finished (vote)
   float team = reward;
@@ -111,6 +114,129 @@ __global__ void __launch_bounds__(THREADS) gate_env_step_kernel(const __grid_con
       for (int wi = 0; wi < THREADS / 32; ++wi) { ta += s_sum[wi]; tb += s_sq[wi]; }
       atomicAdd(&stats->reward_sum, (double)ta);
       atomicAdd(&stats->reward_sq_sum, (double)tb);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Fused env step: the dynamics control step (drone_substeps, one agent per thread, exactly the arithmetic of the scalar
+// step kernel) and the env step above in ONE pass -- the agent's state is read once and written once, the second launch
+// and its 64 B/agent re-read disappear.  Bit-identical to fpv_drone_step (FPV_F_SCALAR) followed by fpv_gate_env_step.
+// ---------------------------------------------------------------------------------------------------------------
+template <int ANG, int THREADS>
+__global__ void __launch_bounds__(THREADS) gate_race_fused_kernel(const __grid_constant__ DroneK k, const DroneIO io,
+                                                                  const __grid_constant__ fpv_gate_env_params_t gp,
+                                                                  float2* prev, int* progress, float* agent_reward,
+                                                                  float* env_reward, unsigned char* env_done, float4* obs) {
+  extern __shared__ __align__(16) float lut_dyn[];
+  __shared__ fpv_gate_t gates[FPV_MAX_GATES];
+  {
+    const float* src = reinterpret_cast<const float*>(gp.gates);
+    float* dst = reinterpret_cast<float*>(gates);
+    for (int j = threadIdx.x; j < gp.n_gates * (int)(sizeof(fpv_gate_t) / sizeof(float)); j += THREADS) dst[j] = src[j];
+    if (k.flags & FPV_F_THRUST_LUT)
+      for (int j = threadIdx.x; j < k.lut_n; j += THREADS) lut_dyn[j] = io.lut[j];
+    __syncthreads();
+  }
+  const long long i = (long long)blockIdx.x * THREADS + threadIdx.x;
+  const int A = gp.agents_per_env;
+  const bool live = i < io.n;
+  if (io.stats && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&io.stats->env_steps, (double)io.n);
+  TileStats st = {0.f, 0.f, 0.f, 0.f, 0.f};
+  float reward = 0.f;
+  bool crashed = false, finished = false;
+  if (live) {
+    // ---- dynamics control step (drone_tile's scalar form)
+    float4 q0 = ldg_stream(io.state + i), q1 = ldg_stream(io.state + io.stride + i);
+    float4 q2 = ldg_stream(io.state + 2 * io.stride + i), q3 = ldg_stream(io.state + 3 * io.stride + i);
+    const float4 act = ldg_stream(io.actions + i);
+    DroneRegs<float> s;
+    s.px = q0.x; s.py = q0.y; s.pz = q0.z; s.pt = q0.w;
+    s.vx = q1.x; s.vy = q1.y; s.vz = q1.z;
+    s.qw = q2.x; s.qx = q2.y; s.qy = q2.z; s.qz = q2.w;
+    s.pr0 = q3.x; s.pr1 = q3.y; s.pr2 = q3.z;
+    s.ax = s.ay = s.az = 0.f;
+    int ep = __float_as_int(q1.w);
+    float spare = q3.w;
+    const float target = (k.flags & FPV_F_THRUST_LUT) ? thrust_lut1(k, lut_dyn, act.w) : thrust_poly<float>(k, act.w);
+    crashed = drone_substeps<float, ANG, false, false>(k, s, act.x, act.y, act.z, target, 0.f, 0.f, 0.f, false, 0.f, 1.f, 0.f,
+                                                       0.f, 0.f);
+    ep += 1;
+    if (io.done) io.done[i] = crashed ? 1 : 0;
+    if (io.acc_out) stg_stream(io.acc_out + i, make_float4(s.ax, s.ay, s.az, 0.f));
+    bool restarted = false;
+    if (crashed) {
+      st.crash += 1.f;
+      if (k.flags & FPV_F_AUTO_RESET) {
+        st.epi += 1.f; st.len += (float)ep;
+        q0 = ldg_stream(io.reset_state + i); q1 = ldg_stream(io.reset_state + io.stride + i);
+        q2 = ldg_stream(io.reset_state + 2 * io.stride + i); q3 = ldg_stream(io.reset_state + 3 * io.stride + i);
+        q1.w = __int_as_float(0);
+        restarted = true;
+      }
+    }
+    if (!restarted) {
+      if (!(fabsf((s.px + s.py) + s.pz) <= 3.0e38f)) st.nf += 1.f;
+      q0 = make_float4(s.px, s.py, s.pz, s.pt);
+      q1 = make_float4(s.vx, s.vy, s.vz, __int_as_float(ep));
+      q2 = make_float4(s.qw, s.qx, s.qy, s.qz);
+      q3 = make_float4(s.pr0, s.pr1, s.pr2, spare);
+    }
+    stg_stream(io.state + i, q0);
+    stg_stream(io.state + io.stride + i, q1);
+    stg_stream(io.state + 2 * io.stride + i, q2);
+    stg_stream(io.state + 3 * io.stride + i, q3);
+    // ---- env step on the state just written (gate_env_step_kernel's body)
+    const float4 p = q0, v = q1, q = q2, w = q3;
+    const float2 pr = prev[i];
+    int prog = progress[i];
+    int g = prog & 0xffff, laps = prog >> 16;
+    float d, r;
+    gate_metrics(gates[g], p.x, p.y, p.z, d, r);
+    bool passed = false;
+    if (!crashed) {
+      passed = pr.x < 0.f && d >= 0.f && __fmaf_rn(r, r, -(d * d)) <= gates[g].half_size * gates[g].half_size;
+      reward = __fmaf_rn(gp.w_progress, pr.y - r, passed ? gp.w_gate : 0.f);
+    } else {
+      reward = -gp.w_crash;
+    }
+    if (passed) {
+      g += 1;
+      if (g == gp.n_gates) { g = 0; laps += 1; }
+    }
+    if (crashed) { g = 0; laps = 0; }
+    finished = gp.laps_to_finish > 0 && laps >= gp.laps_to_finish;
+    if (passed || crashed) gate_metrics(gates[g], p.x, p.y, p.z, d, r);
+    prev[i] = make_float2(d, r);
+    progress[i] = (laps << 16) | g;
+    if (agent_reward) agent_reward[i] = reward;
+    if (obs) gate_observation(p, v, q, w, gates[g], obs + 4 * i);
+  }
+  // ---- per-env reductions inside the aligned A-lane group
+  float team = reward;
+  for (int o = A >> 1; o > 0; o >>= 1) team += __shfl_xor_sync(0xffffffffu, team, o);
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned group_mask = (A == 32 ? 0xffffffffu : ((1u << A) - 1u)) << (lane & ~(unsigned)(A - 1));
+  const unsigned flags = __ballot_sync(0xffffffffu, crashed || finished);
+  const bool done = (flags & group_mask) != 0;
+  const bool head = live && (lane & (unsigned)(A - 1)) == 0;
+  if (head) {
+    const long long e = i / A;
+    env_reward[e] = team;
+    env_done[e] = done ? 1 : 0;
+  }
+  if (io.stats) {
+    stats_warp_flush(io.stats, st);
+    __shared__ float s_sum[THREADS / 32], s_sq[THREADS / 32];
+    float a = head ? team : 0.f, b = head ? team * team : 0.f;
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+    if (lane == 0) { s_sum[threadIdx.x >> 5] = a; s_sq[threadIdx.x >> 5] = b; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float ta = 0.f, tb = 0.f;
+      for (int wi = 0; wi < THREADS / 32; ++wi) { ta += s_sum[wi]; tb += s_sq[wi]; }
+      atomicAdd(&io.stats->reward_sum, (double)ta);
+      atomicAdd(&io.stats->reward_sq_sum, (double)tb);
     }
   }
 }

@@ -668,6 +668,42 @@ int fpv_gate_env_step(const fpv_gate_env_params_t* p, const void* state, int64_t
   return check_launch("fpv_gate_env_step");
 }
 
+int fpv_gate_race_step(const fpv_drone_params_t* p, const fpv_drone_io_t* io, const fpv_gate_env_params_t* gp, void* prev,
+                       int32_t* progress, float* agent_reward, float* env_reward, uint8_t* env_done, float* obs,
+                       void* stream) {
+  DroneK k;
+  DroneIO d;
+  int ang = 0;
+  bool general = false;
+  if (!io) return fail(FPV_EINVAL, "fpv_gate_race_step: null io");
+  if (int rc = check_gate_params(gp, io->n, "fpv_gate_race_step")) return rc;
+  const int rc = prepare_drone(p, io, true, k, d, ang, general);
+  if (rc != FPV_OK) return rc > 0 ? FPV_OK : rc;
+  if (!prev || !progress || !env_reward || !env_done) return fail(FPV_EINVAL, "fpv_gate_race_step: null pointer");
+  if (!aligned16(obs)) return fail(FPV_EINVAL, "fpv_gate_race_step: obs must be 16-byte aligned");
+  const bool wind = p->wind[0] != 0.f || p->wind[1] != 0.f || p->wind[2] != 0.f;
+  if (general || io->wind_env || wind || (p->flags & FPV_F_FREEZE_DONE))
+    return fail(FPV_EINVAL, "fpv_gate_race_step: only the hot-path configuration is supported (no obstacles, overrides, wind "
+                            "or FPV_F_FREEZE_DONE); call fpv_drone_step and fpv_gate_env_step instead");
+  const size_t smem = (k.flags & FPV_F_THRUST_LUT) ? sizeof(float) * (size_t)k.lut_n : 0;
+  constexpr int T = 256;   // same CTA size as gate_env_step_kernel: the block-level reward sums group the same envs
+  auto launch = [&](auto kern) {
+    static size_t attr_set = 0;
+    if (smem > 48 * 1024 && smem > attr_set) {
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      attr_set = smem;
+    }
+    kern<<<(unsigned)((io->n + T - 1) / T), T, smem, (cudaStream_t)stream>>>(k, d, *gp, (float2*)prev, progress, agent_reward,
+                                                                            env_reward, env_done, (float4*)obs);
+  };
+  if (ang == 4) launch(fpv::gate_race_fused_kernel<4, T>);
+  else if (ang == 3) launch(fpv::gate_race_fused_kernel<3, T>);
+  else if (ang == 2) launch(fpv::gate_race_fused_kernel<2, T>);
+  else if (ang == 1) launch(fpv::gate_race_fused_kernel<1, T>);
+  else launch(fpv::gate_race_fused_kernel<0, T>);
+  return check_launch("fpv_gate_race_step");
+}
+
 namespace {
 int make_cam(const fpv_camera_params_t* c, fpv::CamK& k, const char* who) {
   if (!c) return fail(FPV_EINVAL, "%s: null camera params", who);

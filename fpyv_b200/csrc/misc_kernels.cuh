@@ -9,10 +9,12 @@ namespace fpv {
 // Quaternion <-> matrix (reference conventions: src/utils/helper_functions.py:65-80, :100-117)
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void quat_to_matrix(float4 q, float (&R)[9]) {  // q = (w,x,y,z) in .x .y .z .w
+  // explicit fused multiply-adds in a fixed order: the same bits in every kernel this is inlined in
   const float w = q.x, x = q.y, y = q.z, z = q.w;
-  R[0] = 1.f - 2.f * y * y - 2.f * z * z; R[1] = 2.f * x * y - 2.f * z * w;       R[2] = 2.f * x * z + 2.f * y * w;
-  R[3] = 2.f * x * y + 2.f * z * w;       R[4] = 1.f - 2.f * x * x - 2.f * z * z; R[5] = 2.f * y * z - 2.f * x * w;
-  R[6] = 2.f * x * z - 2.f * y * w;       R[7] = 2.f * y * z + 2.f * x * w;       R[8] = 1.f - 2.f * x * x - 2.f * y * y;
+  const float x2 = x + x, y2 = y + y, z2 = z + z;
+  R[0] = __fmaf_rn(-y2, y, __fmaf_rn(-z2, z, 1.f)); R[1] = __fmaf_rn(x2, y, -(z2 * w));              R[2] = __fmaf_rn(x2, z, y2 * w);
+  R[3] = __fmaf_rn(x2, y, z2 * w);                  R[4] = __fmaf_rn(-x2, x, __fmaf_rn(-z2, z, 1.f)); R[5] = __fmaf_rn(y2, z, -(x2 * w));
+  R[6] = __fmaf_rn(x2, z, -(y2 * w));               R[7] = __fmaf_rn(y2, z, x2 * w);                  R[8] = __fmaf_rn(-x2, x, __fmaf_rn(-y2, y, 1.f));
 }
 
 // Robust matrix -> unit quaternion (Shepperd's branch on the largest diagonal term; the reference's

@@ -88,14 +88,27 @@ class GateRaceEnv:
             _lib.ptr(self._progress), _lib.ptr(self._agent_reward), _lib.ptr(self._env_reward), _lib.ptr(self._env_done),
             _lib.ptr(self._obs), C.c_void_p(d._stats.data_ptr()) if stats else None, _lib.current_stream(self.device)))
 
-    def step(self, action):
+    def step(self, action, fused=True):
         """action: dict {agent name: [num_envs,4]} or tensor [num_envs, agents_per_env, 4] (roll, pitch, yaw, throttle).
-        Returns (obs dict, reward [num_envs], done [num_envs] bool, {})."""
+        Returns (obs dict, reward [num_envs], done [num_envs] bool, {}).
+        fused=True: dynamics and env step in ONE launch (fpv_gate_race_step: one agent per thread, state read and
+        written once); fused=False: fpv_drone_step (packed hot kernel) followed by fpv_gate_env_step."""
         if isinstance(action, dict):
             action = torch.stack([torch.as_tensor(action[k]).to(self.device, torch.float32) for k in self.agent_names], dim=1)
-        act = torch.as_tensor(action).to(self.device, torch.float32).reshape(self.n_agents, 4)
-        self.drone.step(act, return_obs=False)
-        self._run_env_kernel(self.drone._done)
+        act = torch.as_tensor(action).to(self.device, torch.float32).reshape(self.n_agents, 4).contiguous()
+        d = self.drone
+        if fused and d._fast_ok and not (d._flags & _lib.F_FREEZE_DONE):
+            d._last_action = act
+            d._chain_ready = False
+            d._p.flags = d._flags
+            d._io.actions = act.data_ptr()
+            d._io.chunk_epoch = None
+            _lib.check(self._lib.fpv_gate_race_step(
+                d._p_ref, d._io_ref, C.byref(self._p), _lib.ptr(self._prev), _lib.ptr(self._progress), _lib.ptr(self._agent_reward),
+                _lib.ptr(self._env_reward), _lib.ptr(self._env_done), _lib.ptr(self._obs), _lib.current_stream(self.device)))
+        else:
+            d.step(act, return_obs=False)      # (also the first call: it configures the drone's io block)
+            self._run_env_kernel(d._done)
         return self._obs_dict(), self._env_reward, self._env_done.bool(), {}
 
     @property

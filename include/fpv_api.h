@@ -317,6 +317,14 @@ int fpv_gate_env_step(const fpv_gate_env_params_t* params, const void* state, in
                       const uint8_t* agent_done, void* prev, int32_t* progress, float* agent_reward, float* env_reward,
                       uint8_t* env_done, float* obs, fpv_stats_t* stats, void* stream);
 
+/* fpv_drone_step and fpv_gate_env_step in ONE launch (one agent per thread, state read once and written once):
+ * bit-identical to fpv_drone_step with FPV_F_SCALAR followed by fpv_gate_env_step.  Hot-path configuration of the
+ * dynamics only (ground plane, no obstacles / overrides / per-env wind, no FPV_F_FREEZE_DONE); io->done receives the
+ * agents' crash flags, io->stats (may be NULL) the dynamics counters and the reward sums. */
+int fpv_gate_race_step(const fpv_drone_params_t* params, const fpv_drone_io_t* io, const fpv_gate_env_params_t* gates,
+                       void* prev, int32_t* progress, float* agent_reward, float* env_reward, uint8_t* env_done, float* obs,
+                       void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Chase pipeline: the callers on either side of Drone.step in src/core/simulator.py:98-110 --
  *   target_img = drone.camera.render_depth_image([target], max_depth)      components.py:614-629

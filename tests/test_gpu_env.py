@@ -100,3 +100,34 @@ def test_env_argument_validation():
     p.agents_per_env = 4
     assert lib.fpv_gate_env_step(C.byref(p), None, 6, 6, None, None, None, None, None, None, None, None, None) == -22
     assert b"multiple" in lib.fpv_last_error()
+
+
+@pytest.mark.parametrize("A", [32, 8])
+def test_fused_env_step_is_bit_identical_to_the_two_launch_path(A):
+    """fpv_gate_race_step (dynamics + env step in one launch) against fpv_drone_step with the scalar kernel followed by
+    fpv_gate_env_step: state, rewards, terminations, observations, race bookkeeping and statistics, bit for bit, over a
+    rollout with gate passes and crashes."""
+    from fpyv_b200.env import GateRaceEnv
+    envs = 512
+    kw = dict(num_envs=envs, agents_per_env=A, device=DEV, substeps=4, dt=2e-3, thrust_lut=2049, packed=False, seed=3,
+              spawn_height=(0.3, 2.5))
+    a, b = GateRaceEnv(None, **kw), GateRaceEnv(None, **kw)
+    a.reset()
+    b.reset()
+    g = torch.Generator(device=DEV).manual_seed(9)
+    passes = crashes = 0
+    for t in range(60):
+        act = torch.rand(envs, A, 4, device=DEV, generator=g) * 2 - 1
+        act[..., 3] = act[..., 3] * 0.25 - 0.72           # around hover and below: some agents sink to the ground
+        oa, ra, da, _ = a.step(act, fused=True)
+        ob, rb, db, _ = b.step(act, fused=False)
+        assert torch.equal(ra, rb) and torch.equal(da, db), t
+        assert torch.equal(a._obs, b._obs), t
+        crashes += int(b.drone.done.sum())
+    torch.cuda.synchronize()
+    assert torch.equal(a.drone._state, b.drone._state)
+    assert torch.equal(a._progress, b._progress) and torch.equal(a._prev, b._prev)
+    assert torch.equal(a.agent_reward, b.agent_reward)
+    sa, sb = a.episode_stats(), b.episode_stats()
+    assert all(sa[k] == sb[k] or (sa[k] != sa[k] and sb[k] != sb[k]) for k in sa), (sa, sb)
+    assert crashes > 0

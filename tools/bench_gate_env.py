@@ -46,6 +46,17 @@ def main():
         t_env.append(e1.elapsed_time(e2))
     med = lambda v: sorted(v)[len(v) // 2]
     ms_all, ms_env = med(t_all), med(t_env)
+    # the same env step in ONE launch (fpv_gate_race_step: dynamics + env logic, one agent per thread)
+    t_fused = []
+    for i in range(30):
+        flush.zero_()
+        e0, e1 = (torch.cuda.Event(enable_timing=True) for _ in range(2))
+        e0.record()
+        env.step(acts[i % 4], fused=True)
+        e1.record()
+        torch.cuda.synchronize()
+        t_fused.append(e0.elapsed_time(e1))
+    ms_fused = med(t_fused)
     env_bytes = n * 157 + envs * 5
     try:
         peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
@@ -58,6 +69,10 @@ def main():
                       "config": {"workload": "BASELINE.json configs[4]: 262,144 drones = 8,192 envs x 32 agents, 8 substeps x 1 ms, "
                                              "8-gate track (generate_track), team reward / termination by warp reduction"},
                       "ms_per_env_step": ms_all, "ms_dynamics": ms_all - ms_env, "ms_env_kernel": ms_env,
+                      "fused_single_launch": {"ms_per_env_step": ms_fused, "agent_steps_per_sec": n / (ms_fused * 1e-3),
+                                              "hbm_GBps_algorithmic": n * (64 + 64 + 16 + 1 + 12 + 12 + 4 + 64) / (ms_fused * 1e-3) / 1e9,
+                                              "api": "GateRaceEnv.step(fused=True) = fpv_gate_race_step; bit-identical to the "
+                                                     "scalar dynamics kernel + fpv_gate_env_step"},
                       "env_steps_per_sec": envs / (ms_all * 1e-3),
                       "roofline": {"kernel": "fpv::gate_env_step_kernel", "bound": "hbm", "achieved": ach, "peak": peak,
                                    "unit": "GB/s", "frac": ach / peak, "peak_source": src,
