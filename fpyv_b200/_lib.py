@@ -181,6 +181,38 @@ def ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
-def current_stream(device):
+def _raw_stream_getter():
+    """torch's raw current-stream getter (an int handle, ~4x cheaper than building a torch.cuda.Stream object); the
+    public API is the fallback."""
     import torch
-    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    fn = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+    if fn is not None:
+        return fn
+    return lambda index: torch.cuda.current_stream(index).cuda_stream
+
+
+_raw_stream = None
+
+
+def raw_stream(device_index: int) -> int:
+    """cudaStream_t of torch's current stream on `device_index`, as an int."""
+    global _raw_stream
+    if _raw_stream is None:
+        _raw_stream = _raw_stream_getter()
+    return _raw_stream(device_index)
+
+
+def current_stream(device):
+    """torch's current stream on `device` for a library call.  The library launches on the CURRENT CUDA device (the CUDA
+    runtime's convention; fpv_api.h "Conventions"), so a call for buffers on another device is refused here with a clear
+    message instead of failing inside the launch.  (The allocation-free fast path of BatchedDrone.step skips this check;
+    there the launch itself fails, just as loudly.)"""
+    import torch
+    index = device.index if isinstance(device, torch.device) else torch.device(device).index
+    cur = torch.cuda.current_device()
+    if index is None:
+        index = cur
+    elif index != cur:
+        raise RuntimeError(f"fpyv_b200: the buffers live on cuda:{index} but the current CUDA device is cuda:{cur}; "
+                           f"wrap the call in `with torch.cuda.device({index}):` or call torch.cuda.set_device({index})")
+    return C.c_void_p(raw_stream(index))

@@ -44,17 +44,39 @@ using fpv::DroneIO;
 using fpv::DroneK;
 using fpv::F2;
 
-int sm_count_of_current_device() {
-  static int cached[64] = {0};
+// cudaFuncSetAttribute, occupancy and the SM count are properties of (kernel, DEVICE): one process may drive several
+// devices through this library, so every launch-fact cache below is indexed by the current device.
+constexpr int kMaxDevices = 64;
+
+int current_device_slot() {   // -1 = beyond the cached range: such devices recompute their facts on every call
   int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return -1;
+  return dev;
+}
+
+int sm_count_of_current_device() {
+  static int cached[kMaxDevices] = {0};
+  const int slot = current_device_slot();
+  if (slot >= 0 && cached[slot]) return cached[slot];
+  int dev = 0, v = 0;
   cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64) dev = 0;
-  if (cached[dev] == 0) {
-    int v = 0;
-    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
-    cached[dev] = v > 0 ? v : 148;
-  }
-  return cached[dev];
+  cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+  v = v > 0 ? v : 148;
+  if (slot >= 0) cached[slot] = v;
+  return v;
+}
+
+// Dynamic shared memory a kernel has been opted into, per device.
+struct SmemOptIn {
+  size_t bytes[kMaxDevices] = {};
+};
+
+template <class K>
+void opt_in_smem(K kern, SmemOptIn& c, size_t smem, size_t above = 48 * 1024) {
+  const int slot = current_device_slot();
+  if (smem <= above || (slot >= 0 && smem <= c.bytes[slot])) return;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (slot >= 0) c.bytes[slot] = smem;
 }
 
 // Persistent launch: one wave of CTAs (SMs x resident CTAs per SM) walking the tiles.
@@ -63,13 +85,16 @@ void launch_drone(const DroneK& k, const DroneIO& io, cudaStream_t st) {
   constexpr int L = fpv::Lane<V>::N;
   auto kern = fpv::drone_step_kernel<V, ANG, GENERAL, kThreads, GENERAL ? 3 : FPV_MINB>;
   const size_t smem = (k.flags & FPV_F_THRUST_LUT) ? sizeof(float) * (size_t)k.lut_n : 0;
-  static int occ_cache[2] = {0, 0};  // [lut?]; per template instantiation
-  int& occ = occ_cache[smem ? 1 : 0];
+  static SmemOptIn opted;                       // per template instantiation
+  static int occ_cache[kMaxDevices][2] = {};    // [device][lut?]
+  if (smem > 48 * 1024) opt_in_smem(kern, opted, 200 * 1024);
+  const int slot = current_device_slot();
+  int occ = slot >= 0 ? occ_cache[slot][smem ? 1 : 0] : 0;
   if (occ == 0) {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     int o = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, kThreads, smem > 48 * 1024 ? 200 * 1024 : smem);
     occ = o > 0 ? o : 1;
+    if (slot >= 0) occ_cache[slot][smem ? 1 : 0] = occ;
   }
   const long long per_block = (long long)kThreads * L;
   const long long tiles = (io.n + per_block - 1) / per_block;
@@ -93,18 +118,17 @@ bool launch_drone_tma(const DroneK& k, const DroneIO& io, cudaStream_t st) {
   const size_t smem = (size_t)lut_bytes + (size_t)STAGES * (FPV_DRONE_PLANES + 1) * TILE * sizeof(float4) +
                       (size_t)(kThreads / 32) * STAGES * sizeof(unsigned long long);
   if (smem > 220 * 1024) return false;
-  static size_t attr_set = 0;  // per instantiation: largest dynamic smem opted in so far
-  static int occ_cache = 0;
-  static size_t occ_smem = 0;
-  if (smem > attr_set) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_set = smem;
-  }
-  if (occ_cache == 0 || occ_smem != smem) {
+  static SmemOptIn opted;  // per instantiation: largest dynamic smem opted in so far, per device
+  static int occ_of[kMaxDevices] = {};
+  static size_t occ_smem[kMaxDevices] = {};
+  opt_in_smem(kern, opted, smem, 0);
+  const int slot = current_device_slot();
+  int occ_cache = (slot >= 0 && occ_smem[slot] == smem) ? occ_of[slot] : 0;
+  if (occ_cache == 0) {
     int o = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, kThreads, smem);
     occ_cache = o > 0 ? o : 1;
-    occ_smem = smem;
+    if (slot >= 0) { occ_of[slot] = occ_cache; occ_smem[slot] = smem; }
   }
   const long long tiles = (io.n + TILE - 1) / TILE;
   static const int occ_env = tune_env("FPV_TUNE_OCC", 0);
@@ -441,11 +465,8 @@ int fpv_drone_rollout(const fpv_drone_params_t* p, const fpv_drone_io_t* io, con
   d.chunk_epoch = nullptr;
   const size_t smem = (k.flags & FPV_F_THRUST_LUT) ? sizeof(float) * (size_t)k.lut_n : 0;
   auto launch = [&](auto kern) {
-    static size_t attr_set = 0;
-    if (smem > 48 * 1024 && smem > attr_set) {
-      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      attr_set = smem;
-    }
+    static SmemOptIn opted;
+    opt_in_smem(kern, opted, smem);
     int occ = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem);
     if (occ < 1) occ = 1;
@@ -688,11 +709,8 @@ int fpv_gate_race_step(const fpv_drone_params_t* p, const fpv_drone_io_t* io, co
   const size_t smem = (k.flags & FPV_F_THRUST_LUT) ? sizeof(float) * (size_t)k.lut_n : 0;
   constexpr int T = 256;   // same CTA size as gate_env_step_kernel: the block-level reward sums group the same envs
   auto launch = [&](auto kern) {
-    static size_t attr_set = 0;
-    if (smem > 48 * 1024 && smem > attr_set) {
-      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      attr_set = smem;
-    }
+    static SmemOptIn opted;
+    opt_in_smem(kern, opted, smem);
     kern<<<(unsigned)((io->n + T - 1) / T), T, smem, (cudaStream_t)stream>>>(k, d, *gp, (float2*)prev, progress, agent_reward,
                                                                             env_reward, env_done, (float4*)obs);
   };
@@ -771,11 +789,8 @@ int fpv_camera_target_pixel(const fpv_camera_params_t* cam, const double* pose, 
   const size_t smem = (((size_t)k.W * k.H + 31) / 32) * sizeof(unsigned);
   if (smem > 200 * 1024) return fail(FPV_EINVAL, "fpv_camera_target_pixel: %dx%d frame bitmap does not fit in shared memory", k.W, k.H);
   if (n == 0) return FPV_OK;
-  static size_t attr_set = 0;
-  if (smem > 48 * 1024 && smem > attr_set) {
-    cudaFuncSetAttribute(fpv::camera_target_pixel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_set = smem;
-  }
+  static SmemOptIn opted;
+  opt_in_smem(fpv::camera_target_pixel_kernel, opted, smem);
   fpv::camera_target_pixel_kernel<<<(unsigned)n, 256, smem, (cudaStream_t)stream>>>(
       k, pose, (const double4*)points, n_points, n_objects, boxes, obj_offset, max_depth, pixel, seen);
   return check_launch("fpv_camera_target_pixel");
@@ -903,11 +918,8 @@ int acro_launch(const fpv_acro_params_t* p, void* state, int64_t n, int64_t plan
   if (n == 0) return FPV_OK;
   const size_t smem = (p->flags & FPV_F_THRUST_LUT) ? sizeof(float) * (size_t)lut_n : 0;
   auto launch = [&](auto kern, int envs_per_thread) {
-    static size_t attr_set = 0;
-    if (smem > 48 * 1024 && smem > attr_set) {
-      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      attr_set = smem;
-    }
+    static SmemOptIn opted;
+    opt_in_smem(kern, opted, smem);
     const long long tile = (long long)kThreads * envs_per_thread;
     kern<<<(unsigned)((n + tile - 1) / tile), kThreads, smem, (cudaStream_t)stream>>>(
         k, (float4*)state, n, plane_stride, (const float4*)actions, lut, done, (float4*)motor_thrust, (const float4*)reset_state, stats,

@@ -102,6 +102,8 @@ class BatchedDrone:
         self._chunk_epoch_ptr = self._chunk_epoch.data_ptr()
         self._epoch = 0
         self._chain_ready = False    # True while the last writer of the state was step() itself
+        self._chain_armed = False    # True while _io.chunk_epoch is set
+        self._dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
         self._lut = None
         if thrust_lut:
             self._lut = torch.from_numpy(config.thrust_table(c, int(thrust_lut), lut_source)).to(dev)
@@ -268,8 +270,10 @@ class BatchedDrone:
             self._io.epoch = self._epoch & 0xFFFFFFFF
             self._epoch += 1
             self._io.chunk_epoch = self._chunk_epoch_ptr
-        else:
+            self._chain_armed = True
+        elif self._chain_armed:
             self._io.chunk_epoch = None
+            self._chain_armed = False
         # fast path (the RL inner loop): device float32 actions, nothing else changed since the last full call --
         # one pointer store and one C call, no allocation (so it can be captured in a CUDA graph)
         if (self._fast_ok and wind_velocity_vector is None and object_list is None and rotation_matrix is None
@@ -278,7 +282,7 @@ class BatchedDrone:
             self._last_action = action
             self._io.actions = action.data_ptr()
             self._p.flags = (self._flags | _lib.F_CHAINED) if chain_now else self._flags
-            rc = self._step_fn(self._p_ref, self._io_ref, torch.cuda.current_stream(dev).cuda_stream)
+            rc = self._step_fn(self._p_ref, self._io_ref, _lib.raw_stream(self._dev_index))
             if rc:
                 _lib.check(rc)
             return self.observe() if return_obs else None

@@ -15,7 +15,10 @@
  *     structs are HOST pointers to PODs that are copied by value into the launch (kernel-parameter
  *     constant bank).  The library keeps no state about the simulation, so it is re-entrant and
  *     usable from one host thread per GPU; the only things it caches are occupancy numbers per
- *     kernel and, for fpv_drone_step_host, two copy streams + events per device.
+ *     kernel and device and, for fpv_drone_step_host, two copy streams + events per device.
+ *   - Like the CUDA runtime, every call launches on the CURRENT device (cudaSetDevice): the
+ *     buffers and `stream` must belong to it.  One process may drive several devices by switching
+ *     the current device between calls.
  *   - Launches are asynchronous and ordered on `stream` (a cudaStream_t / CUstream handle; 0 =
  *     legacy default stream).  No hidden synchronisation, no allocation.  Two documented
  *     relaxations of plain stream order exist, both opt-in: FPV_F_CHAINED (a launch may overlap the

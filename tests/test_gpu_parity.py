@@ -997,3 +997,40 @@ def test_step_host_sticks_matches_the_joystick_path():
     assert torch.equal(a._state, b._state)
     with pytest.raises(ValueError):
         a.step_host_sticks(torch.zeros((n, 4), dtype=torch.int32), done_h)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_one_process_driving_two_devices():
+    """The library's launch facts (dynamic shared memory opt-in, occupancy, SM count, host-step copy streams) are cached
+    per DEVICE: one process stepping batches on cuda:0 and cuda:1 alternately gets the single-device result on both,
+    and a call made while another device is current is refused with a message."""
+    from fpyv_b200 import BatchedDrone
+    n, K = 100_000, 8
+    g = torch.Generator().manual_seed(31)
+    pos = torch.randn(n, 3, generator=g) * 5 + torch.tensor([0.0, 0.0, 3.0])
+    vel, rpy = torch.randn(n, 3, generator=g), (torch.rand(n, 3, generator=g) * 2 - 1) * 30
+    acts = [torch.rand(n, 4, generator=g) * 2 - 1 for _ in range(6)]
+    host_done = [torch.empty(n, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+    pinned = [a.pin_memory() for a in acts]
+    ds = []
+    for i in range(2):
+        with torch.cuda.device(i):
+            d = BatchedDrone(None, num_envs=n, device=f"cuda:{i}", substeps=K, dt=1e-3, thrust_lut=2049, auto_reset=True)
+            d.reset(pos.to(d.device), vel.to(d.device), rpy.to(d.device))
+            ds.append(d)
+    for t, a in enumerate(acts):
+        for i, d in enumerate(ds):
+            with torch.cuda.device(i):
+                if t < 3:
+                    d.step(a.to(d.device), return_obs=False)
+                elif t < 5:
+                    d.step_host(pinned[t], host_done[i])
+                else:
+                    d.rollout(a.to(d.device)[None].contiguous())
+    for i in range(2):
+        torch.cuda.synchronize(i)
+    assert torch.equal(ds[0]._state.cpu(), ds[1]._state.cpu())
+    assert torch.equal(host_done[0], host_done[1])
+    with torch.cuda.device(0):
+        with pytest.raises(RuntimeError, match="current CUDA device"):
+            ds[1].reset(pos.to("cuda:1"), vel.to("cuda:1"), rpy.to("cuda:1"))
