@@ -297,10 +297,20 @@ def run_gpu(args):
         return
 
     # ---- end to end through the public API with HOST buffers (pinned): H2D actions, step, D2H done flags
-    host_actions = [torch.empty(n, 4, dtype=torch.float32, pin_memory=True).uniform_(-1, 1) for _ in range(2)]
+    # A pinned buffer the CPU has just written sits (dirty) in the CPU caches, and DMA reads that hit there run at ~40 % of
+    # the PCIe rate until the lines are evicted (8 MiB in 413 us vs 158 us, profiles/r1_h2d_cpu_cache_effect.txt); which of
+    # the static input buffers is in that state would depend on what the host touched last.  The synthetic inputs are
+    # therefore generated on the device and written into the pinned buffers by a D2H copy: no line of them is in a CPU cache.
+    host_actions = [torch.empty(n, 4, dtype=torch.float32, pin_memory=True) for _ in range(2)]
+    for h in host_actions:
+        h.copy_(torch.rand(n, 4, device=dev, generator=gen) * 2 - 1)
     host_done = torch.empty(n, dtype=torch.uint8, pin_memory=True)
-    for i in range(max(3, W)):
+    torch.cuda.synchronize()
+    crashed = 0
+    for i in range(max(3, W)):      # the timed loop's body exactly (the first CPU-side read of the flags costs milliseconds)
         drone.step_host(host_actions[i % 2], host_done, slices=E2E_SLICES)
+        torch.cuda.current_stream().synchronize()
+        crashed += int(host_done[:64].sum())
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -318,9 +328,14 @@ def run_gpu(args):
     # ---- the same end-to-end step fed the way the reference's simulator feeds it (step(action=None): raw joystick axes,
     #      components.py:227-228, :250-253) in compact transport form: uint16[n][4] raw sticks, calibrated on the device.
     #      Extra metric next to `e2e` (8 B/env instead of 16 over PCIe); `e2e` itself stays on float32 actions.
-    host_sticks = [torch.randint(0, 65536, (n, 4), dtype=torch.int32).to(torch.uint16).pin_memory() for _ in range(2)]
+    host_sticks = [torch.empty((n, 4), dtype=torch.uint16, pin_memory=True) for _ in range(2)]
+    for h in host_sticks:
+        h.copy_(torch.randint(0, 65536, (n, 4), dtype=torch.int32, device=dev, generator=gen).to(torch.uint16))
+    torch.cuda.synchronize()
     for i in range(max(3, W)):
         drone.step_host_sticks(host_sticks[i % 2], host_done, slices=E2E_SLICES)
+        torch.cuda.current_stream().synchronize()
+        crashed += int(host_done[:64].sum())
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -400,7 +415,10 @@ def run_gpu(args):
             "env_substeps_per_sec": value * SUBSTEPS,
             "e2e": {"value": total_envs * K / (ms_e2e * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": 16 * n * world,
                     "d2h_bytes_per_step": n * world, "ms_per_step": ms_e2e / K,
-                    "api": "BatchedDrone.step_host(pinned actions) -> pinned done flags = fpv_drone_step_host: 4 env slices pipelined over H2D / step / D2H streams inside the library; host waits every step"},
+                    "api": "BatchedDrone.step_host(pinned actions) -> pinned done flags = fpv_drone_step_host: 4 env slices pipelined over H2D / step / D2H streams inside the library; host waits every step",
+                    "host_buffers": "2 static pinned action buffers alternated (not rewritten inside the loop), filled by a D2H copy of "
+                                    "device-generated sticks so the DMA reads are served by DRAM (a buffer still dirty in the CPU "
+                                    "caches copies 1.7-2.6x slower, profiles/r1_h2d_cpu_cache_effect.txt)"},
             "e2e_raw_sticks": {"value": total_envs * K / (ms_e2e_sticks * 1e-3), "unit": "env-steps/s", "ms_per_step": ms_e2e_sticks / K,
                                "h2d_bytes_per_step": 8 * n * world, "d2h_bytes_per_step": n * world,
                                "api": "BatchedDrone.step_host_sticks(pinned uint16 raw sticks [n,4]) = fpv_drone_step_host_sticks: the "
