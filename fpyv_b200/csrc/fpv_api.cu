@@ -393,6 +393,29 @@ HostPipe& host_pipe_of_current_device() {
   }
   return p;
 }
+// Env ranges of a sliced host step: (slices - 1) equal ranges followed by one SHORT tail range.  Everything after the
+// last byte of the H2D copy is exposed latency (the last slice's launch and its D2H copy), so the last slice is the
+// smallest one a launch still fills (65,536 envs or n / 16); ranges are multiples of 64 envs (the kernels' chunk) and
+// at least 65,536 envs (below that a slice is launch-latency bound).  Returns the number of ranges; bound[i]..bound[i+1].
+int host_slice_bounds(long long n, int slices, long long* bound) {
+  constexpr long long kMin = 65536;
+  if (slices <= 0) slices = 4;
+  if (slices > 16) slices = 16;
+  long long body = n;
+  if (slices >= 2 && n >= 4 * kMin) {
+    long long tail = n / 16 > kMin ? n / 16 : kMin;
+    body = (n - tail) / 64 * 64;   // the tail range starts on a chunk boundary too
+    --slices;
+  }
+  long long count = body / kMin < slices ? body / kMin : slices;
+  if (count < 1) count = 1;
+  const long long per = ((body + count - 1) / count + 63) / 64 * 64;
+  int c = 0;
+  bound[0] = 0;
+  for (long long a = 0; a < body; a += per) bound[++c] = a + per < body ? a + per : body;
+  if (body < n) bound[++c] = n;
+  return c;
+}
 }  // namespace
 
 int fpv_drone_step_host(const fpv_drone_params_t* p, const fpv_drone_io_t* io, const float* actions_host,
@@ -402,12 +425,9 @@ int fpv_drone_step_host(const fpv_drone_params_t* p, const fpv_drone_io_t* io, c
   if (!io->actions || !io->done) return fail(FPV_EINVAL, "fpv_drone_step_host: io.actions / io.done must be device staging buffers");
   if (io->n < 0 || io->plane_stride < io->n) return fail(FPV_EINVAL, "fpv_drone_step_host: bad n/stride");
   if (io->n == 0) return FPV_OK;
-  if (slices <= 0) slices = 4;
-  if (slices > 16) slices = 16;
   const long long n = io->n;
-  long long per = (n + slices - 1) / slices;
-  per = (per + 63) / 64 * 64;
-  if (per < 65536) per = 65536;   // below this a slice is launch-latency bound
+  long long bound[18];
+  const int n_slices = host_slice_bounds(n, slices, bound);
   HostPipe& hp = host_pipe_of_current_device();
   if (!hp.ok) return fail(FPV_ECUDA, "fpv_drone_step_host: could not create the copy streams");
   cudaStream_t st = (cudaStream_t)stream;
@@ -416,9 +436,8 @@ int fpv_drone_step_host(const fpv_drone_params_t* p, const fpv_drone_io_t* io, c
   cudaStreamWaitEvent(hp.out, hp.ready, 0);
   fpv_drone_params_t pp = *p;
   pp.flags &= ~FPV_F_CHAINED;
-  int c = 0;
-  for (long long a = 0; a < n; a += per, ++c) {
-    const long long b = a + per < n ? a + per : n;
+  for (int c = 0; c < n_slices; ++c) {
+    const long long a = bound[c], b = bound[c + 1];
     cudaMemcpyAsync((char*)io->actions + 16 * a, (const char*)actions_host + 16 * a, (size_t)(16 * (b - a)), cudaMemcpyHostToDevice, hp.in);
     cudaEventRecord(hp.h2d[c], hp.in);
     cudaStreamWaitEvent(st, hp.h2d[c], 0);
@@ -573,12 +592,9 @@ int fpv_drone_step_host_sticks(const fpv_drone_params_t* p, const fpv_drone_io_t
   fpv::StickK k;
   if (int rc = make_sticks(calib, k, "fpv_drone_step_host_sticks")) return rc;
   if (io->n == 0) return FPV_OK;
-  if (slices <= 0) slices = 4;
-  if (slices > 16) slices = 16;
   const long long n = io->n;
-  long long per = (n + slices - 1) / slices;
-  per = (per + 63) / 64 * 64;
-  if (per < 65536) per = 65536;
+  long long bound[18];
+  const int n_slices = host_slice_bounds(n, slices, bound);
   HostPipe& hp = host_pipe_of_current_device();
   if (!hp.ok) return fail(FPV_ECUDA, "fpv_drone_step_host_sticks: could not create the copy streams");
   cudaStream_t st = (cudaStream_t)stream;
@@ -587,9 +603,8 @@ int fpv_drone_step_host_sticks(const fpv_drone_params_t* p, const fpv_drone_io_t
   cudaStreamWaitEvent(hp.out, hp.ready, 0);
   fpv_drone_params_t pp = *p;
   pp.flags &= ~FPV_F_CHAINED;
-  int c = 0;
-  for (long long a = 0; a < n; a += per, ++c) {
-    const long long b = a + per < n ? a + per : n;
+  for (int c = 0; c < n_slices; ++c) {
+    const long long a = bound[c], b = bound[c + 1];
     cudaMemcpyAsync((char*)sticks_dev + 8 * a, (const char*)sticks_host + 8 * a, (size_t)(8 * (b - a)), cudaMemcpyHostToDevice, hp.in);
     cudaEventRecord(hp.h2d[c], hp.in);
     cudaStreamWaitEvent(st, hp.h2d[c], 0);

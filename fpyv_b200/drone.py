@@ -479,11 +479,7 @@ class BatchedDrone:
         return done_host
 
     def _slice_bounds(self, slices):
-        """Env ranges of a sliced step as the library cuts them: multiples of 64 envs, at least 64K envs each."""
-        n = self.num_envs
-        per = -(-n // max(1, int(slices)))
-        per = max(65536, -(-per // 64) * 64)
-        return [(a, min(n, a + per)) for a in range(0, n, per)]
+        return host_slice_bounds(self.num_envs, slices)
 
     # ------------------------------------------------------------------ episode statistics
     def episode_stats(self, all_reduce: bool = False, reset: bool = False) -> dict:
@@ -542,3 +538,21 @@ class Drone:
     thrust = property(lambda self: self._np(self._b.thrust[0]))
     acceleration = property(lambda self: self._np(self._b.acceleration[0]))
     motors_orientation = property(lambda self: self._np(self._b.motors_orientation[0]))
+
+
+def host_slice_bounds(n: int, slices: int):
+    """Env ranges of a sliced host step as the library cuts them (host_slice_bounds, fpv_api.cu): up to slices-1 equal
+    ranges of at least ~65,536 envs and one short tail range (n/16, at least 65,536 envs), all starting on 64-env
+    boundaries."""
+    k_min = 65536
+    slices = min(16, int(slices)) if int(slices) > 0 else 4
+    body = n
+    if slices >= 2 and n >= 4 * k_min:
+        body = (n - max(n // 16, k_min)) // 64 * 64
+        slices -= 1
+    count = max(1, min(slices, body // k_min))
+    per = -(-(-(-body // count)) // 64) * 64
+    out = [(a, min(body, a + per)) for a in range(0, body, per)]
+    if body < n:
+        out.append((body, n))
+    return out

@@ -186,8 +186,9 @@ int fpv_drone_step(const fpv_drone_params_t* params, const fpv_drone_io_t* io, v
 /* Drone.step with HOST buffers (the call a CPU-side caller of the reference makes: NumPy in, flags out):
  * actions_host float[n][4] and done_host uint8[n] are host pointers (page-locked memory for full speed); io->actions
  * must point at a device staging buffer float4[n], io->done at a device uint8[n].  The batch is cut into `slices` env
- * ranges (multiples of 64 envs) pipelined over three streams -- H2D copy of slice c+1 | step of slice c | D2H copy of
- * slice c-1 -- because the call is PCIe-bound (16 B/env in, 1 B/env out).  Everything is ordered after the work already
+ * ranges (multiples of 64 envs, at least 65,536 envs each; the last one short -- n/16 -- because everything after the
+ * last H2D byte is exposed latency) pipelined over three streams -- H2D copy of slice c+1 | step of slice c | D2H copy
+ * of slice c-1 -- because the call is PCIe-bound (16 B/env in, 1 B/env out).  Everything is ordered after the work already
  * queued on `stream`, and `stream` is joined to the last copy: synchronising it means done_host is valid.  The two
  * extra streams and the events are created once per device and cached inside the library (the only state it keeps).
  * io->chunk_epoch / FPV_F_CHAINED are ignored.  slices <= 0: 4. */

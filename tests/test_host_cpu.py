@@ -363,3 +363,24 @@ def test_sass_carries_the_blackwell_paths(lib):
     for prefix in ("_ZN3fpv20drone_rollout_kernelINS_2F2ELi4", "_ZN3fpv17drone_step_kernelINS_2F2ELi4ELb1", "_ZN3fpv16acro_step_kernelINS_2F2E"):
         f = [x for x in funcs if x.startswith(prefix)]
         assert f and len(re.findall(r"\bFFMA2\b", f[0])) >= 60, prefix
+
+
+@pytest.mark.parametrize("n", [1, 63, 65536, 262143, 262144, 300_000, 1 << 20, (1 << 20) + 1, 16_777_216])
+@pytest.mark.parametrize("slices", [0, 1, 2, 4, 8, 16, 99])
+def test_host_step_slices_cover_the_batch(n, slices):
+    """The env ranges of the pipelined host step (mirror of host_slice_bounds in fpv_api.cu): contiguous, covering,
+    starting on 64-env boundaries, none shorter than 65,536 envs unless it is the whole remainder, at most 16 + 1."""
+    from fpyv_b200.drone import host_slice_bounds
+    b = host_slice_bounds(n, slices)
+    want = min(16, slices) if slices > 0 else 4
+    assert b[0][0] == 0 and b[-1][1] == n and 1 <= len(b) <= want
+    for (a0, a1), (b0, b1) in zip(b, b[1:]):
+        assert a1 == b0
+    for a0, a1 in b:
+        assert a0 % 64 == 0 and a1 > a0
+        assert len(b) == 1 or a1 - a0 >= 65536 - 64 * 16
+    if want >= 2 and n >= 4 * 65536:
+        assert len(b) >= 2 and 65536 <= b[-1][1] - b[-1][0] < b[0][1] - b[0][0] + 64      # the tail range is the short one
+        assert b[-1][1] - b[-1][0] < max(65536, n // 16) + 64
+    if n >= 16 * 65536:
+        assert len(b) == want
