@@ -17,13 +17,12 @@ helper_functions.py:65-117); `.rotation_matrix` converts on read and `set_rotati
 from __future__ import annotations
 
 import ctypes as C
-import math
 
 import numpy as np
 import torch
 
 from . import _lib, config
-from .objects import Ground, lower_object_list
+from .objects import lower_object_list
 from .sticks import Joystick
 
 

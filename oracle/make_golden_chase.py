@@ -8,7 +8,6 @@ Writes tests/golden/chase_camera.npz, chase_autopilot.npz, chase_loop.npz.
 """
 from __future__ import annotations
 
-import copy
 import os
 import signal
 import sys

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import GOLDEN, CONFIG
+from conftest import GOLDEN
 from oracle import chase_oracle as co
 from oracle import fpv_oracle as fo
 
@@ -253,7 +253,6 @@ def test_full_frame_batch_against_oracle():
 def test_guard_cells_around_every_output_of_the_chase_kernels():
     """Raw C-ABI calls on ragged sizes with sentinel bytes on both sides of every output buffer (compute-sanitizer is
     not available on the GPU pool: out-of-bounds writes are caught by guard cells instead)."""
-    import ctypes as C
     from fpyv_b200 import BatchedDrone, _lib
     lib = _lib.load()
     g = load("chase_camera")
