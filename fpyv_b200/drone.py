@@ -343,6 +343,26 @@ class BatchedDrone:
             return self.observe()
         return None
 
+    def _configure_plain_io(self):
+        """Point the io block at this drone's own buffers in the plain configuration (no wind, objects or overrides):
+        what the slow path of step() leaves behind after such a call, so the allocation-free fast path may follow."""
+        p, io = self._p, self._io
+        p.flags, p.n_objects = self._flags, 0
+        p.wind[0] = p.wind[1] = p.wind[2] = 0.0
+        io.state, io.n, io.plane_stride = self._state.data_ptr(), self.num_envs, self._stride
+        io.actions = self._actions.data_ptr()
+        io.wind_env = None
+        io.lut = None if self._lut is None else self._lut.data_ptr()
+        io.lut_n = 0 if self._lut is None else self._lut.numel()
+        io.done, io.acc_out = self._done.data_ptr(), self._acc.data_ptr()
+        io.reset_state = None if self._reset_state is None else self._reset_state.data_ptr()
+        io.override_q = io.override_thrust = None
+        io.objects = C.POINTER(_lib.Object)()
+        io.stats, io.work = self._stats.data_ptr(), self._work.data_ptr()
+        io.chunk_epoch = io.trace = None
+        self._chain_armed = False
+        self._fast_ok = getattr(self, "_trace", None) is None
+
     @property
     def cta_slots(self) -> int:
         """CTA slots per SM one step launch takes (0 = all); see fpv_drone_io_t.max_ctas_per_sm."""
