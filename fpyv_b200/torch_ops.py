@@ -73,4 +73,5 @@ def bind(drone):
     def step(actions: torch.Tensor) -> None:
         torch.ops.fpyv_b200.drone_step(state, actions, done, acc, h)
 
+    step.drone = drone      # the registry holds weak references: the callable keeps its drone alive
     return step
