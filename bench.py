@@ -33,6 +33,7 @@ CTA_SLOTS = int(os.environ.get("FPV_BENCH_CTA_SLOTS", "2"))  # CTA slots per SM 
 BYTES_PER_ENV_STEP = 64 + 64 + 16 + 1          # state read + state write + action + done flag
 FLOP_PER_ENV_SUBSTEP = 252                     # 245 arithmetic + 6 sin/cos + 1 sqrt
 FP32_LANES_PER_SM = 128
+SPIN_CYCLES = 500_000                          # ~0.25 ms at 1.965 GHz: lets the host run ahead of the device before e0
 
 
 def ncu_traffic_bytes():
@@ -108,27 +109,61 @@ def synthetic_init(n, device, seed):
 # --------------------------------------------------------------------------------------------
 # CPU arm: the oracle's C restatement of the reference algorithm on the host cores
 # --------------------------------------------------------------------------------------------
-def cpu_arm(steps, warmup, n_sample=65536, target_seconds=None):
-    """env-steps/s of oracle/fpv_oracle.c (float64, all host cores) on a bounded sample of the workload."""
+NUMPY_REFERENCE = {"value": 2.8e3, "unit": "env-steps/s", "cores": 1, "kind": "reference",
+                   "sample": "the reference's own per-object NumPy Drone.step (src/utils/components.py:220-248) driven through "
+                             "oracle/ref_shim.py, 2,000 steps, ground-only object list, stdout swallowed; measured in the build "
+                             "container (SURVEY.md section 6) -- a CONSTANT quoted for scale, not re-measured on this box: the Python "
+                             "reference does not travel to the GPU box"}
+
+
+def _cpu_workload(n, seed=1234):
     import numpy as np
     import yaml
-    from oracle import c_oracle, fpv_oracle as fo
-    c_oracle.build()
+    from oracle import fpv_oracle as fo
     cfg = os.path.join(ROOT, "fpyv_b200", "config")
     with open(os.path.join(cfg, "params.yaml")) as f:
         params = yaml.safe_load(f)
     c = fo.derive_consts(params, os.path.join(cfg, "t_motos_f80_motor_test.csv"), dt=DT)
-    k = c_oracle.make_consts(c)
-    cores = c_oracle.max_threads()
-    rng = np.random.default_rng(1234)
-    n = n_sample
+    rng = np.random.default_rng(seed)
     pos = np.stack([rng.normal(0, 5, n), rng.normal(0, 5, n), rng.uniform(0.05, 3.0, n)], 1)
     vel = rng.normal(0, 1, (n, 3))
     rpy = rng.uniform(-30, 30, (n, 3))
     s = fo.drone_reset(c, pos, vel, rpy)
-    P, V, R = s.pos.copy(), s.vel.copy(), np.ascontiguousarray(s.R)
-    pr, pt = np.zeros((n, 3)), np.zeros(n)
     acts = [np.ascontiguousarray(rng.uniform(-1, 1, (n, 4))) for _ in range(4)]
+    return c, s.pos.copy(), s.vel.copy(), np.ascontiguousarray(s.R), np.zeros((n, 3)), np.zeros(n), acts
+
+
+def numba_arm(n=ENVS_PER_GPU, target_seconds=6.0):
+    """env-steps/s of oracle/numba_oracle.py: a Numba @njit(parallel=True) float64 restatement of Drone.step.  The reference
+    ships NO Numba path (src/utils/kinematics.py:6,14 are commented out) -- this is what north_star's "Numba CPU path" can mean."""
+    import numpy as np
+    from oracle import numba_oracle as no
+    c, P, V, R, pr, pt, acts = _cpu_workload(n)
+    k, mrel = no.make_consts(c)
+    wind, done = np.zeros(3), np.zeros(n, dtype=np.bool_)
+    no.drone_step(k, mrel, P[:64], V[:64], R[:64], pr[:64], pt[:64], acts[0][:64], wind, 1, done[:64])   # JIT compile
+    no.drone_step(k, mrel, P, V, R, pr, pt, acts[0], wind, SUBSTEPS, done)
+    t0, steps = time.perf_counter(), 0
+    while True:
+        no.drone_step(k, mrel, P, V, R, pr, pt, acts[steps % 4], wind, SUBSTEPS, done)
+        steps += 1
+        if time.perf_counter() - t0 > target_seconds:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": n * steps / dt, "unit": "env-steps/s", "cores": no.threads(), "kind": "restatement",
+            "sample": f"{n} envs x {SUBSTEPS} substeps x {steps} control steps, Numba @njit(parallel=True) float64 restatement of "
+                      f"Drone.step (oracle/numba_oracle.py; the reference ships no Numba path: its @jit lines are commented out, "
+                      f"src/utils/kinematics.py:6,14), {no.threads()} threads, {dt:.1f} s"}
+
+
+def cpu_arm(steps, warmup, n_sample=ENVS_PER_GPU, target_seconds=None):
+    """env-steps/s of oracle/fpv_oracle.c (float64, all host cores) on the workload's full batch."""
+    from oracle import c_oracle
+    c_oracle.build()
+    n = n_sample
+    c, P, V, R, pr, pt, acts = _cpu_workload(n)
+    k = c_oracle.make_consts(c)
+    cores = c_oracle.max_threads()
     for i in range(warmup):
         c_oracle.drone_step(k, P, V, R, pr, pt, acts[i % 4], substeps=SUBSTEPS, threads=cores)
     t0 = time.perf_counter()
@@ -153,7 +188,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "env_steps_per_sec", "value": r["value"], "unit": "env-steps/s",
             "n_gpus": args.gpus, "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args.gpus, sample=r["sample"]),
+            "config": workload_config(args.gpus),
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -198,9 +233,8 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # keep stdout to the ONE JSON line: NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION/INFO
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and not os.environ.get("FPV_KEEP_NCCL_DEBUG"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL_DEBUG is left as the environment set it: fd 1 already points at stderr (above), so NCCL's communicator lines
+        # ("... nranks N ...") reach stderr and stdout still carries exactly the ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     n, K, W = args.envs, args.steps, args.warmup
 
@@ -237,6 +271,11 @@ def run_gpu(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+        # The bracket holds DEVICE time of exactly `steps` steps: a ~0.25 ms spin kernel is queued first, so that the host
+        # has enqueued the event and the first launches before the device reaches them (otherwise the first launch's host
+        # latency and the idle-to-busy ramp of the slowest rank -- a fixed ~70 us per bracket, MAX-reduced over the ranks --
+        # are charged to a 20-step run and read as a scaling loss although the step has no collective).
+        torch.cuda._sleep(SPIN_CYCLES)
         e0.record()
         for i in range(steps):
             # the stick commands of every step exist before the loop starts (open-loop rollout), so consecutive
@@ -373,6 +412,42 @@ def run_gpu(args):
 
     t1 = time.time()
     clocks = sampler.stop(t0, t1) if sampler else None      # covers the K=8 loop, the e2e loop and the K=1 loop
+
+    # ---- measured FP32 peak: a pure-FMA probe (fpv_probe_fp32) timed with events, scalar and packed forms
+    def fp32_probe(packed):
+        import ctypes as C
+        from fpyv_b200 import _lib
+        lib = _lib.load()
+        sink = torch.zeros(torch.cuda.get_device_properties(dev).multi_processor_count * 8 * 256, device=dev)
+        flop = C.c_double(0.0)
+        best = None
+        for r in range(6):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _lib.check(lib.fpv_probe_fp32(int(packed), 4096, _lib.ptr(sink), sink.numel(), C.byref(flop), _lib.current_stream(dev)))
+            e1.record()
+            torch.cuda.synchronize()
+            ms_ = e0.elapsed_time(e1)
+            best = ms_ if best is None or ms_ < best else best
+        return flop.value / (best * 1e-3) / 1e12
+    peak_meas = {"ffma_scalar_tflops": fp32_probe(0), "ffma2_packed_tflops": fp32_probe(1)} if rank == 0 else None
+
+    # ---- the other BASELINE configs, short legs (bench_legs.py); configs[3] runs on every rank when N > 1
+    del d1s
+    del drones[1:]
+    torch.cuda.empty_cache()
+    import bench_legs
+    sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+    pk_legs = {"hbm_gbs": peaks()["hbm_gbs"], "fp32_tflops": sm_count * FP32_LANES_PER_SM * 2 * peaks()["sm_max_mhz"] * 1e6 / 1e12}
+    extra = {}
+    if not args.no_extra:
+        if world > 1:
+            try:
+                extra["config3_sharded"] = bench_legs.leg_config3_sharded(dev, pk_legs, None, world, rank)
+            except Exception as e:      # noqa: BLE001
+                extra["config3_sharded"] = {"error": f"{type(e).__name__}: {e}"}
+            dist.barrier()
+        extra.update(bench_legs.run_extra(dev, pk_legs, world, rank))
     t = torch.tensor([ms, ms_e2e, ms_k1, ms_rollout, ms_full_grid, ms_unchained, ms_e2e_sticks], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -403,12 +478,19 @@ def run_gpu(args):
             "frac_chained_full_grid": FLOP_PER_ENV_SUBSTEP * SUBSTEPS * n / (ms_full_grid * 1e-3 / K) / 1e12 / fp32_peak,
             "frac_unchained": FLOP_PER_ENV_SUBSTEP * SUBSTEPS * n / (ms_unchained * 1e-3 / K) / 1e12 / fp32_peak,
             "frac_isolated_launch": FLOP_PER_ENV_SUBSTEP * SUBSTEPS * n / (ms_flushed_per_step * 1e-3) / 1e12 / fp32_peak,
+            "peak_measured": dict(peak_meas, unit="TFLOP/s", frac_of_measured_scalar=fp32_ach / peak_meas["ffma_scalar_tflops"],
+                                  how="fpv_probe_fp32: SMs x 8 CTAs x 256 threads x 4096 iterations x 16 independent FMA chains with "
+                                      "shared multiplicand/addend (operand-reuse hits), best of 6, CUDA events"),
             "hbm": {"achieved": hbm_ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": hbm_ach / pk["hbm_gbs"],
                     "algorithmic": f"{BYTES_PER_ENV_STEP} B/env/control-step x {n} envs per launch", "peak_source": pk["source"]},
             "hbm_bound_variant_k1": {"bound": "hbm", "achieved": hbm_k1, "peak": pk["hbm_gbs"], "unit": "GB/s",
                                      "frac": hbm_k1 / pk["hbm_gbs"], "ms_per_step": ms_k1 / K,
                                      "env_steps_per_sec": total_envs * K / (ms_k1 * 1e-3)}}
-    cpu = cpu_arm(steps=1000, warmup=1, target_seconds=12.0)
+    cpu = cpu_arm(steps=1000, warmup=1, target_seconds=10.0)
+    try:
+        cpu_numba = numba_arm()
+    except Exception as e:      # noqa: BLE001
+        cpu_numba = {"error": f"{type(e).__name__}: {e}"}
     line = {"metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(world),
@@ -431,7 +513,8 @@ def run_gpu(args):
                                      "extra metric, not the headline (the state stays in registers between control steps)"},
             "gpu_launches": K, "roofline": roof,
             "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
-            "clocks": clocks, "episode_stats": stats}
+            "cpu_baseline_numba": cpu_numba, "cpu_baseline_numpy_reference": NUMPY_REFERENCE,
+            "extra": extra, "clocks": clocks, "episode_stats": stats}
     sys.stdout.flush()
     os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
@@ -446,6 +529,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU (default: the BASELINE config)")
     ap.add_argument("--profile", action="store_true", help="kernel loops only (for ncu): no e2e / CPU legs")
+    ap.add_argument("--no-extra", action="store_true", help="skip the legs for the other BASELINE configs (bench_legs.py)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native":
         args.warmup = 3

@@ -17,8 +17,8 @@ MAX_OBJECTS = 16
 DRONE_PLANES, RACER_PLANES = 4, 7
 EXPORTS = ("fpv_abi_version", "fpv_last_error", "fpv_sizeof", "fpv_device_info", "fpv_drone_reset",
            "fpv_drone_step", "fpv_drone_step_host", "fpv_drone_step_host_sticks", "fpv_drone_rollout", "fpv_drone_observe", "fpv_drone_get_rotation", "fpv_drone_set_rotation", "fpv_matrix_to_quat", "fpv_sticks_to_actions", "fpv_racer_reset", "fpv_racer_step", "fpv_gate_env_reset", "fpv_gate_env_step", "fpv_gate_race_step",
-           "fpv_camera_update", "fpv_camera_render", "fpv_camera_target_pixel", "fpv_camera_rays", "fpv_autopilot", "fpv_point_and_shoot",
-           "fpv_acro_reset", "fpv_acro_step", "fpv_acro_rollout")
+           "fpv_camera_update", "fpv_camera_update_pose", "fpv_camera_render", "fpv_camera_target_pixel", "fpv_camera_rays", "fpv_autopilot", "fpv_point_and_shoot",
+           "fpv_acro_reset", "fpv_acro_step", "fpv_acro_rollout", "fpv_probe_fp32")
 
 
 class FpvError(RuntimeError):
@@ -153,6 +153,7 @@ def load():
     P, V, I64, I32, D = C.POINTER, C.c_void_p, C.c_int64, C.c_int32, C.c_double
     lib.fpv_gate_race_step.argtypes = [P(DroneParams), P(DroneIO), P(GateEnvParams), V, V, V, V, V, V, V]
     lib.fpv_camera_update.argtypes = [P(CameraParams), V, I64, I64, V, V]
+    lib.fpv_camera_update_pose.argtypes = [P(CameraParams), V, V, I64, V, V]
     lib.fpv_camera_render.argtypes = [P(CameraParams), V, I64, V, I32, V, I32, V, D, V, V, V]
     lib.fpv_camera_target_pixel.argtypes = [P(CameraParams), V, I64, V, I32, V, I32, V, D, V, V, V]
     lib.fpv_camera_rays.argtypes = [P(CameraParams), V, I64, V, I32, V, V]
@@ -161,6 +162,7 @@ def load():
     lib.fpv_acro_reset.argtypes = [V, I64, I64, V, V, V, V, V]
     lib.fpv_acro_step.argtypes = [P(AcroParams), V, I64, I64, V, V, I32, V, V, V, V, V]
     lib.fpv_acro_rollout.argtypes = [P(AcroParams), V, I64, I64, V, I64, I32, V, I32, V, I64, V, V, V, V, V]
+    lib.fpv_probe_fp32.argtypes = [I32, I32, V, I64, P(D), V]
     v = lib.fpv_abi_version()
     if v != ABI_VERSION:
         raise ImportError(f"{LIB_PATH} has ABI version {v}, this package needs {ABI_VERSION}; rebuild it")

@@ -114,13 +114,15 @@ class BatchedCamera:
         self._has_pose = True
 
     def update(self, drone_position, drone_rotation_matrix):
-        """components.py:501-503 from explicit float64 poses ([n,3], [n,3,3])."""
-        pos = torch.as_tensor(np.asarray(drone_position), dtype=torch.float64, device=self.device).reshape(self.num_envs, 3)
-        R = torch.as_tensor(np.asarray(drone_rotation_matrix), dtype=torch.float64, device=self.device).reshape(self.num_envs, 3, 3)
-        rel_R = torch.as_tensor(self.relative_rotation_matrix, device=self.device)
-        rel_p = torch.as_tensor(self.relative_position, device=self.device)
-        self._pose[:, :9] = (R @ rel_R).reshape(self.num_envs, 9)
-        self._pose[:, 9:] = pos + (R @ rel_p)
+        """components.py:501-503 from explicit poses ([n,3], [n,3,3]; NumPy arrays or torch tensors on any device, e.g.
+        `camera.update(drone.position, drone.rotation_matrix)` with BatchedDrone's CUDA tensors): one launch of
+        fpv_camera_update_pose, float64 arithmetic like the reference."""
+        def dev64(x, shape):
+            t = x if isinstance(x, torch.Tensor) else torch.as_tensor(np.asarray(x))
+            return t.to(self.device, torch.float64).reshape(shape).contiguous()
+        pos, R = dev64(drone_position, (self.num_envs, 3)), dev64(drone_rotation_matrix, (self.num_envs, 9))
+        _lib.check(self._lib.fpv_camera_update_pose(self._params(), _lib.ptr(pos), _lib.ptr(R), self.num_envs, _lib.ptr(self._pose),
+                                                    _lib.current_stream(self.device)))
         self._has_pose = True
 
     reset = update                                                                                   # :497-499

@@ -46,6 +46,24 @@ __global__ void camera_update_kernel(const __grid_constant__ CamK k, const float
     o[9 + i] = pp[i] + (R[3 * i] * k.rel_pos[0] + R[3 * i + 1] * k.rel_pos[1] + R[3 * i + 2] * k.rel_pos[2]);
 }
 
+// The same update from explicit float64 poses (Camera.update(drone_position, drone_rotation_matrix) with arrays):
+// pos double[n][3], R double[n][9] row-major.
+__global__ void camera_update_pose_kernel(const __grid_constant__ CamK k, const double* pos, const double* Rm, long long n,
+                                          double* pose) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const double* R = Rm + 9 * e;
+  double* o = pose + 12 * e;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      o[3 * i + j] = R[3 * i] * k.rel_rot[j] + R[3 * i + 1] * k.rel_rot[3 + j] + R[3 * i + 2] * k.rel_rot[6 + j];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    o[9 + i] = pos[3 * e + i] + (R[3 * i] * k.rel_pos[0] + R[3 * i + 1] * k.rel_pos[1] + R[3 * i + 2] * k.rel_pos[2]);
+}
+
 // K [R t]^-1 applied to a world point (components.py:532-536, :558-568): camera coordinates c = R^T (p - t), then
 // u = fx cx' ... ; returns false when the point is not in front of the camera (depth <= 0).
 __device__ __forceinline__ bool project_point(const CamK& k, const double* pose, double x, double y, double z, int& px, int& py,

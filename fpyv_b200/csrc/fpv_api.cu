@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "../../include/fpv_api.h"
 #include "drone_kernels.cuh"
@@ -12,10 +13,12 @@
 #include "env_kernels.cuh"
 #include "chase_kernels.cuh"
 #include "acro_kernels.cuh"
+#include "probe_kernels.cuh"
 
 namespace {
 
 thread_local char g_err[512] = "";
+std::mutex g_mu;   // guards every launch-fact cache below (occupancy, opted-in shared memory, SM counts, host pipes)
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -57,6 +60,7 @@ int current_device_slot() {   // -1 = beyond the cached range: such devices reco
 int sm_count_of_current_device() {
   static int cached[kMaxDevices] = {0};
   const int slot = current_device_slot();
+  std::lock_guard<std::mutex> lk(g_mu);
   if (slot >= 0 && cached[slot]) return cached[slot];
   int dev = 0, v = 0;
   cudaGetDevice(&dev);
@@ -74,6 +78,7 @@ struct SmemOptIn {
 template <class K>
 void opt_in_smem(K kern, SmemOptIn& c, size_t smem, size_t above = 48 * 1024) {
   const int slot = current_device_slot();
+  std::lock_guard<std::mutex> lk(g_mu);
   if (smem <= above || (slot >= 0 && smem <= c.bytes[slot])) return;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (slot >= 0) c.bytes[slot] = smem;
@@ -89,23 +94,22 @@ void launch_drone(const DroneK& k, const DroneIO& io, cudaStream_t st) {
   static int occ_cache[kMaxDevices][2] = {};    // [device][lut?]
   if (smem > 48 * 1024) opt_in_smem(kern, opted, 200 * 1024);
   const int slot = current_device_slot();
-  int occ = slot >= 0 ? occ_cache[slot][smem ? 1 : 0] : 0;
-  if (occ == 0) {
-    int o = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, kThreads, smem > 48 * 1024 ? 200 * 1024 : smem);
-    occ = o > 0 ? o : 1;
-    if (slot >= 0) occ_cache[slot][smem ? 1 : 0] = occ;
+  int occ;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    occ = slot >= 0 ? occ_cache[slot][smem ? 1 : 0] : 0;
+    if (occ == 0) {
+      int o = 0;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, kThreads, smem > 48 * 1024 ? 200 * 1024 : smem);
+      occ = o > 0 ? o : 1;
+      if (slot >= 0) occ_cache[slot][smem ? 1 : 0] = occ;
+    }
   }
   const long long per_block = (long long)kThreads * L;
   const long long tiles = (io.n + per_block - 1) / per_block;
   const long long wave = (long long)sm_count_of_current_device() * occ;
   const unsigned grid = (unsigned)(tiles < wave ? tiles : wave);
   kern<<<grid, kThreads, smem, st>>>(k, io);
-}
-
-int tune_env(const char* name, int dflt) {
-  const char* v = std::getenv(name);
-  return v ? std::atoi(v) : dflt;
 }
 
 // Hot path: TMA-fed ring (drone_step_tma_kernel).  Returns false if the ring does not fit (huge LUT).
@@ -123,30 +127,28 @@ bool launch_drone_tma(const DroneK& k, const DroneIO& io, cudaStream_t st) {
   static size_t occ_smem[kMaxDevices] = {};
   opt_in_smem(kern, opted, smem, 0);
   const int slot = current_device_slot();
-  int occ_cache = (slot >= 0 && occ_smem[slot] == smem) ? occ_of[slot] : 0;
-  if (occ_cache == 0) {
-    int o = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, kThreads, smem);
-    occ_cache = o > 0 ? o : 1;
-    if (slot >= 0) { occ_of[slot] = occ_cache; occ_smem[slot] = smem; }
+  int occ_cache;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    occ_cache = (slot >= 0 && occ_smem[slot] == smem) ? occ_of[slot] : 0;
+    if (occ_cache == 0) {
+      int o = 0;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, kThreads, smem);
+      occ_cache = o > 0 ? o : 1;
+      if (slot >= 0) { occ_of[slot] = occ_cache; occ_smem[slot] = smem; }
+    }
   }
   const long long tiles = (io.n + TILE - 1) / TILE;
-  static const int occ_env = tune_env("FPV_TUNE_OCC", 0);
-  const int occ_cap = io.cta_cap > 0 ? (int)io.cta_cap : occ_env;
+  const int occ_cap = (int)io.cta_cap;
   const int occ_used = (occ_cap > 0 && occ_cap < occ_cache) ? occ_cap : occ_cache;
   const long long wave = (long long)sm_count_of_current_device() * occ_used;
   const unsigned grid = (unsigned)(tiles < wave ? tiles : wave);
-  static const int no_pdl = tune_env("FPV_TUNE_NOPDL", 0);
   // FPV_F_CHAINED is honoured only by full persistent grids (every CTA slot a launch may use, on every SM): launch i+1
   // cannot become fully resident before launch i has left the slots it needs, which bounds the number of launches alive
   // at once (4 / slots-per-launch + 1) -- what the eight pull-counter pairs and the forward-progress argument of the
   // per-chunk waits rely on (the producer of an awaited chunk is always resident).  Anything else keeps plain stream order.
   DroneK kk = k;
-  if ((kk.flags & FPV_F_CHAINED) && (no_pdl || (long long)grid != wave)) kk.flags &= ~FPV_F_CHAINED;
-  if (no_pdl) {
-    kern<<<grid, kThreads, smem, st>>>(kk, io, lut_bytes);
-    return true;
-  }
+  if ((kk.flags & FPV_F_CHAINED) && (long long)grid != wave) kk.flags &= ~FPV_F_CHAINED;
   // programmatic dependent launch: this grid may become resident while the previous one on the stream drains
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
@@ -181,12 +183,11 @@ void launch_drone_plain(const DroneK& k, const DroneIO& io, cudaStream_t st) {
 
 template <class V, int ANG>
 void launch_drone_g(const DroneK& k, const DroneIO& io, bool general, cudaStream_t st) {
-  static const int no_tma = tune_env("FPV_TUNE_NOTMA", 0);     // developer A/B switches, not part of the ABI
   if (general) { launch_drone_plain<V, ANG, true>(k, io, st); return; }
-  if (!no_tma && fpv::Lane<V>::N == 2) {   // chunk_epoch is indexed by 64-env chunks = the packed kernel's warp-chunk
+  if (fpv::Lane<V>::N == 2) {   // chunk_epoch is indexed by 64-env chunks = the packed kernel's warp-chunk
     if (launch_drone_tma<V, ANG, 2>(k, io, st)) return;
   }
-  if (!no_tma && !io.chunk_epoch) {
+  if (!io.chunk_epoch) {
     if (launch_drone_tma<V, ANG, 2>(k, io, st)) return;
   }
   launch_drone_plain<V, ANG, false>(k, io, st);
@@ -232,6 +233,16 @@ int fpv_device_info(int device, int* sm_count, int* cc_major, int* cc_minor) {
   if (cc_major) *cc_major = p.major;
   if (cc_minor) *cc_minor = p.minor;
   return FPV_OK;
+}
+
+int fpv_probe_fp32(int32_t packed, int32_t iters, float* sink, int64_t sink_floats, double* flop_out, void* stream) {
+  if (iters < 1) return fail(FPV_EINVAL, "fpv_probe_fp32: iters must be >= 1");
+  const int blocks = sm_count_of_current_device() * 8;
+  if (!sink || sink_floats < (int64_t)blocks * 256) return fail(FPV_EINVAL, "fpv_probe_fp32: sink must hold %d floats", blocks * 256);
+  if (packed) fpv::fp32_probe_kernel<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(sink, iters, 1.0001f, 0.5f);
+  else fpv::fp32_probe_kernel<0><<<blocks, 256, 0, (cudaStream_t)stream>>>(sink, iters, 1.0001f, 0.5f);
+  if (flop_out) *flop_out = (double)blocks * 256.0 * (double)iters * 16.0 * (packed ? 2.0 : 1.0) * 2.0;
+  return check_launch("fpv_probe_fp32");
 }
 
 int fpv_drone_reset(void* state, int64_t n, int64_t plane_stride, const float* pos, const float* vel,
@@ -328,8 +339,7 @@ int prepare_drone(const fpv_drone_params_t* p, const fpv_drone_io_t* io, bool ne
   d.override_thrust = io->override_thrust;
   d.stats = io->stats;
   // pulled chunks pay one atomic round trip per chunk: worth it once a chunk carries enough arithmetic to hide it
-  static const int no_dyn = tune_env("FPV_TUNE_STATIC", 0);
-  d.work = (no_dyn || p->substeps < 4) ? nullptr : (unsigned*)io->work;
+  d.work = p->substeps < 4 ? nullptr : (unsigned*)io->work;
   d.chunk_epoch = (unsigned*)io->chunk_epoch;
   d.epoch = io->epoch;
   d.cta_cap = io->max_ctas_per_sm;
@@ -368,11 +378,15 @@ int fpv_drone_step(const fpv_drone_params_t* p, const fpv_drone_io_t* io, void* 
 
 
 namespace {
+// One pipe per device: two copy streams and the events that order them against the caller's stream.  `mu` is held
+// for the whole enqueue of one *_step_host call, so concurrent callers on the same device (other host threads, other
+// caller streams) queue their slices one call after the other instead of re-recording each other's events.
 struct HostPipe {
   cudaStream_t in = nullptr, out = nullptr;
   cudaEvent_t ready = nullptr, joined = nullptr;
   cudaEvent_t h2d[16] = {}, stepped[16] = {};
   bool ok = false;
+  std::mutex mu;
 };
 HostPipe& host_pipe_of_current_device() {
   static HostPipe pipes[64];
@@ -380,6 +394,7 @@ HostPipe& host_pipe_of_current_device() {
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64) dev = 0;
   HostPipe& p = pipes[dev];
+  std::lock_guard<std::mutex> lk(g_mu);
   if (!p.ok) {
     cudaStreamCreateWithFlags(&p.in, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&p.out, cudaStreamNonBlocking);
@@ -430,6 +445,7 @@ int fpv_drone_step_host(const fpv_drone_params_t* p, const fpv_drone_io_t* io, c
   const int n_slices = host_slice_bounds(n, slices, bound);
   HostPipe& hp = host_pipe_of_current_device();
   if (!hp.ok) return fail(FPV_ECUDA, "fpv_drone_step_host: could not create the copy streams");
+  std::lock_guard<std::mutex> pipe_lock(hp.mu);
   cudaStream_t st = (cudaStream_t)stream;
   cudaEventRecord(hp.ready, st);            // everything queued so far (the previous step reads the staging buffer) ...
   cudaStreamWaitEvent(hp.in, hp.ready, 0);  // ... precedes the first byte of the new actions
@@ -453,7 +469,13 @@ int fpv_drone_step_host(const fpv_drone_params_t* p, const fpv_drone_io_t* io, c
     if (io->override_thrust) s.override_thrust = io->override_thrust + a;
     s.chunk_epoch = nullptr;
     s.trace = nullptr;
-    if (int rc = fpv_drone_step(&pp, &s, stream)) return rc;
+    if (int rc = fpv_drone_step(&pp, &s, stream)) {   // the copies already queued still join the caller's stream
+      cudaEventRecord(hp.joined, hp.in);
+      cudaStreamWaitEvent(hp.out, hp.joined, 0);
+      cudaEventRecord(hp.joined, hp.out);
+      cudaStreamWaitEvent(st, hp.joined, 0);
+      return rc;
+    }
     cudaEventRecord(hp.stepped[c], st);
     cudaStreamWaitEvent(hp.out, hp.stepped[c], 0);
     cudaMemcpyAsync(done_host + a, io->done + a, (size_t)(b - a), cudaMemcpyDeviceToHost, hp.out);
@@ -597,6 +619,7 @@ int fpv_drone_step_host_sticks(const fpv_drone_params_t* p, const fpv_drone_io_t
   const int n_slices = host_slice_bounds(n, slices, bound);
   HostPipe& hp = host_pipe_of_current_device();
   if (!hp.ok) return fail(FPV_ECUDA, "fpv_drone_step_host_sticks: could not create the copy streams");
+  std::lock_guard<std::mutex> pipe_lock(hp.mu);
   cudaStream_t st = (cudaStream_t)stream;
   cudaEventRecord(hp.ready, st);
   cudaStreamWaitEvent(hp.in, hp.ready, 0);
@@ -622,7 +645,13 @@ int fpv_drone_step_host_sticks(const fpv_drone_params_t* p, const fpv_drone_io_t
     s.override_thrust = nullptr;
     s.chunk_epoch = nullptr;
     s.trace = nullptr;
-    if (int rc = fpv_drone_step(&pp, &s, stream)) return rc;
+    if (int rc = fpv_drone_step(&pp, &s, stream)) {
+      cudaEventRecord(hp.joined, hp.in);
+      cudaStreamWaitEvent(hp.out, hp.joined, 0);
+      cudaEventRecord(hp.joined, hp.out);
+      cudaStreamWaitEvent(st, hp.joined, 0);
+      return rc;
+    }
     cudaEventRecord(hp.stepped[c], st);
     cudaStreamWaitEvent(hp.out, hp.stepped[c], 0);
     cudaMemcpyAsync(done_host + a, io->done + a, (size_t)(b - a), cudaMemcpyDeviceToHost, hp.out);
@@ -768,6 +797,17 @@ int fpv_camera_update(const fpv_camera_params_t* cam, const void* state, int64_t
   if (n == 0) return FPV_OK;
   fpv::camera_update_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(k, (const float4*)state, n, plane_stride, pose);
   return check_launch("fpv_camera_update");
+}
+
+int fpv_camera_update_pose(const fpv_camera_params_t* cam, const double* pos, const double* rot, int64_t n, double* pose,
+                           void* stream) {
+  fpv::CamK k;
+  if (int rc = make_cam(cam, k, "fpv_camera_update_pose")) return rc;
+  if (!pos || !rot || !pose) return fail(FPV_EINVAL, "fpv_camera_update_pose: null pointer");
+  if (n < 0) return fail(FPV_EINVAL, "fpv_camera_update_pose: bad n");
+  if (n == 0) return FPV_OK;
+  fpv::camera_update_pose_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(k, pos, rot, n, pose);
+  return check_launch("fpv_camera_update_pose");
 }
 
 int fpv_camera_render(const fpv_camera_params_t* cam, const double* pose, int64_t n, const double* points,

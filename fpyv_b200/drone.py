@@ -264,10 +264,12 @@ class BatchedDrone:
         if chained and torch.cuda.is_current_stream_capturing():
             chained = False      # a captured launch would replay a stale epoch: graphs use plain stream order
         chain_now = chained and self._chain_ready
-        self._chain_ready = chained
+        # The chained-launch bookkeeping (epoch counter, "the last writer was step()") is committed only AFTER the launch
+        # has been accepted: an exception on the way (bad action shape, non-zero return code) must not leave a published
+        # epoch that no kernel will ever write -- the next chained launch would wait for it on the device.
+        self._chain_ready = False
         if chained:
             self._io.epoch = self._epoch & 0xFFFFFFFF
-            self._epoch += 1
             self._io.chunk_epoch = self._chunk_epoch_ptr
             self._chain_armed = True
         elif self._chain_armed:
@@ -284,7 +286,11 @@ class BatchedDrone:
             rc = self._step_fn(self._p_ref, self._io_ref, _lib.raw_stream(self._dev_index))
             if rc:
                 _lib.check(rc)
+            if chained:
+                self._epoch += 1
+                self._chain_ready = True
             return self.observe() if return_obs else None
+        self._fast_ok = False        # re-established below only if this call completes in the plain configuration
         if action is None:
             action = self.read_sticks()
         act = _as_dev(action, dev, (n, 4))
@@ -336,6 +342,9 @@ class BatchedDrone:
         io.work = self._work.data_ptr()
         io.trace = None if getattr(self, "_trace", None) is None else self._trace.data_ptr()
         _lib.check(self._lib.fpv_drone_step(C.byref(p), C.byref(io), _lib.current_stream(dev)))
+        if chained:
+            self._epoch += 1
+            self._chain_ready = True
         # the fast path may reuse p / io as they are only if this call left them in the plain configuration
         self._fast_ok = (wind_velocity_vector is None and object_list is None and rotation_matrix is None
                          and getattr(self, "_trace", None) is None)
@@ -441,15 +450,13 @@ class BatchedDrone:
         streams: the H2D copy of slice c+1 runs while slice c is stepped and slice c-1's flags travel back.  The
         caller's current stream is joined to the last D2H copy, so synchronising it means the flags are on the host."""
         n, dev = self.num_envs, self.device
-        if done_host is None:
-            if self._host_done is None:
-                self._host_done = torch.empty(n, dtype=torch.uint8, pin_memory=True)
-            done_host = self._host_done
+        done_host = self._check_done_host(done_host)
         if not self._is_reset:
             raise RuntimeError("call reset() before step() (the reference's state is None until reset)")
+        if not isinstance(actions_host, torch.Tensor) or tuple(actions_host.shape) != (n, 4):
+            raise ValueError("step_host expects a [num_envs, 4] tensor of actions")
         if (not self._fast_ok or actions_host.is_cuda or actions_host.dtype is not torch.float32
-                or not actions_host.is_contiguous() or tuple(actions_host.shape) != (n, 4)
-                or done_host.dtype is not torch.uint8 or not done_host.is_contiguous()):
+                or not actions_host.is_contiguous()):
             self._actions.copy_(actions_host, non_blocking=True)      # first call / odd inputs: the plain path
             self.step(self._actions, return_obs=False)
             done_host.copy_(self._done, non_blocking=True)
@@ -471,10 +478,12 @@ class BatchedDrone:
         n, dev = self.num_envs, self.device
         if self.rc._c is None:
             raise RuntimeError("Joystick is not calibrated: call calibrate(path) first")
-        if done_host is None:
-            if self._host_done is None:
-                self._host_done = torch.empty(n, dtype=torch.uint8, pin_memory=True)
-            done_host = self._host_done
+        done_host = self._check_done_host(done_host)
+        if (not isinstance(sticks_host, torch.Tensor) or sticks_host.is_cuda or sticks_host.dtype is not torch.uint16
+                or not sticks_host.is_contiguous() or tuple(sticks_host.shape) != (n, 4)):
+            raise ValueError("step_host_sticks expects a contiguous uint16 host tensor [num_envs, 4]")
+        if not self._is_reset:
+            raise RuntimeError("call reset() before step() (the reference's state is None until reset)")
         if not self._fast_ok:      # configure the io block once through the plain path
             raw6 = torch.zeros((n, 6), dtype=torch.int32)
             raw6[:, [0, 1, 2, 5]] = sticks_host.to(torch.int32)
@@ -482,9 +491,6 @@ class BatchedDrone:
             self.step(None, return_obs=False)
             done_host.copy_(self._done, non_blocking=True)
             return done_host
-        if (sticks_host.is_cuda or sticks_host.dtype is not torch.uint16 or not sticks_host.is_contiguous()
-                or tuple(sticks_host.shape) != (n, 4)):
-            raise ValueError("step_host_sticks expects a contiguous uint16 host tensor [num_envs, 4]")
         if self._sticks_dev is None:
             self._sticks_dev = torch.empty((n, 4), dtype=torch.uint16, device=dev)
         self._last_action = self._actions
@@ -495,6 +501,18 @@ class BatchedDrone:
         _lib.check(self._lib.fpv_drone_step_host_sticks(self._p_ref, self._io_ref, C.byref(self.rc._c), sticks_host.data_ptr(),
                                                         self._sticks_dev.data_ptr(), done_host.data_ptr(), int(slices),
                                                         torch.cuda.current_stream(dev).cuda_stream))
+        return done_host
+
+    def _check_done_host(self, done_host):
+        """The library DMAs num_envs bytes into done_host: it must be a CPU uint8 tensor of exactly that many contiguous
+        elements (page-locked for full speed).  None -> this drone's own pinned buffer."""
+        if done_host is None:
+            if self._host_done is None:
+                self._host_done = torch.empty(self.num_envs, dtype=torch.uint8, pin_memory=True)
+            return self._host_done
+        if (not isinstance(done_host, torch.Tensor) or done_host.is_cuda or done_host.dtype is not torch.uint8
+                or not done_host.is_contiguous() or done_host.numel() != self.num_envs):
+            raise ValueError("done_host must be a contiguous CPU uint8 tensor with num_envs elements (ideally pinned)")
         return done_host
 
     def _slice_bounds(self, slices):

@@ -9,8 +9,9 @@ STAT_KEYS = ("env_steps", "crashes", "episodes", "episode_len_sum", "reward_sum"
 
 
 def env_shard(total_envs: int, rank: int, world_size: int) -> tuple[int, int]:
-    """Contiguous slice [start, start+count) of `total_envs` owned by `rank`; counts differ by at most one and
-    every start is a multiple of 64 when total_envs/world_size allows it (64 = one warp chunk of the kernel)."""
+    """Contiguous slice [start, start+count) of `total_envs` owned by `rank`.  When total_envs divides evenly the slices are
+    equal; otherwise every start is a multiple of 64 (one warp chunk of the kernel) and the counts differ by at most 64
+    (by at most one when total_envs < 64 * world_size)."""
     if not (0 <= rank < world_size):
         raise ValueError("rank out of range")
     if total_envs < 0:

@@ -169,6 +169,12 @@ int fpv_sizeof(int which);
 /* Number of SMs / compute capability of `device`; used by hosts to size persistent launches. */
 int fpv_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
 
+/* Diagnostic: one launch of a pure-FMA kernel (SMs x 8 CTAs x 256 threads x iters x 16 independent chains with shared
+ * multiplicand / addend; packed != 0: fma.rn.f32x2, else scalar fma.rn.f32).  *flop_out (host) receives the flops of the
+ * launch; the caller times it with events.  bench.py reports the result as roofline.peak_measured next to the nominal
+ * FP32 peak.  sink: device float[>= SMs * 8 * 256] (never written in practice). */
+int fpv_probe_fp32(int32_t packed, int32_t iters, float* sink, int64_t sink_floats, double* flop_out, void* stream);
+
 /* Drone.reset(position, velocity, ypr)  -- components.py:150-169.
  * pos, vel, rpy_deg: float[n][3] row-major (rpy in DEGREES, consumed as roll, pitch, yaw exactly like
  * the reference's `ypr` argument).  mask: uint8[n] or NULL; only envs with mask != 0 are reset. */
@@ -361,6 +367,11 @@ typedef struct fpv_autopilot_params { /* Drone.__init__, components.py:96-97, :1
 /* Camera.update (components.py:501-503) for every env: pose[e] = { R_cam row-major [9], camera position [3] }. */
 int fpv_camera_update(const fpv_camera_params_t* cam, const void* state, int64_t n, int64_t plane_stride, double* pose,
                       void* stream);
+
+/* The same update from explicit poses (the literal call shape of components.py:501: update(drone_position,
+ * drone_rotation_matrix)): pos double[n][3], rot double[n][9] row-major body->world. */
+int fpv_camera_update_pose(const fpv_camera_params_t* cam, const double* pos, const double* rot, int64_t n, double* pose,
+                           void* stream);
 
 /* Camera.render_depth_image (max_depth > 0, components.py:614-629) or Camera.render_image (max_depth <= 0, :601-612),
  * including pruned_objects_list (:584-599), for n cameras looking at ONE shared world:

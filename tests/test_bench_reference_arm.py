@@ -24,8 +24,11 @@ def test_reference_arm_prints_one_contract_line():
     assert d["higher_is_better"] is True and d["steps"] == 2 and d["warmup"] == 1 and d["n_gpus"] == 1
     assert d["value"] > 0 and d["value"] == d["e2e"]["value"] == d["cpu_baseline"]["value"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "65536 envs" in d["cpu_baseline"]["sample"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "1048576 envs" in d["cpu_baseline"]["sample"]
     assert "1,048,576 drones per GPU" in d["config"]["workload"] and d["gpu_launches"] == 0
+    # same config object as the native arm prints (the driver compares them): no sample key, full batch
+    import bench
+    assert d["config"] == bench.workload_config(1)
 
 
 def test_reference_arm_runs_on_rank_0_only():

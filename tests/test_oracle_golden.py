@@ -182,3 +182,25 @@ def test_c_restatement_matches_reference(name):
                     rel(pr, g["prev_rates"][t]), rel(pt, g["prev_thrust"][t]))
         assert np.array_equal(done.astype(bool), g["done"][t].astype(bool))
     assert worst < 1e-11, worst
+
+
+@pytest.mark.parametrize("name", ["drone_kat", "drone_random", "drone_ground", "drone_wind", "drone_1ms_k8"])
+def test_numba_restatement_matches_reference(name):
+    """oracle/numba_oracle.py (bench.py's `cpu_baseline_numba` leg; the reference itself ships no Numba path,
+    kinematics.py:6,14 are commented out) against the same golden vectors."""
+    from oracle import numba_oracle as no
+    g = load(name)
+    c = consts(dt=float(g["dt"]))
+    k, mrel = no.make_consts(c)
+    s = fo.drone_reset(c, g["pos0"], g["vel0"], g["rpy0"])
+    pos, vel, R = s.pos.copy(), s.vel.copy(), np.ascontiguousarray(s.R)
+    pr, pt = np.zeros_like(pos), np.zeros(len(pos))
+    wind = np.ascontiguousarray(g["wind"], dtype=np.float64) if "wind" in g else np.zeros(3)
+    done = np.zeros(len(pos), dtype=np.bool_)
+    worst = 0.0
+    for t in range(g["actions"].shape[0]):
+        no.drone_step(k, mrel, pos, vel, R, pr, pt, np.ascontiguousarray(g["actions"][t], dtype=np.float64), wind, 1, done)
+        worst = max(worst, rel(np.concatenate([pos, vel], 1), g["state"][t]), rel(R, g["R"][t]),
+                    rel(pr, g["prev_rates"][t]), rel(pt, g["prev_thrust"][t]))
+        assert np.array_equal(done, g["done"][t].astype(bool))
+    assert worst < 1e-11, worst
