@@ -8,15 +8,15 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 # FPYV_B200_LIB: developer override used to A/B differently tuned builds of the same ABI
 LIB_PATH = os.environ.get("FPYV_B200_LIB") or os.path.join(HERE, "libfpyv_b200.so")
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 # flags (fpv_api.h)
 F_GROUND, F_AUTO_RESET, F_FREEZE_DONE, F_THRUST_LUT, F_SCALAR, F_CHAINED, F_RATE_CURVE = 1, 2, 4, 8, 32, 64, 128
 OBJ_SPHERE, OBJ_CYLINDER = 1, 2
 MAX_OBJECTS = 16
-DRONE_PLANES, RACER_PLANES = 4, 7
+DRONE_PLANES, RACER_PLANES = 4, 5
 EXPORTS = ("fpv_abi_version", "fpv_last_error", "fpv_sizeof", "fpv_device_info", "fpv_drone_reset",
-           "fpv_drone_step", "fpv_drone_step_host", "fpv_drone_step_host_sticks", "fpv_drone_rollout", "fpv_drone_observe", "fpv_drone_get_rotation", "fpv_drone_set_rotation", "fpv_matrix_to_quat", "fpv_sticks_to_actions", "fpv_racer_reset", "fpv_racer_step", "fpv_gate_env_reset", "fpv_gate_env_step", "fpv_gate_race_step",
+           "fpv_drone_step", "fpv_drone_step_host", "fpv_drone_step_host_sticks", "fpv_drone_rollout", "fpv_drone_observe", "fpv_drone_get_rotation", "fpv_drone_set_rotation", "fpv_matrix_to_quat", "fpv_sticks_to_actions", "fpv_racer_reset", "fpv_racer_step", "fpv_racer_observe", "fpv_gate_env_reset", "fpv_gate_env_step", "fpv_gate_race_step",
            "fpv_camera_update", "fpv_camera_update_pose", "fpv_camera_render", "fpv_camera_target_pixel", "fpv_camera_rays", "fpv_autopilot", "fpv_point_and_shoot",
            "fpv_acro_reset", "fpv_acro_step", "fpv_acro_rollout", "fpv_probe_fp32")
 
@@ -49,7 +49,7 @@ class Stats(C.Structure):
 class DroneIO(C.Structure):
     _fields_ = [("state", C.c_void_p), ("n", C.c_int64), ("plane_stride", C.c_int64), ("actions", C.c_void_p),
                 ("wind_env", C.c_void_p), ("lut", C.c_void_p), ("lut_n", C.c_int32), ("done", C.c_void_p),
-                ("acc_out", C.c_void_p), ("reset_state", C.c_void_p), ("override_q", C.c_void_p),
+                ("done_bits", C.c_void_p), ("acc_out", C.c_void_p), ("reset_state", C.c_void_p), ("override_q", C.c_void_p),
                 ("override_thrust", C.c_void_p),
                 ("objects", C.POINTER(Object)), ("stats", C.c_void_p), ("work", C.c_void_p), ("chunk_epoch", C.c_void_p),
                 ("epoch", C.c_uint32), ("max_ctas_per_sm", C.c_uint32), ("trace", C.c_void_p)]
@@ -145,7 +145,8 @@ def load():
                                           C.c_void_p]
     lib.fpv_racer_reset.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
     lib.fpv_racer_step.argtypes = [C.POINTER(RacerParams), C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
-                                   C.c_void_p, C.c_void_p]
+                                   C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.fpv_racer_observe.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.fpv_gate_env_reset.argtypes = [C.POINTER(GateEnvParams), C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p]
     lib.fpv_gate_env_step.argtypes = [C.POINTER(GateEnvParams), C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
@@ -160,7 +161,7 @@ def load():
     lib.fpv_autopilot.argtypes = [P(AutopilotParams), P(CameraParams), V, I64, I64, V, V, V, V, V, V, V, V, V]
     lib.fpv_point_and_shoot.argtypes = [P(AutopilotParams), P(CameraParams), V, I64, I64, V, V, V, V, V, V, V, V, V]
     lib.fpv_acro_reset.argtypes = [V, I64, I64, V, V, V, V, V]
-    lib.fpv_acro_step.argtypes = [P(AcroParams), V, I64, I64, V, V, I32, V, V, V, V, V]
+    lib.fpv_acro_step.argtypes = [P(AcroParams), V, I64, I64, V, V, I32, V, V, V, V, V, V]
     lib.fpv_acro_rollout.argtypes = [P(AcroParams), V, I64, I64, V, I64, I32, V, I32, V, I64, V, V, V, V, V]
     lib.fpv_probe_fp32.argtypes = [I32, I32, V, I64, P(D), V]
     v = lib.fpv_abi_version()

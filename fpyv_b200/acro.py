@@ -49,6 +49,7 @@ class BatchedAcroDrone:
         self._done = torch.zeros(n, dtype=torch.uint8, device=dev)
         self._motor = torch.zeros((n, 4), dtype=torch.float32, device=dev)
         self._stats = torch.zeros(8, dtype=torch.float64, device=dev)
+        self._work = torch.zeros(32, dtype=torch.int32, device=dev)       # chunk counters of the ring kernel
         self._lut = torch.from_numpy(config.thrust_table(c, int(thrust_lut), "poly")).to(dev) if thrust_lut else None
         self._flags = ((_lib.F_GROUND if ground else 0) | (_lib.F_AUTO_RESET if auto_reset else 0) |
                        (_lib.F_THRUST_LUT if thrust_lut else 0) | (0 if packed else _lib.F_SCALAR))
@@ -113,7 +114,7 @@ class BatchedAcroDrone:
         _lib.check(self._lib.fpv_acro_step(C.byref(self._p), _lib.ptr(self._state), n, self._stride, _lib.ptr(act),
                                            _lib.ptr(self._lut), 0 if self._lut is None else self._lut.numel(),
                                            _lib.ptr(self._done), _lib.ptr(self._motor), _lib.ptr(self._reset_state),
-                                           _lib.ptr(self._stats), _lib.current_stream(dev)))
+                                           _lib.ptr(self._stats), _lib.ptr(self._work), _lib.current_stream(dev)))
         return self._done
 
     def rollout(self, actions, done_out=None):

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfpyv_b200.so")
 SOURCES = ["fpv_api.cu"]
-HEADERS = ["drone_kernels.cuh", "misc_kernels.cuh", "env_kernels.cuh", "chase_kernels.cuh", "acro_kernels.cuh", "probe_kernels.cuh", "vec.cuh", os.path.join("..", "..", "include", "fpv_api.h")]
+HEADERS = ["drone_kernels.cuh", "misc_kernels.cuh", "env_kernels.cuh", "chase_kernels.cuh", "acro_kernels.cuh", "probe_kernels.cuh", "ring_kernels.cuh", "racer_kernels.cuh", "vec.cuh", os.path.join("..", "..", "include", "fpv_api.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

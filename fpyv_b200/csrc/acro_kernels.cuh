@@ -122,39 +122,24 @@ template <> __device__ __forceinline__ void sinc_cos<F2>(F2 a2, F2& sinc, F2& cs
   cs = f2_pack(c0, c1);
 }
 
-// One thread owns L envs (1 = float, 2 = packed F2: FFMA2/FMUL2/FADD2); CTA tile = THREADS*L envs, slot l of thread t
-// is env tile*TILE + l*THREADS + t (every 128-bit access of a warp is one contiguous 512 B run).
-template <class V, int THREADS>
-__global__ void __launch_bounds__(THREADS) acro_step_kernel(const __grid_constant__ AcroK k, float4* state, long long n,
-                                                            long long stride, const float4* actions, const float* lut,
-                                                            unsigned char* done_out, float4* motor_out,
-                                                            const float4* reset_state, fpv_stats_t* stats, const int T,
-                                                            const long long act_stride, unsigned char* done_seq,
-                                                            const long long done_stride) {
-  // T control steps per launch (T = 1: fpv_acro_step; T > 1: fpv_acro_rollout, the open-loop form -- the state stays in
-  // registers from the first step to the last, step t reads actions[t * act_stride + env] and writes
-  // done_seq[t * done_stride + env]; crashes restart from the snapshot IN REGISTERS, so the result is bit-identical to
-  // T launches with T = 1).
+// The control steps of the L envs one thread owns (1 = float, 2 = packed F2: FFMA2/FMUL2/FADD2), shared by the plain
+// kernel (acro_step_kernel: T >= 1 control steps per launch, slot l of thread t = env tile*TILE + l*THREADS + t) and the
+// ring form (AcroMode: T = 1, slot l of lane t = env chunk*64 + 32 l + t).  q = the 7 state rows, act = the first step's
+// actions; everything after the loads happens here, stores included.
+// T control steps per launch (T = 1: fpv_acro_step; T > 1: fpv_acro_rollout, the open-loop form -- the state stays in
+// registers from the first step to the last, step t reads actions[t * act_stride + env] and writes
+// done_seq[t * done_stride + env]; crashes restart from the snapshot IN REGISTERS, so the result is bit-identical to
+// T launches with T = 1).
+template <class V, int SLOT_STRIDE>
+__device__ __forceinline__ void acro_body(const AcroK& k, float4* state, long long n, long long stride, const float4* actions,
+                                          const float* lut_s, unsigned char* done_out, float4* motor_out,
+                                          const float4* reset_state, TileStats& st, const int T, const long long act_stride,
+                                          unsigned char* done_seq, const long long done_stride,
+                                          const float4 (&q)[FPV_ACRO_PLANES][Lane<V>::N], float4 (&act)[Lane<V>::N],
+                                          const long long (&ei)[Lane<V>::N], const long long base) {
   constexpr int L = Lane<V>::N;
-  constexpr int TILE = THREADS * L;
   using M = typename Lane<V>::Mask;
-  extern __shared__ float lut_s[];
-  if (k.flags & FPV_F_THRUST_LUT) {
-    for (int i = threadIdx.x; i < k.lut_n; i += THREADS) lut_s[i] = lut[i];
-    __syncthreads();
-  }
-  const long long base = (long long)blockIdx.x * TILE + threadIdx.x;
-  if (base >= n) return;
-  long long ei[L];
-#pragma unroll
-  for (int l = 0; l < L; ++l) ei[l] = min(base + (long long)l * THREADS, n - 1);   // a slot past the end is never stored
-  float4 q[FPV_ACRO_PLANES][L], act[L], act_next[L];
-#pragma unroll
-  for (int p = 0; p < FPV_ACRO_PLANES; ++p)
-#pragma unroll
-    for (int l = 0; l < L; ++l) q[p][l] = ldg_stream(state + p * stride + ei[l]);
-#pragma unroll
-  for (int l = 0; l < L; ++l) act[l] = ldg_stream(actions + ei[l]);
+  float4 act_next[L];
   V px = Pack<V>::x(q[0]), py = Pack<V>::y(q[0]), pz = Pack<V>::z(q[0]), thr = Pack<V>::w(q[0]);
   V vx = Pack<V>::x(q[1]), vy = Pack<V>::y(q[1]), vz = Pack<V>::z(q[1]);
   V qw = Pack<V>::x(q[2]), qx = Pack<V>::y(q[2]), qy = Pack<V>::z(q[2]), qz = Pack<V>::w(q[2]);
@@ -277,16 +262,16 @@ __global__ void __launch_bounds__(THREADS) acro_step_kernel(const __grid_constan
   // ---- per-step bookkeeping on registers: flags, statistics, restart from the snapshot
 #pragma unroll
   for (int l = 0; l < L; ++l) {
-    const long long e = base + (long long)l * THREADS;
+    const long long e = base + (long long)l * SLOT_STRIDE;
     if (e >= n) break;
     const bool d = mask_get(done, l);
     epi[l] += 1;
     first_flag[l] = 0.f;   // the PIDs have been called
     if (done_seq) done_seq[(long long)t * done_stride + e] = d ? 1 : 0;
     if (done_out && t == T - 1) done_out[e] = d ? 1 : 0;
-    if (d && stats) {
-      atomicAdd(&stats->crashes, 1.0);
-      if (k.flags & FPV_F_AUTO_RESET) { atomicAdd(&stats->episodes, 1.0); atomicAdd(&stats->episode_len_sum, (double)epi[l]); }
+    if (d) {   // rare events: accumulated per thread, flushed once per launch (stats_warp_flush)
+      st.crash += 1.f;
+      if (k.flags & FPV_F_AUTO_RESET) { st.epi += 1.f; st.len += (float)epi[l]; }
     }
     if (d && (k.flags & FPV_F_AUTO_RESET)) {
       float4 v[FPV_ACRO_PLANES];
@@ -310,7 +295,7 @@ __global__ void __launch_bounds__(THREADS) acro_step_kernel(const __grid_constan
   // ---- the state goes back once
 #pragma unroll
   for (int l = 0; l < L; ++l) {
-    const long long e = base + (long long)l * THREADS;
+    const long long e = base + (long long)l * SLOT_STRIDE;
     if (e >= n) break;
     if (motor_out)
       stg_stream(motor_out + e, make_float4(Lane<V>::get(fm[0], l), Lane<V>::get(fm[1], l), Lane<V>::get(fm[2], l), Lane<V>::get(fm[3], l)));
@@ -324,5 +309,98 @@ __global__ void __launch_bounds__(THREADS) acro_step_kernel(const __grid_constan
     stg_stream(state + 6 * stride + e, make_float4(g(le[0]), g(le[1]), g(le[2]), 0.f));
   }
 }
+
+// One thread owns L envs; CTA tile = THREADS*L envs, slot l of thread t is env tile*TILE + l*THREADS + t (every 128-bit
+// access of a warp is one contiguous 512 B run).  Used for rollouts (T > 1), the scalar cross-check and as the fallback.
+template <class V, int THREADS>
+__global__ void __launch_bounds__(THREADS) acro_step_kernel(const __grid_constant__ AcroK k, float4* state, long long n,
+                                                            long long stride, const float4* actions, const float* lut,
+                                                            unsigned char* done_out, float4* motor_out,
+                                                            const float4* reset_state, fpv_stats_t* stats, const int T,
+                                                            const long long act_stride, unsigned char* done_seq,
+                                                            const long long done_stride) {
+  constexpr int L = Lane<V>::N;
+  constexpr int TILE = THREADS * L;
+  extern __shared__ float lut_s[];
+  if (k.flags & FPV_F_THRUST_LUT) {
+    for (int i = threadIdx.x; i < k.lut_n; i += THREADS) lut_s[i] = lut[i];
+    __syncthreads();
+  }
+  const long long base = (long long)blockIdx.x * TILE + threadIdx.x;
+  TileStats st = {0.f, 0.f, 0.f, 0.f, 0.f};
+  if (base < n) {
+    long long ei[L];
+#pragma unroll
+    for (int l = 0; l < L; ++l) ei[l] = min(base + (long long)l * THREADS, n - 1);   // a slot past the end is never stored
+    float4 q[FPV_ACRO_PLANES][L], act[L];
+#pragma unroll
+    for (int p = 0; p < FPV_ACRO_PLANES; ++p)
+#pragma unroll
+      for (int l = 0; l < L; ++l) q[p][l] = ldg_stream(state + p * stride + ei[l]);
+#pragma unroll
+    for (int l = 0; l < L; ++l) act[l] = ldg_stream(actions + ei[l]);
+    acro_body<V, THREADS>(k, state, n, stride, actions, lut_s, done_out, motor_out, reset_state, st, T, act_stride, done_seq,
+                          done_stride, q, act, ei, base);
+  }
+  if (stats) stats_warp_flush(stats, st);
+}
+
+// The ring form of one control step (fpv_acro_step, packed): 7 state planes + actions per chunk, LUT staged once per CTA.
+struct AcroIO {
+  float4* state;
+  long long n, stride;
+  const float4* actions;
+  const float* lut;
+  unsigned char* done;
+  float4* motor_out;
+  const float4* reset_state;
+  fpv_stats_t* stats;
+  unsigned* work;
+  unsigned* chunk_epoch;   // always null: mode C has no chained form
+  unsigned epoch;
+  unsigned* err;
+  unsigned long long* trace;
+};
+
+template <class V_>
+struct AcroMode {
+  using V = V_;
+  using K = AcroK;
+  using IO = AcroIO;
+  static constexpr int ROWS = FPV_ACRO_PLANES + 1;
+  struct Ctx {
+    TileStats st;
+  };
+  static __device__ __forceinline__ bool chained(const K&) { return false; }
+  static __device__ __forceinline__ const float4* row(const IO& io, int r) {
+    return r < FPV_ACRO_PLANES ? io.state + r * io.stride : io.actions;
+  }
+  static __device__ __forceinline__ void stage(const K& k, const IO& io, unsigned char* smem, int tid, int nthreads) {
+    float* lut_s = reinterpret_cast<float*>(smem);
+    if (k.flags & FPV_F_THRUST_LUT)
+      for (int i = tid; i < k.lut_n; i += nthreads) lut_s[i] = io.lut[i];
+  }
+  static __device__ __forceinline__ Ctx begin(const K&, const IO&) { return Ctx{TileStats{0.f, 0.f, 0.f, 0.f, 0.f}}; }
+  template <class PreStore>
+  static __device__ __forceinline__ void tile(const K& k, const IO& io, const unsigned char* staged,
+                                              const float4 (&rows)[ROWS][Lane<V>::N], const long long (&ei)[Lane<V>::N],
+                                              long long base, Ctx& c, PreStore pre_store) {
+    constexpr int L = Lane<V>::N;
+    pre_store();
+    if (base >= io.n) return;
+    float4 q[FPV_ACRO_PLANES][L], act[L];
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+#pragma unroll
+      for (int p = 0; p < FPV_ACRO_PLANES; ++p) q[p][l] = rows[p][l];
+      act[l] = rows[FPV_ACRO_PLANES][l];
+    }
+    acro_body<V, 32>(k, io.state, io.n, io.stride, io.actions, reinterpret_cast<const float*>(staged), io.done, io.motor_out,
+                     io.reset_state, c.st, 1, 0, nullptr, 0, q, act, ei, base);
+  }
+  static __device__ __forceinline__ void finish(const K&, const IO& io, Ctx& c) {
+    if (io.stats) stats_warp_flush(io.stats, c.st);
+  }
+};
 
 }  // namespace fpv

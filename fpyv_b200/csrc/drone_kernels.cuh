@@ -10,6 +10,7 @@
 #pragma once
 #include "../../include/fpv_api.h"
 #include "vec.cuh"
+#include "ring_kernels.cuh"
 
 namespace fpv {
 
@@ -24,6 +25,7 @@ struct DroneK {
   float ttr;
   float one_minus_ttr;      // components.py:192-193
   float kd0, kd_a, kd_b;    // k_drag[0], k_drag[1]-k_drag[0], k_drag[2]-k_drag[0]   (kinematics.py:36)
+  float kd_max;             // max |k_drag[i]| * 1.001: bound on the drag force per |u|^2
   float neg_motor_xy[4][2]; // -motor offsets                       components.py:123-125
   float motor_xy[4][2];
   float motor_radius;
@@ -50,6 +52,7 @@ struct DroneIO {
   const float4* wind_env;
   const float* lut;
   unsigned char* done;
+  unsigned* done_bits;           // [ceil(n / 32)]: the same flags as a bitmask (bit e % 32 of word e / 32), or null
   float4* acc_out;
   const float4* reset_state;
   const float4* override_q;      // [n]: rotation override as a quaternion (w,x,y,z)
@@ -59,6 +62,7 @@ struct DroneIO {
   unsigned* chunk_epoch;       // [n_chunks] per-chunk step count (chained launches), or null
   unsigned epoch;              // value chunk_epoch[] holds before this launch; the launch publishes epoch + 1
   unsigned cta_cap;            // host only: cap on resident CTAs per SM (0 = none)
+  unsigned* err;               // [0] += 1 when a chained wait timed out (fpv_drone_io_t.work[16]), or null
   unsigned long long* trace;
 };
 
@@ -116,8 +120,9 @@ template <class V, int ANG, bool GENERAL, bool WIND>
 __device__ __forceinline__ typename Lane<V>::Mask drone_substeps(const DroneK& k, DroneRegs<V>& s, V a0, V a1, V a2,
                                                                    V thrust_target, V wx, V wy, V wz,
                                                                    bool has_override, V o_thrust, V oqw, V oqx, V oqy,
-                                                                   V oqz) {
+                                                                   V oqz, const fpv_object_t* objs = nullptr) {
   using M = typename Lane<V>::Mask;
+  if (GENERAL && objs == nullptr) objs = k.objects;   // kernels without a staged table read the kernel-parameter copy
   // action2force invariants (the action is held for the whole control step), components.py:185-193
   // The rate filter runs on the half Euler angles h_i = rates_i * (deg2rad*dt/2) directly (same linear recurrence,
   // scaled), so no per-substep rescaling is needed; rates are recovered once after the loop.
@@ -138,6 +143,51 @@ __device__ __forceinline__ typename Lane<V>::Mask drone_substeps(const DroneK& k
   const bool ground = (k.flags & FPV_F_GROUND) != 0;
   M done = vlt(one, zero);  // all false
   V Fx = zero, Fy = zero, Fz = zero;
+
+  // GENERAL: which obstacles can any motor of this thread's envs REACH during this control step?  Decided once, outside
+  // the substep loop.  Positions tested by the substeps are x_0 .. x_{K-1} = x_0 + dt * sum of earlier velocities, so an
+  // obstacle whose surface is further from x_0 than  arm_reach + K dt V*  (V* = a bound on the speed over the step)
+  // fails the per-substep reach test in EVERY substep and contributes exactly nothing: skipping it is bit-identical.
+  // V*: |F| <= |thrust| + kmax (|v| + |wind|)^2 + m g + contact springs, the thrust filter is a convex mix of its state and
+  // its target, an obstacle / the ground pushes with at most 4 (k r_m + c |v|); with G = 1.5 K dt a(|v0|) + 0.01,
+  // K dt a(|v0| + G) <= G proves |v_i| <= |v0| + G for all substeps by induction.  An env whose bound does not close (or an
+  // override, which replaces thrust and attitude) keeps every obstacle and is tested substep by substep as before.
+  unsigned step_mask = 0u;
+  if (GENERAL && k.n_objects > 0) {
+    const V Kdt = S<V>((float)k.substeps * k.dt);
+    const V v0 = vsqrt_fast(vfma(s.vx, s.vx, vfma(s.vy, s.vy, s.vz * s.vz))) * S<V>(1.0001f);
+    const V wn = WIND ? vsqrt_fast(vfma(wx, wx, vfma(wy, wy, wz * wz))) * S<V>(1.0001f) : zero;
+    V T = vmax(vabs(s.pt), vabs(thrust_target));
+    if (has_override) T = vmax(T, vabs(o_thrust));
+    const V spring = S<V>(4.f * (float)(k.n_objects + 1) * k.spring_k * k.motor_radius);
+    const V damp = S<V>(4.f * (float)(k.n_objects + 1) * fabsf(k.spring_c));
+    const V kmax = S<V>(k.kd_max);
+    const V base_f = T + spring + S<V>(fabsf(k.grav_force_z));
+    auto acc_bound = [&](V vb) {
+      const V u = vb + wn;
+      return vfma(kmax * u, u, vfma(damp, vb, base_f)) * S<V>(k.inv_mass * 1.001f);
+    };
+    const V G = vfma(Kdt * acc_bound(v0), S<V>(1.5f), S<V>(0.01f));
+    const M closes = vle(Kdt * acc_bound(v0 + G), G);      // false for NaN as well
+    const V travel = Kdt * (v0 + G);
+    const V reach = S<V>(k.arm_reach) + travel;
+    for (int o = 0; o < k.n_objects; ++o) {
+      const fpv_object_t& ob = k.objects[o];               // warp-uniform index: kernel-parameter constant bank
+      const V dx = s.px - S<V>(ob.x), dy = s.py - S<V>(ob.y);
+      const V lim = S<V>(ob.a) + reach;
+      M near;
+      if (ob.kind == FPV_OBJ_SPHERE) {
+        const V dz = s.pz - S<V>(ob.z);
+        near = vlt(vfma(dx, dx, vfma(dy, dy, dz * dz)), lim * lim);
+      } else {
+        near = vand(vlt(vfma(dx, dx, dy * dy), lim * lim),
+                    vand(vlt(S<V>(ob.z) - reach, s.pz), vlt(s.pz, S<V>(ob.z + ob.b) + reach)));
+      }
+      near = vor(near, vnot(closes));
+      step_mask |= vany(near) ? (1u << o) : 0u;
+    }
+    if (has_override) step_mask = (k.n_objects >= 32) ? 0xffffffffu : ((1u << k.n_objects) - 1u);
+  }
 
 #pragma unroll 2
   for (int it = 0; it < k.substeps; ++it) {
@@ -205,10 +255,12 @@ __device__ __forceinline__ typename Lane<V>::Mask drone_substeps(const DroneK& k
       //     within the arm length of the drone's centre, so an obstacle whose surface is further away than
       //     arm + motor_radius contributes exactly nothing and skipping it leaves the result bit-identical.
       unsigned near_mask = 0u;
-      {
+      if (step_mask) {
         const V reach = S<V>(k.arm_reach);
-        for (int o = 0; o < k.n_objects; ++o) {
-          const fpv_object_t& ob = k.objects[o];
+        for (unsigned rem = step_mask; rem;) {
+          const int o = __ffs(rem) - 1;
+          rem &= rem - 1u;
+          const fpv_object_t ob = objs[o];
           const V dx = s.px - S<V>(ob.x), dy = s.py - S<V>(ob.y);
           const V lim = S<V>(ob.a) + reach;
           M near;
@@ -237,11 +289,12 @@ __device__ __forceinline__ typename Lane<V>::Mask drone_substeps(const DroneK& k
         while (near_mask) {
           const int o = __ffs(near_mask) - 1;
           near_mask &= near_mask - 1u;
+          const fpv_object_t ob = objs[o];
           V d[4];
           M hit = vlt(one, zero), touch = hit;
 #pragma unroll
           for (int m = 0; m < 4; ++m) {
-            d[m] = object_distance<V>(k.objects[o], mxw[m], myw[m], mzw[m]);
+            d[m] = object_distance<V>(ob, mxw[m], myw[m], mzw[m]);
             hit = vor(hit, vlt(d[m], zero));
             touch = vor(touch, vlt(d[m], S<V>(k.motor_radius)));
           }
@@ -253,7 +306,7 @@ __device__ __forceinline__ typename Lane<V>::Mask drone_substeps(const DroneK& k
 #pragma unroll
             for (int m = 0; m < 4; ++m) {
               V nx, ny, nz;
-              object_normal<V>(k.objects[o], mxw[m], myw[m], mzw[m], nx, ny, nz);
+              object_normal<V>(ob, mxw[m], myw[m], mzw[m], nx, ny, nz);
               const V pen = d[m] - S<V>(k.motor_radius);
               const V vn = vfma(s.vx, nx, vfma(s.vy, ny, s.vz * nz));
               const V f = vneg(vfma(S<V>(k.spring_k), pen, S<V>(k.spring_c) * vn));
@@ -364,20 +417,6 @@ __device__ __forceinline__ float thrust_lut1(const DroneK& k, const float* lut, 
   return fmaf(f, b - a, a);
 }
 
-template <class V> struct Pack;
-template <> struct Pack<float> {
-  static __device__ __forceinline__ float x(const float4* q) { return q[0].x; }
-  static __device__ __forceinline__ float y(const float4* q) { return q[0].y; }
-  static __device__ __forceinline__ float z(const float4* q) { return q[0].z; }
-  static __device__ __forceinline__ float w(const float4* q) { return q[0].w; }
-};
-template <> struct Pack<F2> {
-  static __device__ __forceinline__ F2 x(const float4* q) { return f2_pack(q[0].x, q[1].x); }
-  static __device__ __forceinline__ F2 y(const float4* q) { return f2_pack(q[0].y, q[1].y); }
-  static __device__ __forceinline__ F2 z(const float4* q) { return f2_pack(q[0].z, q[1].z); }
-  static __device__ __forceinline__ F2 w(const float4* q) { return f2_pack(q[0].w, q[1].w); }
-};
-
 // Episode statistics: every counter is a RARE event (crash / episode end / non-finite / frozen), so the common
 // path is one warp vote and no memory traffic; a warp that saw an event reduces with shuffles and issues one
 // fire-and-forget red.global.add.f64 per non-zero counter.  No block barrier.  env_steps = n per launch (added by
@@ -405,17 +444,30 @@ __device__ __forceinline__ void stats_warp_flush(fpv_stats_t* stats, const TileS
 // One tile worth of work for this thread: unpack L envs from their float4 rows, run the substeps in registers,
 // episode bookkeeping, stores.  q[p][l] = plane p of slot l; slot l is env base + l*SLOT_STRIDE (ei[l] = the same
 // index clamped to n-1, used for the side inputs).
-struct NoHook {
-  __device__ __forceinline__ void operator()() const {}
+// Per-chunk epilogue hook of drone_tile (see DroneMode below): nothing.
+struct NoPost {
+  static constexpr bool enabled = false;
+  struct Ctx {};
+  template <class IO> static __device__ __forceinline__ Ctx begin(const IO&) { return Ctx{}; }
+  template <class IO> static __device__ __forceinline__ void stage(const IO&, unsigned char*, int, int) {}
+  template <class IO> static __device__ __forceinline__ int bytes(const IO&) { return 0; }
+  template <class IO, int L>
+  static __device__ __forceinline__ void run(const IO&, const unsigned char*, const float4 (&)[FPV_DRONE_PLANES][L],
+                                             const bool (&)[L], const bool (&)[L], const long long (&)[L], Ctx&) {}
+  template <class IO> static __device__ __forceinline__ void finish(const IO&, Ctx&) {}
 };
+
 // `pre_store` runs between the arithmetic and the first store of the tile (used by the ring kernel to publish the
-// PREVIOUS chunk's epoch once its stores have had a whole substep loop to land).
-template <class V, int ANG, bool GENERAL, int SLOT_STRIDE, class PreStore = NoHook>
-__device__ __forceinline__ void drone_tile(const DroneK& k, const DroneIO& io, const float* lut_s,
+// PREVIOUS chunk's epoch once its stores have had a whole substep loop to land).  `Post` (NoPost, or the gate-race env
+// step) runs after the stores on the FINAL rows of the thread's envs -- what the next step will read -- with all 32 lanes
+// converged, so that it may use warp shuffles / votes.
+template <class V, int ANG, bool GENERAL, int SLOT_STRIDE, class PreStore = NoHook, class Post = NoPost, class IO = DroneIO>
+__device__ __forceinline__ void drone_tile(const DroneK& k, const IO& io, const float* lut_s, const fpv_object_t* objs,
                                            const float4 (&q)[FPV_DRONE_PLANES][Lane<V>::N],
                                            const float4 (&act)[Lane<V>::N], const long long (&ei)[Lane<V>::N],
                                            long long base, TileStats& st, const bool wind_on,
-                                           PreStore pre_store = PreStore()) {
+                                           PreStore pre_store = PreStore(), const unsigned char* staged = nullptr,
+                                           typename Post::Ctx* post_ctx = nullptr) {
   constexpr int L = Lane<V>::N;
   DroneRegs<V> s;
   s.px = Pack<V>::x(q[0]); s.py = Pack<V>::y(q[0]); s.pz = Pack<V>::z(q[0]); s.pt = Pack<V>::w(q[0]);
@@ -457,22 +509,43 @@ __device__ __forceinline__ void drone_tile(const DroneK& k, const DroneIO& io, c
   }
 
   typename Lane<V>::Mask done;
-  if (wind_on) done = drone_substeps<V, ANG, GENERAL, true>(k, s, a0, a1, a2, target, wx, wy, wz, has_ovr, o_thrust, oqw, oqx, oqy, oqz);
-  else done = drone_substeps<V, ANG, GENERAL, false>(k, s, a0, a1, a2, target, wx, wy, wz, has_ovr, o_thrust, oqw, oqx, oqy, oqz);
+  if (wind_on) done = drone_substeps<V, ANG, GENERAL, true>(k, s, a0, a1, a2, target, wx, wy, wz, has_ovr, o_thrust, oqw, oqx, oqy, oqz, objs);
+  else done = drone_substeps<V, ANG, GENERAL, false>(k, s, a0, a1, a2, target, wx, wy, wz, has_ovr, o_thrust, oqw, oqx, oqy, oqz, objs);
 
   pre_store();
+  // ---- the done flags as a bitmask: one ballot per slot, one 32-bit store per 32 envs (SLOT_STRIDE == 32: the ring
+  //      layout, where slot l of lane t is env chunk*64 + 32 l + t, i.e. bit t of word chunk*2 + l)
+  if (SLOT_STRIDE == 32 && io.done_bits) {
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+      const long long e = base + (long long)l * SLOT_STRIDE;
+      const bool flag = e < io.n && (mask_get(done, l) || epi[l] < 0);
+      const unsigned word = __ballot_sync(0xffffffffu, flag);
+      if ((threadIdx.x & 31) == 0 && e < io.n) io.done_bits[e >> 5] = word;
+    }
+  }
   // ---- epilogue per env: episode bookkeeping, freeze / auto-reset, stores
+  float4 fin[FPV_DRONE_PLANES][L];   // the rows the next step will read (only materialised when a Post hook consumes them)
+  bool crashed_l[L], live_l[L];
 #pragma unroll
   for (int l = 0; l < L; ++l) {
     const long long e = base + (long long)l * SLOT_STRIDE;
-    if (e >= io.n) break;
+    crashed_l[l] = false;
+    live_l[l] = e < io.n;
+    if (Post::enabled) {
+#pragma unroll
+      for (int p = 0; p < FPV_DRONE_PLANES; ++p) fin[p][l] = q[p][l];
+    }
+    if (e >= io.n) continue;
     const bool d = mask_get(done, l);
     int ep = epi[l];
     if (ep < 0) {  // frozen after a crash (FPV_F_FREEZE_DONE): state in memory stays as it is, done is sticky
       if (io.done) io.done[e] = 1;
       st.frozen += 1.f;
+      crashed_l[l] = true;
       continue;
     }
+    crashed_l[l] = d;
     ep += 1;
     float4* const dst = io.state + e;
     if (io.done) io.done[e] = d ? 1 : 0;
@@ -489,6 +562,10 @@ __device__ __forceinline__ void drone_tile(const DroneK& k, const DroneIO& io, c
         v[1].w = __int_as_float(0);
 #pragma unroll
         for (int p = 0; p < FPV_DRONE_PLANES; ++p) stg_stream(dst + p * io.stride, v[p]);
+        if (Post::enabled) {
+#pragma unroll
+          for (int p = 0; p < FPV_DRONE_PLANES; ++p) fin[p][l] = v[p];
+        }
         continue;
       }
       if (k.flags & FPV_F_FREEZE_DONE) {
@@ -500,11 +577,17 @@ __device__ __forceinline__ void drone_tile(const DroneK& k, const DroneIO& io, c
     const float vx = Lane<V>::get(s.vx, l), vy = Lane<V>::get(s.vy, l), vz = Lane<V>::get(s.vz, l);
     // NaN/Inf guard on the position: a non-finite velocity or attitude reaches it within one more step
     if (!(fabsf((px + py) + pz) <= 3.0e38f)) st.nf += 1.f;
-    stg_stream(dst, make_float4(px, py, pz, Lane<V>::get(s.pt, l)));
-    stg_stream(dst + io.stride, make_float4(vx, vy, vz, __int_as_float(ep)));
-    stg_stream(dst + 2 * io.stride, make_float4(Lane<V>::get(s.qw, l), Lane<V>::get(s.qx, l), Lane<V>::get(s.qy, l), Lane<V>::get(s.qz, l)));
-    stg_stream(dst + 3 * io.stride, make_float4(Lane<V>::get(s.pr0, l), Lane<V>::get(s.pr1, l), Lane<V>::get(s.pr2, l), spare[l]));
+    const float4 o0 = make_float4(px, py, pz, Lane<V>::get(s.pt, l));
+    const float4 o1 = make_float4(vx, vy, vz, __int_as_float(ep));
+    const float4 o2 = make_float4(Lane<V>::get(s.qw, l), Lane<V>::get(s.qx, l), Lane<V>::get(s.qy, l), Lane<V>::get(s.qz, l));
+    const float4 o3 = make_float4(Lane<V>::get(s.pr0, l), Lane<V>::get(s.pr1, l), Lane<V>::get(s.pr2, l), spare[l]);
+    stg_stream(dst, o0);
+    stg_stream(dst + io.stride, o1);
+    stg_stream(dst + 2 * io.stride, o2);
+    stg_stream(dst + 3 * io.stride, o3);
+    if (Post::enabled) { fin[0][l] = o0; fin[1][l] = o1; fin[2][l] = o2; fin[3][l] = o3; }
   }
+  if (Post::enabled) Post::run(io, staged, fin, crashed_l, live_l, ei, *post_ctx);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -540,247 +623,80 @@ __global__ void __launch_bounds__(THREADS, MINB) drone_step_kernel(const __grid_
       for (int l = 0; l < L; ++l) q[p][l] = ldg_stream(io.state + p * io.stride + ei[l]);
 #pragma unroll
     for (int l = 0; l < L; ++l) act[l] = ldg_stream(io.actions + ei[l]);
-    drone_tile<V, ANG, GENERAL, THREADS>(k, io, lut_dyn, q, act, ei, base, st, wind_on);
+    drone_tile<V, ANG, GENERAL, THREADS>(k, io, lut_dyn, nullptr, q, act, ei, base, st, wind_on);
   }
   if (io.stats) stats_warp_flush(io.stats, st);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Kernel 2 (the hot path): the five float4 rows of a chunk (4 state planes + actions) are brought into shared
-// memory by the TMA engine (cp.async.bulk, completion on an mbarrier) one chunk AHEAD of the arithmetic, so HBM
-// latency and bandwidth overlap the substep loop instead of preceding it.  STAGES ring slots per warp.
-//   smem: [ LUT | WARPS x STAGES x 5 x CHUNK float4 | WARPS x STAGES mbarriers ]
+// Kernel 2 (the ring form of the step): ring_step_kernel<DroneMode<...>> (ring_kernels.cuh).  Rows of a chunk = the four
+// state planes + the actions; staged table = the motor-curve LUT.  GENERAL = false is the hot path (the reference's own
+// configuration: ground plane, undamped spring); GENERAL = true adds obstacles / overrides / damped contact.  `Post` is the
+// per-chunk epilogue run on the FINAL rows of the chunk (after auto-reset), all lanes converged: the gate-race env step
+// plugs in there (env_kernels.cuh); NoPost for the plain step.
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ bool elect_one() {
-  unsigned pred;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "elect.sync _|p, 0xffffffff;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(smem_dst)),
-               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-
-// Every WARP owns a private ring: one elected lane is the producer for the warp's own 32*L-env chunks, the 32 lanes
-// are the consumers, and __syncwarp() is the only synchronisation -- warps of a CTA never wait for one another (a
-// CTA exists only to share the staged LUT).  Warp-chunk c covers envs [c*32*L, (c+1)*32*L); chunks are dealt
-// round-robin over all warps of the grid.
-template <class V, int ANG, int THREADS, int MINB, int STAGES>
-__global__ void __launch_bounds__(THREADS, MINB) drone_step_tma_kernel(const __grid_constant__ DroneK k, const DroneIO io,
-                                                                       const int lut_bytes) {
-  constexpr int L = Lane<V>::N;
-  constexpr int CHUNK = 32 * L;               // envs per warp-chunk
-  constexpr int ROWS = FPV_DRONE_PLANES + 1;  // 4 state planes + actions
-  constexpr int WARPS = THREADS / 32;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  float* lut_s = reinterpret_cast<float*>(smem_raw);
-  float4* ring_all = reinterpret_cast<float4*>(smem_raw + lut_bytes);  // [WARPS][STAGES][ROWS][CHUNK]
-  unsigned long long* full_all = reinterpret_cast<unsigned long long*>(ring_all + WARPS * STAGES * ROWS * CHUNK);
-
-  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // warp-uniform id
-  float4* ring = ring_all + (size_t)warp * STAGES * ROWS * CHUNK;
-  unsigned long long* full = full_all + warp * STAGES;
-  if (lane == 0) {
-#pragma unroll
-    for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+template <class V_, int ANG, bool GENERAL, class Post = NoPost, class IO_ = DroneIO>
+struct DroneMode {
+  using V = V_;
+  using K = DroneK;
+  using IO = IO_;
+  static constexpr int ROWS = FPV_DRONE_PLANES + 1;
+  struct Ctx {
+    TileStats st;
+    bool wind_on;
+    typename Post::Ctx post;
+  };
+  static __device__ __forceinline__ bool chained(const K& k) { return (k.flags & FPV_F_CHAINED) != 0; }
+  static __device__ __forceinline__ const float4* row(const IO& io, int r) {
+    return r < FPV_DRONE_PLANES ? io.state + r * io.stride : io.actions;
   }
-  __syncwarp();  // this warp's mbarriers are initialised: its ring can be primed before the CTA-wide LUT staging
-  // Programmatic dependent launch: let the NEXT launch on the stream become resident as our CTAs retire (its
-  // prologue then overlaps our tail), and wait for the PREVIOUS launch -- which may have written this very state --
-  // before the first byte of state is touched.  Without the launch attribute both instructions are no-ops.
-  // A CHAINED launch skips the grid-wide wait: the caller vouches for the side inputs, and the state is ordered chunk
-  // by chunk through io.chunk_epoch (acquire before a chunk's TMA loads, release after its stores), so this grid's
-  // first chunks run on the SMs the previous grid has already left while that grid's last chunks are still computing.
-  const bool chained = (k.flags & FPV_F_CHAINED) != 0;
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  if (!chained) asm volatile("griddepcontrol.wait;" ::: "memory");
-
-  const long long n_chunks = (io.n + CHUNK - 1) / CHUNK;
-  const long long my_warp = (long long)blockIdx.x * WARPS + warp;
-  const long long total_warps = (long long)gridDim.x * WARPS;
-  const bool wind_on = io.wind_env != nullptr || k.wind[0] != 0.f || k.wind[1] != 0.f || k.wind[2] != 0.f;
-
-  // producer: arm the slot's mbarrier with the byte count, then one bulk copy per row (all operands warp-uniform)
-  auto issue = [&](long long chunk, int slot) {
-    const long long first = chunk * CHUNK;
-    const long long rem = io.n - first;
-    const unsigned count = (unsigned)(rem < (long long)CHUNK ? rem : (long long)CHUNK);
-    const unsigned bytes = count * (unsigned)sizeof(float4);
-    float4* dst = ring + (size_t)slot * ROWS * CHUNK;
-    if (chained) {  // the previous step of THIS chunk must have been stored (possibly by a grid that is still running)
-      const unsigned* f = io.chunk_epoch + chunk;
-      unsigned v;
-      for (unsigned spins = 0;; ++spins) {
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-        if (v == io.epoch) break;
-        __nanosleep(64);
-        // a chunk that never reaches this epoch means the caller broke the FPV_F_CHAINED contract (e.g. replayed a
-        // captured launch with a stale epoch): fail the launch after ~1 s instead of hanging the device
-        if (spins > (1u << 23)) __trap();
-      }
-      asm volatile("fence.proxy.async.global;" ::: "memory");  // generic-proxy stores -> async-proxy (TMA) loads
+  static __device__ __forceinline__ int lut_bytes(const K& k) {
+    return (k.flags & FPV_F_THRUST_LUT) ? (int)(((size_t)k.lut_n * sizeof(float) + 127) / 128 * 128) : 0;
+  }
+  static __device__ __forceinline__ void stage(const K& k, const IO& io, unsigned char* smem, int tid, int nthreads) {
+    float* lut_s = reinterpret_cast<float*>(smem);
+    if (k.flags & FPV_F_THRUST_LUT)
+      for (int i = tid; i < k.lut_n; i += nthreads) lut_s[i] = io.lut[i];
+    if (GENERAL) {   // obstacle table behind the LUT: indexed PER THREAD in the contact loop (a divergent index into the
+                     // kernel-parameter constant bank would serialise every field load)
+      float* ob = reinterpret_cast<float*>(smem + lut_bytes(k));
+      const float* src = reinterpret_cast<const float*>(k.objects);
+      for (int i = tid; i < k.n_objects * (int)(sizeof(fpv_object_t) / sizeof(float)); i += nthreads) ob[i] = src[i];
     }
-    mbar_expect_tx(&full[slot], bytes * ROWS);
-#pragma unroll
-    for (int p = 0; p < FPV_DRONE_PLANES; ++p) tma_load_1d(dst + p * CHUNK, io.state + p * io.stride + first, bytes, &full[slot]);
-    tma_load_1d(dst + FPV_DRONE_PLANES * CHUNK, io.actions + first, bytes, &full[slot]);
-  };
-
-  // Work distribution.  The SM's warp arbiter is not fair (among the warps sharing a scheduler one runs ahead and
-  // the last one finishes alone at a fraction of the pipe rate), so chunks are PULLED: the first STAGES chunks of a
-  // warp are static (no start-up burst of atomics), every further one comes from a global counter.  The last warp
-  // to finish puts the two counters back to zero for the next launch.
-  const bool dynamic = io.work != nullptr;
-  unsigned long long t_start = 0;
-  if (io.trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
-  const bool leader = elect_one();
-  const int leader_lane = __ffs(__ballot_sync(0xffffffffu, leader)) - 1;
-  // a pull is split in two so that the atomic's round trip (~1k cycles) hides behind the substep loop:
-  // pull_begin() fires the atomic from the elected lane, pull_end() broadcasts its result after the arithmetic
-  auto pull_begin = [&]() -> unsigned {
-    unsigned v = 0;
-    if (dynamic && leader) v = atomicAdd(io.work, 1u);
-    return v;
-  };
-  auto pull_end = [&](unsigned v, long long static_next) -> long long {
-    if (!dynamic) return static_next;
-    v = __shfl_sync(0xffffffffu, v, leader_lane);
-    return 2 * total_warps + (long long)v;   // chunks [0, 2*total_warps) are the static first two of every warp
-  };
-
-  // Ring protocol (STAGES == 2): slot (it & 1) holds the chunk computed at iteration it.  At the top of iteration it
-  // the OTHER slot -- drained at it-1 -- is refilled with the next chunk, which then lands while chunk `it` is being
-  // computed.  A chunk is therefore pulled one chunk-time before it is needed (late commitment keeps the
-  // end-of-kernel tail to about one chunk); the pull's ~1k-cycle atomic round trip is covered by the other warps
-  // of the scheduler.
-  static_assert(STAGES == 2, "ring protocol below is written for two slots");
-  long long cur = my_warp;                 // static first chunk
-  if (cur < n_chunks && leader) issue(cur, 0);
-  long long static_next = my_warp + total_warps;
-  // while the first chunk is in flight: stage the motor curve (the only CTA-wide barrier of the kernel)
-  if (k.flags & FPV_F_THRUST_LUT)
-    for (int i = threadIdx.x; i < k.lut_n; i += THREADS) lut_s[i] = io.lut[i];
-  __syncthreads();
-  if (io.stats && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&io.stats->env_steps, (double)io.n);
-  TileStats st = {0.f, 0.f, 0.f, 0.f, 0.f};
-#ifdef FPV_TRACE_PHASES
-  long long ph_wait = 0, ph_read = 0, ph_tile = 0;
-  const long long c_begin = clock64();
-#endif
-#ifndef FPV_PUBLISH_BATCH
-#define FPV_PUBLISH_BATCH 4
-#endif
-  unsigned pend[FPV_PUBLISH_BATCH + 1];   // chunks whose stores are issued but whose epochs are not published yet
-  int n_pend = 0;
-  for (int it = 0; cur < n_chunks; ++it) {
-    const int slot = it & 1;
-#ifdef FPV_TRACE_PHASES
-    const long long c_a = clock64();
-#endif
-    // next chunk: the second one is static too (no start-up burst of atomics), later ones are pulled
-    long long nxt = static_next;
-    if (dynamic && it > 0) nxt = pull_end(pull_begin(), 0);
-    static_next += total_warps;
-    if (nxt < n_chunks && leader) issue(nxt, slot ^ 1);
-    mbar_wait(&full[slot], (unsigned)(it >> 1) & 1u);
-#ifdef FPV_TRACE_PHASES
-    const long long c_b = clock64();
-#endif
-    const float4* src = ring + (size_t)slot * ROWS * CHUNK;
-    const long long base = cur * CHUNK + lane;
-    long long ei[L];
-    float4 q[FPV_DRONE_PLANES][L];
-    float4 act[L];
+    Post::stage(io, smem + post_off(k), tid, nthreads);
+  }
+  static __device__ __forceinline__ int post_off(const K& k) {
+    return lut_bytes(k) + (GENERAL ? (k.n_objects * (int)sizeof(fpv_object_t) + 15) / 16 * 16 : 0);
+  }
+  static __device__ __forceinline__ Ctx begin(const K& k, const IO& io) {
+    if (io.stats && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&io.stats->env_steps, (double)io.n);
+    Ctx c;
+    c.st = TileStats{0.f, 0.f, 0.f, 0.f, 0.f};
+    c.wind_on = io.wind_env != nullptr || k.wind[0] != 0.f || k.wind[1] != 0.f || k.wind[2] != 0.f;
+    c.post = Post::begin(io);
+    return c;
+  }
+  template <class PreStore>
+  static __device__ __forceinline__ void tile(const K& k, const IO& io, const unsigned char* staged,
+                                              const float4 (&rows)[ROWS][Lane<V>::N], const long long (&ei)[Lane<V>::N],
+                                              long long base, Ctx& c, PreStore pre_store) {
+    constexpr int L = Lane<V>::N;
+    float4 q[FPV_DRONE_PLANES][L], act[L];
 #pragma unroll
     for (int l = 0; l < L; ++l) {
-      ei[l] = min(base + (long long)l * 32, io.n - 1);
 #pragma unroll
-      for (int p = 0; p < FPV_DRONE_PLANES; ++p) q[p][l] = src[p * CHUNK + l * 32 + lane];
-      act[l] = src[FPV_DRONE_PLANES * CHUNK + l * 32 + lane];
+      for (int p = 0; p < FPV_DRONE_PLANES; ++p) q[p][l] = rows[p][l];
+      act[l] = rows[FPV_DRONE_PLANES][l];
     }
-    __syncwarp();  // all lanes have drained this slot: it is refilled at the top of the next iteration
-#ifdef FPV_TRACE_PHASES
-    const long long c_c = clock64();
-#endif
-    // Publishing a chunk's epoch needs its stores to be performed first: a release is MEMBAR.GPU + ERRBAR, which
-    // drains the warp's memory pipeline.  Two things keep that off the critical path: the flags go out in the MIDDLE of
-    // a later chunk (after that chunk's substep loop, when the stores are long done), and they go out in batches of
-    // FPV_PUBLISH_BATCH chunks under ONE fence -- a consumer launch only gets onto the SMs when this launch's first
-    // CTAs retire, tens of microseconds after the early chunks were stored, so a few chunks of publication lag are
-    // invisible to it.  Order: all lanes' stores of chunk i -> the __syncwarp() of a later iteration -> the leader's
-    // fence -> the flag stores.
-    const bool flush_now = n_pend >= FPV_PUBLISH_BATCH;   // warp-uniform
-    auto publish_pending = [&]() {
-      if (flush_now && leader) {
-        asm volatile("fence.acq_rel.gpu;" ::: "memory");
-        for (int j = 0; j < n_pend; ++j)
-          asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(io.chunk_epoch + pend[j]), "r"(io.epoch + 1u) : "memory");
-      }
-    };
-    if (base < io.n) drone_tile<V, ANG, false, 32>(k, io, lut_s, q, act, ei, base, st, wind_on, publish_pending);
-    if (flush_now) n_pend = 0;
-    if (io.chunk_epoch) pend[n_pend++] = (unsigned)cur;
-#ifdef FPV_TRACE_PHASES
-    const long long c_d = clock64();
-    ph_wait += c_b - c_a; ph_read += c_c - c_b; ph_tile += c_d - c_c;
-#endif
-    cur = nxt;
+    const fpv_object_t* objs = GENERAL ? reinterpret_cast<const fpv_object_t*>(staged + lut_bytes(k)) : nullptr;
+    drone_tile<V, ANG, GENERAL, 32, PreStore, Post>(k, io, reinterpret_cast<const float*>(staged), objs, q, act, ei, base, c.st,
+                                                    c.wind_on, pre_store, staged + post_off(k), &c.post);
   }
-  if (n_pend > 0) {  // whatever is still unpublished, the warp's last chunk included
-    __syncwarp();
-    if (leader) {
-      asm volatile("fence.acq_rel.gpu;" ::: "memory");
-      for (int j = 0; j < n_pend; ++j)
-        asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(io.chunk_epoch + pend[j]), "r"(io.epoch + 1u) : "memory");
-    }
+  static __device__ __forceinline__ void finish(const K&, const IO& io, Ctx& c) {
+    if (io.stats) stats_warp_flush(io.stats, c.st);
+    Post::finish(io, c.post);
   }
-  if (dynamic && leader) {
-    const unsigned finished = atomicAdd(io.work + 1, 1u);
-    if (finished == (unsigned)total_warps - 1u) { io.work[0] = 0u; io.work[1] = 0u; }
-  }
-  if (io.stats) stats_warp_flush(io.stats, st);
-  if (io.trace && lane == 0) {
-    unsigned long long t_end;
-    unsigned smid;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
-    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    unsigned long long* o = io.trace + 3 * ((size_t)blockIdx.x * WARPS + warp);
-    o[0] = t_start; o[1] = t_end; o[2] = smid;
-#ifdef FPV_TRACE_PHASES
-    o[0] = (unsigned long long)ph_wait; o[1] = (unsigned long long)ph_read; o[2] = (unsigned long long)ph_tile;
-    io.trace[3 * (size_t)gridDim.x * WARPS + ((size_t)blockIdx.x * WARPS + warp)] = (unsigned long long)(clock64() - c_begin);
-#endif
-  }
-}
+};
 
 // ---------------------------------------------------------------------------------------------------------------
 // Kernel 3 (open-loop rollouts): T control steps per launch with the state held in REGISTERS across the steps.
@@ -790,14 +706,6 @@ __global__ void __launch_bounds__(THREADS, MINB) drone_step_tma_kernel(const __g
 // rollout is BIT-IDENTICAL to T launches of fpv_drone_step, episode bookkeeping, auto-reset and statistics included.
 // Warp-chunks of 32*L envs are pulled dynamically; the next step's actions are fetched while the current step computes.
 // ---------------------------------------------------------------------------------------------------------------
-template <class V> __device__ __forceinline__ V lane_set(V v, int l, float x);
-template <> __device__ __forceinline__ float lane_set<float>(float, int, float x) { return x; }
-template <> __device__ __forceinline__ F2 lane_set<F2>(F2 v, int l, float x) {
-  float a, b;
-  f2_unpack(v, a, b);
-  return l ? f2_pack(a, x) : f2_pack(x, b);
-}
-
 template <class V, int ANG, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) drone_rollout_kernel(const __grid_constant__ DroneK k, const DroneIO io,
                                                                       const float4* actions_seq, const long long act_stride,

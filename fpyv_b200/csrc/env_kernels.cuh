@@ -119,126 +119,103 @@ __global__ void __launch_bounds__(THREADS) gate_env_step_kernel(const __grid_con
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Fused env step: the dynamics control step (drone_substeps, one agent per thread, exactly the arithmetic of the scalar
-// step kernel) and the env step above in ONE pass -- the agent's state is read once and written once, the second launch
-// and its 64 B/agent re-read disappear.  Bit-identical to fpv_drone_step (FPV_F_SCALAR) followed by fpv_gate_env_step.
+// Fused env step (fpv_gate_race_step): the env step above as the per-chunk epilogue (`Post`) of the packed ring kernel
+// (ring_step_kernel<DroneMode<F2, ANG, false, GatePost, GateIO>>).  A warp's chunk is 64 agents; lane t holds agent
+// 64c + t in the low halves of its packed registers and agent 64c + 32 + t in the high halves, so with 32 agents per env
+// the warp holds two whole envs and every aligned group of A <= 32 lanes of one slot is one env: the team reward is the
+// same xor-shuffle sum over the same lanes as in gate_env_step_kernel, the termination the same ballot.  The agent's state
+// is read once (TMA) and written once; the env logic runs on the FINAL rows (after auto-reset) straight from registers.
+// Bit-identical to fpv_drone_step (packed hot kernel) followed by fpv_gate_env_step.
 // ---------------------------------------------------------------------------------------------------------------
-template <int ANG, int THREADS>
-__global__ void __launch_bounds__(THREADS) gate_race_fused_kernel(const __grid_constant__ DroneK k, const DroneIO io,
-                                                                  const __grid_constant__ fpv_gate_env_params_t gp,
-                                                                  float2* prev, int* progress, float* agent_reward,
-                                                                  float* env_reward, unsigned char* env_done, float4* obs) {
-  extern __shared__ __align__(16) float lut_dyn[];
-  __shared__ fpv_gate_t gates[FPV_MAX_GATES];
-  {
-    const float* src = reinterpret_cast<const float*>(gp.gates);
-    float* dst = reinterpret_cast<float*>(gates);
-    for (int j = threadIdx.x; j < gp.n_gates * (int)(sizeof(fpv_gate_t) / sizeof(float)); j += THREADS) dst[j] = src[j];
-    if (k.flags & FPV_F_THRUST_LUT)
-      for (int j = threadIdx.x; j < k.lut_n; j += THREADS) lut_dyn[j] = io.lut[j];
-    __syncthreads();
+struct GateIO : DroneIO {
+  fpv_gate_env_params_t gp;
+  float2* prev;
+  int* progress;
+  float* agent_reward;
+  float* env_reward;
+  unsigned char* env_done;
+  float4* obs;
+};
+
+struct GatePost {
+  static constexpr bool enabled = true;
+  struct Ctx {
+    float sum, sq;   // this lane's share of the env-reward statistics
+  };
+  static __device__ __forceinline__ Ctx begin(const GateIO&) { return Ctx{0.f, 0.f}; }
+  static __device__ __forceinline__ int bytes(const GateIO& io) { return io.gp.n_gates * (int)sizeof(fpv_gate_t); }
+  // the gate table is indexed PER AGENT (every agent is at its own gate): staged in shared memory, see gate_env_step_kernel
+  static __device__ __forceinline__ void stage(const GateIO& io, unsigned char* smem, int tid, int nthreads) {
+    const float* src = reinterpret_cast<const float*>(io.gp.gates);
+    float* dst = reinterpret_cast<float*>(smem);
+    for (int j = tid; j < io.gp.n_gates * (int)(sizeof(fpv_gate_t) / sizeof(float)); j += nthreads) dst[j] = src[j];
   }
-  const long long i = (long long)blockIdx.x * THREADS + threadIdx.x;
-  const int A = gp.agents_per_env;
-  const bool live = i < io.n;
-  if (io.stats && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&io.stats->env_steps, (double)io.n);
-  TileStats st = {0.f, 0.f, 0.f, 0.f, 0.f};
-  float reward = 0.f;
-  bool crashed = false, finished = false;
-  if (live) {
-    // ---- dynamics control step (drone_tile's scalar form)
-    float4 q0 = ldg_stream(io.state + i), q1 = ldg_stream(io.state + io.stride + i);
-    float4 q2 = ldg_stream(io.state + 2 * io.stride + i), q3 = ldg_stream(io.state + 3 * io.stride + i);
-    const float4 act = ldg_stream(io.actions + i);
-    DroneRegs<float> s;
-    s.px = q0.x; s.py = q0.y; s.pz = q0.z; s.pt = q0.w;
-    s.vx = q1.x; s.vy = q1.y; s.vz = q1.z;
-    s.qw = q2.x; s.qx = q2.y; s.qy = q2.z; s.qz = q2.w;
-    s.pr0 = q3.x; s.pr1 = q3.y; s.pr2 = q3.z;
-    s.ax = s.ay = s.az = 0.f;
-    int ep = __float_as_int(q1.w);
-    float spare = q3.w;
-    const float target = (k.flags & FPV_F_THRUST_LUT) ? thrust_lut1(k, lut_dyn, act.w) : thrust_poly<float>(k, act.w);
-    crashed = drone_substeps<float, ANG, false, false>(k, s, act.x, act.y, act.z, target, 0.f, 0.f, 0.f, false, 0.f, 1.f, 0.f,
-                                                       0.f, 0.f);
-    ep += 1;
-    if (io.done) io.done[i] = crashed ? 1 : 0;
-    if (io.acc_out) stg_stream(io.acc_out + i, make_float4(s.ax, s.ay, s.az, 0.f));
-    bool restarted = false;
-    if (crashed) {
-      st.crash += 1.f;
-      if (k.flags & FPV_F_AUTO_RESET) {
-        st.epi += 1.f; st.len += (float)ep;
-        q0 = ldg_stream(io.reset_state + i); q1 = ldg_stream(io.reset_state + io.stride + i);
-        q2 = ldg_stream(io.reset_state + 2 * io.stride + i); q3 = ldg_stream(io.reset_state + 3 * io.stride + i);
-        q1.w = __int_as_float(0);
-        restarted = true;
+  template <int L>
+  static __device__ __forceinline__ void run(const GateIO& io, const unsigned char* staged,
+                                             const float4 (&fin)[FPV_DRONE_PLANES][L], const bool (&crashed_l)[L],
+                                             const bool (&live_l)[L], const long long (&ei)[L], Ctx& c) {
+    const fpv_gate_t* gates = reinterpret_cast<const fpv_gate_t*>(staged);
+    const fpv_gate_env_params_t& gp = io.gp;
+    const int A = gp.agents_per_env;
+    const unsigned lane = threadIdx.x & 31;
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+      const long long i = ei[l];
+      const bool live = live_l[l];
+      float reward = 0.f;
+      bool crashed = false, finished = false;
+      if (live) {
+        const float4 p = fin[0][l], v = fin[1][l], q = fin[2][l], w = fin[3][l];
+        const float2 pr = io.prev[i];
+        int prog = io.progress[i];
+        int g = prog & 0xffff, laps = prog >> 16;
+        crashed = crashed_l[l];
+        float d, r;
+        gate_metrics(gates[g], p.x, p.y, p.z, d, r);
+        bool passed = false;
+        if (!crashed) {
+          passed = pr.x < 0.f && d >= 0.f && __fmaf_rn(r, r, -(d * d)) <= gates[g].half_size * gates[g].half_size;
+          reward = __fmaf_rn(gp.w_progress, pr.y - r, passed ? gp.w_gate : 0.f);
+        } else {
+          reward = -gp.w_crash;
+        }
+        if (passed) {
+          g += 1;
+          if (g == gp.n_gates) { g = 0; laps += 1; }
+        }
+        if (crashed) { g = 0; laps = 0; }
+        finished = gp.laps_to_finish > 0 && laps >= gp.laps_to_finish;
+        if (passed || crashed) gate_metrics(gates[g], p.x, p.y, p.z, d, r);  // re-base on the agent's next gate
+        io.prev[i] = make_float2(d, r);
+        io.progress[i] = (laps << 16) | g;
+        if (io.agent_reward) io.agent_reward[i] = reward;
+        if (io.obs) gate_observation(p, v, q, w, gates[g], io.obs + 4 * i);
+      }
+      // ---- per-env reductions inside the aligned A-lane group of this slot
+      float team = reward;
+      for (int o = A >> 1; o > 0; o >>= 1) team += __shfl_xor_sync(0xffffffffu, team, o);
+      const unsigned group_mask = (A == 32 ? 0xffffffffu : ((1u << A) - 1u)) << (lane & ~(unsigned)(A - 1));
+      const unsigned flags = __ballot_sync(0xffffffffu, crashed || finished);
+      const bool done = (flags & group_mask) != 0;
+      const bool head = live && (lane & (unsigned)(A - 1)) == 0;
+      if (head) {
+        const long long e = i / A;
+        io.env_reward[e] = team;
+        io.env_done[e] = done ? 1 : 0;
+        c.sum += team;
+        c.sq += team * team;
       }
     }
-    if (!restarted) {
-      if (!(fabsf((s.px + s.py) + s.pz) <= 3.0e38f)) st.nf += 1.f;
-      q0 = make_float4(s.px, s.py, s.pz, s.pt);
-      q1 = make_float4(s.vx, s.vy, s.vz, __int_as_float(ep));
-      q2 = make_float4(s.qw, s.qx, s.qy, s.qz);
-      q3 = make_float4(s.pr0, s.pr1, s.pr2, spare);
-    }
-    stg_stream(io.state + i, q0);
-    stg_stream(io.state + io.stride + i, q1);
-    stg_stream(io.state + 2 * io.stride + i, q2);
-    stg_stream(io.state + 3 * io.stride + i, q3);
-    // ---- env step on the state just written (gate_env_step_kernel's body)
-    const float4 p = q0, v = q1, q = q2, w = q3;
-    const float2 pr = prev[i];
-    int prog = progress[i];
-    int g = prog & 0xffff, laps = prog >> 16;
-    float d, r;
-    gate_metrics(gates[g], p.x, p.y, p.z, d, r);
-    bool passed = false;
-    if (!crashed) {
-      passed = pr.x < 0.f && d >= 0.f && __fmaf_rn(r, r, -(d * d)) <= gates[g].half_size * gates[g].half_size;
-      reward = __fmaf_rn(gp.w_progress, pr.y - r, passed ? gp.w_gate : 0.f);
-    } else {
-      reward = -gp.w_crash;
-    }
-    if (passed) {
-      g += 1;
-      if (g == gp.n_gates) { g = 0; laps += 1; }
-    }
-    if (crashed) { g = 0; laps = 0; }
-    finished = gp.laps_to_finish > 0 && laps >= gp.laps_to_finish;
-    if (passed || crashed) gate_metrics(gates[g], p.x, p.y, p.z, d, r);
-    prev[i] = make_float2(d, r);
-    progress[i] = (laps << 16) | g;
-    if (agent_reward) agent_reward[i] = reward;
-    if (obs) gate_observation(p, v, q, w, gates[g], obs + 4 * i);
   }
-  // ---- per-env reductions inside the aligned A-lane group
-  float team = reward;
-  for (int o = A >> 1; o > 0; o >>= 1) team += __shfl_xor_sync(0xffffffffu, team, o);
-  const unsigned lane = threadIdx.x & 31;
-  const unsigned group_mask = (A == 32 ? 0xffffffffu : ((1u << A) - 1u)) << (lane & ~(unsigned)(A - 1));
-  const unsigned flags = __ballot_sync(0xffffffffu, crashed || finished);
-  const bool done = (flags & group_mask) != 0;
-  const bool head = live && (lane & (unsigned)(A - 1)) == 0;
-  if (head) {
-    const long long e = i / A;
-    env_reward[e] = team;
-    env_done[e] = done ? 1 : 0;
-  }
-  if (io.stats) {
-    stats_warp_flush(io.stats, st);
-    __shared__ float s_sum[THREADS / 32], s_sq[THREADS / 32];
-    float a = head ? team : 0.f, b = head ? team * team : 0.f;
+  static __device__ __forceinline__ void finish(const GateIO& io, Ctx& c) {
+    if (!io.stats) return;
+    float a = c.sum, b = c.sq;
     for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
-    if (lane == 0) { s_sum[threadIdx.x >> 5] = a; s_sq[threadIdx.x >> 5] = b; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      float ta = 0.f, tb = 0.f;
-      for (int wi = 0; wi < THREADS / 32; ++wi) { ta += s_sum[wi]; tb += s_sq[wi]; }
-      atomicAdd(&io.stats->reward_sum, (double)ta);
-      atomicAdd(&io.stats->reward_sq_sum, (double)tb);
+    if ((threadIdx.x & 31) == 0 && (a != 0.f || b != 0.f)) {
+      atomicAdd(&io.stats->reward_sum, (double)a);
+      atomicAdd(&io.stats->reward_sq_sum, (double)b);
     }
   }
-}
+};
 
 }  // namespace fpv

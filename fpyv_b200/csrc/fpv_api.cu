@@ -10,6 +10,7 @@
 #include "../../include/fpv_api.h"
 #include "drone_kernels.cuh"
 #include "misc_kernels.cuh"
+#include "racer_kernels.cuh"
 #include "env_kernels.cuh"
 #include "chase_kernels.cuh"
 #include "acro_kernels.cuh"
@@ -112,44 +113,45 @@ void launch_drone(const DroneK& k, const DroneIO& io, cudaStream_t st) {
   kern<<<grid, kThreads, smem, st>>>(k, io);
 }
 
-// Hot path: TMA-fed ring (drone_step_tma_kernel).  Returns false if the ring does not fit (huge LUT).
-template <class V, int ANG, int STAGES>
-bool launch_drone_tma(const DroneK& k, const DroneIO& io, cudaStream_t st) {
-  constexpr int L = fpv::Lane<V>::N;
+// The persistent TMA-ring kernel (ring_kernels.cuh) for any mode.  One wave of CTAs: SMs x resident CTAs per SM (capped by
+// `cta_cap` when > 0).  Launched with the programmatic-stream-serialisation attribute, so the grid may become resident
+// while the previous one on the stream drains (the kernel itself waits for it before touching the state unless chained).
+// Returns false if the ring does not fit into shared memory.  `chained_ok` tells the caller whether FPV_F_CHAINED could
+// be honoured (full persistent grid only); the caller clears the flag in `k` beforehand otherwise.
+template <class Mode, int MINB>
+bool launch_ring(typename Mode::K& k, const typename Mode::IO& io, size_t stage_bytes, unsigned cta_cap, bool wants_chain,
+                 unsigned* chain_flag_word, unsigned chain_flag_bit, cudaStream_t st) {
+  constexpr int L = fpv::Lane<typename Mode::V>::N;
   constexpr int TILE = kThreads * L;
-  auto kern = fpv::drone_step_tma_kernel<V, ANG, kThreads, FPV_MINB, STAGES>;
-  const int lut_bytes = (k.flags & FPV_F_THRUST_LUT) ? (int)(((size_t)k.lut_n * sizeof(float) + 127) / 128 * 128) : 0;
-  const size_t smem = (size_t)lut_bytes + (size_t)STAGES * (FPV_DRONE_PLANES + 1) * TILE * sizeof(float4) +
-                      (size_t)(kThreads / 32) * STAGES * sizeof(unsigned long long);
+  auto kern = fpv::ring_step_kernel<Mode, kThreads, MINB>;
+  stage_bytes = (stage_bytes + 127) / 128 * 128;
+  const size_t smem = stage_bytes + (size_t)2 * Mode::ROWS * TILE * sizeof(float4) + (size_t)(kThreads / 32) * 2 * sizeof(unsigned long long);
   if (smem > 220 * 1024) return false;
   static SmemOptIn opted;  // per instantiation: largest dynamic smem opted in so far, per device
   static int occ_of[kMaxDevices] = {};
   static size_t occ_smem[kMaxDevices] = {};
   opt_in_smem(kern, opted, smem, 0);
   const int slot = current_device_slot();
-  int occ_cache;
+  int occ;
   {
     std::lock_guard<std::mutex> lk(g_mu);
-    occ_cache = (slot >= 0 && occ_smem[slot] == smem) ? occ_of[slot] : 0;
-    if (occ_cache == 0) {
+    occ = (slot >= 0 && occ_smem[slot] == smem) ? occ_of[slot] : 0;
+    if (occ == 0) {
       int o = 0;
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, kThreads, smem);
-      occ_cache = o > 0 ? o : 1;
-      if (slot >= 0) { occ_of[slot] = occ_cache; occ_smem[slot] = smem; }
+      occ = o > 0 ? o : 1;
+      if (slot >= 0) { occ_of[slot] = occ; occ_smem[slot] = smem; }
     }
   }
   const long long tiles = (io.n + TILE - 1) / TILE;
-  const int occ_cap = (int)io.cta_cap;
-  const int occ_used = (occ_cap > 0 && occ_cap < occ_cache) ? occ_cap : occ_cache;
+  const int occ_used = (cta_cap > 0 && (int)cta_cap < occ) ? (int)cta_cap : occ;
   const long long wave = (long long)sm_count_of_current_device() * occ_used;
   const unsigned grid = (unsigned)(tiles < wave ? tiles : wave);
   // FPV_F_CHAINED is honoured only by full persistent grids (every CTA slot a launch may use, on every SM): launch i+1
   // cannot become fully resident before launch i has left the slots it needs, which bounds the number of launches alive
   // at once (4 / slots-per-launch + 1) -- what the eight pull-counter pairs and the forward-progress argument of the
   // per-chunk waits rely on (the producer of an awaited chunk is always resident).  Anything else keeps plain stream order.
-  DroneK kk = k;
-  if ((kk.flags & FPV_F_CHAINED) && (long long)grid != wave) kk.flags &= ~FPV_F_CHAINED;
-  // programmatic dependent launch: this grid may become resident while the previous one on the stream drains
+  if (wants_chain && (long long)grid != wave && chain_flag_word) *chain_flag_word &= ~chain_flag_bit;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kThreads);
@@ -160,13 +162,30 @@ bool launch_drone_tma(const DroneK& k, const DroneIO& io, cudaStream_t st) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaLaunchKernelEx(&cfg, kern, kk, io, lut_bytes);
+  cudaLaunchKernelEx(&cfg, kern, k, io, (int)stage_bytes);
   return true;
+}
+
+// mode A on the ring: hot path (GENERAL = false) or general path (obstacles / overrides / damped spring)
+template <class V, int ANG, bool GENERAL>
+bool launch_drone_ring(const DroneK& k, const DroneIO& io, cudaStream_t st) {
+  using Mode = fpv::DroneMode<V, ANG, GENERAL>;
+  DroneK kk = k;
+  size_t stage = (k.flags & FPV_F_THRUST_LUT) ? ((size_t)k.lut_n * sizeof(float) + 127) / 128 * 128 : 0;
+  if (GENERAL) stage += ((size_t)k.n_objects * sizeof(fpv_object_t) + 15) / 16 * 16;
+  return launch_ring<Mode, GENERAL ? 3 : FPV_MINB>(kk, io, stage, io.cta_cap, (kk.flags & FPV_F_CHAINED) != 0, &kk.flags,
+                                                   FPV_F_CHAINED, st);
 }
 
 __global__ void fill_u32_kernel(unsigned* p, long long n, unsigned v) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
+}
+
+__global__ void pack_done_bits_kernel(const unsigned char* done, long long n, unsigned* bits) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned word = __ballot_sync(0xffffffffu, e < n && done[e] != 0);
+  if ((threadIdx.x & 31) == 0 && e < n) bits[e >> 5] = word;
 }
 
 // Kernels without the per-chunk protocol run in plain stream order and publish all epochs afterwards.
@@ -175,6 +194,8 @@ void launch_drone_plain(const DroneK& k, const DroneIO& io, cudaStream_t st) {
   DroneK kk = k;
   kk.flags &= ~FPV_F_CHAINED;
   launch_drone<V, ANG, GENERAL>(kk, io, st);
+  if (io.done_bits && io.done)
+    pack_done_bits_kernel<<<(unsigned)((io.n + 255) / 256), 256, 0, st>>>(io.done, io.n, io.done_bits);
   if (io.chunk_epoch) {
     const long long chunks = (io.n + 63) / 64;
     fill_u32_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, st>>>(io.chunk_epoch, chunks, io.epoch + 1u);
@@ -183,14 +204,13 @@ void launch_drone_plain(const DroneK& k, const DroneIO& io, cudaStream_t st) {
 
 template <class V, int ANG>
 void launch_drone_g(const DroneK& k, const DroneIO& io, bool general, cudaStream_t st) {
-  if (general) { launch_drone_plain<V, ANG, true>(k, io, st); return; }
-  if (fpv::Lane<V>::N == 2) {   // chunk_epoch is indexed by 64-env chunks = the packed kernel's warp-chunk
-    if (launch_drone_tma<V, ANG, 2>(k, io, st)) return;
+  // chunk_epoch is indexed by 64-env chunks = the packed kernels' warp-chunk: the scalar instantiations (32-env
+  // chunks) take the ring only when no epochs are kept
+  if (fpv::Lane<V>::N == 2 || !io.chunk_epoch) {
+    if (general ? launch_drone_ring<V, ANG, true>(k, io, st) : launch_drone_ring<V, ANG, false>(k, io, st)) return;
   }
-  if (!io.chunk_epoch) {
-    if (launch_drone_tma<V, ANG, 2>(k, io, st)) return;
-  }
-  launch_drone_plain<V, ANG, false>(k, io, st);
+  if (general) launch_drone_plain<V, ANG, true>(k, io, st);
+  else launch_drone_plain<V, ANG, false>(k, io, st);
 }
 template <class V>
 void launch_drone_a(const DroneK& k, const DroneIO& io, int ang, bool general, cudaStream_t st) {
@@ -282,6 +302,10 @@ int prepare_drone(const fpv_drone_params_t* p, const fpv_drone_io_t* io, bool ne
     return fail(FPV_EINVAL, "fpv_drone_step: FPV_F_AUTO_RESET needs io.reset_state");
   if ((p->flags & FPV_F_AUTO_RESET) && (p->flags & FPV_F_FREEZE_DONE))
     return fail(FPV_EINVAL, "fpv_drone_step: AUTO_RESET and FREEZE_DONE are mutually exclusive");
+  if (io->done_bits && !io->done)
+    return fail(FPV_EINVAL, "fpv_drone_step: io.done_bits needs io.done as well (the scalar fallback packs the bytes)");
+  if (io->done_bits && (reinterpret_cast<uintptr_t>(io->done_bits) & 3u))
+    return fail(FPV_EINVAL, "fpv_drone_step: io.done_bits must be 4-byte aligned");
   if (p->flags & FPV_F_THRUST_LUT) {
     if (!io->lut || io->lut_n < 2) return fail(FPV_EINVAL, "fpv_drone_step: FPV_F_THRUST_LUT needs io.lut with lut_n >= 2");
     if ((size_t)io->lut_n * sizeof(float) > 200 * 1024) return fail(FPV_EINVAL, "fpv_drone_step: lut_n=%d does not fit in shared memory", io->lut_n);
@@ -299,6 +323,12 @@ int prepare_drone(const fpv_drone_params_t* p, const fpv_drone_io_t* io, bool ne
   k.kd0 = p->k_drag[0];
   k.kd_a = (float)((double)p->k_drag[1] - (double)p->k_drag[0]);
   k.kd_b = (float)((double)p->k_drag[2] - (double)p->k_drag[0]);
+  {  // bound on the drag force per |u|^2 for the per-control-step reach test of the general path; NaN (= "no bound, test
+     // every obstacle every substep") when the low-pass weights are not convex weights
+    const double kmax = std::fmax(std::fabs((double)p->k_drag[0]), std::fmax(std::fabs((double)p->k_drag[1]), std::fabs((double)p->k_drag[2])));
+    const bool convex = rtr >= 0.0 && rtr <= 1.0 && ttr >= 0.0 && ttr <= 1.0;
+    k.kd_max = convex ? (float)(kmax * 1.001) : NAN;
+  }
   for (int m = 0; m < 4; ++m)
     for (int j = 0; j < 2; ++j) { k.motor_xy[m][j] = p->motor_xy[m][j]; k.neg_motor_xy[m][j] = -p->motor_xy[m][j]; }
   k.motor_radius = p->motor_radius;
@@ -333,6 +363,7 @@ int prepare_drone(const fpv_drone_params_t* p, const fpv_drone_io_t* io, bool ne
   d.wind_env = (const float4*)io->wind_env;
   d.lut = io->lut;
   d.done = io->done;
+  d.done_bits = (unsigned*)io->done_bits;
   d.acc_out = (float4*)io->acc_out;
   d.reset_state = (const float4*)io->reset_state;
   d.override_q = (const float4*)io->override_q;
@@ -343,6 +374,7 @@ int prepare_drone(const fpv_drone_params_t* p, const fpv_drone_io_t* io, bool ne
   d.chunk_epoch = (unsigned*)io->chunk_epoch;
   d.epoch = io->epoch;
   d.cta_cap = io->max_ctas_per_sm;
+  d.err = io->work ? (unsigned*)io->work + 16 : nullptr;
   // launches that overlap (FPV_F_CHAINED) must not share the pull counters.  A chained launch is honoured only as a full
   // persistent grid of k CTA slots per SM, so at most 4/k + 1 <= 5 launches are ever resident together: eight counter
   // pairs indexed by the epoch are never shared by two live launches.
@@ -462,6 +494,7 @@ int fpv_drone_step_host(const fpv_drone_params_t* p, const fpv_drone_io_t* io, c
     s.n = b - a;
     s.actions = (const char*)io->actions + 16 * a;
     s.done = io->done + a;
+    if (io->done_bits) s.done_bits = (char*)io->done_bits + a / 8;
     if (io->wind_env) s.wind_env = (const char*)io->wind_env + 16 * a;
     if (io->acc_out) s.acc_out = (char*)io->acc_out + 16 * a;
     if (io->reset_state) s.reset_state = (const char*)io->reset_state + 16 * a;
@@ -478,7 +511,10 @@ int fpv_drone_step_host(const fpv_drone_params_t* p, const fpv_drone_io_t* io, c
     }
     cudaEventRecord(hp.stepped[c], st);
     cudaStreamWaitEvent(hp.out, hp.stepped[c], 0);
-    cudaMemcpyAsync(done_host + a, io->done + a, (size_t)(b - a), cudaMemcpyDeviceToHost, hp.out);
+    if (io->done_bits)   // bitmask form: slices start on 64-env boundaries, so every slice owns whole 32-bit words
+      cudaMemcpyAsync(done_host + a / 8, (const char*)io->done_bits + a / 8, (size_t)((b - a + 31) / 32 * 4), cudaMemcpyDeviceToHost, hp.out);
+    else
+      cudaMemcpyAsync(done_host + a, io->done + a, (size_t)(b - a), cudaMemcpyDeviceToHost, hp.out);
   }
   cudaEventRecord(hp.joined, hp.out);
   cudaStreamWaitEvent(st, hp.joined, 0);
@@ -638,6 +674,7 @@ int fpv_drone_step_host_sticks(const fpv_drone_params_t* p, const fpv_drone_io_t
     s.n = b - a;
     s.actions = (const char*)io->actions + 16 * a;
     s.done = io->done + a;
+    if (io->done_bits) s.done_bits = (char*)io->done_bits + a / 8;
     if (io->wind_env) s.wind_env = (const char*)io->wind_env + 16 * a;
     if (io->acc_out) s.acc_out = (char*)io->acc_out + 16 * a;
     if (io->reset_state) s.reset_state = (const char*)io->reset_state + 16 * a;
@@ -654,7 +691,10 @@ int fpv_drone_step_host_sticks(const fpv_drone_params_t* p, const fpv_drone_io_t
     }
     cudaEventRecord(hp.stepped[c], st);
     cudaStreamWaitEvent(hp.out, hp.stepped[c], 0);
-    cudaMemcpyAsync(done_host + a, io->done + a, (size_t)(b - a), cudaMemcpyDeviceToHost, hp.out);
+    if (io->done_bits)   // bitmask form: slices start on 64-env boundaries, so every slice owns whole 32-bit words
+      cudaMemcpyAsync(done_host + a / 8, (const char*)io->done_bits + a / 8, (size_t)((b - a + 31) / 32 * 4), cudaMemcpyDeviceToHost, hp.out);
+    else
+      cudaMemcpyAsync(done_host + a, io->done + a, (size_t)(b - a), cudaMemcpyDeviceToHost, hp.out);
   }
   cudaEventRecord(hp.joined, hp.out);
   cudaStreamWaitEvent(st, hp.joined, 0);
@@ -671,8 +711,16 @@ int fpv_racer_reset(void* state, int64_t n, int64_t plane_stride, const uint8_t*
   return check_launch("fpv_racer_reset");
 }
 
+int fpv_racer_observe(const void* state, int64_t n, int64_t plane_stride, float* R, float* omega, void* stream) {
+  if (!state) return fail(FPV_EINVAL, "fpv_racer_observe: null state");
+  if (n < 0 || plane_stride < n || !aligned16(state)) return fail(FPV_EINVAL, "fpv_racer_observe: bad n/stride/alignment");
+  if (n == 0) return FPV_OK;
+  fpv::racer_observe_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const float4*)state, n, plane_stride, R, omega);
+  return check_launch("fpv_racer_observe");
+}
+
 int fpv_racer_step(const fpv_racer_params_t* p, void* state, int64_t n, int64_t plane_stride, const void* actions,
-                   void* torque_out, void* stream) {
+                   void* torque_out, void* work, void* stream) {
   if (!p || !state || !actions) return fail(FPV_EINVAL, "fpv_racer_step: null pointer");
   if (n < 0 || plane_stride < n) return fail(FPV_EINVAL, "fpv_racer_step: bad n/stride");
   if (!aligned16(state) || !aligned16(actions) || !aligned16(torque_out))
@@ -682,7 +730,7 @@ int fpv_racer_step(const fpv_racer_params_t* p, void* state, int64_t n, int64_t 
   k.dt = p->dt;
   k.inv_dt = (float)(1.0 / (double)p->dt);
   k.substeps = p->substeps;
-  k.inv_mass = (float)(1.0 / (double)p->mass);
+  k.dt_over_m = (float)((double)p->dt / (double)p->mass);
   for (int i = 0; i < 3; ++i) {
     if (!(p->inertia[i] > 0.f)) return fail(FPV_EINVAL, "fpv_racer_step: inertia must be positive");
     k.dt_over_I[i] = (float)((double)p->dt / (double)p->inertia[i]);
@@ -690,9 +738,15 @@ int fpv_racer_step(const fpv_racer_params_t* p, void* state, int64_t n, int64_t 
   }
   k.vel_decay = p->vel_decay;
   if (n == 0) return FPV_OK;
-  const unsigned grid = (unsigned)((n + kThreads - 1) / kThreads);
-  fpv::racer_step_kernel<kThreads><<<grid, kThreads, 0, (cudaStream_t)stream>>>(k, (float4*)state, n, plane_stride,
-                                                                                   (const float4*)actions, (float4*)torque_out);
+  fpv::RacerIO io = {};
+  io.state = (float4*)state;
+  io.n = n;
+  io.stride = plane_stride;
+  io.actions = (const float4*)actions;
+  io.torque_out = (float4*)torque_out;
+  io.work = p->substeps >= 4 ? (unsigned*)work : nullptr;
+  if (p->flags & FPV_F_SCALAR) launch_ring<fpv::RacerMode<float>, 4>(k, io, 0, 0, false, nullptr, 0, (cudaStream_t)stream);
+  else launch_ring<fpv::RacerMode<F2>, 4>(k, io, 0, 0, false, nullptr, 0, (cudaStream_t)stream);
   return check_launch("fpv_racer_step");
 }
 
@@ -750,19 +804,31 @@ int fpv_gate_race_step(const fpv_drone_params_t* p, const fpv_drone_io_t* io, co
   if (general || io->wind_env || wind || (p->flags & FPV_F_FREEZE_DONE))
     return fail(FPV_EINVAL, "fpv_gate_race_step: only the hot-path configuration is supported (no obstacles, overrides, wind "
                             "or FPV_F_FREEZE_DONE); call fpv_drone_step and fpv_gate_env_step instead");
-  const size_t smem = (k.flags & FPV_F_THRUST_LUT) ? sizeof(float) * (size_t)k.lut_n : 0;
-  constexpr int T = 256;   // same CTA size as gate_env_step_kernel: the block-level reward sums group the same envs
-  auto launch = [&](auto kern) {
-    static SmemOptIn opted;
-    opt_in_smem(kern, opted, smem);
-    kern<<<(unsigned)((io->n + T - 1) / T), T, smem, (cudaStream_t)stream>>>(k, d, *gp, (float2*)prev, progress, agent_reward,
-                                                                            env_reward, env_done, (float4*)obs);
+  if (p->flags & FPV_F_SCALAR) return fail(FPV_EINVAL, "fpv_gate_race_step: the fused step runs the packed kernel (no FPV_F_SCALAR)");
+  fpv::GateIO g;
+  static_cast<DroneIO&>(g) = d;
+  g.chunk_epoch = nullptr;          // the env bookkeeping is ordered by plain stream order only
+  g.gp = *gp;
+  g.prev = (float2*)prev;
+  g.progress = progress;
+  g.agent_reward = agent_reward;
+  g.env_reward = env_reward;
+  g.env_done = env_done;
+  g.obs = (float4*)obs;
+  k.flags &= ~FPV_F_CHAINED;
+  const size_t stage = ((k.flags & FPV_F_THRUST_LUT) ? ((size_t)k.lut_n * sizeof(float) + 127) / 128 * 128 : 0) +
+                       (size_t)gp->n_gates * sizeof(fpv_gate_t);
+  auto launch = [&](auto mode_tag) {
+    using Mode = decltype(mode_tag);
+    return launch_ring<Mode, FPV_MINB>(k, g, stage, d.cta_cap, false, nullptr, 0, (cudaStream_t)stream);
   };
-  if (ang == 4) launch(fpv::gate_race_fused_kernel<4, T>);
-  else if (ang == 3) launch(fpv::gate_race_fused_kernel<3, T>);
-  else if (ang == 2) launch(fpv::gate_race_fused_kernel<2, T>);
-  else if (ang == 1) launch(fpv::gate_race_fused_kernel<1, T>);
-  else launch(fpv::gate_race_fused_kernel<0, T>);
+  bool ok;
+  if (ang == 4) ok = launch(fpv::DroneMode<F2, 4, false, fpv::GatePost, fpv::GateIO>{});
+  else if (ang == 3) ok = launch(fpv::DroneMode<F2, 3, false, fpv::GatePost, fpv::GateIO>{});
+  else if (ang == 2) ok = launch(fpv::DroneMode<F2, 2, false, fpv::GatePost, fpv::GateIO>{});
+  else if (ang == 1) ok = launch(fpv::DroneMode<F2, 1, false, fpv::GatePost, fpv::GateIO>{});
+  else ok = launch(fpv::DroneMode<F2, 0, false, fpv::GatePost, fpv::GateIO>{});
+  if (!ok) return fail(FPV_EINVAL, "fpv_gate_race_step: the motor-curve table does not fit next to the ring in shared memory");
   return check_launch("fpv_gate_race_step");
 }
 
@@ -922,7 +988,8 @@ int fpv_acro_reset(void* state, int64_t n, int64_t plane_stride, const float* po
 namespace {
 int acro_launch(const fpv_acro_params_t* p, void* state, int64_t n, int64_t plane_stride, const void* actions,
                 const float* lut, int32_t lut_n, uint8_t* done, void* motor_thrust, const void* reset_state,
-                fpv_stats_t* stats, int32_t T, int64_t act_stride, uint8_t* done_seq, int64_t done_stride, void* stream) {
+                fpv_stats_t* stats, int32_t T, int64_t act_stride, uint8_t* done_seq, int64_t done_stride, void* work,
+                void* stream) {
   if (!p || !state || !actions) return fail(FPV_EINVAL, "fpv_acro_step: null pointer");
   if (n < 0 || plane_stride < n) return fail(FPV_EINVAL, "fpv_acro_step: bad n/stride");
   if (!aligned16(state) || !aligned16(actions) || !aligned16(motor_thrust) || !aligned16(reset_state))
@@ -980,6 +1047,20 @@ int acro_launch(const fpv_acro_params_t* p, void* state, int64_t n, int64_t plan
         k, (float4*)state, n, plane_stride, (const float4*)actions, lut, done, (float4*)motor_thrust, (const float4*)reset_state, stats,
         (int)T, (long long)act_stride, done_seq, (long long)done_stride);
   };
+  if (T == 1 && !(p->flags & FPV_F_SCALAR)) {   // one control step, packed: the ring kernel
+    fpv::AcroIO io = {};
+    io.state = (float4*)state;
+    io.n = n;
+    io.stride = plane_stride;
+    io.actions = (const float4*)actions;
+    io.lut = lut;
+    io.done = done;
+    io.motor_out = (float4*)motor_thrust;
+    io.reset_state = (const float4*)reset_state;
+    io.stats = stats;
+    io.work = p->substeps >= 4 ? (unsigned*)work : nullptr;
+    if (launch_ring<fpv::AcroMode<F2>, 3>(k, io, smem, 0, false, nullptr, 0, (cudaStream_t)stream)) return check_launch("fpv_acro_step");
+  }
   if (p->flags & FPV_F_SCALAR) launch(fpv::acro_step_kernel<float, kThreads>, 1);
   else launch(fpv::acro_step_kernel<F2, kThreads>, 2);
   return check_launch("fpv_acro_step");
@@ -988,8 +1069,9 @@ int acro_launch(const fpv_acro_params_t* p, void* state, int64_t n, int64_t plan
 
 int fpv_acro_step(const fpv_acro_params_t* p, void* state, int64_t n, int64_t plane_stride, const void* actions,
                   const float* lut, int32_t lut_n, uint8_t* done, void* motor_thrust, const void* reset_state,
-                  fpv_stats_t* stats, void* stream) {
-  return acro_launch(p, state, n, plane_stride, actions, lut, lut_n, done, motor_thrust, reset_state, stats, 1, 0, nullptr, 0, stream);
+                  fpv_stats_t* stats, void* work, void* stream) {
+  return acro_launch(p, state, n, plane_stride, actions, lut, lut_n, done, motor_thrust, reset_state, stats, 1, 0, nullptr, 0, work,
+                     stream);
 }
 
 int fpv_acro_rollout(const fpv_acro_params_t* p, void* state, int64_t n, int64_t plane_stride, const void* actions_seq,
@@ -1001,7 +1083,7 @@ int fpv_acro_rollout(const fpv_acro_params_t* p, void* state, int64_t n, int64_t
   if (action_stride < n) return fail(FPV_EINVAL, "fpv_acro_rollout: action_stride must be >= n");
   if (done_seq && done_stride < n) return fail(FPV_EINVAL, "fpv_acro_rollout: done_stride must be >= n");
   return acro_launch(p, state, n, plane_stride, actions_seq, lut, lut_n, done_last, motor_thrust, reset_state, stats, n_steps,
-                     action_stride, done_seq, done_stride, stream);
+                     action_stride, done_seq, done_stride, nullptr, stream);
 }
 
 }  // extern "C"

@@ -220,6 +220,30 @@ template <int ANG> __device__ __forceinline__ void vsincos(F2 x, F2& s, F2& c) {
   }
 }
 
+// ---- float4 rows <-> lane values: component c of the L float4 rows a thread holds (one per env), as one lane value
+template <class V> struct Pack;
+template <> struct Pack<float> {
+  static __device__ __forceinline__ float x(const float4* q) { return q[0].x; }
+  static __device__ __forceinline__ float y(const float4* q) { return q[0].y; }
+  static __device__ __forceinline__ float z(const float4* q) { return q[0].z; }
+  static __device__ __forceinline__ float w(const float4* q) { return q[0].w; }
+};
+template <> struct Pack<F2> {
+  static __device__ __forceinline__ F2 x(const float4* q) { return f2_pack(q[0].x, q[1].x); }
+  static __device__ __forceinline__ F2 y(const float4* q) { return f2_pack(q[0].y, q[1].y); }
+  static __device__ __forceinline__ F2 z(const float4* q) { return f2_pack(q[0].z, q[1].z); }
+  static __device__ __forceinline__ F2 w(const float4* q) { return f2_pack(q[0].w, q[1].w); }
+};
+
+// replace lane l of a lane value
+template <class V> __device__ __forceinline__ V lane_set(V v, int l, float x);
+template <> __device__ __forceinline__ float lane_set<float>(float, int, float x) { return x; }
+template <> __device__ __forceinline__ F2 lane_set<F2>(F2 v, int l, float x) {
+  float a, b;
+  f2_unpack(v, a, b);
+  return l ? f2_pack(a, x) : f2_pack(x, b);
+}
+
 // 128-bit global access.  State/action streams are touched exactly once per control step, so they
 // bypass L1 allocation (streaming) -- L2 still serves the re-reads of small batches.
 __device__ __forceinline__ float4 ldg_stream(const float4* p) {

@@ -37,7 +37,7 @@ def _as_dev(x, device, shape=None, dtype=torch.float32):
 class BatchedDrone:
     def __init__(self, params=None, num_envs: int = 1, device="cuda:0", substeps: int = 1, dt: float | None = None,
                  auto_reset: bool = False, freeze_done: bool = False, thrust_lut: int = 0, lut_source: str = "poly",
-                 packed: bool = True, ground: bool = True, joystick=None, cta_slots: int = 0):
+                 packed: bool = True, ground: bool = True, joystick=None, cta_slots: int = 0, done_bits: bool = False):
         self._lib = _lib.load()
         if isinstance(params, str) or params is None:
             params = config.load_params(params)
@@ -92,10 +92,12 @@ class BatchedDrone:
         self._state = torch.zeros((_lib.DRONE_PLANES, self._stride, 4), dtype=torch.float32, device=dev)
         self._reset_state = torch.zeros_like(self._state) if auto_reset else None
         self._done = torch.zeros(n, dtype=torch.uint8, device=dev)
+        # done_bits=True: the step also writes the flags as a bitmask (bit e % 32 of word e // 32; fpv_drone_io_t.done_bits)
+        self._done_bits = torch.zeros((n + 31) // 32, dtype=torch.int32, device=dev) if done_bits else None
         self._acc = torch.zeros((n, 4), dtype=torch.float32, device=dev)
         self._actions = torch.zeros((n, 4), dtype=torch.float32, device=dev)
         self._stats = torch.zeros(8, dtype=torch.float64, device=dev)
-        self._work = torch.zeros(16, dtype=torch.int32, device=dev)      # dynamic chunk counters (fpv_drone_io_t.work)
+        self._work = torch.zeros(32, dtype=torch.int32, device=dev)      # chunk counters [0..15] + error words (fpv_drone_io_t.work)
         # chained launches (fpv_drone_io_t.chunk_epoch): one step count per 64-env chunk, and the host's copy of it
         self._chunk_epoch = torch.zeros((n + 63) // 64, dtype=torch.int32, device=dev)
         self._chunk_epoch_ptr = self._chunk_epoch.data_ptr()
@@ -210,6 +212,11 @@ class BatchedDrone:
     @property
     def done(self):
         return self._done.bool()
+
+    @property
+    def done_bits(self):
+        """int32[ceil(n/32)]: the done flags of the last step as a bitmask (only with done_bits=True)."""
+        return self._done_bits
 
     @property
     def motors_orientation(self):
@@ -333,6 +340,7 @@ class BatchedDrone:
         io.lut = None if self._lut is None else self._lut.data_ptr()
         io.lut_n = 0 if self._lut is None else self._lut.numel()
         io.done = self._done.data_ptr()
+        io.done_bits = None if self._done_bits is None else self._done_bits.data_ptr()
         io.acc_out = self._acc.data_ptr()
         io.reset_state = None if self._reset_state is None else self._reset_state.data_ptr()
         io.override_q = None if ovr_q is None else ovr_q.data_ptr()
@@ -364,6 +372,7 @@ class BatchedDrone:
         io.lut = None if self._lut is None else self._lut.data_ptr()
         io.lut_n = 0 if self._lut is None else self._lut.numel()
         io.done, io.acc_out = self._done.data_ptr(), self._acc.data_ptr()
+        io.done_bits = None if self._done_bits is None else self._done_bits.data_ptr()
         io.reset_state = None if self._reset_state is None else self._reset_state.data_ptr()
         io.override_q = io.override_thrust = None
         io.objects = C.POINTER(_lib.Object)()
@@ -459,7 +468,7 @@ class BatchedDrone:
                 or not actions_host.is_contiguous()):
             self._actions.copy_(actions_host, non_blocking=True)      # first call / odd inputs: the plain path
             self.step(self._actions, return_obs=False)
-            done_host.copy_(self._done, non_blocking=True)
+            done_host.copy_(self._done if self._done_bits is None else self._done_bits, non_blocking=True)
             return done_host
         self._last_action = self._actions
         self._chain_ready = False
@@ -489,7 +498,7 @@ class BatchedDrone:
             raw6[:, [0, 1, 2, 5]] = sticks_host.to(torch.int32)
             self.rc.feed(raw6)
             self.step(None, return_obs=False)
-            done_host.copy_(self._done, non_blocking=True)
+            done_host.copy_(self._done if self._done_bits is None else self._done_bits, non_blocking=True)
             return done_host
         if self._sticks_dev is None:
             self._sticks_dev = torch.empty((n, 4), dtype=torch.uint16, device=dev)
@@ -504,15 +513,20 @@ class BatchedDrone:
         return done_host
 
     def _check_done_host(self, done_host):
-        """The library DMAs num_envs bytes into done_host: it must be a CPU uint8 tensor of exactly that many contiguous
-        elements (page-locked for full speed).  None -> this drone's own pinned buffer."""
+        """The library DMAs the flags into done_host: num_envs bytes (uint8 [num_envs]) -- or, for a drone built with
+        done_bits=True, the bitmask (int32 [ceil(num_envs / 32)], 1/8 of the bytes).  It must be a contiguous CPU tensor of
+        exactly that shape (page-locked for full speed).  None -> this drone's own pinned buffer."""
+        bits = self._done_bits is not None
+        want_n = (self.num_envs + 31) // 32 if bits else self.num_envs
+        want_t = torch.int32 if bits else torch.uint8
         if done_host is None:
             if self._host_done is None:
-                self._host_done = torch.empty(self.num_envs, dtype=torch.uint8, pin_memory=True)
+                self._host_done = torch.empty(want_n, dtype=want_t, pin_memory=True)
             return self._host_done
-        if (not isinstance(done_host, torch.Tensor) or done_host.is_cuda or done_host.dtype is not torch.uint8
-                or not done_host.is_contiguous() or done_host.numel() != self.num_envs):
-            raise ValueError("done_host must be a contiguous CPU uint8 tensor with num_envs elements (ideally pinned)")
+        if (not isinstance(done_host, torch.Tensor) or done_host.is_cuda or done_host.dtype is not want_t
+                or not done_host.is_contiguous() or done_host.numel() != want_n):
+            raise ValueError(f"done_host must be a contiguous CPU {want_t} tensor with {want_n} elements (ideally pinned)"
+                             + (" -- this drone returns the done flags as a bitmask (done_bits=True)" if bits else ""))
         return done_host
 
     def _slice_bounds(self, slices):
@@ -526,7 +540,11 @@ class BatchedDrone:
         s = reduce_stats(self._stats) if all_reduce else self._stats.clone()
         if reset:
             self._stats.zero_()
-        return stats_dict(s)
+        out = stats_dict(s)
+        # chained launches whose per-chunk wait timed out and fell back to a grid-wide wait (fpv_api.h, FPV_F_CHAINED):
+        # non-zero means the chaining contract was broken or the device was too slow for it -- never a hang or a trap
+        out["chain_timeouts"] = int(self._work[16].item())
+        return out
 
 
 class Drone:

@@ -50,10 +50,15 @@ class GateRaceEnv:
         self._gen = torch.Generator(device=dev).manual_seed(seed)
         self.spawn_height = spawn_height
         self.agent_names = [f"agent_{a}" for a in range(self.agents_per_env)]
+        self._obs_views = None
 
     # -- helpers
     def _obs_dict(self):
-        return {name: self._obs[:, a] for a, name in enumerate(self.agent_names)}
+        # views into the persistent observation buffer: built once (32 slicing calls per step would cost more host time
+        # than the env step takes on the device)
+        if self._obs_views is None:
+            self._obs_views = {name: self._obs[:, a] for a, name in enumerate(self.agent_names)}
+        return self._obs_views
 
     def _spawn(self):
         """Start grid behind gate 0 (on its negative side), agents of an env spread laterally."""
@@ -91,13 +96,14 @@ class GateRaceEnv:
     def step(self, action, fused=True):
         """action: dict {agent name: [num_envs,4]} or tensor [num_envs, agents_per_env, 4] (roll, pitch, yaw, throttle).
         Returns (obs dict, reward [num_envs], done [num_envs] bool, {}).
-        fused=True: dynamics and env step in ONE launch (fpv_gate_race_step: one agent per thread, state read and
-        written once); fused=False: fpv_drone_step (packed hot kernel) followed by fpv_gate_env_step."""
+        fused=True: dynamics and env step in ONE launch (fpv_gate_race_step: the env step is the per-chunk epilogue of the
+        packed TMA-ring kernel, every agent's state is read once and written once); fused=False (or a scalar-kernel
+        drone): fpv_drone_step followed by fpv_gate_env_step.  Both give the same bits."""
         if isinstance(action, dict):
             action = torch.stack([torch.as_tensor(action[k]).to(self.device, torch.float32) for k in self.agent_names], dim=1)
         act = torch.as_tensor(action).to(self.device, torch.float32).reshape(self.n_agents, 4).contiguous()
         d = self.drone
-        if fused and d._fast_ok and not (d._flags & _lib.F_FREEZE_DONE):
+        if fused and d._fast_ok and not (d._flags & (_lib.F_FREEZE_DONE | _lib.F_SCALAR)):
             d._last_action = act
             d._chain_ready = False
             d._p.flags = d._flags

@@ -26,6 +26,7 @@ class BatchedRacer:
         self._stride = (n + 3) // 4 * 4
         self._state = torch.zeros((_lib.RACER_PLANES, self._stride, 4), dtype=torch.float32, device=self.device)
         self._torque = torch.zeros((n, 4), dtype=torch.float32, device=self.device)
+        self._work = torch.zeros(32, dtype=torch.int32, device=self.device)     # chunk counters of the ring kernel
         p = self._p = _lib.RacerParams()
         p.dt, p.substeps, p.mass, p.vel_decay, p.flags = self.dt, self.substeps, self.mass, 0.9, 0
         for i, k in enumerate(("roll", "pitch", "yaw")):
@@ -35,9 +36,25 @@ class BatchedRacer:
 
     position = property(lambda self: self._state[0, :self.num_envs, :3])
     linear_velocity = property(lambda self: self._state[1, :self.num_envs, :3])
-    orientation = property(lambda self: self._state[2:5, :self.num_envs, :3].permute(1, 0, 2))
-    angular_velocity = property(lambda self: self._state[2:5, :self.num_envs, 3].t())
+    quaternion = property(lambda self: self._state[2, :self.num_envs])
     torque = property(lambda self: self._torque[:, :3])
+
+    def _observe(self, want_R, want_w):
+        n = self.num_envs
+        R = torch.empty((n, 3, 3), dtype=torch.float32, device=self.device) if want_R else None
+        w = torch.empty((n, 3), dtype=torch.float32, device=self.device) if want_w else None
+        _lib.check(self._lib.fpv_racer_observe(_lib.ptr(self._state), n, self._stride, _lib.ptr(R), _lib.ptr(w),
+                                               _lib.current_stream(self.device)))
+        return R, w
+
+    @property
+    def orientation(self):
+        """[n,3,3]: the matrix the reference keeps (racer_drone_test.py:73), converted from the quaternion plane."""
+        return self._observe(True, False)[0]
+
+    @property
+    def angular_velocity(self):
+        return self._observe(False, True)[1]
 
     def reset(self, mask=None):
         m = None if mask is None else torch.as_tensor(mask).to(self.device, torch.uint8).contiguous()
@@ -52,7 +69,8 @@ class BatchedRacer:
             a = torch.broadcast_to(a, (self.num_envs, 4))
         a = a.contiguous()
         _lib.check(self._lib.fpv_racer_step(C.byref(self._p), _lib.ptr(self._state), self.num_envs, self._stride,
-                                            _lib.ptr(a), _lib.ptr(self._torque), _lib.current_stream(self.device)))
+                                            _lib.ptr(a), _lib.ptr(self._torque), _lib.ptr(self._work),
+                                            _lib.current_stream(self.device)))
 
 
 class Racer:

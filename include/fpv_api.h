@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define FPV_ABI_VERSION 11
+#define FPV_ABI_VERSION 12
 
 /* error codes */
 #define FPV_OK 0
@@ -77,8 +77,11 @@ extern "C" {
                                    written by work that may still be running, and (2) the last writer of `state` was a
                                    fpv_drone_step launch with the same chunk_epoch and epoch - 1.  Ignored (plain stream
                                    order) whenever the launch cannot honour it.  Do not capture a chained launch in a
-                                   CUDA graph (the replay would carry a stale epoch); a chunk that never reaches the
-                                   expected epoch traps the launch after about a second instead of hanging.        */
+                                   CUDA graph (the replay would carry a stale epoch).  A chunk that does not reach the
+                                   expected epoch within 2 s of wall-clock time does not hang or poison the context:
+                                   the launch adds 1 to work[16], falls back to waiting for the whole previous grid
+                                   and goes on; the host reads the word when it wants to know (BatchedDrone.
+                                   episode_stats()["chain_timeouts"]).                                            */
 #define FPV_F_RATE_CURVE 128u    /* fpv_acro_params_t.rate_curve is used (mode C only)                            */
 #define FPV_F_SCALAR 32u        /* one env per thread (plain FP32 instructions) instead of the
                                    default two envs per thread on packed f32x2 instructions     */
@@ -133,6 +136,9 @@ typedef struct fpv_drone_io {
   const float* lut;         /* float[lut_n] thrust [N] sampled at throttle -1..1, or NULL         */
   int32_t lut_n;
   uint8_t* done;            /* uint8[n] out: 1 if any substep raised done (components.py:236-240); may be NULL */
+  void* done_bits;          /* uint32[ceil(n / 32)] out or NULL: the same flags as a bitmask, bit (e % 32) of word e / 32
+                               (written with one warp ballot per 32 envs; 1/8 of the bytes of `done` for a host that
+                               only needs to know WHICH envs ended).  Needs `done` as well.                   */
   void* acc_out;            /* float4[n] out: world acceleration of the last substep (components.py:243); may be NULL */
   const void* reset_state;  /* float4[FPV_DRONE_PLANES][plane_stride]: source for FPV_F_AUTO_RESET */
   const void* override_q;   /* float4[n]: rotation override as quaternion (w,x,y,z), see fpv_matrix_to_quat
@@ -141,9 +147,10 @@ typedef struct fpv_drone_io {
   const float* override_thrust; /* float[n]: thrust_force of the same call; NaN = no override for that env */
   const fpv_object_t* objects; /* HOST pointer, params.n_objects entries, or NULL                  */
   fpv_stats_t* stats;       /* device, may be NULL                                                */
-  void* work;               /* device uint32[16], zeroed ONCE by the caller: chunk counter for dynamic load balancing
-                               (warps pull the next 64-env chunk with one atomic); every launch leaves it zeroed.
-                               NULL = static round-robin distribution.                                     */
+  void* work;               /* device uint32[32], zeroed ONCE by the caller.  [0..15]: chunk counters for dynamic load
+                               balancing (warps pull the next 64-env chunk with one atomic); every launch leaves them
+                               zeroed.  [16]: number of chained waits that timed out (see FPV_F_CHAINED), never reset
+                               by the library.  NULL = static round-robin distribution, no error word.        */
   void* chunk_epoch;        /* device uint32[ceil(n / 64)], zeroed once by the caller, or NULL.  After the launch
                                every entry holds epoch + 1 (published chunk by chunk as the chunk's state is stored);
                                with FPV_F_CHAINED chunk c is loaded only once chunk_epoch[c] == epoch.            */
@@ -197,7 +204,9 @@ int fpv_drone_step(const fpv_drone_params_t* params, const fpv_drone_io_t* io, v
  * of slice c-1 -- because the call is PCIe-bound (16 B/env in, 1 B/env out).  Everything is ordered after the work already
  * queued on `stream`, and `stream` is joined to the last copy: synchronising it means done_host is valid.  The two
  * extra streams and the events are created once per device and cached inside the library (the only state it keeps).
- * io->chunk_epoch / FPV_F_CHAINED are ignored.  slices <= 0: 4. */
+ * io->chunk_epoch / FPV_F_CHAINED are ignored.  slices <= 0: 4.
+ * With io->done_bits set, done_host receives the BITMASK instead (uint32[ceil(n / 32)], 1/8 of the bytes; done_host must
+ * then be 4-byte aligned and hold ceil(n / 32) * 4 bytes). */
 int fpv_drone_step_host(const fpv_drone_params_t* params, const fpv_drone_io_t* io, const float* actions_host,
                         uint8_t* done_host, int32_t slices, void* stream);
 
@@ -254,14 +263,17 @@ int fpv_drone_step_host_sticks(const fpv_drone_params_t* params, const fpv_drone
 
 /* ---------------------------------------------------------------------------------------------
  * Mode B: the acro rate-PID drone of tests/racer_drone_test.py (`PID` :11-32, `Racer` :68-103).
- * State: 7 float4 planes
+ * State: 5 float4 planes (80 B per env)
  *   0: position xyz, first-call flag of the PIDs (1.0 / 0.0)      :20, :47-51
- *   1: velocity xyz, unused
- *   2..4: rows of the orientation matrix, .w = angular_velocity[row]
- *   5: PID integral per axis, unused
- *   6: PID last error per axis, unused
+ *   1: velocity xyz, angular_velocity[0]
+ *   2: orientation as a unit quaternion w x y z (the reference keeps the 3x3 matrix and re-orthonormalises it every
+ *      step through scipy's Rotation, :99; same rotation, see fpv_racer_observe)
+ *   3: PID integral per axis, angular_velocity[1]
+ *   4: PID last error per axis, angular_velocity[2]
+ * Runs on the packed TMA-ring kernel (two envs per thread); sin/cos of the half angles are accurate for every
+ * argument a finite-gain PID produces (|omega| ~ 80 rad in the reference's own demo).
  * -------------------------------------------------------------------------------------------*/
-#define FPV_RACER_PLANES 7
+#define FPV_RACER_PLANES 5
 
 typedef struct fpv_racer_params {
   float dt;              /* racer_drone_test.py:8  */
@@ -270,16 +282,21 @@ typedef struct fpv_racer_params {
   float inertia[3];      /* :83 (m r^2 on every axis in the reference) */
   float gains[3][3];     /* [axis roll/pitch/yaw][P,I,D], :113 */
   float vel_decay;       /* :102 (0.9) */
-  uint32_t flags;        /* reserved, must be 0 */
+  uint32_t flags;        /* 0, or FPV_F_SCALAR (one env per thread: the cross-check instantiation) */
 } fpv_racer_params_t;
 
 /* Racer.reset -- :86-93 (mask as in fpv_drone_reset). */
 int fpv_racer_reset(void* state, int64_t n, int64_t plane_stride, const uint8_t* mask, void* stream);
 
 /* Racer.step(action) -- :95-103.  actions: float4[n] = [roll, pitch, yaw rate set-points, thrust N].
- * torque_out: float4[n] (last substep's PID output) or NULL. */
+ * torque_out: float4[n] (last substep's PID output) or NULL.  work: device uint32[32] zeroed once by the caller (chunk
+ * counters, as fpv_drone_io_t.work) or NULL. */
 int fpv_racer_step(const fpv_racer_params_t* params, void* state, int64_t n, int64_t plane_stride,
-                   const void* actions, void* torque_out, void* stream);
+                   const void* actions, void* torque_out, void* work, void* stream);
+
+/* Racer.orientation (the 3x3 matrix of :73, float[n][9] row-major) and Racer.angular_velocity (float[n][3]) read from
+ * the state planes; either output may be NULL. */
+int fpv_racer_observe(const void* state, int64_t n, int64_t plane_stride, float* R, float* omega, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Multi-agent gate-race environment (BASELINE.json configs[4]; API style of tests/ma_com_simple_env.py:17-57:
@@ -327,10 +344,12 @@ int fpv_gate_env_step(const fpv_gate_env_params_t* params, const void* state, in
                       const uint8_t* agent_done, void* prev, int32_t* progress, float* agent_reward, float* env_reward,
                       uint8_t* env_done, float* obs, fpv_stats_t* stats, void* stream);
 
-/* fpv_drone_step and fpv_gate_env_step in ONE launch (one agent per thread, state read once and written once):
- * bit-identical to fpv_drone_step with FPV_F_SCALAR followed by fpv_gate_env_step.  Hot-path configuration of the
- * dynamics only (ground plane, no obstacles / overrides / per-env wind, no FPV_F_FREEZE_DONE); io->done receives the
- * agents' crash flags, io->stats (may be NULL) the dynamics counters and the reward sums. */
+/* fpv_drone_step and fpv_gate_env_step in ONE launch: the env step runs as the per-chunk epilogue of the packed TMA-ring
+ * kernel (a warp's 64-agent chunk holds whole envs; team reward / termination by warp shuffle / ballot; every agent's
+ * state is read once and written once).  Bit-identical to fpv_drone_step followed by fpv_gate_env_step.  Hot-path
+ * configuration of the dynamics only (ground plane, no obstacles / overrides / per-env wind, no FPV_F_FREEZE_DONE, no
+ * FPV_F_SCALAR); io->done receives the agents' crash flags, io->stats (may be NULL) the dynamics counters and the reward
+ * sums (summed in a different order than by fpv_gate_env_step: equal to rounding). */
 int fpv_gate_race_step(const fpv_drone_params_t* params, const fpv_drone_io_t* io, const fpv_gate_env_params_t* gates,
                        void* prev, int32_t* progress, float* agent_reward, float* env_reward, uint8_t* env_done, float* obs,
                        void* stream);
@@ -461,7 +480,7 @@ int fpv_acro_reset(void* state, int64_t n, int64_t plane_stride, const float* po
  * FPV_F_AUTO_RESET; stats: crashes / episodes / episode_len_sum, may be NULL. */
 int fpv_acro_step(const fpv_acro_params_t* params, void* state, int64_t n, int64_t plane_stride, const void* actions,
                   const float* lut, int32_t lut_n, uint8_t* done, void* motor_thrust, const void* reset_state,
-                  fpv_stats_t* stats, void* stream);
+                  fpv_stats_t* stats, void* work /* uint32[32] zeroed once, or NULL */, void* stream);
 
 /* Open-loop rollout of mode C: n_steps control steps in one launch, state in registers across them, bit-identical to
  * n_steps calls of fpv_acro_step (restarts from the snapshot included).  actions_seq: float4[n_steps][action_stride];

@@ -164,7 +164,7 @@ def test_ragged_sizes_leave_padding_and_guards_untouched(n):
         big.step(act)
         _lib.check(lib.fpv_acro_step(C.byref(d._p), _lib.ptr(d._state), n, d._stride, _lib.ptr(a), _lib.ptr(d._lut),
                                      d._lut.numel(), C.c_void_p(done.data_ptr() + G), C.c_void_p(motor.data_ptr() + 16 * G),
-                                     None, None, _lib.current_stream(torch.device(DEV))))
+                                     None, None, None, _lib.current_stream(torch.device(DEV))))
     torch.cuda.synchronize()
     assert bool((d._state[:, n:] == 123.0).all())
     assert bool((done[:G] == 0xAB).all()) and bool((done[G + n:] == 0xAB).all())

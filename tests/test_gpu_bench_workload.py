@@ -1,0 +1,125 @@
+"""Parity ON THE BENCH WORKLOAD ITSELF: bench.py's exact configuration -- 1,048,576 drones, initial heights
+0.05..3 m (ground contact, bounces, crashes), K = 8 substeps of 1 ms, motor-curve LUT with 2049 entries, auto-reset, fresh
+random sticks every control step -- stepped 125 control steps (1 s) on the GPU, with a 4,096-env subsample stepped by the
+float64 oracle (oracle/fpv_oracle.py, pinned to the reference) INCLUDING the oracle-side restart of every env that raises
+`done`.  Asserted: the done flags agree at EVERY step (an env may differ only if one of its motors came within 1e-5 m of the
+crash plane in the oracle -- such an env is dropped from the comparison from then on and counted), the single-step error is
+<= 1e-5 relative, and the free-running divergence curve over the horizon is printed and bounded."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import CONFIG
+from oracle import fpv_oracle as fo
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from test_gpu_parity import FLOOR, group_err  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def oracle_consts(dt):
+    import yaml
+    with open(os.path.join(CONFIG, "params.yaml")) as f:
+        params = yaml.safe_load(f)
+    return fo.derive_consts(params, os.path.join(CONFIG, "t_motos_f80_motor_test.csv"), dt=dt)
+
+
+def state_err(d, idx, s):
+    t = lambda x: x[idx].cpu().numpy()
+    errs = [group_err(t(d.position), s.pos, FLOOR["position"]), group_err(t(d.velocity), s.vel, FLOOR["velocity"]),
+            group_err(d.rotation_matrix[idx].cpu().numpy(), s.R, FLOOR["R"]),
+            group_err(t(d.prev_rates), s.prev_rates, FLOOR["rates"]),
+            group_err(t(d.prev_thrust)[:, None], s.prev_thrust[:, None], FLOOR["thrust"])]
+    return np.max(np.stack(errs), axis=0)
+
+
+@pytest.mark.parametrize("form", ["step", "chained", "rollout"])
+def test_bench_workload_against_oracle_over_1s(form):
+    import bench
+    from fpyv_b200 import BatchedDrone
+    n, K, dt, steps, n_sub = bench.ENVS_PER_GPU, bench.SUBSTEPS, bench.DT, 125, 4096
+    dev = torch.device(DEV)
+    d = BatchedDrone(None, num_envs=n, device=dev, substeps=K, dt=dt, auto_reset=True, thrust_lut=bench.LUT_N)
+    pos, vel, rpy, gen = bench.synthetic_init(n, dev, 1234)          # bench.py's own initial state, rank 0
+    d.reset(pos, vel, rpy)
+    ring = [torch.rand(n, 4, device=dev, generator=gen) * 2 - 1 for _ in range(4)]   # bench.py's own stick ring
+    idx = torch.from_numpy(np.sort(np.random.default_rng(7).choice(n, n_sub, replace=False))).to(dev)
+    c = oracle_consts(dt)
+    f64 = lambda x: x[idx].double().cpu().numpy()
+    p0, v0, r0 = f64(pos), f64(vel), f64(rpy)
+    s = fo.drone_reset(c, p0, v0, r0)
+    s0 = s.copy()
+    acts = [f64(a) for a in ring]
+    # the oracle evaluates the cubic; the bench runs the 2049-entry LUT (interpolation error <= 6e-6 N):
+    # the oracle gets the same table so that the comparison is about the dynamics
+    from fpyv_b200 import config
+    table = config.thrust_table(d.constants, bench.LUT_N, "poly").astype(np.float64)
+
+    def lut_thrust(x):
+        u = (np.asarray(x, dtype=np.float32).astype(np.float64) + 1.0) * ((bench.LUT_N - 1) * 0.5)
+        i = np.clip(np.floor(u).astype(np.int64), 0, bench.LUT_N - 2)
+        return table[i] + (u - i) * (table[i + 1] - table[i])
+
+    orig = fo.throttle2thrust
+    fo.throttle2thrust = lambda cc, x: lut_thrust(x)
+    try:
+        alive = np.ones(n_sub, dtype=bool)      # envs whose done flags have agreed so far
+        curve, first_err, dropped, crashes = [], None, 0, 0
+        done_rows = torch.empty((steps, n), dtype=torch.uint8, device=dev) if form == "rollout" else None
+        if form == "rollout":
+            seq = torch.stack([ring[t % 4] for t in range(steps)]).contiguous()
+            d.rollout(seq, done_out=done_rows, fused=True)
+        for t in range(steps):
+            if form == "step":
+                d.step(ring[t % 4], return_obs=False)
+                done_gpu = d._done[idx].cpu().numpy().astype(bool)
+            elif form == "chained":
+                d.step(ring[t % 4], return_obs=False, chained=True)
+                done_gpu = d._done[idx].cpu().numpy().astype(bool)
+            else:
+                done_gpu = done_rows[t][idx].cpu().numpy().astype(bool)
+            # oracle: K reference steps with the action held, tracking how close any motor came to the crash plane
+            margin = np.full(n_sub, np.inf)
+            done_ref = np.zeros(n_sub, dtype=bool)
+            for _ in range(K):
+                mz = s.pos[:, None, 2] + np.einsum("mj,nj->nm", c.motor_rel, s.R[:, 2, :])
+                margin = np.minimum(margin, np.abs(mz).min(axis=1))
+                fo.drone_substep(c, s, acts[t % 4])
+                done_ref |= s.done
+            mism = (done_ref != done_gpu) & alive
+            assert (margin[mism] <= 1e-5).all(), (f"step {t}: {int(mism.sum())} done flags differ, "
+                                                  f"closest motor heights {np.sort(margin[mism])[-3:]}")
+            dropped += int(mism.sum())
+            alive &= ~mism
+            crashes += int((done_ref & alive).sum())
+            # oracle-side restart of crashed envs (what FPV_F_AUTO_RESET does at the end of the control step)
+            r = done_ref
+            s.pos[r], s.vel[r], s.R[r] = s0.pos[r], s0.vel[r], s0.R[r]
+            s.prev_rates[r], s.prev_thrust[r] = 0.0, 0.0
+            if form != "rollout":
+                e = state_err(d, idx, s)[alive]
+                if first_err is None:
+                    first_err = float(e.max())
+                curve.append((t + 1, float(np.median(e)), float(e.max())))
+        if form == "rollout":      # the state is only visible after the last step
+            e = state_err(d, idx, s)[alive]
+            curve.append((steps, float(np.median(e)), float(e.max())))
+    finally:
+        fo.throttle2thrust = orig
+    marks = [m for m in curve if m[0] in (1, 2, 5, 10, 30, 60, 125)]
+    print(f"\nbench workload [{form}] {n} envs, K={K}, {steps} control steps (1 s), {n_sub}-env subsample vs float64 oracle: "
+          f"crashes+restarts {crashes}, done flags equal every step ({dropped} envs dropped at the 1e-5 m margin); "
+          "divergence (median / max): " + " ".join(f"@{t}:{m:.1e}/{x:.1e}" for t, m, x in marks))
+    assert crashes > 100, "the workload must exercise ground contact and restarts"
+    assert dropped <= n_sub // 500
+    if first_err is not None:
+        assert first_err <= 1e-5, first_err
+    # free running over 1 s through bounces and restarts: the median stays at fp32 round-off level; the maximum is
+    # bounded loosely (a bouncing env amplifies round-off by the contact spring's stiffness)
+    assert curve[-1][1] <= 1e-4, curve[-1]
+    assert curve[-1][2] <= 5e-2, curve[-1]

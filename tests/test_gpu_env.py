@@ -104,12 +104,13 @@ def test_env_argument_validation():
 
 @pytest.mark.parametrize("A", [32, 8])
 def test_fused_env_step_is_bit_identical_to_the_two_launch_path(A):
-    """fpv_gate_race_step (dynamics + env step in one launch) against fpv_drone_step with the scalar kernel followed by
-    fpv_gate_env_step: state, rewards, terminations, observations, race bookkeeping and statistics, bit for bit, over a
-    rollout with gate passes and crashes."""
+    """fpv_gate_race_step (the env step as the per-chunk epilogue of the packed ring kernel, one launch) against
+    fpv_drone_step (packed hot kernel) followed by fpv_gate_env_step: state, rewards, terminations, observations, race
+    bookkeeping and the event counters bit for bit over a rollout with gate passes and crashes; the reward sums of the
+    statistics are accumulated in a different order (per warp instead of per CTA), so those agree to rounding."""
     from fpyv_b200.env import GateRaceEnv
     envs = 512
-    kw = dict(num_envs=envs, agents_per_env=A, device=DEV, substeps=4, dt=2e-3, thrust_lut=2049, packed=False, seed=3,
+    kw = dict(num_envs=envs, agents_per_env=A, device=DEV, substeps=4, dt=2e-3, thrust_lut=2049, seed=3,
               spawn_height=(0.3, 2.5))
     a, b = GateRaceEnv(None, **kw), GateRaceEnv(None, **kw)
     a.reset()
@@ -129,5 +130,9 @@ def test_fused_env_step_is_bit_identical_to_the_two_launch_path(A):
     assert torch.equal(a._progress, b._progress) and torch.equal(a._prev, b._prev)
     assert torch.equal(a.agent_reward, b.agent_reward)
     sa, sb = a.episode_stats(), b.episode_stats()
-    assert all(sa[k] == sb[k] or (sa[k] != sa[k] and sb[k] != sb[k]) for k in sa), (sa, sb)
+    for k in sa:
+        if k in ("reward_sum", "reward_sq_sum"):
+            assert abs(sa[k] - sb[k]) <= 1e-6 * max(1.0, abs(sb[k])), (k, sa[k], sb[k])
+        else:
+            assert sa[k] == sb[k] or (sa[k] != sa[k] and sb[k] != sb[k]), (k, sa, sb)
     assert crashes > 0

@@ -1,0 +1,198 @@
+"""The modes that moved onto the persistent TMA-ring kernel in round 2 (general / obstacle path with the per-control-step
+reach test, gate-race epilogue, packed quaternion `Racer`, acro) and the features added to the ring (done bitmask, the
+error word that replaced the device trap of a broken chaining contract)."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import fpv_oracle as fo
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from test_gpu_parity import TOL_STEP, drone_err, fo_consts, make  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.mark.parametrize("packed", [True, False])
+@pytest.mark.parametrize("K,dt", [(8, 2e-3), (4, 1 / 240), (16, 1e-3)])
+def test_general_path_reach_test_hoisted_out_of_the_substep_loop(packed, K, dt):
+    """The general kernel decides ONCE per control step which obstacles any motor can reach during the K substeps (bound on
+    the speed over the step, drone_kernels.cuh) and skips the others in every substep.  Drones are placed 0.05 .. 3 m outside
+    the reach of a sphere and a cylinder and thrown AT them at up to 60 m/s (plus bystanders far away and drones already in
+    contact), so that many enter the contact shell or crash in the middle of the control step: state and crash flags must
+    match the float64 oracle, which tests every obstacle in every substep."""
+    from fpyv_b200 import Cylinder, Ground, Target
+    n = 24_000
+    rng = np.random.default_rng(91 + K)
+    sph_c, sph_r = np.array([2.0, -1.0, 6.0]), 1.3
+    cyl_p, cyl_r, cyl_h = np.array([-4.0, 3.0, 0.0]), 0.8, 7.0
+    reach = 0.127 + 0.1
+    gap = rng.choice([-0.02, 0.05, 0.2, 0.5, 1.0, 2.0, 3.0, 40.0], n) + reach + rng.normal(0, 0.01, n)
+    u = rng.normal(size=(n, 3))
+    u /= np.linalg.norm(u, axis=1, keepdims=True)
+    pos = sph_c + u * (sph_r + gap)[:, None]
+    speed = rng.choice([0.0, 5.0, 20.0, 40.0, 60.0], n)
+    vel = -u * speed[:, None] + rng.normal(0, 0.5, (n, 3))
+    half = n // 2                                                    # second half: around the cylinder's side
+    ang = rng.uniform(0, 2 * np.pi, half)
+    rad = cyl_r + gap[half:]
+    pos[half:] = np.stack([cyl_p[0] + rad * np.cos(ang), cyl_p[1] + rad * np.sin(ang), rng.uniform(1.0, cyl_h - 1.0, half)], axis=1)
+    vel[half:] = np.stack([-np.cos(ang), -np.sin(ang), np.zeros(half)], 1) * speed[half:, None] + rng.normal(0, 0.5, (half, 3))
+    pos[:, 2] = np.maximum(pos[:, 2], 0.5)
+    rpy = rng.uniform(-40, 40, (n, 3))
+    act = rng.uniform(-1, 1, (n, 4))
+    c = fo_consts(dt)
+    s = fo.drone_reset(c, pos, vel, rpy)
+    d = make(n, packed=packed, substeps=K, dt=dt)
+    d.reset(pos, vel, rpy)
+    s.pos, s.vel = d.position.double().cpu().numpy(), d.velocity.double().cpu().numpy()
+    s.R = fo.quaternion_to_matrix(d.quaternion.double().cpu().numpy())
+    objs = [Target(sph_c, sph_r), Cylinder(cyl_p, cyl_r, cyl_h), Ground()]
+    extra = [fo.SphereObj(sph_c, sph_r), fo.CylinderObj(cyl_p, cyl_r, cyl_h)]
+    touched = np.zeros(n, dtype=bool)
+    for _ in range(2):                                               # two control steps: the second starts mid-contact
+        a0 = np.abs(s.acc).max(1)
+        fo.drone_step(c, s, act, substeps=K, extra_objects=extra)
+        d.step(act, np.zeros(3), objs, return_obs=False)
+        touched |= np.abs(s.acc).max(1) > 150
+        done = d.done.cpu().numpy()
+        mism = done != s.done
+        err = drone_err(d, np.concatenate([s.pos, s.vel], 1), s.R, s.prev_rates, s.prev_thrust)
+        ok = ~mism & ~s.done                    # a crashed env keeps integrating; compare the survivors tightly
+        print(f"\nhoisted reach K={K} dt={dt:.4f} packed={packed}: max rel err {err[ok].max():.2e}, crashed {int(s.done.sum())}, "
+              f"flag mismatches {int(mism.sum())}")
+        assert mism.sum() <= 6, mism.sum()       # a motor within fp32 rounding of a surface may flip the flag
+        assert err[ok].max() <= 2e-5 * K         # K free-running substeps through stiff contact springs
+        # re-synchronise the oracle on the device state so that the second step is a single control step again
+        s.pos, s.vel = d.position.double().cpu().numpy(), d.velocity.double().cpu().numpy()
+        s.R = fo.quaternion_to_matrix(d.quaternion.double().cpu().numpy())
+        s.prev_rates, s.prev_thrust = d.prev_rates.double().cpu().numpy(), d.prev_thrust.double().cpu().numpy()
+    assert s.done.sum() > 200
+
+
+@pytest.mark.parametrize("n", [1, 63, 1000, 65_537, 1 << 18])
+@pytest.mark.parametrize("mode", ["hot", "general", "scalar", "freeze"])
+def test_done_bitmask_equals_the_done_bytes(n, mode):
+    """fpv_drone_io_t.done_bits: one ballot per 32 envs.  Bit e % 32 of word e // 32 == done[e], every kernel form, ragged
+    sizes, frozen envs (sticky) included; words past the batch are never written."""
+    from fpyv_b200 import BatchedDrone, Cylinder, Ground
+    rng = np.random.default_rng(n)
+    pos = np.stack([rng.normal(0, 3, n), rng.normal(0, 3, n), rng.uniform(0.05, 0.6, n)], 1)
+    vel, rpy = rng.normal(size=(n, 3)), rng.uniform(-50, 50, (n, 3))
+    kw = dict(packed=mode != "scalar", freeze_done=mode == "freeze", auto_reset=mode == "hot")
+    d = BatchedDrone(None, num_envs=n, device=DEV, substeps=4, dt=2e-3, done_bits=True, **kw)
+    d.reset(pos, vel, rpy)
+    objs = [Cylinder(np.array([50.0, 50.0, 0.0]), 1.0, 5.0), Ground()] if mode == "general" else None
+    seen = 0
+    for t in range(6):
+        a = rng.uniform(-1, 1, (n, 4))
+        a[:, 3] = rng.uniform(-1, -0.5, n)           # low throttle: the drones sink and crash
+        d._done_bits.fill_(0x5A5A5A5A)
+        d.step(a, None, objs, return_obs=False)
+        by = d._done.cpu().numpy().astype(bool)
+        words = d.done_bits.cpu().numpy().view(np.uint32)
+        bits = ((words[:, None] >> np.arange(32, dtype=np.uint32)[None, :]) & 1).astype(bool).reshape(-1)[:n]
+        assert np.array_equal(bits, by), t
+        if n % 32:
+            assert (words[-1] >> np.uint32(n % 32)) == 0        # bits past the batch inside the last word are clear
+        seen += int(by.sum())
+    assert seen > 0 or n < 8
+
+
+def test_broken_chaining_contract_raises_the_error_word_not_a_trap():
+    """A chained launch whose epoch never arrives (here: the host's epoch counter is pushed ahead, as a replayed captured
+    launch would) used to __trap() the context after a spin count.  Now: the launch waits 2 s of wall-clock time, adds to the
+    error word, falls back to the grid-wide wait and completes -- with the right result; the context stays usable."""
+    from fpyv_b200 import BatchedDrone
+    n, K = 200_000, 2
+    rng = np.random.default_rng(5)
+    pos = np.stack([rng.normal(0, 5, n), rng.normal(0, 5, n), rng.uniform(1, 3, n)], 1)
+    vel, rpy = rng.normal(size=(n, 3)), rng.uniform(-30, 30, (n, 3))
+    acts = [torch.as_tensor(rng.uniform(-1, 1, (n, 4)), dtype=torch.float32, device=DEV) for _ in range(3)]
+    a, b = (BatchedDrone(None, num_envs=n, device=DEV, substeps=K, dt=1e-3) for _ in range(2))
+    a.reset(pos, vel, rpy)
+    b.reset(pos, vel, rpy)
+    for t in range(2):
+        a.step(acts[t], return_obs=False, chained=True)
+        b.step(acts[t], return_obs=False)
+    assert a.episode_stats()["chain_timeouts"] == 0
+    a._epoch += 7                                   # break the contract: the kernel will wait for an epoch nobody publishes
+    a.step(acts[2], return_obs=False, chained=True)
+    b.step(acts[2], return_obs=False)
+    torch.cuda.synchronize()                        # (about 2 s)
+    assert a.episode_stats()["chain_timeouts"] > 0
+    assert torch.equal(a._state, b._state)
+    a.step(acts[0], return_obs=False, chained=True)  # the epochs are consistent again: no further timeouts
+    b.step(acts[0], return_obs=False)
+    t0 = a.episode_stats()["chain_timeouts"]
+    a.step(acts[1], return_obs=False, chained=True)
+    b.step(acts[1], return_obs=False)
+    torch.cuda.synchronize()
+    assert a.episode_stats()["chain_timeouts"] == t0 and torch.equal(a._state, b._state)
+
+
+def test_racer_packed_matches_scalar_and_the_oracle_at_large_rates():
+    """Mode B on the ring: the packed (two envs per thread) and scalar instantiations agree bit for bit (the same FP32
+    operations per env), ragged sizes leave the padding alone, and set-points that drive |omega| to ~100 rad (half angles far
+    outside the polynomial range: Cody-Waite reduction) still match the float64 oracle."""
+    from fpyv_b200 import BatchedRacer, _lib
+    n = 3001
+    gains = {"roll": [2, 0.1, 1e-4], "pitch": [1.5, 0.2, 0], "yaw": [0.1, 0, 0]}
+    rng = np.random.default_rng(3)
+    sp = np.concatenate([rng.uniform(-100, 100, (n, 3)), rng.uniform(0, 10, (n, 1))], 1)
+    sp[: n // 3, :3] = rng.uniform(-3, 3, (n // 3, 3))
+    rp = BatchedRacer(5, gains, num_envs=n, device=DEV, dt=1e-3, substeps=5)
+    rs = BatchedRacer(5, gains, num_envs=n, device=DEV, dt=1e-3, substeps=5)
+    rs._p.flags = _lib.F_SCALAR
+    for r in (rp, rs):
+        r.reset()
+        r._state[:, n:] = 77.0
+    for t in range(4):
+        rp.step(sp)
+        rs.step(sp)
+    torch.cuda.synchronize()
+    assert torch.equal(rp._state[:, :n], rs._state[:, :n])
+    assert bool((rp._state[:, n:] == 77.0).all())
+    rc = fo.RacerConsts(gains=np.array(list(gains.values()), dtype=np.float64))
+    s = fo.RacerState(n)
+    for t in range(20):
+        fo.racer_step(rc, s, sp)
+    R, w, x = (v.double().cpu().numpy() for v in (rp.orientation, rp.angular_velocity, rp.position))
+    worst = max(np.abs(R - s.R).max(), (np.abs(w - s.omega).max(1) / np.maximum(1.0, np.abs(s.omega).max(1))).max(),
+                (np.abs(x - s.pos).max(1) / np.maximum(1e-2, np.abs(s.pos).max(1))).max())
+    print(f"\nracer packed vs oracle after 20 steps, |omega| up to {np.abs(rp.angular_velocity.cpu().numpy()).max():.0f} rad/s: {worst:.2e}")
+    assert worst <= 2e-4
+
+
+def test_step_host_returns_the_done_bitmask():
+    """fpv_drone_step_host with io.done_bits: the D2H copy carries ceil(n/32) words instead of n bytes; same flags, same state
+    as the plain step."""
+    from fpyv_b200 import BatchedDrone
+    n = 300_037
+    rng = np.random.default_rng(8)
+    pos = np.stack([rng.normal(0, 3, n), rng.normal(0, 3, n), rng.uniform(0.05, 1.0, n)], 1)
+    vel, rpy = rng.normal(size=(n, 3)), rng.uniform(-40, 40, (n, 3))
+    a = BatchedDrone(None, num_envs=n, device=DEV, substeps=4, dt=1e-3, auto_reset=True, thrust_lut=513, done_bits=True)
+    b = BatchedDrone(None, num_envs=n, device=DEV, substeps=4, dt=1e-3, auto_reset=True, thrust_lut=513)
+    a.reset(pos, vel, rpy)
+    b.reset(pos, vel, rpy)
+    host_a = torch.empty((n, 4), dtype=torch.float32, pin_memory=True)
+    bits_host = torch.zeros((n + 31) // 32, dtype=torch.int32, pin_memory=True)
+    with pytest.raises(ValueError):
+        a.step_host(host_a, torch.empty(n, dtype=torch.uint8, pin_memory=True))
+    crashed = 0
+    for t in range(5):
+        host_a.copy_(torch.as_tensor(rng.uniform(-1, 1, (n, 4)), dtype=torch.float32))
+        a.step_host(host_a, bits_host, slices=4)
+        b.step(host_a.to(DEV), return_obs=False)
+        torch.cuda.synchronize()
+        words = bits_host.numpy().view(np.uint32)
+        bits = ((words[:, None] >> np.arange(32, dtype=np.uint32)[None, :]) & 1).astype(bool).reshape(-1)[:n]
+        assert np.array_equal(bits, b._done.cpu().numpy().astype(bool)), t
+        crashed += int(bits.sum())
+    assert torch.equal(a._state, b._state) and crashed > 0

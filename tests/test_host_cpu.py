@@ -55,7 +55,7 @@ def test_argument_validation_needs_no_gpu(lib):
     io.n = 0
     io.plane_stride = 0
     assert lib.fpv_drone_step(C.byref(p), C.byref(io), None) == 0       # empty batch is a no-op
-    assert lib.fpv_racer_step(None, None, 0, 0, None, None, None) == -22
+    assert lib.fpv_racer_step(None, None, 0, 0, None, None, None, None) == -22
     assert lib.fpv_sticks_to_actions(None, None, 0, None, None, None) == -22
 
 
@@ -249,7 +249,7 @@ def test_new_entry_points_validate_without_a_gpu(lib):
     ap.dt = 0.01
     assert lib.fpv_autopilot(C.byref(ap), C.byref(cam), dummy, 0, 0, dummy, None, dummy, dummy, dummy, None, None, None, None) == -22
     assert b"Unknown reference frame" in lib.fpv_last_error()
-    assert lib.fpv_acro_step(C.byref(ac), dummy, 0, 0, dummy, None, 0, None, None, None, None, None) == -22
+    assert lib.fpv_acro_step(C.byref(ac), dummy, 0, 0, dummy, None, 0, None, None, None, None, None, None) == -22
     assert lib.fpv_acro_reset(None, 0, 0, None, None, None, None, None) == -22
 
 
@@ -350,7 +350,7 @@ def test_sass_carries_the_blackwell_paths(lib):
     out = subprocess.run([cuobjdump, "-sass", so], capture_output=True, text=True).stdout
     assert "sm_100a" in subprocess.run([cuobjdump, "-lelf", so], capture_output=True, text=True).stdout
     funcs = re.split(r"\n\s*Function : ", out)[1:]
-    hot = [f for f in funcs if f.startswith("_ZN3fpv21drone_step_tma_kernelINS_2F2ELi4")]
+    hot = [f for f in funcs if f.startswith("_ZN3fpv16ring_step_kernelINS_9DroneModeINS_2F2ELi4ELb0ENS_6NoPost")]
     assert len(hot) == 1
     sass = hot[0]
     count = lambda op: len(re.findall(r"\b" + op + r"\b", sass))
@@ -359,10 +359,15 @@ def test_sass_carries_the_blackwell_paths(lib):
     assert "SYNCS.ARRIVE.TRANS64" in sass and "SYNCS.PHASECHK.TRANS64.TRYWAIT" in sass
     assert "ACQBULK" in sass and "PREEXIT" in sass
     assert "LDG.E.STRONG.GPU" in sass and "MEMBAR.ALL.GPU" in sass and "FENCE.VIEW.ASYNC" in sass
-    # the rollout, obstacle and acro kernels use the packed pipe as well
-    for prefix in ("_ZN3fpv20drone_rollout_kernelINS_2F2ELi4", "_ZN3fpv17drone_step_kernelINS_2F2ELi4ELb1", "_ZN3fpv16acro_step_kernelINS_2F2E"):
+    # the rollout kernel and every other mode of the ring kernel (obstacle path, gate-race epilogue, Racer, acro) use the
+    # packed pipe and the TMA ring as well
+    f = [x for x in funcs if x.startswith("_ZN3fpv20drone_rollout_kernelINS_2F2ELi4")]
+    assert f and len(re.findall(r"\bFFMA2\b", f[0])) >= 60
+    for prefix in ("_ZN3fpv16ring_step_kernelINS_9DroneModeINS_2F2ELi4ELb1ENS_6NoPost", "_ZN3fpv16ring_step_kernelINS_9DroneModeINS_2F2ELi4ELb0ENS_8GatePost",
+                   "_ZN3fpv16ring_step_kernelINS_9RacerModeINS_2F2E", "_ZN3fpv16ring_step_kernelINS_8AcroModeINS_2F2E"):
         f = [x for x in funcs if x.startswith(prefix)]
         assert f and len(re.findall(r"\bFFMA2\b", f[0])) >= 60, prefix
+        assert len(re.findall(r"UBLKCP\.S\.G", f[0])) >= 5 and "SYNCS.PHASECHK.TRANS64.TRYWAIT" in f[0], prefix
 
 
 @pytest.mark.parametrize("n", [1, 63, 65536, 262143, 262144, 300_000, 1 << 20, (1 << 20) + 1, 16_777_216])
