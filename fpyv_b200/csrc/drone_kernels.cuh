@@ -80,6 +80,7 @@ __device__ __forceinline__ V object_distance(const fpv_object_t& o, V px, V py, 
   const V d2 = vsqrt_fast(vfma(dx, dx, dy * dy)) - S<V>(o.a);
   const V top = S<V>(o.z + o.b);
   const auto inside = vand(vlt(S<V>(o.z), pz), vlt(pz, top));
+  if (!vany(vnot(inside))) return d2;   // every env of this thread is inside the height band: no cap distance needed
   const V dh = vmin(vabs(pz - S<V>(o.z)), vabs(pz - top));
   return vsel(inside, d2, vsqrt_fast(vfma(d2, d2, dh * dh)));
 }
@@ -323,7 +324,20 @@ __device__ __forceinline__ typename Lane<V>::Mask drone_substeps(const DroneK& k
       }
       // (3) the ground plane, last in the list (distance = z, normal = +z, components.py:674-680), and the crash test
       //     on the motor heights that holds with or without it (:239)
-      {
+      if (ground && k.spring_c == 0.f) {   // the reference's own ground configuration: the hot path's formula (same bits)
+        const V h = S<V>(k.motor_radius) - s.pz;
+        V tmax, pen_sum;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          const V t = vfma(S<V>(k.neg_motor_xy[m][0]), r20, vfma(S<V>(k.neg_motor_xy[m][1]), r21, h));
+          tmax = m == 0 ? t : vmax(tmax, t);
+          pen_sum = m == 0 ? vmax(t, zero) : pen_sum + vmax(t, zero);
+        }
+        const M below = vlt(S<V>(k.motor_radius), tmax);
+        const M live = vnot(vor(crashed, below));
+        cfz = vfma(S<V>(k.spring_k), vsel(live, pen_sum, zero), cfz);
+        crashed = vor(crashed, below);
+      } else {
         V mz[4];
         V minz;
 #pragma unroll

@@ -169,9 +169,18 @@ struct RacerMode {
       notfirst = one;
       // orientation <- orientation @ Rx(w0) Ry(w1) Rz(w2)   (:99; angle = omega).  qE = qx (x) qy (x) qz of the half angles
       V sa, ca, sb, cb, sc, cc;
-      sincos_reduced<V>(w[0] * half, sa, ca);
-      sincos_reduced<V>(w[1] * half, sb, cb);
-      sincos_reduced<V>(w[2] * half, sc, cc);
+      const V h0 = w[0] * half, h1 = w[1] * half, h2 = w[2] * half;
+      // one test for the three angles: inside the polynomial kernels' range (the common case) no reduction is needed, and
+      // sincos_reduced would return the same values there (its j is 0)
+      if (!vany(vlt(S<V>(0.785f), vmax(vmax(vabs(h0), vabs(h1)), vabs(h2))))) {
+        sincos_poly<V>(h0, sa, ca);
+        sincos_poly<V>(h1, sb, cb);
+        sincos_poly<V>(h2, sc, cc);
+      } else {
+        sincos_reduced<V>(h0, sa, ca);
+        sincos_reduced<V>(h1, sb, cb);
+        sincos_reduced<V>(h2, sc, cc);
+      }
       const V aw = ca * cb, ax = sa * cb, ay = ca * sb, az = sa * sb;             // qx (x) qy
       const V ew = vfma(aw, cc, vneg(az * sc)), ex = vfma(ax, cc, ay * sc);
       const V ey = vfma(ay, cc, vneg(ax * sc)), ez = vfma(az, cc, aw * sc);

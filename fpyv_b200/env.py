@@ -115,7 +115,7 @@ class GateRaceEnv:
         else:
             d.step(act, return_obs=False)      # (also the first call: it configures the drone's io block)
             self._run_env_kernel(d._done)
-        return self._obs_dict(), self._env_reward, self._env_done.bool(), {}
+        return self._obs_dict(), self._env_reward, self._env_done.view(torch.bool), {}
 
     @property
     def next_gate(self):

@@ -92,27 +92,85 @@ class Cylinder:
     bbox3d = property(lambda self: _bbox3d(self.points))
 
 
+def generate_circular_path(center, radius, resolution):
+    """helper_functions.py:151-153: `resolution` way-points of a horizontal circle around `center`."""
+    theta = np.linspace(0, 2 * np.pi, resolution + 1)[:-1]
+    return np.vstack((np.cos(theta) * radius, np.sin(theta) * radius, np.zeros_like(theta))).T + np.array(center)
+
+
+class CircularPath:
+    """components.py:743-752: an endless iterator over the way-points of a circle."""
+
+    def __init__(self, center, radius, resolution):
+        self.path = generate_circular_path(center, radius, resolution)
+        self.count = 0
+
+    def __iter__(self):
+        while True:
+            yield self.path[self.count % len(self.path)]
+            self.count += 1
+
+
 class Target:
     """Sphere: centre `position`, `radius` (components.py:757-777); `vertices` (unit-sphere points scaled by the
-    radius, :761-763) default to the geodesic icosahedron of frequency `nu`."""
+    radius, :761-763) default to the geodesic icosahedron of frequency `nu`.  `path` = dict(radius=, resolution=) makes it
+    a moving target exactly like the reference (:764-765): every `update()` (:769-771) steps to the next way-point of a
+    `CircularPath` around the initial position.  `offset` is the displacement from the initial position -- the value a
+    `World` built at construction time needs per env (`BatchedCamera.render_*(..., offsets=)`, fpv_camera_render's
+    obj_offset); `target_offsets()` below packs it for a batch."""
 
     def __init__(self, position, radius, nu=None, path=None, vertices=None):
         self.position = np.asarray(position, dtype=np.float64)
+        self.initial_position = self.position.copy()
         self.radius = float(radius)
         self.vertices = None
         if vertices is not None:
             self.vertices = np.asarray(vertices, dtype=np.float64) * self.radius
         elif nu is not None:
             self.vertices = icosphere_vertices(int(nu)) * self.radius
+        self.path = None
+        self._way_points, self._n_updates = None, 0
+        if path is not None:
+            cp = CircularPath(self.position, **path)
+            self._way_points = cp.path
+            self.path = iter(cp)
 
     @property
     def points(self):                                                       # components.py:766-768
         return None if self.vertices is None else self.vertices + self.position
 
+    def update(self):                                                       # components.py:769-771
+        if self.path is None:
+            raise TypeError("'NoneType' object is not an iterator")         # what next(None) raises in the reference
+        self.position = np.asarray(next(self.path), dtype=np.float64)
+        self._n_updates += 1
+
+    @property
+    def offset(self):
+        return self.position - self.initial_position
+
     bbox3d = property(lambda self: _bbox3d(self.points))
 
     def calculate_distance(self, point):                                    # :773-774
         return float(np.linalg.norm(np.asarray(point, dtype=np.float64) - self.position) - self.radius)
+
+
+def target_offsets(objects_list, num_envs, per_env_phase=None):
+    """obj_offset block [num_envs, n_objects, 3] (float64) for a world whose `Target`s have moved since the `World` was
+    built: object j's current displacement, the same for every env -- or, with per_env_phase (int [num_envs] >= 0), env e
+    sees every moving target as it will be after `per_env_phase[e]` MORE update() calls (a batch of chase envs started at
+    different times).  Static objects get zeros."""
+    out = np.zeros((num_envs, len(objects_list), 3))
+    for j, o in enumerate(objects_list):
+        if not isinstance(o, Target) or o.path is None:
+            continue
+        if per_env_phase is None:
+            out[:, j] = o.offset
+        else:
+            total = o._n_updates + np.asarray(per_env_phase, dtype=np.int64)      # update() calls seen by env e
+            way = o._way_points[(total - 1) % len(o._way_points)] - o.initial_position
+            out[:, j] = np.where((total > 0)[:, None], way, 0.0)
+    return out
 
 
 class Gate:

@@ -37,13 +37,16 @@ def group_err(a, b, floor=1.0):
     return np.max(np.abs(a - b), axis=1) / np.maximum(floor, np.max(np.abs(b), axis=1))
 
 
-def drone_err(d, state, R, prev_rates, prev_thrust):
-    """Per-env worst group error, every group relative to its own magnitude (floors in FLOOR)."""
+def drone_err(d, state, R, prev_rates, prev_thrust, vel_floor=None):
+    """Per-env worst group error, every group relative to its own magnitude (floors in FLOOR).  vel_floor: contact tests
+    pass the velocity scale of the contact itself (a stiff spring changes v by up to ~1 m/s per step, and the motor-surface
+    distance it acts on is a difference of metre-sized float32 numbers)."""
     errs = [group_err(d.position.cpu().numpy(), state[:, :3], FLOOR["position"]),
-            group_err(d.velocity.cpu().numpy(), state[:, 3:], FLOOR["velocity"]),
+            group_err(d.velocity.cpu().numpy(), state[:, 3:], FLOOR["velocity"] if vel_floor is None else vel_floor),
             group_err(d.rotation_matrix.cpu().numpy(), R, FLOOR["R"]),
             group_err(d.prev_rates.cpu().numpy(), prev_rates, FLOOR["rates"]),
             group_err(d.prev_thrust.cpu().numpy()[:, None], np.asarray(prev_thrust)[:, None], FLOOR["thrust"])]
+    drone_err.last = {k: float(e.max()) for k, e in zip(("position", "velocity", "R", "rates", "thrust"), errs)}
     return np.max(np.stack(errs), axis=0)
 
 
@@ -751,7 +754,7 @@ def test_obstacle_reach_test_is_exact_against_oracle(packed):
     pos[half:] = np.stack([cyl_p[0] + rad * np.cos(ang), cyl_p[1] + rad * np.sin(ang), np.maximum(z, 0.35)], axis=1)
     vel = rng.normal(0, 2, (n, 3))
     rpy = rng.uniform(-40, 40, (n, 3))
-    act = rng.uniform(-1, 1, (n, 4))
+    act = rng.uniform(-1, 1, (n, 4)).astype(np.float32).astype(np.float64)   # identical inputs on both sides
     c = fo_consts()
     s = fo.drone_reset(c, pos, vel, rpy)
     d = make(n, packed=packed)
@@ -761,13 +764,13 @@ def test_obstacle_reach_test_is_exact_against_oracle(packed):
     objs = [Target(sph_c, sph_r), Cylinder(cyl_p, cyl_r, cyl_h), Ground()]
     fo.drone_step(c, s, act, extra_objects=[fo.SphereObj(sph_c, sph_r), fo.CylinderObj(cyl_p, cyl_r, cyl_h)])
     d.step(act, np.zeros(3), objs, return_obs=False)
-    err = drone_err(d, np.concatenate([s.pos, s.vel], 1), s.R, s.prev_rates, s.prev_thrust)
+    err = drone_err(d, np.concatenate([s.pos, s.vel], 1), s.R, s.prev_rates, s.prev_thrust, vel_floor=1.0)
     done = d.done.cpu().numpy()
     # a motor within float32 rounding of a surface may flip the crash flag: excuse envs whose motors sit at |d| < 2e-6
     mism = done != s.done
     print(f"\nobstacle shells: max rel err {err[~mism].max():.2e}, crashed {int(s.done.sum())}, in contact without crash "
           f"{int((np.abs(s.acc).max(1) > 30).sum())}, flag mismatches {int(mism.sum())}")
-    assert err[~mism].max() <= TOL_STEP and mism.sum() <= 3
+    assert err[~mism].max() <= TOL_STEP and mism.sum() <= 3, drone_err.last
     assert s.done.sum() > 500 and (~s.done).sum() > 5000
 
 
@@ -790,13 +793,13 @@ def test_every_angle_kernel_variant_vs_oracle(max_rates, dt, K, ang, packed):
     rng = np.random.default_rng(int(max_rates))
     pos = np.stack([rng.normal(0, 5, n), rng.normal(0, 5, n), rng.uniform(0.05, 6, n)], 1)
     vel, rpy = rng.normal(0, 1, (n, 3)), rng.uniform(-40, 40, (n, 3))
-    acts = rng.uniform(-1, 1, (20, n, 4))
+    acts = rng.uniform(-1, 1, (20, n, 4)).astype(np.float32).astype(np.float64)   # identical inputs: float32-representable sticks
     far = Cylinder(np.array([300.0, 0.0, 0.0]), 1.0, 5.0)
     for objs in (None, [far, Ground()]):                       # hot kernel / general kernel
         d = BatchedDrone(params, num_envs=n, device=DEV, substeps=K, dt=dt, packed=packed)
         d.reset(pos, vel, rpy)
         s = fo.drone_reset(c, pos, vel, rpy)
-        worst1 = 0.0
+        worst1, worst_groups = 0.0, {}
         for t in range(20):
             if t < 6:                                          # teacher-forced single steps first
                 set_state(d, np.concatenate([s.pos, s.vel], 1), s.R, s.prev_rates, s.prev_thrust)
@@ -808,9 +811,10 @@ def test_every_angle_kernel_variant_vs_oracle(max_rates, dt, K, ang, packed):
             e = drone_err(d, np.concatenate([s.pos, s.vel], 1), s.R, s.prev_rates, s.prev_thrust)
             if t < 6:
                 assert np.array_equal(d.done.cpu().numpy(), s.done)
-                worst1 = max(worst1, float(e.max()))
+                if float(e.max()) > worst1:
+                    worst1, worst_groups = float(e.max()), dict(drone_err.last)
         flying = ~s.done & (s.pos[:, 2] > 0.5)
-        assert worst1 <= TOL_STEP, (worst1, objs is not None)
+        assert worst1 <= TOL_STEP, (worst1, objs is not None, worst_groups)
         assert float(e[flying].max()) <= 2e-4, float(e[flying].max())      # 14 free-running steps
     if packed:                                                 # the fused rollout uses the same angle kernels
         a = BatchedDrone(params, num_envs=n, device=DEV, substeps=K, dt=dt)
@@ -833,7 +837,7 @@ def test_general_path_without_ground_and_with_damped_spring(packed):
     rng = np.random.default_rng(91)
     pos = np.stack([rng.normal(0, 3, n), rng.normal(0, 3, n), rng.uniform(-0.05, 0.6, n)], 1)
     vel, rpy = rng.normal(0, 1.5, (n, 3)), rng.uniform(-30, 30, (n, 3))
-    act = rng.uniform(-1, 1, (n, 4))
+    act = rng.uniform(-1, 1, (n, 4)).astype(np.float32).astype(np.float64)       # identical inputs on both sides
     for ground, damping in ((False, 0.0), (True, 7.5)):
         c = fo_consts()
         c.ground, c.spring_c = ground, damping
@@ -848,7 +852,7 @@ def test_general_path_without_ground_and_with_damped_spring(packed):
         err = drone_err(d, np.concatenate([s.pos, s.vel], 1), s.R, s.prev_rates, s.prev_thrust)
         done = d.done.cpu().numpy()
         mism = done != s.done
-        assert err[~mism].max() <= TOL_STEP, (ground, damping, err.max())
+        assert err[~mism].max() <= TOL_STEP, (ground, damping, err.max(), drone_err.last)
         assert mism.sum() <= 2 and s.done.sum() > 100 and (~s.done).sum() > 100
         if damping:
             assert np.abs(s.acc[~s.done & (s.pos[:, 2] < 0.15)]).max() > 15       # springs engaged
