@@ -190,7 +190,7 @@ __device__ __forceinline__ typename Lane<V>::Mask drone_substeps(const DroneK& k
     if (has_override) step_mask = (k.n_objects >= 32) ? 0xffffffffu : ((1u << k.n_objects) - 1u);
   }
 
-#pragma unroll 2
+#pragma unroll(GENERAL ? 1 : 2)
   for (int it = 0; it < k.substeps; ++it) {
     // ---- low-pass filters on rates and thrust, components.py:187-194
     h0 = vfma(h0, omr, c0); h1 = vfma(h1, omr, c1); h2 = vfma(h2, omr, c2);
@@ -278,48 +278,43 @@ __device__ __forceinline__ typename Lane<V>::Mask drone_substeps(const DroneK& k
       // (2) the obstacles in reach (rare): 4 motor distances each; normals and spring forces only where a motor is
       //     inside the contact shell
       if (near_mask) {
+        // Code size matters here: this block is rarely executed but, fully unrolled (4 motors x sphere / cylinder distance and
+        // normal code, twice if the substep loop is unrolled), it made the kernel ~130 KB of SASS and the no-contact path
+        // stalled on instruction fetch.  One copy: the loop over the motors is NOT unrolled and every motor position is
+        // recomputed from the (warp-uniform) offset table.
         const V r00 = vfma(vneg(s.qy), s.qy, vfma(vneg(s.qz), s.qz, one)), r10 = vfma(s.qw, s.qz, xy);
-        V mxw[4], myw[4], mzw[4];
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-          const V ox = S<V>(k.motor_xy[m][0]), oy = S<V>(k.motor_xy[m][1]);
-          mxw[m] = vfma(ox, r00, vfma(oy, r01, s.px));
-          myw[m] = vfma(ox, r10, vfma(oy, r11, s.py));
-          mzw[m] = vfma(ox, r20, vfma(oy, r21, s.pz));
-        }
         while (near_mask) {
           const int o = __ffs(near_mask) - 1;
           near_mask &= near_mask - 1u;
           const fpv_object_t ob = objs[o];
-          V d[4];
-          M hit = vlt(one, zero), touch = hit;
-#pragma unroll
+          M hit = vlt(one, zero);
+          V ox = zero, oy = zero, oz = zero;
+#pragma unroll 1
           for (int m = 0; m < 4; ++m) {
-            d[m] = object_distance<V>(ob, mxw[m], myw[m], mzw[m]);
-            hit = vor(hit, vlt(d[m], zero));
-            touch = vor(touch, vlt(d[m], S<V>(k.motor_radius)));
-          }
-          hit = vand(hit, vnot(crashed));
-          crashed = vor(crashed, hit);
-          const M live = vnot(crashed);
-          if (vany(vand(touch, live))) {   // spring forces of the motors inside the contact shell, :207-214
-            V ox = zero, oy = zero, oz = zero;
-#pragma unroll
-            for (int m = 0; m < 4; ++m) {
+            const V mx_ = S<V>(k.motor_xy[m][0]), my_ = S<V>(k.motor_xy[m][1]);
+            const V wxm = vfma(mx_, r00, vfma(my_, r01, s.px));
+            const V wym = vfma(mx_, r10, vfma(my_, r11, s.py));
+            const V wzm = vfma(mx_, r20, vfma(my_, r21, s.pz));
+            const V dm = object_distance<V>(ob, wxm, wym, wzm);
+            hit = vor(hit, vlt(dm, zero));
+            const V pen = dm - S<V>(k.motor_radius);
+            const M act = vlt(pen, zero);
+            if (vany(act)) {   // spring force of a motor inside the contact shell, :207-214
               V nx, ny, nz;
-              object_normal<V>(ob, mxw[m], myw[m], mzw[m], nx, ny, nz);
-              const V pen = d[m] - S<V>(k.motor_radius);
+              object_normal<V>(ob, wxm, wym, wzm, nx, ny, nz);
               const V vn = vfma(s.vx, nx, vfma(s.vy, ny, s.vz * nz));
               const V f = vneg(vfma(S<V>(k.spring_k), pen, S<V>(k.spring_c) * vn));
-              const M act = vlt(pen, zero);
               ox = ox + vsel(act, f * nx, zero);
               oy = oy + vsel(act, f * ny, zero);
               oz = oz + vsel(act, f * nz, zero);
             }
-            cfx = cfx + vsel(live, ox, zero);
-            cfy = cfy + vsel(live, oy, zero);
-            cfz = cfz + vsel(live, oz, zero);
           }
+          hit = vand(hit, vnot(crashed));
+          crashed = vor(crashed, hit);
+          const M live = vnot(crashed);       // an object any motor penetrates contributes nothing and ends the pass (:205-210)
+          cfx = cfx + vsel(live, ox, zero);
+          cfy = cfy + vsel(live, oy, zero);
+          cfz = cfz + vsel(live, oz, zero);
         }
       }
       // (3) the ground plane, last in the list (distance = z, normal = +z, components.py:674-680), and the crash test
@@ -465,6 +460,7 @@ struct NoPost {
   template <class IO> static __device__ __forceinline__ Ctx begin(const IO&) { return Ctx{}; }
   template <class IO> static __device__ __forceinline__ void stage(const IO&, unsigned char*, int, int) {}
   template <class IO> static __device__ __forceinline__ int bytes(const IO&) { return 0; }
+  template <class IO, int L> static __device__ __forceinline__ void prefetch(const IO&, const long long (&)[L], Ctx&) {}
   template <class IO, int L>
   static __device__ __forceinline__ void run(const IO&, const unsigned char*, const float4 (&)[FPV_DRONE_PLANES][L],
                                              const bool (&)[L], const bool (&)[L], const long long (&)[L], Ctx&) {}
@@ -483,6 +479,7 @@ __device__ __forceinline__ void drone_tile(const DroneK& k, const IO& io, const 
                                            PreStore pre_store = PreStore(), const unsigned char* staged = nullptr,
                                            typename Post::Ctx* post_ctx = nullptr) {
   constexpr int L = Lane<V>::N;
+  if (Post::enabled) Post::prefetch(io, ei, *post_ctx);   // the hook's own per-env inputs travel during the substep loop
   DroneRegs<V> s;
   s.px = Pack<V>::x(q[0]); s.py = Pack<V>::y(q[0]); s.pz = Pack<V>::z(q[0]); s.pt = Pack<V>::w(q[0]);
   s.vx = Pack<V>::x(q[1]); s.vy = Pack<V>::y(q[1]); s.vz = Pack<V>::z(q[1]);

@@ -140,9 +140,20 @@ struct GateIO : DroneIO {
 struct GatePost {
   static constexpr bool enabled = true;
   struct Ctx {
-    float sum, sq;   // this lane's share of the env-reward statistics
+    float sum, sq;       // this lane's share of the env-reward statistics
+    float2 prev[2];      // race bookkeeping of the thread's two agents, fetched before the substep loop
+    int prog[2];
   };
-  static __device__ __forceinline__ Ctx begin(const GateIO&) { return Ctx{0.f, 0.f}; }
+  static __device__ __forceinline__ Ctx begin(const GateIO&) {
+    Ctx c;
+    c.sum = 0.f; c.sq = 0.f;
+    return c;
+  }
+  template <int L>
+  static __device__ __forceinline__ void prefetch(const GateIO& io, const long long (&ei)[L], Ctx& c) {
+#pragma unroll
+    for (int l = 0; l < L; ++l) { c.prev[l] = io.prev[ei[l]]; c.prog[l] = io.progress[ei[l]]; }
+  }
   static __device__ __forceinline__ int bytes(const GateIO& io) { return io.gp.n_gates * (int)sizeof(fpv_gate_t); }
   // the gate table is indexed PER AGENT (every agent is at its own gate): staged in shared memory, see gate_env_step_kernel
   static __device__ __forceinline__ void stage(const GateIO& io, unsigned char* smem, int tid, int nthreads) {
@@ -166,8 +177,8 @@ struct GatePost {
       bool crashed = false, finished = false;
       if (live) {
         const float4 p = fin[0][l], v = fin[1][l], q = fin[2][l], w = fin[3][l];
-        const float2 pr = io.prev[i];
-        int prog = io.progress[i];
+        const float2 pr = c.prev[l];
+        int prog = c.prog[l];
         int g = prog & 0xffff, laps = prog >> 16;
         crashed = crashed_l[l];
         float d, r;

@@ -43,6 +43,9 @@ constexpr int kThreads = 128;
 #ifndef FPV_MINB
 #define FPV_MINB 4  // resident CTAs per SM the compiler must fit (register budget = 65536 / (kThreads * FPV_MINB))
 #endif
+#ifndef FPV_GENERAL_MINB
+#define FPV_GENERAL_MINB 3  // the general (obstacle) path needs ~140 registers; 4 CTAs/SM would spill
+#endif
 
 using fpv::DroneIO;
 using fpv::DroneK;
@@ -173,7 +176,7 @@ bool launch_drone_ring(const DroneK& k, const DroneIO& io, cudaStream_t st) {
   DroneK kk = k;
   size_t stage = (k.flags & FPV_F_THRUST_LUT) ? ((size_t)k.lut_n * sizeof(float) + 127) / 128 * 128 : 0;
   if (GENERAL) stage += ((size_t)k.n_objects * sizeof(fpv_object_t) + 15) / 16 * 16;
-  return launch_ring<Mode, GENERAL ? 3 : FPV_MINB>(kk, io, stage, io.cta_cap, (kk.flags & FPV_F_CHAINED) != 0, &kk.flags,
+  return launch_ring<Mode, GENERAL ? FPV_GENERAL_MINB : FPV_MINB>(kk, io, stage, io.cta_cap, (kk.flags & FPV_F_CHAINED) != 0, &kk.flags,
                                                    FPV_F_CHAINED, st);
 }
 
@@ -806,21 +809,20 @@ int fpv_gate_race_step(const fpv_drone_params_t* p, const fpv_drone_io_t* io, co
                             "or FPV_F_FREEZE_DONE); call fpv_drone_step and fpv_gate_env_step instead");
   if (p->flags & FPV_F_SCALAR) return fail(FPV_EINVAL, "fpv_gate_race_step: the fused step runs the packed kernel (no FPV_F_SCALAR)");
   fpv::GateIO g;
-  static_cast<DroneIO&>(g) = d;
-  g.chunk_epoch = nullptr;          // the env bookkeeping is ordered by plain stream order only
-  g.gp = *gp;
+  static_cast<DroneIO&>(g) = d;       // chunk_epoch / FPV_F_CHAINED carry over: the env arrays are per agent, i.e. per chunk,
+  g.gp = *gp;                         // and are read after / written before the chunk's epoch like the state itself
   g.prev = (float2*)prev;
   g.progress = progress;
   g.agent_reward = agent_reward;
   g.env_reward = env_reward;
   g.env_done = env_done;
   g.obs = (float4*)obs;
-  k.flags &= ~FPV_F_CHAINED;
   const size_t stage = ((k.flags & FPV_F_THRUST_LUT) ? ((size_t)k.lut_n * sizeof(float) + 127) / 128 * 128 : 0) +
                        (size_t)gp->n_gates * sizeof(fpv_gate_t);
   auto launch = [&](auto mode_tag) {
     using Mode = decltype(mode_tag);
-    return launch_ring<Mode, FPV_MINB>(k, g, stage, d.cta_cap, false, nullptr, 0, (cudaStream_t)stream);
+    return launch_ring<Mode, FPV_MINB>(k, g, stage, d.cta_cap, (k.flags & FPV_F_CHAINED) != 0, &k.flags, FPV_F_CHAINED,
+                                       (cudaStream_t)stream);
   };
   bool ok;
   if (ang == 4) ok = launch(fpv::DroneMode<F2, 4, false, fpv::GatePost, fpv::GateIO>{});

@@ -68,35 +68,40 @@ __global__ void racer_observe_kernel(const float4* state, long long n, long long
 }
 
 // sin/cos for ANY argument the Racer produces (|omega| reaches ~80 rad in the reference's own demo, so half angles of
-// ~40 rad): Cody-Waite reduction by pi/2 in three FMA steps (exact products for |j| < 2^15, i.e. |x| < 5e4 rad), the
-// minimax kernels of sincos_poly on the remainder, quadrant fix-up per lane.  Arguments beyond 3e4 rad (never reached by a
-// finite-gain PID at these step sizes) go through sincosf.  Small arguments (the common case: every lane below pi/4) skip
-// the reduction; the branch is per thread and both paths give the same values where they overlap (j = 0).
-template <class V> __device__ __forceinline__ void sincos_reduced(V x, V& s, V& c);
-__device__ __forceinline__ void quadrant_fix(int q, float& s, float& c) {
-  const float s0 = s, c0 = c;
-  s = (q & 1) ? c0 : s0;
-  c = (q & 1) ? s0 : c0;
-  if (q & 2) s = -s;
-  if ((q + 1) & 2) c = -c;
+// ~40 rad).  Reduction by PI, not pi/2: x = j pi + r with |r| <= pi/2, sin x = (-1)^j sin r, cos x = (-1)^j cos r -- the
+// fix-up is ONE sign flip shared by both results (an XOR of the sign bits, done on the packed 64-bit value) instead of a
+// per-lane quadrant swap.  Cody-Waite in three FMA steps (products exact for |j| < 2^15, i.e. |x| < 1e5 rad); the kernels
+// are least-squares fits on [-pi/2, pi/2]: sin r = r + r^3 Q(r^2) (degree 9), cos r = 1 + r^2 R(r^2) (degree 10), both
+// within 1.3e-7 absolute of the exact functions in float32 evaluation.  Arguments beyond 3e4 rad (never reached by a
+// finite-gain PID at these step sizes) go through sincosf per lane.
+template <class V> __device__ __forceinline__ void sincos_pi_kernels(V r, V& s, V& c) {
+  const V r2 = r * r;
+  V q = vfma(S<V>(2.6050197e-06f), r2, S<V>(-1.9808984e-04f));
+  q = vfma(q, r2, S<V>(8.33305e-03f));
+  q = vfma(q, r2, S<V>(-1.6666658e-01f));
+  s = vfma(q, r2 * r, r);
+  V p = vfma(S<V>(-2.6049608e-07f), r2, S<V>(2.4760055e-05f));
+  p = vfma(p, r2, S<V>(-1.388836e-03f));
+  p = vfma(p, r2, S<V>(4.1666634e-02f));
+  p = vfma(p, r2, S<V>(-0.5f));
+  c = vfma(p, r2, S<V>(1.0f));
 }
+template <class V> __device__ __forceinline__ void sincos_reduced(V x, V& s, V& c);
 template <> __device__ __forceinline__ void sincos_reduced<float>(float x, float& s, float& c) {
   if (!(fabsf(x) <= 3.0e4f)) { sincosf(x, &s, &c); return; }
-  const float t = fmaf(x, 0.636619772f, 12582912.f);
+  const float t = fmaf(x, 0.318309886f, 12582912.f);
   const float j = t - 12582912.f;
-  float r = fmaf(j, -1.57079601e+00f, x);
-  r = fmaf(j, -3.13916473e-07f, r);
-  r = fmaf(j, -5.39030253e-15f, r);
-  sincos_poly<float>(r, s, c);
-  quadrant_fix(__float_as_int(t), s, c);
+  float r = fmaf(j, -3.14159203e+00f, x);
+  r = fmaf(j, -6.27832947e-07f, r);
+  r = fmaf(j, -1.07806051e-14f, r);
+  sincos_pi_kernels<float>(r, s, c);
+  const unsigned flip = (unsigned)__float_as_int(t) << 31;        // j odd: both signs flip
+  s = __int_as_float(__float_as_int(s) ^ flip);
+  c = __int_as_float(__float_as_int(c) ^ flip);
 }
 template <> __device__ __forceinline__ void sincos_reduced<F2>(F2 x, F2& s, F2& c) {
   float x0, x1;
   f2_unpack(x, x0, x1);
-  if (fmaxf(fabsf(x0), fabsf(x1)) <= 0.785f) {   // both lanes inside the kernels' range: no reduction (j would be 0)
-    sincos_poly<F2>(x, s, c);
-    return;
-  }
   if (!(fmaxf(fabsf(x0), fabsf(x1)) <= 3.0e4f)) {
     float s0, c0, s1, c1;
     sincos_reduced<float>(x0, s0, c0);
@@ -106,20 +111,16 @@ template <> __device__ __forceinline__ void sincos_reduced<F2>(F2 x, F2& s, F2& 
     return;
   }
   const F2 magic = S<F2>(12582912.f);
-  const F2 t = vfma(x, S<F2>(0.636619772f), magic);
+  const F2 t = vfma(x, S<F2>(0.318309886f), magic);
   const F2 j = t - magic;
-  F2 r = vfma(j, S<F2>(-1.57079601e+00f), x);
-  r = vfma(j, S<F2>(-3.13916473e-07f), r);
-  r = vfma(j, S<F2>(-5.39030253e-15f), r);
-  sincos_poly<F2>(r, s, c);
-  float t0, t1, s0, s1, c0, c1;
-  f2_unpack(t, t0, t1);
-  f2_unpack(s, s0, s1);
-  f2_unpack(c, c0, c1);
-  quadrant_fix(__float_as_int(t0), s0, c0);
-  quadrant_fix(__float_as_int(t1), s1, c1);
-  s = f2_pack(s0, s1);
-  c = f2_pack(c0, c1);
+  F2 r = vfma(j, S<F2>(-3.14159203e+00f), x);
+  r = vfma(j, S<F2>(-6.27832947e-07f), r);
+  r = vfma(j, S<F2>(-1.07806051e-14f), r);
+  sincos_pi_kernels<F2>(r, s, c);
+  // bit 0 of each half of t (the parity of j) moved to that half's sign position
+  const unsigned long long flip = (t.v << 31) & 0x8000000080000000ull;
+  s.v ^= flip;
+  c.v ^= flip;
 }
 
 template <class V_>
@@ -169,18 +170,9 @@ struct RacerMode {
       notfirst = one;
       // orientation <- orientation @ Rx(w0) Ry(w1) Rz(w2)   (:99; angle = omega).  qE = qx (x) qy (x) qz of the half angles
       V sa, ca, sb, cb, sc, cc;
-      const V h0 = w[0] * half, h1 = w[1] * half, h2 = w[2] * half;
-      // one test for the three angles: inside the polynomial kernels' range (the common case) no reduction is needed, and
-      // sincos_reduced would return the same values there (its j is 0)
-      if (!vany(vlt(S<V>(0.785f), vmax(vmax(vabs(h0), vabs(h1)), vabs(h2))))) {
-        sincos_poly<V>(h0, sa, ca);
-        sincos_poly<V>(h1, sb, cb);
-        sincos_poly<V>(h2, sc, cc);
-      } else {
-        sincos_reduced<V>(h0, sa, ca);
-        sincos_reduced<V>(h1, sb, cb);
-        sincos_reduced<V>(h2, sc, cc);
-      }
+      sincos_reduced<V>(w[0] * half, sa, ca);
+      sincos_reduced<V>(w[1] * half, sb, cb);
+      sincos_reduced<V>(w[2] * half, sc, cc);
       const V aw = ca * cb, ax = sa * cb, ay = ca * sb, az = sa * sb;             // qx (x) qy
       const V ew = vfma(aw, cc, vneg(az * sc)), ex = vfma(ax, cc, ay * sc);
       const V ey = vfma(ay, cc, vneg(ax * sc)), ez = vfma(az, cc, aw * sc);

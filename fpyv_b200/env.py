@@ -51,6 +51,8 @@ class GateRaceEnv:
         self.spawn_height = spawn_height
         self.agent_names = [f"agent_{a}" for a in range(self.agents_per_env)]
         self._obs_views = None
+        self._chain_env = False
+        self._fused_args = None
 
     # -- helpers
     def _obs_dict(self):
@@ -93,26 +95,51 @@ class GateRaceEnv:
             _lib.ptr(self._progress), _lib.ptr(self._agent_reward), _lib.ptr(self._env_reward), _lib.ptr(self._env_done),
             _lib.ptr(self._obs), C.c_void_p(d._stats.data_ptr()) if stats else None, _lib.current_stream(self.device)))
 
-    def step(self, action, fused=True):
+    def step(self, action, fused=True, chained=False):
         """action: dict {agent name: [num_envs,4]} or tensor [num_envs, agents_per_env, 4] (roll, pitch, yaw, throttle).
         Returns (obs dict, reward [num_envs], done [num_envs] bool, {}).
         fused=True: dynamics and env step in ONE launch (fpv_gate_race_step: the env step is the per-chunk epilogue of the
         packed TMA-ring kernel, every agent's state is read once and written once); fused=False (or a scalar-kernel
-        drone): fpv_drone_step followed by fpv_gate_env_step.  Both give the same bits."""
-        if isinstance(action, dict):
-            action = torch.stack([torch.as_tensor(action[k]).to(self.device, torch.float32) for k in self.agent_names], dim=1)
-        act = torch.as_tensor(action).to(self.device, torch.float32).reshape(self.n_agents, 4).contiguous()
+        drone): fpv_drone_step followed by fpv_gate_env_step.  Both give the same bits.
+        chained=True (fused only; open-loop use: the actions of several steps exist up front): the launch may start on the
+        SMs the previous step's launch has already left (FPV_F_CHAINED, see BatchedDrone.step) -- the env's per-agent arrays
+        are ordered chunk by chunk together with the state."""
+        if type(action) is torch.Tensor and action.is_cuda and action.dtype is torch.float32 and action.is_contiguous() \
+                and action.numel() == 4 * self.n_agents:
+            act = action.view(self.n_agents, 4)          # the trainer's own device tensor: no conversion, no copy
+        else:
+            if isinstance(action, dict):
+                action = torch.stack([torch.as_tensor(action[k]).to(self.device, torch.float32) for k in self.agent_names], dim=1)
+            act = torch.as_tensor(action).to(self.device, torch.float32).reshape(self.n_agents, 4).contiguous()
         d = self.drone
         if fused and d._fast_ok and not (d._flags & (_lib.F_FREEZE_DONE | _lib.F_SCALAR)):
             d._last_action = act
+            if chained and torch.cuda.is_current_stream_capturing():
+                chained = False
+            chain_now = chained and d._chain_ready and self._chain_env
             d._chain_ready = False
-            d._p.flags = d._flags
+            d._p.flags = (d._flags | _lib.F_CHAINED) if chain_now else d._flags
             d._io.actions = act.data_ptr()
-            d._io.chunk_epoch = None
-            _lib.check(self._lib.fpv_gate_race_step(
-                d._p_ref, d._io_ref, C.byref(self._p), _lib.ptr(self._prev), _lib.ptr(self._progress), _lib.ptr(self._agent_reward),
-                _lib.ptr(self._env_reward), _lib.ptr(self._env_done), _lib.ptr(self._obs), _lib.current_stream(self.device)))
+            if chained:
+                d._io.epoch = d._epoch & 0xFFFFFFFF
+                d._io.chunk_epoch = d._chunk_epoch_ptr
+                d._chain_armed = True
+            else:
+                d._io.chunk_epoch = None
+                d._chain_armed = False
+            if self._fused_args is None:       # the env's own buffers never move: their pointers are built once
+                self._fused_args = (d._p_ref, d._io_ref, C.byref(self._p), _lib.ptr(self._prev), _lib.ptr(self._progress),
+                                    _lib.ptr(self._agent_reward), _lib.ptr(self._env_reward), _lib.ptr(self._env_done),
+                                    _lib.ptr(self._obs))
+            rc = self._lib.fpv_gate_race_step(*self._fused_args, _lib.raw_stream(d._dev_index))
+            if rc:
+                _lib.check(rc)
+            if chained:
+                d._epoch += 1
+                d._chain_ready = True
+            self._chain_env = chained      # the previous writer of the env arrays was a (chain-published) fused step
         else:
+            self._chain_env = False
             d.step(act, return_obs=False)      # (also the first call: it configures the drone's io block)
             self._run_env_kernel(d._done)
         return self._obs_dict(), self._env_reward, self._env_done.view(torch.bool), {}

@@ -136,3 +136,33 @@ def test_fused_env_step_is_bit_identical_to_the_two_launch_path(A):
         else:
             assert sa[k] == sb[k] or (sa[k] != sa[k] and sb[k] != sb[k]), (k, sa, sb)
     assert crashes > 0
+
+
+def test_chained_fused_env_steps_are_bit_identical():
+    """GateRaceEnv.step(fused=True, chained=True): launches that overlap the end of the previous one (FPV_F_CHAINED; the env's
+    per-agent arrays are ordered per 64-agent chunk together with the state) against plain stream order, BASELINE configs[4]
+    size, with crashes, restarts and gate passes in the rollout."""
+    from fpyv_b200.env import GateRaceEnv
+    envs, A = 8192, 32
+    kw = dict(num_envs=envs, agents_per_env=A, device=DEV, substeps=8, dt=1e-3, thrust_lut=2049, seed=5, spawn_height=(0.3, 2.5))
+    a, b = GateRaceEnv(None, **kw), GateRaceEnv(None, **kw)
+    a.reset()
+    b.reset()
+    g = torch.Generator(device=DEV).manual_seed(11)
+    acts = [(torch.rand(envs, A, 4, device=DEV, generator=g) * 2 - 1) for _ in range(6)]
+    for x in acts:
+        x[..., 3] = x[..., 3] * 0.25 - 0.72
+    ra, rb = [], []
+    for t in range(40):
+        _, r1, d1, _ = a.step(acts[t % 6], fused=True, chained=True)
+        ra.append((r1.clone(), d1.clone()))
+    for t in range(40):
+        _, r2, d2, _ = b.step(acts[t % 6], fused=True)
+        rb.append((r2.clone(), d2.clone()))
+    torch.cuda.synchronize()
+    for t, ((r1, d1), (r2, d2)) in enumerate(zip(ra, rb)):
+        assert torch.equal(r1, r2) and torch.equal(d1, d2), t
+    assert torch.equal(a.drone._state, b.drone._state) and torch.equal(a._obs, b._obs)
+    assert torch.equal(a._progress, b._progress) and torch.equal(a._prev, b._prev)
+    assert a.episode_stats()["crashes"] == b.episode_stats()["crashes"] > 0
+    assert a.episode_stats()["chain_timeouts"] == 0
