@@ -335,66 +335,92 @@ def run_gpu(args):
                               "k1_fl_min_med_max": [p[0], p[len(p) // 2], p[-1]], "k8_fl_sorted": k8_sorted[:3] + k8_sorted[-3:]}))
         return
 
-    # ---- end to end through the public API with HOST buffers (pinned): H2D actions, step, D2H done flags
-    # A pinned buffer the CPU has just written sits (dirty) in the CPU caches, and DMA reads that hit there run at ~40 % of
-    # the PCIe rate until the lines are evicted (8 MiB in 413 us vs 158 us, profiles/r1_h2d_cpu_cache_effect.txt); which of
-    # the static input buffers is in that state would depend on what the host touched last.  The synthetic inputs are
-    # therefore generated on the device and written into the pinned buffers by a D2H copy: no line of them is in a CPU cache.
-    host_actions = [torch.empty(n, 4, dtype=torch.float32, pin_memory=True) for _ in range(2)]
-    for h in host_actions:
-        h.copy_(torch.rand(n, 4, device=dev, generator=gen) * 2 - 1)
-    # the step's result travels back as the done BITMASK (fpv_drone_io_t.done_bits: one ballot per 32 envs in the step's
-    # epilogue): n / 8 bytes instead of n
+    # ---- end to end through the public API with HOST buffers (page-locked): actions in, step, done flags out.
+    # The step's result travels back as the done BITMASK (fpv_drone_io_t.done_bits: one ballot per 32 envs in the step's
+    # epilogue): n / 8 bytes instead of n.  Two forms of the same call are timed and the faster one is `e2e`:
+    #   zero copy   ONE launch; the step's TMA engine reads the host buffer over PCIe chunk by chunk while earlier chunks
+    #               compute, the warps write the flag words straight to host memory
+    #   sliced      fpv_drone_step_host: 4 env slices pipelined over H2D / step / D2H streams (round 1's form)
+    # Static inputs are generated on the device and written into the pinned buffers by a D2H copy, so no line of them sits
+    # dirty in a CPU cache (a buffer the CPU has just written is read ~1.7x slower: profiles/r1_h2d_cpu_cache_effect.txt);
+    # `e2e_producer` below is the honest case of a CPU that REWRITES its input every step.
+    from fpyv_b200 import hostmem
+    from fpyv_b200.sticks import pack_crsf
     drone_bytes = drone
     drone = BatchedDrone(None, num_envs=n, device=dev, substeps=SUBSTEPS, dt=DT, auto_reset=True, thrust_lut=LUT_N, done_bits=True)
     pos_, vel_, rpy_, _ = synthetic_init(n, dev, 1234 + rank)
     drone.reset(pos_, vel_, rpy_)
     del pos_, vel_, rpy_
     drone.step(ring[0], return_obs=False)
-    host_done = torch.empty((n + 31) // 32, dtype=torch.int32, pin_memory=True)
+    host_done = hostmem.pinned(((n + 31) // 32,), torch.int32)
+    host_actions = [hostmem.pinned((n, 4), torch.float32) for _ in range(2)]
+    for h in host_actions:
+        h.copy_(torch.rand(n, 4, device=dev, generator=gen) * 2 - 1)
+    host_u16 = [hostmem.pinned((n, 4), torch.uint16) for _ in range(2)]
+    host_crsf = [hostmem.pinned((n, 6), torch.uint8) for _ in range(2)]
+    for h16, h11 in zip(host_u16, host_crsf):
+        v11 = torch.randint(0, 2048, (n, 4), dtype=torch.int32, device=dev, generator=gen)
+        h16.copy_(((v11 << 5) | (v11 >> 6)).to(torch.uint16))
+        bits = (v11[:, 0].long() | (v11[:, 1].long() << 11) | (v11[:, 2].long() << 22) | (v11[:, 3].long() << 33))
+        h11.copy_(torch.stack([(bits >> (8 * b)) & 0xFF for b in range(6)], 1).to(torch.uint8))
     torch.cuda.synchronize()
-    crashed = 0
-    for i in range(max(3, W)):      # the timed loop's body exactly (the first CPU-side read of the flags costs milliseconds)
-        drone.step_host(host_actions[i % 2], host_done, slices=E2E_SLICES)
-        torch.cuda.current_stream().synchronize()
-        crashed += int(host_done[:64].sum())
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    crashed = 0
-    for i in range(K):
-        drone.step_host(host_actions[i % 2], host_done, slices=E2E_SLICES)
-        torch.cuda.current_stream().synchronize()      # the caller consumes the done flags every step
-        crashed += int(host_done[:64].sum())
-    e1.record()
-    torch.cuda.synchronize()
-    ms_e2e = e0.elapsed_time(e1)
+    flagged = [0]
 
+    def e2e_loop(call, bufs):
+        """K calls, the host waits for and reads the flags every step; device time of the whole loop (events)."""
+        for i in range(max(3, W)):      # the timed loop's body exactly (the first CPU-side read of the flags costs milliseconds)
+            call(bufs[i % 2])
+            torch.cuda.current_stream().synchronize()
+            flagged[0] += int(host_done[:64].count_nonzero())
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(K):
+            call(bufs[i % 2])
+            torch.cuda.current_stream().synchronize()      # the caller consumes the done flags every step
+            flagged[0] += int(host_done[:64].count_nonzero())
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    ms_e2e_zero = e2e_loop(lambda h: drone.step_host(h, host_done, zero_copy=True), host_actions)
+    ms_e2e_sliced = e2e_loop(lambda h: drone.step_host(h, host_done, slices=E2E_SLICES), host_actions)
     # ---- the same end-to-end step fed the way the reference's simulator feeds it (step(action=None): raw joystick axes,
-    #      components.py:227-228, :250-253) in compact transport form: uint16[n][4] raw sticks, calibrated on the device.
-    #      Extra metric next to `e2e` (8 B/env instead of 16 over PCIe); `e2e` itself stays on float32 actions.
-    host_sticks = [torch.empty((n, 4), dtype=torch.uint16, pin_memory=True) for _ in range(2)]
-    for h in host_sticks:
-        h.copy_(torch.randint(0, 65536, (n, 4), dtype=torch.int32, device=dev, generator=gen).to(torch.uint16))
-    torch.cuda.synchronize()
-    for i in range(max(3, W)):
-        drone.step_host_sticks(host_sticks[i % 2], host_done, slices=E2E_SLICES)
-        torch.cuda.current_stream().synchronize()
-        crashed += int(host_done[:64].sum())
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(K):
-        drone.step_host_sticks(host_sticks[i % 2], host_done, slices=E2E_SLICES)
-        torch.cuda.current_stream().synchronize()
-        crashed += int(host_done[:64].sum())
-    e1.record()
-    torch.cuda.synchronize()
-    ms_e2e_sticks = e0.elapsed_time(e1)
+    #      components.py:227-228, :250-253) in compact transport form, calibrated on the device: uint16 x 4 (8 B/env) and the
+    #      6-byte CRSF packing of four 11-bit channels (what an RC link carries).  Extra metrics; `e2e` stays on float32 actions.
+    ms_st = {"u16_zero_copy": e2e_loop(lambda h: drone.step_host_sticks(h, host_done, zero_copy=True), host_u16),
+             "u16_sliced": e2e_loop(lambda h: drone.step_host_sticks(h, host_done, slices=E2E_SLICES), host_u16),
+             "crsf_zero_copy": e2e_loop(lambda h: drone.step_host_sticks(h, host_done, zero_copy=True), host_crsf),
+             "crsf_sliced": e2e_loop(lambda h: drone.step_host_sticks(h, host_done, slices=E2E_SLICES), host_crsf)}
+
+    # ---- a producer that REWRITES its action buffer every step (double-buffered: while the device works on buffer A the
+    #      CPU fills buffer B from pageable memory), ordinary pinned memory vs write-combined memory; host wall clock
+    def producer_loop(bufs, zero_copy):
+        src = [torch.rand(n, 4) * 2 - 1 for _ in range(2)]
+        bufs[0].copy_(src[0])
+        call = (lambda h: drone.step_host(h, host_done, zero_copy=True)) if zero_copy else (lambda h: drone.step_host(h, host_done, slices=E2E_SLICES))
+        for i in range(3):
+            call(bufs[i % 2])
+            bufs[(i + 1) % 2].copy_(src[(i + 1) % 2])
+            torch.cuda.current_stream().synchronize()
+        t0 = time.perf_counter()
+        for i in range(K):
+            call(bufs[i % 2])
+            bufs[(i + 1) % 2].copy_(src[(i + 1) % 2])      # the next step's actions are produced while this step runs
+            torch.cuda.current_stream().synchronize()
+            flagged[0] += int(host_done[:64].count_nonzero())
+        return (time.perf_counter() - t0) * 1e3
+
+    best_zero = ms_e2e_zero <= ms_e2e_sliced
+    wc = [hostmem.pinned((n, 4), torch.float32, write_combined=True) for _ in range(2)]
+    ms_prod = {"pinned": producer_loop(host_actions, best_zero), "write_combined": producer_loop(wc, best_zero)}
+    del wc
+    for h in host_actions:      # leave the static buffers as they were (not dirty in the CPU caches)
+        h.copy_(torch.rand(n, 4, device=dev, generator=gen) * 2 - 1)
+    ms_e2e = min(ms_e2e_zero, ms_e2e_sliced)
+    ms_e2e_sticks = min(ms_st.values())
     drone = drone_bytes
 
     # ---- the same workload as an open-loop rollout in ONE launch per 16 control steps (fpv_drone_rollout: state in
@@ -458,9 +484,14 @@ def run_gpu(args):
             dist.barrier()
         extra.update(bench_legs.run_extra(dev, pk_legs, world, rank))
     t = torch.tensor([ms, ms_e2e, ms_k1, ms_rollout, ms_full_grid, ms_unchained, ms_e2e_sticks], dtype=torch.float64, device=dev)
+    t_forms = torch.tensor([ms_e2e_zero, ms_e2e_sliced] + [ms_st[k_] for k_ in sorted(ms_st)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t_forms, op=dist.ReduceOp.MAX)
     ms, ms_e2e, ms_k1, ms_rollout, ms_full_grid, ms_unchained, ms_e2e_sticks = t.tolist()
+    ms_e2e_zero, ms_e2e_sliced = t_forms.tolist()[:2]
+    ms_st = dict(zip(sorted(ms_st), t_forms.tolist()[2:]))
+    ms_e2e, ms_e2e_sticks = min(ms_e2e_zero, ms_e2e_sliced), min(ms_st.values())
     stats = drone.episode_stats(all_reduce=world > 1)      # the engine's only collective (NCCL), outside the timed loop
     ms_flushed_per_step = ms_flushed / K_fl
     if rank != 0:
@@ -506,14 +537,27 @@ def run_gpu(args):
             "env_substeps_per_sec": value * SUBSTEPS,
             "e2e": {"value": total_envs * K / (ms_e2e * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": 16 * n * world,
                     "d2h_bytes_per_step": 4 * ((n + 31) // 32) * world, "ms_per_step": ms_e2e / K,
-                    "api": "BatchedDrone(done_bits=True).step_host(pinned actions) -> pinned done BITMASK = fpv_drone_step_host: 4 env slices pipelined over H2D / step / D2H streams inside the library; host waits every step",
-                    "host_buffers": "2 static pinned action buffers alternated (not rewritten inside the loop), filled by a D2H copy of "
-                                    "device-generated sticks so the DMA reads are served by DRAM (a buffer still dirty in the CPU "
-                                    "caches copies 1.7-2.6x slower, profiles/r1_h2d_cpu_cache_effect.txt)"},
+                    "form": "zero copy" if ms_e2e_zero <= ms_e2e_sliced else "sliced copies",
+                    "ms_per_step_zero_copy": ms_e2e_zero / K, "ms_per_step_sliced_copies": ms_e2e_sliced / K,
+                    "api": "BatchedDrone(done_bits=True).step_host(pinned actions [n,4] float32, pinned done bitmask): zero copy = ONE "
+                           "fpv_drone_step launch whose TMA loads read the host buffer over PCIe and whose warps write the flag "
+                           "words to host memory; sliced copies = fpv_drone_step_host (4 env slices over H2D / step / D2H streams). "
+                           "The host waits for and reads the flags every step.",
+                    "host_buffers": "2 static page-locked action buffers alternated (not rewritten inside the loop), filled by a D2H copy "
+                                    "of device-generated sticks so no line is dirty in a CPU cache; see e2e_producer for a CPU that "
+                                    "rewrites its input every step"},
+            "e2e_producer": {"unit": "env-steps/s", "form": "zero copy" if best_zero else "sliced copies",
+                             "pinned": {"value": total_envs * K / (ms_prod["pinned"] * 1e-3), "ms_per_step": ms_prod["pinned"] / K},
+                             "write_combined": {"value": total_envs * K / (ms_prod["write_combined"] * 1e-3), "ms_per_step": ms_prod["write_combined"] / K},
+                             "note": "the CPU copies 16 MiB of fresh actions from pageable memory into the other input buffer while the "
+                                     "device steps (torch CPU copy, all host threads); host wall clock, rank 0's own loop"},
             "e2e_raw_sticks": {"value": total_envs * K / (ms_e2e_sticks * 1e-3), "unit": "env-steps/s", "ms_per_step": ms_e2e_sticks / K,
-                               "h2d_bytes_per_step": 8 * n * world, "d2h_bytes_per_step": 4 * ((n + 31) // 32) * world,
-                               "api": "BatchedDrone.step_host_sticks(pinned uint16 raw sticks [n,4]) = fpv_drone_step_host_sticks: the "
-                                      "reference's step(action=None) joystick path, calibration on the device; extra metric"},
+                               "form": min(ms_st, key=ms_st.get), "ms_per_step_by_form": {k_: v_ / K for k_, v_ in ms_st.items()},
+                               "h2d_bytes_per_step": (6 if "crsf" in min(ms_st, key=ms_st.get) else 8) * n * world,
+                               "d2h_bytes_per_step": 4 * ((n + 31) // 32) * world,
+                               "api": "BatchedDrone.step_host_sticks(pinned raw sticks): the reference's step(action=None) joystick path, "
+                                      "calibrated on the device; uint16 x 4 (8 B/env) or CRSF 4 x 11 bit (6 B/env); zero copy = the step "
+                                      "itself reads the sticks from host memory and calibrates them in registers; extra metric"},
             "ms_per_step_flushed": ms_flushed_per_step,
             "ms_per_step_chained_full_grid": ms_full_grid / K, "ms_per_step_unchained": ms_unchained / K,
             "rollout_fused": {"ms_per_step": ms_rollout, "env_steps_per_sec": total_envs / (ms_rollout * 1e-3),

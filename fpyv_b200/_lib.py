@@ -8,7 +8,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 # FPYV_B200_LIB: developer override used to A/B differently tuned builds of the same ABI
 LIB_PATH = os.environ.get("FPYV_B200_LIB") or os.path.join(HERE, "libfpyv_b200.so")
-ABI_VERSION = 12
+ABI_VERSION = 13
 
 # flags (fpv_api.h)
 F_GROUND, F_AUTO_RESET, F_FREEZE_DONE, F_THRUST_LUT, F_SCALAR, F_CHAINED, F_RATE_CURVE = 1, 2, 4, 8, 32, 64, 128
@@ -18,7 +18,7 @@ DRONE_PLANES, RACER_PLANES = 4, 5
 EXPORTS = ("fpv_abi_version", "fpv_last_error", "fpv_sizeof", "fpv_device_info", "fpv_drone_reset",
            "fpv_drone_step", "fpv_drone_step_host", "fpv_drone_step_host_sticks", "fpv_drone_rollout", "fpv_drone_observe", "fpv_drone_get_rotation", "fpv_drone_set_rotation", "fpv_matrix_to_quat", "fpv_sticks_to_actions", "fpv_racer_reset", "fpv_racer_step", "fpv_racer_observe", "fpv_gate_env_reset", "fpv_gate_env_step", "fpv_gate_race_step",
            "fpv_camera_update", "fpv_camera_update_pose", "fpv_camera_render", "fpv_camera_target_pixel", "fpv_camera_rays", "fpv_autopilot", "fpv_point_and_shoot",
-           "fpv_acro_reset", "fpv_acro_step", "fpv_acro_rollout", "fpv_probe_fp32")
+           "fpv_acro_reset", "fpv_acro_step", "fpv_acro_rollout", "fpv_probe_fp32", "fpv_host_alloc", "fpv_host_free")
 
 
 class FpvError(RuntimeError):
@@ -46,18 +46,22 @@ class Stats(C.Structure):
                                           "reward_sq_sum", "nonfinite", "reserved")]
 
 
-class DroneIO(C.Structure):
-    _fields_ = [("state", C.c_void_p), ("n", C.c_int64), ("plane_stride", C.c_int64), ("actions", C.c_void_p),
-                ("wind_env", C.c_void_p), ("lut", C.c_void_p), ("lut_n", C.c_int32), ("done", C.c_void_p),
-                ("done_bits", C.c_void_p), ("acc_out", C.c_void_p), ("reset_state", C.c_void_p), ("override_q", C.c_void_p),
-                ("override_thrust", C.c_void_p),
-                ("objects", C.POINTER(Object)), ("stats", C.c_void_p), ("work", C.c_void_p), ("chunk_epoch", C.c_void_p),
-                ("epoch", C.c_uint32), ("max_ctas_per_sm", C.c_uint32), ("trace", C.c_void_p)]
+STICKS_U16, STICKS_CRSF = 1, 2
 
 
 class StickCalib(C.Structure):
     _fields_ = [("min_vals", C.c_float * 6), ("max_vals", C.c_float * 6), ("sign_reverse", C.c_float * 6),
                 ("stick_idx", C.c_int32 * 4), ("stick_center", C.c_float * 4)]
+
+
+class DroneIO(C.Structure):
+    _fields_ = [("state", C.c_void_p), ("n", C.c_int64), ("plane_stride", C.c_int64), ("actions", C.c_void_p),
+                ("sticks", C.c_void_p), ("stick_calib", C.POINTER(StickCalib)), ("stick_format", C.c_int32),
+                ("wind_env", C.c_void_p), ("lut", C.c_void_p), ("lut_n", C.c_int32), ("done", C.c_void_p),
+                ("done_bits", C.c_void_p), ("acc_out", C.c_void_p), ("reset_state", C.c_void_p), ("override_q", C.c_void_p),
+                ("override_thrust", C.c_void_p),
+                ("objects", C.POINTER(Object)), ("stats", C.c_void_p), ("work", C.c_void_p), ("chunk_epoch", C.c_void_p),
+                ("epoch", C.c_uint32), ("max_ctas_per_sm", C.c_uint32), ("trace", C.c_void_p)]
 
 
 class RacerParams(C.Structure):
@@ -133,7 +137,9 @@ def load():
     lib.fpv_drone_step_host.argtypes = [C.POINTER(DroneParams), C.POINTER(DroneIO), C.c_void_p, C.c_void_p, C.c_int32,
                                         C.c_void_p]
     lib.fpv_drone_step_host_sticks.argtypes = [C.POINTER(DroneParams), C.POINTER(DroneIO), C.POINTER(StickCalib), C.c_void_p,
-                                               C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+                                               C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
+    lib.fpv_host_alloc.argtypes = [C.c_int64, C.c_int32, C.POINTER(C.c_void_p)]
+    lib.fpv_host_free.argtypes = [C.c_void_p]
     lib.fpv_drone_rollout.argtypes = [C.POINTER(DroneParams), C.POINTER(DroneIO), C.c_void_p, C.c_int64, C.c_int32,
                                       C.c_void_p, C.c_int64, C.c_void_p]
     lib.fpv_drone_observe.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,

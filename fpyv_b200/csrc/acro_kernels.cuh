@@ -372,8 +372,9 @@ struct AcroMode {
     TileStats st;
   };
   static __device__ __forceinline__ bool chained(const K&) { return false; }
-  static __device__ __forceinline__ const float4* row(const IO& io, int r) {
-    return r < FPV_ACRO_PLANES ? io.state + r * io.stride : io.actions;
+  static __device__ __forceinline__ constexpr int row_bytes(int) { return 16; }
+  static __device__ __forceinline__ const void* row_ptr(const IO& io, int r, long long first) {
+    return (r < FPV_ACRO_PLANES ? io.state + r * io.stride : io.actions) + first;
   }
   static __device__ __forceinline__ void stage(const K& k, const IO& io, unsigned char* smem, int tid, int nthreads) {
     float* lut_s = reinterpret_cast<float*>(smem);

@@ -11,6 +11,7 @@
 #include "../../include/fpv_api.h"
 #include "vec.cuh"
 #include "ring_kernels.cuh"
+#include "misc_kernels.cuh"
 
 namespace fpv {
 
@@ -49,6 +50,8 @@ struct DroneIO {
   float4* state;
   long long n, stride;
   const float4* actions;
+  const void* sticks;          // raw stick readings instead of actions (FPV_STICKS_U16: uint16[n][4]; FPV_STICKS_CRSF: 6 B per env),
+  StickK stick;                // calibrated in registers by the step itself; device memory or pinned host memory
   const float4* wind_env;
   const float* lut;
   unsigned char* done;
@@ -124,27 +127,6 @@ __device__ __forceinline__ typename Lane<V>::Mask drone_substeps(const DroneK& k
                                                                    V oqz, const fpv_object_t* objs = nullptr) {
   using M = typename Lane<V>::Mask;
   if (GENERAL && objs == nullptr) objs = k.objects;   // kernels without a staged table read the kernel-parameter copy
-  // action2force invariants (the action is held for the whole control step), components.py:185-193
-  // The rate filter runs on the half Euler angles h_i = rates_i * (deg2rad*dt/2) directly (same linear recurrence,
-  // scaled), so no per-substep rescaling is needed; rates are recovered once after the loop.
-  const V mr = S<V>(k.max_rates);
-  const V cs = S<V>(k.rtr * k.half_ang_scale);
-  const V c0 = vmin(vmax(vneg(a0) * mr, vneg(mr)), mr) * cs;
-  const V c1 = vmin(vmax(vneg(a1) * mr, vneg(mr)), mr) * cs;
-  const V c2 = vmin(vmax(vneg(a2) * mr, vneg(mr)), mr) * cs;
-  const V tt = thrust_target * S<V>(k.ttr);
-  const V omr = S<V>(k.one_minus_rtr), omt = S<V>(k.one_minus_ttr);
-  const V dt = S<V>(k.dt), dt_m = S<V>(k.dt_over_mass);
-  V h0 = s.pr0 * S<V>(k.half_ang_scale), h1 = s.pr1 * S<V>(k.half_ang_scale), h2 = s.pr2 * S<V>(k.half_ang_scale);
-  {  // s = sqrt(2) q for the duration of the loop (see the R(q) entries below)
-    const V r2 = S<V>(1.41421356237f);
-    s.qw = s.qw * r2; s.qx = s.qx * r2; s.qy = s.qy * r2; s.qz = s.qz * r2;
-  }
-  const V zero = S<V>(0.f), one = S<V>(1.f);
-  const bool ground = (k.flags & FPV_F_GROUND) != 0;
-  M done = vlt(one, zero);  // all false
-  V Fx = zero, Fy = zero, Fz = zero;
-
   // GENERAL: which obstacles can any motor of this thread's envs REACH during this control step?  Decided once, outside
   // the substep loop.  Positions tested by the substeps are x_0 .. x_{K-1} = x_0 + dt * sum of earlier velocities, so an
   // obstacle whose surface is further from x_0 than  arm_reach + K dt V*  (V* = a bound on the speed over the step)
@@ -154,10 +136,11 @@ __device__ __forceinline__ typename Lane<V>::Mask drone_substeps(const DroneK& k
   // K dt a(|v0| + G) <= G proves |v_i| <= |v0| + G for all substeps by induction.  An env whose bound does not close (or an
   // override, which replaces thrust and attitude) keeps every obstacle and is tested substep by substep as before.
   unsigned step_mask = 0u;
+  const V zero_h = S<V>(0.f);
   if (GENERAL && k.n_objects > 0) {
     const V Kdt = S<V>((float)k.substeps * k.dt);
     const V v0 = vsqrt_fast(vfma(s.vx, s.vx, vfma(s.vy, s.vy, s.vz * s.vz))) * S<V>(1.0001f);
-    const V wn = WIND ? vsqrt_fast(vfma(wx, wx, vfma(wy, wy, wz * wz))) * S<V>(1.0001f) : zero;
+    const V wn = WIND ? vsqrt_fast(vfma(wx, wx, vfma(wy, wy, wz * wz))) * S<V>(1.0001f) : zero_h;
     V T = vmax(vabs(s.pt), vabs(thrust_target));
     if (has_override) T = vmax(T, vabs(o_thrust));
     const V spring = S<V>(4.f * (float)(k.n_objects + 1) * k.spring_k * k.motor_radius);
@@ -189,6 +172,36 @@ __device__ __forceinline__ typename Lane<V>::Mask drone_substeps(const DroneK& k
     }
     if (has_override) step_mask = (k.n_objects >= 32) ? 0xffffffffu : ((1u << k.n_objects) - 1u);
   }
+
+  // No obstacle in reach of ANY env of this warp during this control step, and the reference's own ground configuration:
+  // the whole warp runs the hot loop.  The general loop below computes the very same bits for an env without contact (the
+  // obstacle forces are added as exact zeros), so an env's result does not depend on which path its warp took.
+  if (GENERAL) {
+    const bool simple = !has_override && (k.flags & FPV_F_GROUND) != 0 && k.spring_c == 0.f;
+    if (simple && !__any_sync(__activemask(), step_mask != 0u))
+      return drone_substeps<V, ANG, false, WIND>(k, s, a0, a1, a2, thrust_target, wx, wy, wz, false, o_thrust, oqw, oqx, oqy, oqz,
+                                                  nullptr);
+  }
+  // action2force invariants (the action is held for the whole control step), components.py:185-193
+  // The rate filter runs on the half Euler angles h_i = rates_i * (deg2rad*dt/2) directly (same linear recurrence,
+  // scaled), so no per-substep rescaling is needed; rates are recovered once after the loop.
+  const V mr = S<V>(k.max_rates);
+  const V cs = S<V>(k.rtr * k.half_ang_scale);
+  const V c0 = vmin(vmax(vneg(a0) * mr, vneg(mr)), mr) * cs;
+  const V c1 = vmin(vmax(vneg(a1) * mr, vneg(mr)), mr) * cs;
+  const V c2 = vmin(vmax(vneg(a2) * mr, vneg(mr)), mr) * cs;
+  const V tt = thrust_target * S<V>(k.ttr);
+  const V omr = S<V>(k.one_minus_rtr), omt = S<V>(k.one_minus_ttr);
+  const V dt = S<V>(k.dt), dt_m = S<V>(k.dt_over_mass);
+  V h0 = s.pr0 * S<V>(k.half_ang_scale), h1 = s.pr1 * S<V>(k.half_ang_scale), h2 = s.pr2 * S<V>(k.half_ang_scale);
+  {  // s = sqrt(2) q for the duration of the loop (see the R(q) entries below)
+    const V r2 = S<V>(1.41421356237f);
+    s.qw = s.qw * r2; s.qx = s.qx * r2; s.qy = s.qy * r2; s.qz = s.qz * r2;
+  }
+  const V zero = S<V>(0.f), one = S<V>(1.f);
+  const bool ground = (k.flags & FPV_F_GROUND) != 0;
+  M done = vlt(one, zero);  // all false
+  V Fx = zero, Fy = zero, Fz = zero;
 
 #pragma unroll(GENERAL ? 1 : 2)
   for (int it = 0; it < k.substeps; ++it) {
@@ -328,10 +341,8 @@ __device__ __forceinline__ typename Lane<V>::Mask drone_substeps(const DroneK& k
           tmax = m == 0 ? t : vmax(tmax, t);
           pen_sum = m == 0 ? vmax(t, zero) : pen_sum + vmax(t, zero);
         }
-        const M below = vlt(S<V>(k.motor_radius), tmax);
-        const M live = vnot(vor(crashed, below));
-        cfz = vfma(S<V>(k.spring_k), vsel(live, pen_sum, zero), cfz);
-        crashed = vor(crashed, below);
+        crashed = vor(crashed, vlt(S<V>(k.motor_radius), tmax));
+        Fz = vfma(S<V>(k.spring_k), vsel(crashed, zero, pen_sum), Fz);   // the hot path's expression, bit for bit
       } else {
         V mz[4];
         V minz;
@@ -646,7 +657,9 @@ __global__ void __launch_bounds__(THREADS, MINB) drone_step_kernel(const __grid_
 // per-chunk epilogue run on the FINAL rows of the chunk (after auto-reset), all lanes converged: the gate-race env step
 // plugs in there (env_kernels.cuh); NoPost for the plain step.
 // ---------------------------------------------------------------------------------------------------------------
-template <class V_, int ANG, bool GENERAL, class Post = NoPost, class IO_ = DroneIO>
+// STICKS: 0 = row 4 of a chunk are the float4 actions; FPV_STICKS_U16 / FPV_STICKS_CRSF = row 4 are raw stick readings
+// (8 / 6 bytes per env), turned into actions in registers with the arithmetic of sticks4_u16_kernel / sticks4_crsf_kernel.
+template <class V_, int ANG, bool GENERAL, class Post = NoPost, class IO_ = DroneIO, int STICKS = 0>
 struct DroneMode {
   using V = V_;
   using K = DroneK;
@@ -658,8 +671,13 @@ struct DroneMode {
     typename Post::Ctx post;
   };
   static __device__ __forceinline__ bool chained(const K& k) { return (k.flags & FPV_F_CHAINED) != 0; }
-  static __device__ __forceinline__ const float4* row(const IO& io, int r) {
-    return r < FPV_DRONE_PLANES ? io.state + r * io.stride : io.actions;
+  static __device__ __forceinline__ constexpr int row_bytes(int r) {
+    return r < FPV_DRONE_PLANES ? 16 : (STICKS == 0 ? 16 : (STICKS == FPV_STICKS_U16 ? 8 : 6));
+  }
+  static __device__ __forceinline__ const void* row_ptr(const IO& io, int r, long long first) {
+    if (r < FPV_DRONE_PLANES) return io.state + r * io.stride + first;
+    if (STICKS == 0) return io.actions + first;
+    return static_cast<const char*>(io.sticks) + first * row_bytes(FPV_DRONE_PLANES);
   }
   static __device__ __forceinline__ int lut_bytes(const K& k) {
     return (k.flags & FPV_F_THRUST_LUT) ? (int)(((size_t)k.lut_n * sizeof(float) + 127) / 128 * 128) : 0;
@@ -697,7 +715,15 @@ struct DroneMode {
     for (int l = 0; l < L; ++l) {
 #pragma unroll
       for (int p = 0; p < FPV_DRONE_PLANES; ++p) q[p][l] = rows[p][l];
-      act[l] = rows[FPV_DRONE_PLANES][l];
+      const float4 a = rows[FPV_DRONE_PLANES][l];
+      if (STICKS == 0) {
+        act[l] = a;
+      } else if (STICKS == FPV_STICKS_U16) {
+        const unsigned lo = __float_as_uint(a.x), hi = __float_as_uint(a.y);
+        act[l] = sticks4_to_action(io.stick, (float)(lo & 0xffffu), (float)(lo >> 16), (float)(hi & 0xffffu), (float)(hi >> 16));
+      } else {
+        act[l] = crsf_to_action(io.stick, __float_as_uint(a.x), __float_as_uint(a.y), __float_as_uint(a.z));
+      }
     }
     const fpv_object_t* objs = GENERAL ? reinterpret_cast<const fpv_object_t*>(staged + lut_bytes(k)) : nullptr;
     drone_tile<V, ANG, GENERAL, 32, PreStore, Post>(k, io, reinterpret_cast<const float*>(staged), objs, q, act, ei, base, c.st,

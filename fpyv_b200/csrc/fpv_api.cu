@@ -205,6 +205,23 @@ void launch_drone_plain(const DroneK& k, const DroneIO& io, cudaStream_t st) {
   }
 }
 
+// hot path with the raw sticks calibrated inside the step (io.sticks): row 4 of every chunk is 8 or 6 bytes per env
+template <int ANG, int FMT>
+bool launch_drone_ring_sticks(const DroneK& k, const DroneIO& io, cudaStream_t st) {
+  using Mode = fpv::DroneMode<F2, ANG, false, fpv::NoPost, DroneIO, FMT>;
+  DroneK kk = k;
+  const size_t stage = (k.flags & FPV_F_THRUST_LUT) ? ((size_t)k.lut_n * sizeof(float) + 127) / 128 * 128 : 0;
+  return launch_ring<Mode, FPV_MINB>(kk, io, stage, io.cta_cap, (kk.flags & FPV_F_CHAINED) != 0, &kk.flags, FPV_F_CHAINED, st);
+}
+template <int FMT>
+bool launch_drone_sticks(const DroneK& k, const DroneIO& io, int ang, cudaStream_t st) {
+  if (ang == 4) return launch_drone_ring_sticks<4, FMT>(k, io, st);
+  if (ang == 3) return launch_drone_ring_sticks<3, FMT>(k, io, st);
+  if (ang == 2) return launch_drone_ring_sticks<2, FMT>(k, io, st);
+  if (ang == 1) return launch_drone_ring_sticks<1, FMT>(k, io, st);
+  return launch_drone_ring_sticks<0, FMT>(k, io, st);
+}
+
 template <class V, int ANG>
 void launch_drone_g(const DroneK& k, const DroneIO& io, bool general, cudaStream_t st) {
   // chunk_epoch is indexed by 64-env chunks = the packed kernels' warp-chunk: the scalar instantiations (32-env
@@ -258,6 +275,20 @@ int fpv_device_info(int device, int* sm_count, int* cc_major, int* cc_minor) {
   return FPV_OK;
 }
 
+int fpv_host_alloc(int64_t bytes, int32_t write_combined, void** out) {
+  if (!out || bytes <= 0) return fail(FPV_EINVAL, "fpv_host_alloc: bad arguments");
+  const cudaError_t e = cudaHostAlloc(out, (size_t)bytes, write_combined ? cudaHostAllocWriteCombined : cudaHostAllocDefault);
+  if (e != cudaSuccess) return fail(FPV_ECUDA, "fpv_host_alloc(%lld bytes): %s", (long long)bytes, cudaGetErrorString(e));
+  return FPV_OK;
+}
+
+int fpv_host_free(void* p) {
+  if (!p) return FPV_OK;
+  const cudaError_t e = cudaFreeHost(p);
+  if (e != cudaSuccess) return fail(FPV_ECUDA, "fpv_host_free: %s", cudaGetErrorString(e));
+  return FPV_OK;
+}
+
 int fpv_probe_fp32(int32_t packed, int32_t iters, float* sink, int64_t sink_floats, double* flop_out, void* stream) {
   if (iters < 1) return fail(FPV_EINVAL, "fpv_probe_fp32: iters must be >= 1");
   const int blocks = sm_count_of_current_device() * 8;
@@ -280,6 +311,29 @@ int fpv_drone_reset(void* state, int64_t n, int64_t plane_stride, const float* p
 }
 
 namespace {
+int make_sticks(const fpv_stick_calib_t* c, fpv::StickK& k, const char* who) {
+  if (!c) return fail(FPV_EINVAL, "%s: null calibration", who);
+  for (int i = 0; i < 6; ++i) {
+    const double span = (double)c->max_vals[i] - (double)c->min_vals[i];
+    if (span == 0.0) return fail(FPV_EINVAL, "%s: axis %d has max == min", who, i);
+    k.min_v[i] = c->min_vals[i];
+    k.inv_span2[i] = (float)(2.0 / span);
+    k.sign[i] = c->sign_reverse[i];
+  }
+  for (int s = 0; s < 4; ++s) {
+    if (c->stick_idx[s] < 0 || c->stick_idx[s] > 5) return fail(FPV_EINVAL, "%s: stick idx out of range", who);
+    const double ctr = c->stick_center[s];
+    if (ctr <= -1.0 || ctr >= 1.0) return fail(FPV_EINVAL, "%s: stick centre must be inside (-1,1)", who);
+    k.idx[s] = c->stick_idx[s];
+    k.center[s] = c->stick_center[s];
+    k.inv_lo[s] = (float)(1.0 / (ctr + 1.0));
+    k.inv_hi[s] = (float)(1.0 / (1.0 - ctr));
+  }
+  return FPV_OK;
+}
+}  // namespace
+
+namespace {
 // Validation and the double-precision derivation of the launch constants shared by fpv_drone_step and
 // fpv_drone_rollout.  Returns FPV_OK, a negative error, or 1 for an empty batch.
 int prepare_drone(const fpv_drone_params_t* p, const fpv_drone_io_t* io, bool need_actions, DroneK& k, DroneIO& d,
@@ -288,7 +342,14 @@ int prepare_drone(const fpv_drone_params_t* p, const fpv_drone_io_t* io, bool ne
   if (io->n < 0 || io->plane_stride < io->n)
     return fail(FPV_EINVAL, "fpv_drone_step: bad n=%lld stride=%lld", (long long)io->n, (long long)io->plane_stride);
   if (io->n == 0) return 1;   /* empty batch: nothing to launch */
-  if (!io->state || (need_actions && !io->actions)) return fail(FPV_EINVAL, "fpv_drone_step: state/actions must not be null");
+  if (!io->state || (need_actions && !io->actions && !io->sticks))
+    return fail(FPV_EINVAL, "fpv_drone_step: state/actions must not be null");
+  if (io->sticks) {
+    if (io->stick_format != FPV_STICKS_U16 && io->stick_format != FPV_STICKS_CRSF)
+      return fail(FPV_EINVAL, "fpv_drone_step: io.sticks needs stick_format FPV_STICKS_U16 or FPV_STICKS_CRSF");
+    if (!aligned16(io->sticks)) return fail(FPV_EINVAL, "fpv_drone_step: io.sticks must be 16-byte aligned");
+    if (int rc = make_sticks(io->stick_calib, d.stick, "fpv_drone_step")) return rc;
+  }
   if (!aligned16(io->state) || !aligned16(io->actions) || !aligned16(io->wind_env) || !aligned16(io->acc_out) ||
       !aligned16(io->reset_state) || !aligned16(io->override_q))
     return fail(FPV_EINVAL, "fpv_drone_step: float4 planes must be 16-byte aligned");
@@ -363,6 +424,7 @@ int prepare_drone(const fpv_drone_params_t* p, const fpv_drone_io_t* io, bool ne
   d.n = io->n;
   d.stride = io->plane_stride;
   d.actions = (const float4*)io->actions;
+  d.sticks = io->sticks;
   d.wind_env = (const float4*)io->wind_env;
   d.lut = io->lut;
   d.done = io->done;
@@ -406,6 +468,15 @@ int fpv_drone_step(const fpv_drone_params_t* p, const fpv_drone_io_t* io, void* 
   const int rc = prepare_drone(p, io, true, k, d, ang, general);
   if (rc != FPV_OK) return rc > 0 ? FPV_OK : rc;
   cudaStream_t st = (cudaStream_t)stream;
+  if (d.sticks) {
+    if (general || (p->flags & FPV_F_SCALAR))
+      return fail(FPV_EINVAL, "fpv_drone_step: io.sticks is served by the packed hot-path kernel only (no obstacles, overrides, "
+                              "damped spring or FPV_F_SCALAR); convert with fpv_sticks_to_actions instead");
+    const bool ok = io->stick_format == FPV_STICKS_U16 ? launch_drone_sticks<FPV_STICKS_U16>(k, d, ang, st)
+                                                        : launch_drone_sticks<FPV_STICKS_CRSF>(k, d, ang, st);
+    if (!ok) return fail(FPV_EINVAL, "fpv_drone_step: the motor-curve table does not fit next to the ring in shared memory");
+    return check_launch("fpv_drone_step");
+  }
   if (p->flags & FPV_F_SCALAR) launch_drone_a<float>(k, d, ang, general, st);
   else launch_drone_a<F2>(k, d, ang, general, st);
   return check_launch("fpv_drone_step");
@@ -537,7 +608,7 @@ int fpv_drone_rollout(const fpv_drone_params_t* p, const fpv_drone_io_t* io, con
   if (!actions_seq || !aligned16(actions_seq) || action_stride < io->n)
     return fail(FPV_EINVAL, "fpv_drone_rollout: actions_seq must be a 16-byte aligned float4[T][action_stride >= n]");
   if (done_seq && done_stride < io->n) return fail(FPV_EINVAL, "fpv_drone_rollout: done_stride must be >= n");
-  if (general || io->wind_env || (p->flags & (FPV_F_SCALAR | FPV_F_FREEZE_DONE)) || io->chunk_epoch)
+  if (general || io->wind_env || io->sticks || (p->flags & (FPV_F_SCALAR | FPV_F_FREEZE_DONE)) || io->chunk_epoch)
     return fail(FPV_EINVAL, "fpv_drone_rollout: only the hot-path configuration is supported (no obstacles, overrides, "
                             "per-env wind, FPV_F_SCALAR, FPV_F_FREEZE_DONE or chunk_epoch); step instead");
   if (!io->work) return fail(FPV_EINVAL, "fpv_drone_rollout: io.work is required");
@@ -606,28 +677,6 @@ int fpv_drone_observe(const void* state, int64_t n, int64_t plane_stride, const 
   return check_launch("fpv_drone_observe");
 }
 
-namespace {
-int make_sticks(const fpv_stick_calib_t* c, fpv::StickK& k, const char* who) {
-  if (!c) return fail(FPV_EINVAL, "%s: null calibration", who);
-  for (int i = 0; i < 6; ++i) {
-    const double span = (double)c->max_vals[i] - (double)c->min_vals[i];
-    if (span == 0.0) return fail(FPV_EINVAL, "%s: axis %d has max == min", who, i);
-    k.min_v[i] = c->min_vals[i];
-    k.inv_span2[i] = (float)(2.0 / span);
-    k.sign[i] = c->sign_reverse[i];
-  }
-  for (int s = 0; s < 4; ++s) {
-    if (c->stick_idx[s] < 0 || c->stick_idx[s] > 5) return fail(FPV_EINVAL, "%s: stick idx out of range", who);
-    const double ctr = c->stick_center[s];
-    if (ctr <= -1.0 || ctr >= 1.0) return fail(FPV_EINVAL, "%s: stick centre must be inside (-1,1)", who);
-    k.idx[s] = c->stick_idx[s];
-    k.center[s] = c->stick_center[s];
-    k.inv_lo[s] = (float)(1.0 / (ctr + 1.0));
-    k.inv_hi[s] = (float)(1.0 / (1.0 - ctr));
-  }
-  return FPV_OK;
-}
-}  // namespace
 
 int fpv_sticks_to_actions(const fpv_stick_calib_t* c, const int32_t* raw, int64_t n, void* actions, float* calibrated,
                           void* stream) {
@@ -643,8 +692,11 @@ int fpv_sticks_to_actions(const fpv_stick_calib_t* c, const int32_t* raw, int64_
 }
 
 int fpv_drone_step_host_sticks(const fpv_drone_params_t* p, const fpv_drone_io_t* io, const fpv_stick_calib_t* calib,
-                               const uint16_t* sticks_host, void* sticks_dev, uint8_t* done_host, int32_t slices,
+                               const void* sticks_host, void* sticks_dev, int32_t format, uint8_t* done_host, int32_t slices,
                                void* stream) {
+  if (format != FPV_STICKS_U16 && format != FPV_STICKS_CRSF)
+    return fail(FPV_EINVAL, "fpv_drone_step_host_sticks: format must be FPV_STICKS_U16 or FPV_STICKS_CRSF");
+  const long long esz = format == FPV_STICKS_U16 ? 8 : 6;
   if (!p || !io) return fail(FPV_EINVAL, "fpv_drone_step_host_sticks: null params/io");
   if (!sticks_host || !sticks_dev || !done_host) return fail(FPV_EINVAL, "fpv_drone_step_host_sticks: null buffer");
   if (!io->actions || !io->done) return fail(FPV_EINVAL, "fpv_drone_step_host_sticks: io.actions / io.done must be device buffers");
@@ -667,11 +719,15 @@ int fpv_drone_step_host_sticks(const fpv_drone_params_t* p, const fpv_drone_io_t
   pp.flags &= ~FPV_F_CHAINED;
   for (int c = 0; c < n_slices; ++c) {
     const long long a = bound[c], b = bound[c + 1];
-    cudaMemcpyAsync((char*)sticks_dev + 8 * a, (const char*)sticks_host + 8 * a, (size_t)(8 * (b - a)), cudaMemcpyHostToDevice, hp.in);
+    cudaMemcpyAsync((char*)sticks_dev + esz * a, (const char*)sticks_host + esz * a, (size_t)(esz * (b - a)), cudaMemcpyHostToDevice, hp.in);
     cudaEventRecord(hp.h2d[c], hp.in);
     cudaStreamWaitEvent(st, hp.h2d[c], 0);
-    fpv::sticks4_u16_kernel<<<(unsigned)((b - a + 255) / 256), 256, 0, st>>>(k, (const ushort4*)sticks_dev + a, b - a,
-                                                                             (float4*)io->actions + a);
+    if (format == FPV_STICKS_U16)
+      fpv::sticks4_u16_kernel<<<(unsigned)((b - a + 255) / 256), 256, 0, st>>>(k, (const ushort4*)sticks_dev + a, b - a,
+                                                                               (float4*)io->actions + a);
+    else
+      fpv::sticks4_crsf_kernel<<<(unsigned)((b - a + 255) / 256), 256, 0, st>>>(k, (const unsigned short*)sticks_dev + 3 * a, b - a,
+                                                                                (float4*)io->actions + a);
     fpv_drone_io_t s = *io;
     s.state = (char*)io->state + 16 * a;
     s.n = b - a;
@@ -683,6 +739,7 @@ int fpv_drone_step_host_sticks(const fpv_drone_params_t* p, const fpv_drone_io_t
     if (io->reset_state) s.reset_state = (const char*)io->reset_state + 16 * a;
     s.override_q = nullptr;
     s.override_thrust = nullptr;
+    s.sticks = nullptr;
     s.chunk_epoch = nullptr;
     s.trace = nullptr;
     if (int rc = fpv_drone_step(&pp, &s, stream)) {

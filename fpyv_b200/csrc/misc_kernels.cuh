@@ -160,15 +160,12 @@ __global__ void sticks_kernel(const __grid_constant__ StickK k, const int* raw, 
   }
 }
 
-// The same map for the compact transport format of fpv_drone_step_host_sticks: uint16[n][4] = the raw readings of
-// axes 0, 1, 2 and 5 -- the four values Drone.read_sticks keeps of calib_read's six (components.py:251-252) -- as the
-// joystick driver reports them (0..65535).  Identical arithmetic per axis, so the actions are bit-identical.
-__global__ void sticks4_u16_kernel(const __grid_constant__ StickK k, const ushort4* raw, long long n, float4* actions) {
-  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= n) return;
-  const ushort4 r = raw[e];
+// The same map for the compact transport formats of fpv_drone_step_host_sticks: the raw readings of axes 0, 1, 2 and 5 --
+// the four values Drone.read_sticks keeps of calib_read's six (components.py:251-252) -- as the joystick driver reports
+// them (0..65535).  Identical arithmetic per axis, so the actions are bit-identical to sticks_kernel's.
+__device__ __forceinline__ float4 sticks4_to_action(const StickK& k, float r0, float r1, float r2, float r3) {
   const int axis[4] = {0, 1, 2, 5};
-  const float in[4] = {(float)r.x, (float)r.y, (float)r.z, (float)r.w};
+  const float in[4] = {r0, r1, r2, r3};
   float v[4];
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
@@ -185,7 +182,34 @@ __global__ void sticks4_u16_kernel(const __grid_constant__ StickK k, const ushor
       }
     }
   }
-  actions[e] = make_float4(-v[1], v[2], v[3], v[0]);
+  return make_float4(-v[1], v[2], v[3], v[0]);
+}
+
+// FPV_STICKS_U16: uint16[n][4].
+__global__ void sticks4_u16_kernel(const __grid_constant__ StickK k, const ushort4* raw, long long n, float4* actions) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const ushort4 r = raw[e];
+  actions[e] = sticks4_to_action(k, (float)r.x, (float)r.y, (float)r.z, (float)r.w);
+}
+
+// FPV_STICKS_CRSF: what an RC link actually carries -- four 11-bit channels (CRSF / SBUS resolution) packed little-endian
+// into 6 bytes per env (channel c = bits [11 c, 11 c + 11); the top 4 bits are unused).  An 11-bit value v is widened to
+// the driver's 16-bit range by bit replication, raw = (v << 5) | (v >> 6) (0 -> 0, 2047 -> 65535), then calibrated as above.
+__device__ __forceinline__ float4 crsf_to_action(const StickK& k, unsigned h0, unsigned h1, unsigned h2) {
+  const unsigned long long bits = (unsigned long long)h0 | ((unsigned long long)h1 << 16) | ((unsigned long long)h2 << 32);
+  float r[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const unsigned v = (unsigned)(bits >> (11 * c)) & 0x7ffu;
+    r[c] = (float)((v << 5) | (v >> 6));
+  }
+  return sticks4_to_action(k, r[0], r[1], r[2], r[3]);
+}
+__global__ void sticks4_crsf_kernel(const __grid_constant__ StickK k, const unsigned short* raw, long long n, float4* actions) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  actions[e] = crsf_to_action(k, raw[3 * e], raw[3 * e + 1], raw[3 * e + 2]);
 }
 
 }  // namespace fpv

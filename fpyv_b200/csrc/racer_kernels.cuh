@@ -132,7 +132,10 @@ struct RacerMode {
   static constexpr int ROWS = PLANES + 1;
   struct Ctx {};
   static __device__ __forceinline__ bool chained(const K&) { return false; }
-  static __device__ __forceinline__ const float4* row(const IO& io, int r) { return r < PLANES ? io.state + r * io.stride : io.actions; }
+  static __device__ __forceinline__ constexpr int row_bytes(int) { return 16; }
+  static __device__ __forceinline__ const void* row_ptr(const IO& io, int r, long long first) {
+    return (r < PLANES ? io.state + r * io.stride : io.actions) + first;
+  }
   static __device__ __forceinline__ void stage(const K&, const IO&, unsigned char*, int, int) {}
   static __device__ __forceinline__ Ctx begin(const K&, const IO&) { return Ctx{}; }
   static __device__ __forceinline__ void finish(const K&, const IO&, Ctx&) {}

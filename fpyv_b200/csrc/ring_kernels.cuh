@@ -16,7 +16,8 @@
 //   using V (float or F2), K (launch constants, passed by value), IO (pointers; must carry n, work, chunk_epoch, epoch, err,
 //   trace), Ctx (per-thread accumulators);  static constexpr int ROWS;
 //   static bool chained(const K&);                         FPV_F_CHAINED honoured by this launch
-//   static const float4* row(const IO&, int r);            global base of row r (element i = env i)
+//   static int row_bytes(int r);                           bytes per env of row r: 16 (a float4 plane), 8 or 6 (raw sticks)
+//   static const void* row_ptr(const IO&, int r, long long first);   global address of env `first` in row r
 //   static void stage(const K&, const IO&, unsigned char* smem, int tid, int nthreads);   fill the staged tables
 //   static Ctx begin(const K&, const IO&);                 once per thread (also the grid-wide "env_steps" bookkeeping)
 //   static void tile(const K&, const IO&, const unsigned char* staged, const float4 (&rows)[ROWS][L], const long long (&ei)[L],
@@ -121,7 +122,6 @@ __global__ void __launch_bounds__(THREADS, MINB) ring_step_kernel(const __grid_c
     const long long first = chunk * CHUNK;
     const long long rem = io.n - first;
     const unsigned count = (unsigned)(rem < (long long)CHUNK ? rem : (long long)CHUNK);
-    const unsigned bytes = count * (unsigned)sizeof(float4);
     float4* dst = ring + (size_t)slot * ROWS * CHUNK;
     if (chained && !chain_broken) {  // the previous step of THIS chunk must have been stored (possibly by a grid still running)
       const unsigned* f = io.chunk_epoch + chunk;
@@ -150,9 +150,13 @@ __global__ void __launch_bounds__(THREADS, MINB) ring_step_kernel(const __grid_c
       }
       asm volatile("fence.proxy.async.global;" ::: "memory");  // generic-proxy stores -> async-proxy (TMA) loads
     }
-    mbar_expect_tx(&full[slot], bytes * ROWS);
+    unsigned total = 0;   // every copy is a multiple of 16 bytes (a narrow row of a ragged tail chunk is rounded up; the
+#pragma unroll          // caller pads such a buffer to 16 bytes)
+    for (int r = 0; r < ROWS; ++r) total += (count * (unsigned)Mode::row_bytes(r) + 15u) & ~15u;
+    mbar_expect_tx(&full[slot], total);
 #pragma unroll
-    for (int r = 0; r < ROWS; ++r) tma_load_1d(dst + r * CHUNK, Mode::row(io, r) + first, bytes, &full[slot]);
+    for (int r = 0; r < ROWS; ++r)
+      tma_load_1d(dst + r * CHUNK, Mode::row_ptr(io, r, first), (count * (unsigned)Mode::row_bytes(r) + 15u) & ~15u, &full[slot]);
   };
 
   const bool dynamic = io.work != nullptr;
@@ -195,7 +199,17 @@ __global__ void __launch_bounds__(THREADS, MINB) ring_step_kernel(const __grid_c
     for (int l = 0; l < L; ++l) {
       ei[l] = min(base + (long long)l * 32, io.n - 1);
 #pragma unroll
-      for (int r = 0; r < ROWS; ++r) rows[r][l] = src[r * CHUNK + l * 32 + lane];
+      for (int r = 0; r < ROWS; ++r) {
+        if (Mode::row_bytes(r) == 16) {
+          rows[r][l] = src[r * CHUNK + l * 32 + lane];
+        } else if (Mode::row_bytes(r) == 8) {    // 8-byte elements (uint16 x 4): bit patterns in .x .y
+          const uint2 u = reinterpret_cast<const uint2*>(src + r * CHUNK)[l * 32 + lane];
+          rows[r][l] = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), 0.f, 0.f);
+        } else {                                 // 6-byte elements (3 half-words): one per component
+          const unsigned short* h = reinterpret_cast<const unsigned short*>(src + r * CHUNK) + 3 * (l * 32 + lane);
+          rows[r][l] = make_float4(__uint_as_float((unsigned)h[0]), __uint_as_float((unsigned)h[1]), __uint_as_float((unsigned)h[2]), 0.f);
+        }
+      }
     }
     __syncwarp();  // all lanes have drained this slot: it is refilled at the top of the next iteration
     // Publishing a chunk's epoch needs its stores to be performed first: a release is MEMBAR.GPU + ERRBAR, which drains the

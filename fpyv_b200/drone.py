@@ -451,13 +451,18 @@ class BatchedDrone:
         return Rt, gyro, accel
 
     # ------------------------------------------------------------------ host-buffer entry (end-to-end path)
-    def step_host(self, actions_host: torch.Tensor, done_host: torch.Tensor | None = None, slices: int = 4):
-        """One control step with HOST buffers: pinned actions [n,4] -> device, step, done flags -> pinned host
-        (fpv_drone_step_host).  This is the call timed as `e2e` in bench.py (H2D 16 B/env, D2H 1 B/env per step).
+    def step_host(self, actions_host: torch.Tensor, done_host: torch.Tensor | None = None, slices: int = 4,
+                  zero_copy: bool = False):
+        """One control step with HOST buffers: pinned actions [n,4] -> device, step, done flags -> pinned host.
+        This is the call timed as `e2e` in bench.py.
 
-        The step is PCIe-bound, so the library cuts the batch into `slices` env ranges and pipelines them over three
-        streams: the H2D copy of slice c+1 runs while slice c is stepped and slice c-1's flags travel back.  The
-        caller's current stream is joined to the last D2H copy, so synchronising it means the flags are on the host."""
+        zero_copy=False (fpv_drone_step_host): the library cuts the batch into `slices` env ranges and pipelines them over
+        three streams -- the H2D copy of slice c+1 runs while slice c is stepped and slice c-1's flags travel back.
+        zero_copy=True: ONE launch of the step itself with the pinned host buffers as its `actions` input and `done_bits`
+        output (fpv_drone_io_t: "may be a pinned host pointer"): the kernel's TMA engine fetches every 64-env chunk of
+        actions straight over PCIe while earlier chunks compute, and the flags go back as 32-bit words written by the warps.
+        No staging copy, no copy-engine hand-offs; needs a drone built with done_bits=True and page-locked buffers.
+        Either way the caller's current stream is ordered after the flags: synchronising it means they are on the host."""
         n, dev = self.num_envs, self.device
         done_host = self._check_done_host(done_host)
         if not self._is_reset:
@@ -473,42 +478,88 @@ class BatchedDrone:
         self._last_action = self._actions
         self._chain_ready = False
         self._p.flags = self._flags
-        self._io.actions = self._actions.data_ptr()
         self._io.chunk_epoch = None
+        if zero_copy:
+            self._require_zero_copy(actions_host, done_host)
+            self._io.actions = actions_host.data_ptr()
+            self._io.done_bits = done_host.data_ptr()
+            try:
+                _lib.check(self._step_fn(self._p_ref, self._io_ref, _lib.raw_stream(self._dev_index)))
+            finally:
+                self._io.actions = self._actions.data_ptr()
+                self._io.done_bits = self._done_bits.data_ptr()
+            self._last_action = None          # the actions never existed on the device
+            return done_host
+        self._io.actions = self._actions.data_ptr()
         _lib.check(self._lib.fpv_drone_step_host(self._p_ref, self._io_ref, actions_host.data_ptr(), done_host.data_ptr(),
                                                  int(slices), torch.cuda.current_stream(dev).cuda_stream))
         return done_host
 
-    def step_host_sticks(self, sticks_host: torch.Tensor, done_host: torch.Tensor | None = None, slices: int = 4):
-        """`step(action=None)` -- the reference's joystick path (components.py:227-228, :250-253) -- with HOST buffers in
-        the compact transport form: sticks_host uint16 [n,4] (pinned) = raw readings 0..65535 of axes 0, 1, 2, 5
-        (throttle, roll, pitch, yaw), calibrated on the device by this drone's `rc` calibration (bit-identical to
-        `rc.feed(raw); step(None)`), stepped, flags back to pinned host memory.  8 B/env in, 1 B/env out."""
+    def _require_zero_copy(self, in_host, done_host):
+        if self._done_bits is None:
+            raise ValueError("zero_copy needs a drone built with done_bits=True (the flags go back as a bitmask)")
+        if not (in_host.is_pinned() or hasattr(in_host, "_fpv_block")) or not (done_host.is_pinned() or hasattr(done_host, "_fpv_block")):
+            raise ValueError("zero_copy needs page-locked host buffers (pin_memory=True or fpyv_b200.hostmem.pinned)")
+        if in_host.data_ptr() % 16 or done_host.data_ptr() % 4:
+            raise ValueError("zero_copy: the input buffer must be 16-byte aligned")
+
+    def step_host_sticks(self, sticks_host: torch.Tensor, done_host: torch.Tensor | None = None, slices: int = 4,
+                         zero_copy: bool = False):
+        """`step(action=None)` -- the reference's joystick path (components.py:227-228, :250-253) -- with HOST buffers in a
+        compact transport form, calibrated on the device by this drone's `rc` calibration (bit-identical to
+        `rc.feed(raw); step(None)`), stepped, flags back to pinned host memory.  sticks_host (pinned):
+          uint16 [n,4]  raw readings 0..65535 of axes 0, 1, 2, 5 (throttle, roll, pitch, yaw): 8 B/env   (FPV_STICKS_U16)
+          uint8  [n,6]  four 11-bit channels as an RC link carries them (`sticks.pack_crsf`): 6 B/env    (FPV_STICKS_CRSF)
+        zero_copy=True: one launch, the step reads the raw sticks straight from the pinned host buffer and calibrates them
+        in registers (fpv_drone_io_t.sticks); else the sliced copy pipeline of fpv_drone_step_host_sticks."""
         n, dev = self.num_envs, self.device
         if self.rc._c is None:
             raise RuntimeError("Joystick is not calibrated: call calibrate(path) first")
         done_host = self._check_done_host(done_host)
-        if (not isinstance(sticks_host, torch.Tensor) or sticks_host.is_cuda or sticks_host.dtype is not torch.uint16
-                or not sticks_host.is_contiguous() or tuple(sticks_host.shape) != (n, 4)):
-            raise ValueError("step_host_sticks expects a contiguous uint16 host tensor [num_envs, 4]")
+        ok16 = isinstance(sticks_host, torch.Tensor) and sticks_host.dtype is torch.uint16 and tuple(sticks_host.shape) == (n, 4)
+        ok11 = isinstance(sticks_host, torch.Tensor) and sticks_host.dtype is torch.uint8 and tuple(sticks_host.shape) == (n, 6)
+        if not (ok16 or ok11) or sticks_host.is_cuda or not sticks_host.is_contiguous():
+            raise ValueError("step_host_sticks expects a contiguous host tensor uint16 [num_envs, 4] or uint8 [num_envs, 6]")
+        fmt = _lib.STICKS_U16 if ok16 else _lib.STICKS_CRSF
         if not self._is_reset:
             raise RuntimeError("call reset() before step() (the reference's state is None until reset)")
         if not self._fast_ok:      # configure the io block once through the plain path
             raw6 = torch.zeros((n, 6), dtype=torch.int32)
-            raw6[:, [0, 1, 2, 5]] = sticks_host.to(torch.int32)
+            if ok16:
+                raw6[:, [0, 1, 2, 5]] = sticks_host.to(torch.int32)
+            else:
+                from .sticks import crsf_to_raw16
+                b = sticks_host.numpy().astype(np.uint64)
+                bits = sum(b[:, i] << np.uint64(8 * i) for i in range(6))
+                v11 = np.stack([(bits >> np.uint64(11 * c)) & np.uint64(0x7FF) for c in range(4)], 1)
+                raw6[:, [0, 1, 2, 5]] = torch.from_numpy(crsf_to_raw16(v11).astype(np.int32))
             self.rc.feed(raw6)
             self.step(None, return_obs=False)
             done_host.copy_(self._done if self._done_bits is None else self._done_bits, non_blocking=True)
             return done_host
-        if self._sticks_dev is None:
-            self._sticks_dev = torch.empty((n, 4), dtype=torch.uint16, device=dev)
         self._last_action = self._actions
         self._chain_ready = False
         self._p.flags = self._flags
         self._io.actions = self._actions.data_ptr()
         self._io.chunk_epoch = None
+        if zero_copy:
+            self._require_zero_copy(sticks_host, done_host)
+            if sticks_host.numel() * sticks_host.element_size() % 16 and not hasattr(sticks_host, "_fpv_block"):
+                raise ValueError("zero_copy: the stick buffer must be padded to a multiple of 16 bytes (fpyv_b200.hostmem.pinned)")
+            io = self._io
+            io.sticks, io.stick_calib, io.stick_format = sticks_host.data_ptr(), C.pointer(self.rc._c), fmt
+            io.done_bits = done_host.data_ptr()
+            try:
+                _lib.check(self._step_fn(self._p_ref, self._io_ref, _lib.raw_stream(self._dev_index)))
+            finally:
+                io.sticks, io.stick_format = None, 0
+                io.done_bits = self._done_bits.data_ptr()
+            self._last_action = None
+            return done_host
+        if self._sticks_dev is None or self._sticks_dev.numel() < 8 * n:
+            self._sticks_dev = torch.empty(8 * n, dtype=torch.uint8, device=dev)
         _lib.check(self._lib.fpv_drone_step_host_sticks(self._p_ref, self._io_ref, C.byref(self.rc._c), sticks_host.data_ptr(),
-                                                        self._sticks_dev.data_ptr(), done_host.data_ptr(), int(slices),
+                                                        self._sticks_dev.data_ptr(), fmt, done_host.data_ptr(), int(slices),
                                                         torch.cuda.current_stream(dev).cuda_stream))
         return done_host
 

@@ -13,6 +13,23 @@ import torch
 from . import _lib, config
 
 
+def pack_crsf(raw11):
+    """[n,4] integer channel values 0..2047 (throttle, roll, pitch, yaw -- the resolution of a CRSF / SBUS link) -> uint8
+    [n,6]: the four 11-bit channels packed little-endian, channel c in bits [11c, 11c+11) (fpv_api.h FPV_STICKS_CRSF)."""
+    v = np.asarray(raw11.cpu() if isinstance(raw11, torch.Tensor) else raw11).astype(np.uint64) & 0x7FF
+    bits = v[:, 0] | (v[:, 1] << np.uint64(11)) | (v[:, 2] << np.uint64(22)) | (v[:, 3] << np.uint64(33))
+    out = np.empty((len(v), 6), dtype=np.uint8)
+    for b in range(6):
+        out[:, b] = (bits >> np.uint64(8 * b)) & np.uint64(0xFF)
+    return torch.from_numpy(out)
+
+
+def crsf_to_raw16(raw11):
+    """The 16-bit driver reading an 11-bit channel value stands for: (v << 5) | (v >> 6) (0 -> 0, 2047 -> 65535)."""
+    v = np.asarray(raw11.cpu() if isinstance(raw11, torch.Tensor) else raw11).astype(np.int64) & 0x7FF
+    return (v << 5) | (v >> 6)
+
+
 class Joystick:
     def __init__(self, source=None, device="cuda:0"):
         """source: callable returning raw axes [n,6] (tensor/array of ints) or None (set later with feed())."""

@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define FPV_ABI_VERSION 12
+#define FPV_ABI_VERSION 13
 
 /* error codes */
 #define FPV_OK 0
@@ -127,11 +127,31 @@ typedef struct fpv_stats {
   double reserved;
 } fpv_stats_t;
 
+/* Stick calibration (Joystick.calib_read, get_sticks.py:245-265) -- see "Stick front-end" below. */
+typedef struct fpv_stick_calib {
+  float min_vals[6], max_vals[6], sign_reverse[6];   /* calibration JSON arrays           */
+  int32_t stick_idx[4];                              /* JSON "sticks" in file order: Throttle, Roll, Pitch, Yaw */
+  float stick_center[4];
+} fpv_stick_calib_t;
+
+/* raw-stick transport formats (fpv_drone_io_t.stick_format, fpv_drone_step_host_sticks) */
+#define FPV_STICKS_U16 1    /* uint16[n][4]: raw readings 0..65535 of axes 0, 1, 2, 5 (throttle, roll, pitch, yaw): 8 B per env */
+#define FPV_STICKS_CRSF 2   /* what an RC link carries: four 11-bit channels (same order) packed little-endian into 6 B per
+                               env; an 11-bit value v stands for the raw reading (v << 5) | (v >> 6)                      */
+
 typedef struct fpv_drone_io {
   void* state;              /* float4[FPV_DRONE_PLANES][plane_stride], in/out                     */
   int64_t n;                /* number of envs                                                     */
   int64_t plane_stride;     /* elements between planes, >= n                                      */
-  const void* actions;      /* float4[n]: roll, pitch, yaw, throttle in [-1,1] (components.py:220) */
+  const void* actions;      /* float4[n]: roll, pitch, yaw, throttle in [-1,1] (components.py:220).  Like `sticks` this may be
+                               a PINNED HOST pointer (UVA): the step's TMA engine then fetches the chunks straight over
+                               PCIe while earlier chunks compute -- one launch instead of copy + launch ("zero copy").   */
+  const void* sticks;       /* Drone.step(action=None): raw stick readings in `stick_format` instead of actions (then
+                               `actions` may be NULL), calibrated inside the step with the arithmetic of
+                               fpv_sticks_to_actions (bit-identical).  Device or pinned host memory, 16-byte aligned, padded
+                               to a multiple of 16 bytes.  Hot-path configuration and packed kernel only.  NULL = actions. */
+  const fpv_stick_calib_t* stick_calib;  /* HOST pointer; required with `sticks`                                */
+  int32_t stick_format;     /* FPV_STICKS_U16 or FPV_STICKS_CRSF                                                  */
   const void* wind_env;     /* float4[n] per-env wind (xyz), or NULL -> params.wind               */
   const float* lut;         /* float[lut_n] thrust [N] sampled at throttle -1..1, or NULL         */
   int32_t lut_n;
@@ -240,11 +260,6 @@ int fpv_drone_observe(const void* state, int64_t n, int64_t plane_stride, const 
  * Stick front-end: Joystick.calib_read + Drone.read_sticks
  * (src/utils/get_sticks.py:245-265, components.py:250-253).
  * -------------------------------------------------------------------------------------------*/
-typedef struct fpv_stick_calib {
-  float min_vals[6], max_vals[6], sign_reverse[6];   /* calibration JSON arrays           */
-  int32_t stick_idx[4];                              /* JSON "sticks" in file order: Throttle, Roll, Pitch, Yaw */
-  float stick_center[4];
-} fpv_stick_calib_t;
 
 /* raw: int32[n][6] axis readings (dwXpos..dwVpos order, get_sticks.py:55-60).
  * actions: float4[n] = [-roll, pitch, yaw, throttle]; calibrated: float[n][6] or NULL. */
@@ -254,12 +269,19 @@ int fpv_sticks_to_actions(const fpv_stick_calib_t* calib, const int32_t* raw, in
 /* Drone.step(action=None, ...) with HOST buffers: the joystick path of the reference (components.py:227-228, :250-253 ->
  * get_sticks.py:254-265) in the compact transport form of a radio link.  sticks_host: uint16[n][4] = the raw readings of
  * axes 0, 1, 2 and 5 (throttle, roll, pitch, yaw of the stock calibrations -- the four of calib_read's six values that
- * read_sticks keeps), 0..65535 as the joystick driver reports them; sticks_dev: device staging uint16[n][4]; the
+ * read_sticks keeps), 0..65535 as the joystick driver reports them -- or, format FPV_STICKS_CRSF, the 6-byte packing of
+ * four 11-bit channels; sticks_dev: device staging buffer of the same size; the
  * calibrated actions are written to io->actions (float4[n]) by the same per-axis arithmetic as fpv_sticks_to_actions
  * (bit-identical), then the step runs and the flags return like in fpv_drone_step_host.  8 B/env in, 1 B/env out. */
 int fpv_drone_step_host_sticks(const fpv_drone_params_t* params, const fpv_drone_io_t* io, const fpv_stick_calib_t* calib,
-                               const uint16_t* sticks_host, void* sticks_dev, uint8_t* done_host, int32_t slices,
-                               void* stream);
+                               const void* sticks_host, void* sticks_dev, int32_t format /* FPV_STICKS_U16 | FPV_STICKS_CRSF */,
+                               uint8_t* done_host, int32_t slices, void* stream);
+
+/* Page-locked host memory for the *_host entries and for zero-copy inputs.  write_combined != 0: the CPU writes it through
+ * write-combining buffers (never cached, so the device's reads do not snoop the CPU caches; CPU reads of it are slow --
+ * use it for producer-written inputs only).  fpv_host_free releases it. */
+int fpv_host_alloc(int64_t bytes, int32_t write_combined, void** out);
+int fpv_host_free(void* p);
 
 /* ---------------------------------------------------------------------------------------------
  * Mode B: the acro rate-PID drone of tests/racer_drone_test.py (`PID` :11-32, `Racer` :68-103).

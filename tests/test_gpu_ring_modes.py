@@ -196,3 +196,111 @@ def test_step_host_returns_the_done_bitmask():
         assert np.array_equal(bits, b._done.cpu().numpy().astype(bool)), t
         crashed += int(bits.sum())
     assert torch.equal(a._state, b._state) and crashed > 0
+
+
+@pytest.mark.parametrize("K", [1, 8])
+def test_general_path_without_contact_gives_the_hot_path_bits(K):
+    """An env that touches no obstacle gets, from the general kernel, exactly the bits the hot kernel gives it -- whether its
+    warp ran the hot loop (no env of the warp in reach of anything) or the general loop (a neighbour in contact).  One batch:
+    the first half far from the obstacles, the second half mixed into contact (so warps of both kinds exist, and warps that
+    contain both kinds of env)."""
+    from fpyv_b200 import BatchedDrone, Cylinder, Ground, Target
+    n = 40_000
+    rng = np.random.default_rng(13)
+    pos = np.stack([rng.normal(60, 5, n), rng.normal(60, 5, n), rng.uniform(0.05, 3.0, n)], 1)      # far away: ground only
+    near = rng.random(n) < 0.3
+    near[: n // 2] = False
+    pos[near] = np.array([0.0, 0.0, 3.0]) + rng.normal(0, 1.2, (int(near.sum()), 3))                 # around the sphere
+    pos[:, 2] = np.maximum(pos[:, 2], 0.05)
+    vel, rpy = rng.normal(0, 2, (n, 3)), rng.uniform(-30, 30, (n, 3))
+    objs = [Target(np.array([0.0, 0.0, 3.0]), 1.0), Cylinder(np.array([5.0, -4.0, 0.0]), 1.0, 6.0), Ground()]
+    a = BatchedDrone(None, num_envs=n, device=DEV, substeps=K, dt=2e-3, thrust_lut=1025)
+    b = BatchedDrone(None, num_envs=n, device=DEV, substeps=K, dt=2e-3, thrust_lut=1025)
+    a.reset(pos, vel, rpy)
+    b.reset(pos, vel, rpy)
+    far = torch.as_tensor(~near, device=DEV)
+    touched = 0
+    for t in range(5):
+        act = torch.as_tensor(rng.uniform(-1, 1, (n, 4)), dtype=torch.float32, device=DEV)
+        a.step(act, None, objs, return_obs=False)       # general kernel
+        b.step(act, return_obs=False)                   # hot kernel (no object list: ground only)
+        assert torch.equal(a._state[:, :n][:, far], b._state[:, :n][:, far]), t
+        assert torch.equal(a._done[far], b._done[far]) and torch.equal(a._acc[far], b._acc[far])
+        touched += int((a._done != b._done).sum())
+        # keep the two batches on the same trajectory for the next comparison
+        b._state.copy_(a._state)
+    assert touched > 50          # the near envs really did hit the obstacles
+
+
+def _bits_to_bool(words, n):
+    w = words.numpy().view(np.uint32)
+    return ((w[:, None] >> np.arange(32, dtype=np.uint32)[None, :]) & 1).astype(bool).reshape(-1)[:n]
+
+
+@pytest.mark.parametrize("write_combined", [False, True])
+def test_zero_copy_host_step_matches_plain_step(write_combined):
+    """step_host(zero_copy=True): ONE launch whose TMA engine reads the actions straight from page-locked HOST memory and
+    whose warps write the done bitmask straight back to it -- same state and flags as copy + step, ragged batch size,
+    ordinary pinned and write-combined input buffers."""
+    from fpyv_b200 import BatchedDrone, hostmem
+    n = 300_037
+    rng = np.random.default_rng(21)
+    pos = np.stack([rng.normal(0, 3, n), rng.normal(0, 3, n), rng.uniform(0.05, 1.0, n)], 1)
+    vel, rpy = rng.normal(size=(n, 3)), rng.uniform(-40, 40, (n, 3))
+    a = BatchedDrone(None, num_envs=n, device=DEV, substeps=8, dt=1e-3, auto_reset=True, thrust_lut=2049, done_bits=True)
+    b = BatchedDrone(None, num_envs=n, device=DEV, substeps=8, dt=1e-3, auto_reset=True, thrust_lut=2049)
+    a.reset(pos, vel, rpy)
+    b.reset(pos, vel, rpy)
+    host_a = hostmem.pinned((n, 4), torch.float32, write_combined=write_combined)
+    bits_host = hostmem.pinned(((n + 31) // 32,), torch.int32)
+    with pytest.raises(ValueError):
+        a.step_host(torch.zeros(n, 4), bits_host, zero_copy=True)        # pageable memory is refused
+    crashed = 0
+    for t in range(5):
+        act = torch.as_tensor(rng.uniform(-1, 1, (n, 4)), dtype=torch.float32)
+        host_a.copy_(act)
+        a.step_host(host_a, bits_host, zero_copy=True)
+        b.step(act.to(DEV), return_obs=False)
+        torch.cuda.synchronize()
+        assert np.array_equal(_bits_to_bool(bits_host, n), b._done.cpu().numpy().astype(bool)), t
+        crashed += int(b._done.sum())
+    assert torch.equal(a._state, b._state) and crashed > 0
+    a.step(act.to(DEV), return_obs=False)                               # the drone's own buffers are back in place
+    b.step(act.to(DEV), return_obs=False)
+    assert torch.equal(a._state, b._state) and np.array_equal(_bits_to_bool(a.done_bits.cpu(), n), b._done.cpu().numpy().astype(bool))
+
+
+@pytest.mark.parametrize("fmt", ["u16", "crsf"])
+@pytest.mark.parametrize("zero_copy", [False, True])
+def test_host_stick_formats_match_the_joystick_path(fmt, zero_copy):
+    """step_host_sticks in both transport formats (uint16 x 4 = 8 B/env, CRSF 4 x 11 bit = 6 B/env), as the sliced copy
+    pipeline and as ONE zero-copy launch that calibrates the sticks in registers: bit-identical to the reference's joystick
+    path `rc.feed(raw axes); step(action=None)` (components.py:227-228, :250-253)."""
+    from fpyv_b200 import BatchedDrone, hostmem
+    from fpyv_b200.sticks import crsf_to_raw16, pack_crsf
+    n = 200_011
+    rng = np.random.default_rng(31)
+    pos = np.stack([rng.normal(0, 3, n), rng.normal(0, 3, n), rng.uniform(0.05, 1.5, n)], 1)
+    vel, rpy = rng.normal(size=(n, 3)), rng.uniform(-40, 40, (n, 3))
+    a = BatchedDrone(None, num_envs=n, device=DEV, substeps=4, dt=1e-3, auto_reset=True, thrust_lut=2049, done_bits=True)
+    b = BatchedDrone(None, num_envs=n, device=DEV, substeps=4, dt=1e-3, auto_reset=True, thrust_lut=2049)
+    a.reset(pos, vel, rpy)
+    b.reset(pos, vel, rpy)
+    sticks = hostmem.pinned((n, 4), torch.uint16) if fmt == "u16" else hostmem.pinned((n, 6), torch.uint8)
+    bits_host = hostmem.pinned(((n + 31) // 32,), torch.int32)
+    for t in range(4):
+        if fmt == "u16":
+            raw4 = rng.integers(0, 65536, (n, 4))
+            sticks.copy_(torch.from_numpy(raw4.astype(np.uint16)))
+        else:
+            v11 = rng.integers(0, 2048, (n, 4))
+            sticks.copy_(pack_crsf(v11))
+            raw4 = crsf_to_raw16(v11)
+        a.step_host_sticks(sticks, bits_host, zero_copy=zero_copy)
+        raw6 = np.zeros((n, 6), dtype=np.int32)
+        raw6[:, [0, 1, 2, 5]] = raw4
+        b.rc.feed(raw6)
+        b.step(None, return_obs=False)
+        torch.cuda.synchronize()
+        assert np.array_equal(_bits_to_bool(bits_host, n), b._done.cpu().numpy().astype(bool)), t
+    assert torch.equal(a._state, b._state)

@@ -350,7 +350,7 @@ def test_sass_carries_the_blackwell_paths(lib):
     out = subprocess.run([cuobjdump, "-sass", so], capture_output=True, text=True).stdout
     assert "sm_100a" in subprocess.run([cuobjdump, "-lelf", so], capture_output=True, text=True).stdout
     funcs = re.split(r"\n\s*Function : ", out)[1:]
-    hot = [f for f in funcs if f.startswith("_ZN3fpv16ring_step_kernelINS_9DroneModeINS_2F2ELi4ELb0ENS_6NoPost")]
+    hot = [f for f in funcs if f.startswith("_ZN3fpv16ring_step_kernelINS_9DroneModeINS_2F2ELi4ELb0ENS_6NoPostENS_7DroneIOELi0E")]
     assert len(hot) == 1
     sass = hot[0]
     count = lambda op: len(re.findall(r"\b" + op + r"\b", sass))
@@ -364,7 +364,9 @@ def test_sass_carries_the_blackwell_paths(lib):
     f = [x for x in funcs if x.startswith("_ZN3fpv20drone_rollout_kernelINS_2F2ELi4")]
     assert f and len(re.findall(r"\bFFMA2\b", f[0])) >= 60
     for prefix in ("_ZN3fpv16ring_step_kernelINS_9DroneModeINS_2F2ELi4ELb1ENS_6NoPost", "_ZN3fpv16ring_step_kernelINS_9DroneModeINS_2F2ELi4ELb0ENS_8GatePost",
-                   "_ZN3fpv16ring_step_kernelINS_9RacerModeINS_2F2E", "_ZN3fpv16ring_step_kernelINS_8AcroModeINS_2F2E"):
+                   "_ZN3fpv16ring_step_kernelINS_9RacerModeINS_2F2E", "_ZN3fpv16ring_step_kernelINS_8AcroModeINS_2F2E",
+                   "_ZN3fpv16ring_step_kernelINS_9DroneModeINS_2F2ELi4ELb0ENS_6NoPostENS_7DroneIOELi1E",       # raw uint16 sticks in the ring
+                   "_ZN3fpv16ring_step_kernelINS_9DroneModeINS_2F2ELi4ELb0ENS_6NoPostENS_7DroneIOELi2E"):      # CRSF sticks in the ring
         f = [x for x in funcs if x.startswith(prefix)]
         assert f and len(re.findall(r"\bFFMA2\b", f[0])) >= 60, prefix
         assert len(re.findall(r"UBLKCP\.S\.G", f[0])) >= 5 and "SYNCS.PHASECHK.TRANS64.TRYWAIT" in f[0], prefix
