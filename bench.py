@@ -413,6 +413,16 @@ def run_gpu(args):
             flagged[0] += int(host_done[:64].count_nonzero())
         return (time.perf_counter() - t0) * 1e3
 
+    # the link itself: one plain pinned -> device copy of the same 16 MiB, best of 7 (the roofline `e2e` sits on)
+    link_ms = None
+    for _ in range(7):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        drone._actions.copy_(host_actions[0], non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        link_ms = e0.elapsed_time(e1) if link_ms is None else min(link_ms, e0.elapsed_time(e1))
+    link_gbs = 16 * n / (link_ms * 1e-3) / 1e9
     best_zero = ms_e2e_zero <= ms_e2e_sliced
     wc = [hostmem.pinned((n, 4), torch.float32, write_combined=True) for _ in range(2)]
     ms_prod = {"pinned": producer_loop(host_actions, best_zero), "write_combined": producer_loop(wc, best_zero)}
@@ -538,6 +548,10 @@ def run_gpu(args):
             "e2e": {"value": total_envs * K / (ms_e2e * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": 16 * n * world,
                     "d2h_bytes_per_step": 4 * ((n + 31) // 32) * world, "ms_per_step": ms_e2e / K,
                     "form": "zero copy" if ms_e2e_zero <= ms_e2e_sliced else "sliced copies",
+                    "link": {"bound": "pcie", "h2d_copy_gbs_measured": link_gbs, "achieved_gbs": (16 * n + 4 * ((n + 31) // 32)) / (ms_e2e / K * 1e-3) / 1e9,
+                             "frac": (16 * n + 4 * ((n + 31) // 32)) / (ms_e2e / K * 1e-3) / 1e9 / link_gbs,
+                             "note": "e2e moves 16 B/env in and 1 bit/env out; a bare cudaMemcpyAsync of the same 16 MiB (best of 7, "
+                                     "this run) is the link rate it is compared with"},
                     "ms_per_step_zero_copy": ms_e2e_zero / K, "ms_per_step_sliced_copies": ms_e2e_sliced / K,
                     "api": "BatchedDrone(done_bits=True).step_host(pinned actions [n,4] float32, pinned done bitmask): zero copy = ONE "
                            "fpv_drone_step launch whose TMA loads read the host buffer over PCIe and whose warps write the flag "

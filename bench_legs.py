@@ -381,6 +381,30 @@ def leg_chase(dev, pk, tm, n=4096):
                          "algorithmic": f"{W * H} B frame + 32 B x {world.n_points} points per camera x {n} cameras"}}
 
 
+def leg_plain_order_vs_batch(dev, pk, tm, K=8):
+    """The headline kernel in PLAIN STREAM ORDER (what a closed-loop policy can use: every launch waits for the previous grid)
+    as a function of the batch size.  A launch has a fixed cost that does not scale with the batch (~4 us start-up, ~6 us of
+    end-of-kernel imbalance: the ring commits every warp to two 64-env chunks); at 1,048,576 envs that is ~25 % of the step,
+    from 2,097,152 envs per GPU the plain-order launch is above 0.70 of the FP32 roofline."""
+    from fpyv_b200 import BatchedDrone
+    out = {"workload": f"configs[2] kernel and inputs, {K} substeps, plain stream order, 3 independent batches round-robin (cold L2)"}
+    g = torch.Generator(device=dev).manual_seed(12)
+    for n in (1 << 20, 1 << 21, 1 << 22, 1 << 23):
+        ds, acts = [], []
+        for j in range(3):
+            d = BatchedDrone(None, num_envs=n, device=dev, substeps=K, dt=1e-3, auto_reset=True, thrust_lut=2049)
+            d.reset(*_rand_init(n, dev, g))
+            ds.append(d)
+            acts.append((torch.rand(n, 4, device=dev, generator=g) * 2 - 1).contiguous())
+        ms = tm.stream([(lambda d=d, a=a: d.step(a, return_obs=False)) for d, a in zip(ds, acts)], steps=18, warm=6)
+        r = _roof(n, ms, FLOP_DRONE_SUBSTEP * K, BYTES_DRONE_STEP, pk, "ring_step_kernel<DroneMode<F2, hot>>", "ms_stream")
+        out[str(n)] = {"ms_per_step": ms, "env_steps_per_sec": n / (ms * 1e-3), "fp32_frac": r["fp32_frac"], "hbm_frac": r["hbm_frac"]}
+        del ds, acts
+        torch.cuda.empty_cache()
+    out["roofline"] = {"bound": "fp32", "unit": "TFLOP/s", "frac_by_envs": {k: v["fp32_frac"] for k, v in out.items() if k.isdigit()}}
+    return out
+
+
 def leg_config3_sharded(dev, pk, tm, world, rank, K=8, total=1 << 24, steps=12):
     """configs[3]: 16,777,216 drones sharded over `world` ranks (contiguous env slices, fpyv_b200.shard.env_shard), stepped K = 8
     with no data-path collective, then the engine's only collective: the all-reduce of the episode statistics (NCCL)."""
@@ -442,7 +466,8 @@ def run_extra(dev, pk, world=1, rank=0, which=None):
     tm = Timer(dev)
     out = {}
     legs = [("config1_small", leg_config1_small), ("config4_gate_race", leg_config4_gate_race), ("config0_racer", leg_config0_racer),
-            ("mode_c", leg_mode_c), ("general_path", leg_general_path), ("chase", leg_chase)]
+            ("mode_c", leg_mode_c), ("general_path", leg_general_path), ("chase", leg_chase),
+            ("plain_order_vs_batch", leg_plain_order_vs_batch)]
     if rank == 0:
         for name, fn in legs:
             if which and name not in which:

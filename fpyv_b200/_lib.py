@@ -6,8 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-# FPYV_B200_LIB: developer override used to A/B differently tuned builds of the same ABI
-LIB_PATH = os.environ.get("FPYV_B200_LIB") or os.path.join(HERE, "libfpyv_b200.so")
+LIB_PATH = os.path.join(HERE, "libfpyv_b200.so")
 ABI_VERSION = 13
 
 # flags (fpv_api.h)

@@ -469,6 +469,8 @@ class BatchedDrone:
             raise RuntimeError("call reset() before step() (the reference's state is None until reset)")
         if not isinstance(actions_host, torch.Tensor) or tuple(actions_host.shape) != (n, 4):
             raise ValueError("step_host expects a [num_envs, 4] tensor of actions")
+        if zero_copy:
+            self._require_zero_copy(actions_host, done_host)
         if (not self._fast_ok or actions_host.is_cuda or actions_host.dtype is not torch.float32
                 or not actions_host.is_contiguous()):
             self._actions.copy_(actions_host, non_blocking=True)      # first call / odd inputs: the plain path
@@ -480,7 +482,6 @@ class BatchedDrone:
         self._p.flags = self._flags
         self._io.chunk_epoch = None
         if zero_copy:
-            self._require_zero_copy(actions_host, done_host)
             self._io.actions = actions_host.data_ptr()
             self._io.done_bits = done_host.data_ptr()
             try:
@@ -521,6 +522,10 @@ class BatchedDrone:
         if not (ok16 or ok11) or sticks_host.is_cuda or not sticks_host.is_contiguous():
             raise ValueError("step_host_sticks expects a contiguous host tensor uint16 [num_envs, 4] or uint8 [num_envs, 6]")
         fmt = _lib.STICKS_U16 if ok16 else _lib.STICKS_CRSF
+        if zero_copy:
+            self._require_zero_copy(sticks_host, done_host)
+            if sticks_host.numel() * sticks_host.element_size() % 16 and not hasattr(sticks_host, "_fpv_block"):
+                raise ValueError("zero_copy: the stick buffer must be padded to a multiple of 16 bytes (fpyv_b200.hostmem.pinned)")
         if not self._is_reset:
             raise RuntimeError("call reset() before step() (the reference's state is None until reset)")
         if not self._fast_ok:      # configure the io block once through the plain path
@@ -543,9 +548,6 @@ class BatchedDrone:
         self._io.actions = self._actions.data_ptr()
         self._io.chunk_epoch = None
         if zero_copy:
-            self._require_zero_copy(sticks_host, done_host)
-            if sticks_host.numel() * sticks_host.element_size() % 16 and not hasattr(sticks_host, "_fpv_block"):
-                raise ValueError("zero_copy: the stick buffer must be padded to a multiple of 16 bytes (fpyv_b200.hostmem.pinned)")
             io = self._io
             io.sticks, io.stick_calib, io.stick_format = sticks_host.data_ptr(), C.pointer(self.rc._c), fmt
             io.done_bits = done_host.data_ptr()
