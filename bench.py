@@ -39,10 +39,8 @@ SPIN_CYCLES = 500_000                          # ~0.25 ms at 1.965 GHz: lets the
 def ncu_traffic_bytes():
     """DRAM bytes per K=8 launch from the committed ncu capture (None if the profile is absent)."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_ncu_drone_step.json")) as f:
-            k8 = json.load(f)[0]
-        mb = lambda s: float(s.split()[0]) * (1e6 if "Mbyte" in s else 1e9 if "Gbyte" in s else 1e3 if "Kbyte" in s else 1.0)
-        return mb(k8["dram__bytes_read.sum"]) + mb(k8["dram__bytes_write.sum"])
+        with open(os.path.join(ROOT, "profiles", "r2_ncu_drone_step.json")) as f:
+            return float(json.load(f)[0]["traffic_bytes"])
     except Exception:
         return None
 
@@ -519,9 +517,9 @@ def run_gpu(args):
     hbm_ach = BYTES_PER_ENV_STEP * n / per_gpu_launch_s / 1e9
     hbm_k1 = BYTES_PER_ENV_STEP * n / (ms_k1 * 1e-3 / K) / 1e9
     roof = {"bound": "fp32", "achieved": fp32_ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": fp32_ach / fp32_peak,
-            "traffic": ncu_traffic_bytes(), "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one K=8 launch, "
-            "ncu --set full capture of this command (profiles/r1_ncu_drone_step.json); stores of the state are still in L2 at kernel end",
-            "kernel": "fpv::drone_step_tma_kernel<F2, ANG=2, 128 threads, 4 CTAs/SM, 2-slot ring> (K=8)",
+            "traffic": ncu_traffic_bytes(), "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one K=8 launch of this kernel on this workload, "
+            "ncu --set full (profiles/r2_ncu_drone_step.json, tools/profile_modes.py hot); part of the state stores is still in L2 at kernel end",
+            "kernel": "fpv::ring_step_kernel<DroneMode<F2, ANG=4, hot path>, 128 threads, 4 CTAs/SM, 2-slot TMA ring per warp> (K=8)",
             "peak_source": f"{sm_count} SMs x {FP32_LANES_PER_SM} FP32 lanes x 2 x {pk['sm_max_mhz']:.0f} MHz (clocks.max.sm); "
                            "tensor cores unused by design (no dense contraction on this path)",
             "algorithmic": f"{FLOP_PER_ENV_SUBSTEP} flop/env/substep x {SUBSTEPS} substeps x {n} envs per launch",
