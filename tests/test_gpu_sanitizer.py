@@ -2,7 +2,10 @@
 chained run, zero-copy host inputs).  ONE tool per process and per GPU lease: the B200 profiling guide reports that running
 several sanitizer tools in one call can leave the device unusable for everyone, so this test only runs when
 FPV_RUN_SANITIZER names the tool (memcheck / racecheck / initcheck / synccheck); the builder runs each tool in its own
-gpurun call and commits the summaries under profiles/ (profiles/r2_sanitizer_*.txt)."""
+gpurun call.  Round 2: the pool's wrapper answered "compute-sanitizer is closed on this pool and stays closed" (exit 86), so
+the test skips there; what stands in for it are the guard-cell tests (sentinel padding around every state plane and output
+of every kernel form at ragged sizes, tests/test_gpu_parity.py, test_gpu_acro.py, test_gpu_chase.py, test_gpu_ring_modes.py)
+and the bit-identity tests between kernel forms."""
 import os
 import shutil
 import subprocess
@@ -24,5 +27,7 @@ def test_compute_sanitizer_is_clean():
     r = subprocess.run([cs, "--tool", tool, "--error-exitcode", "9", sys.executable, os.path.join(ROOT, "tools", "sanitize_small.py")],
                        capture_output=True, text=True, timeout=1500)
     tail = (r.stdout + r.stderr)[-3000:]
+    if r.returncode == 86 or "closed on this pool" in tail:
+        pytest.skip("compute-sanitizer is closed on this GPU pool (the wrapper refuses to run it): " + tail.strip()[:160])
     assert r.returncode == 0 and "sanitize_small: ok" in r.stdout, tail
     assert "ERROR SUMMARY: 0 errors" in r.stdout + r.stderr, tail
