@@ -385,6 +385,15 @@ def run_gpu(args):
 
     ms_e2e_zero = e2e_loop(lambda h: drone.step_host(h, host_done, zero_copy=True), host_actions)
     ms_e2e_sliced = e2e_loop(lambda h: drone.step_host(h, host_done, slices=E2E_SLICES), host_actions)
+    # sliced H2D copies (the copy engine's rate) + flag words written straight to host memory by the step kernels (no D2H)
+    ms_e2e_direct = {sl: e2e_loop(lambda h, sl=sl: drone.step_host(h, host_done, slices=sl, flags_direct=True), host_actions)
+                     for sl in (2, 3, 4, 6)}
+    best_sl = min(ms_e2e_direct, key=ms_e2e_direct.get)
+    ms_e2e_direct_all = dict(ms_e2e_direct)
+    if ms_e2e_direct[best_sl] < ms_e2e_sliced:
+        ms_e2e_sliced, sliced_form = ms_e2e_direct[best_sl], f"sliced copies ({best_sl} slices), flags written to host memory by the kernels"
+    else:
+        sliced_form = f"sliced copies ({E2E_SLICES} slices), flags copied back"
     # ---- the same end-to-end step fed the way the reference's simulator feeds it (step(action=None): raw joystick axes,
     #      components.py:227-228, :250-253) in compact transport form, calibrated on the device: uint16 x 4 (8 B/env) and the
     #      6-byte CRSF packing of four 11-bit channels (what an RC link carries).  Extra metrics; `e2e` stays on float32 actions.
@@ -545,7 +554,8 @@ def run_gpu(args):
             "env_substeps_per_sec": value * SUBSTEPS,
             "e2e": {"value": total_envs * K / (ms_e2e * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": 16 * n * world,
                     "d2h_bytes_per_step": 4 * ((n + 31) // 32) * world, "ms_per_step": ms_e2e / K,
-                    "form": "zero copy" if ms_e2e_zero <= ms_e2e_sliced else "sliced copies",
+                    "form": "zero copy" if ms_e2e_zero <= ms_e2e_sliced else sliced_form,
+                    "ms_per_step_sliced_flags_direct_by_slices": {str(k_): v_ / K for k_, v_ in ms_e2e_direct_all.items()},
                     "link": {"bound": "pcie", "h2d_copy_gbs_measured": link_gbs, "achieved_gbs": (16 * n + 4 * ((n + 31) // 32)) / (ms_e2e / K * 1e-3) / 1e9,
                              "frac": (16 * n + 4 * ((n + 31) // 32)) / (ms_e2e / K * 1e-3) / 1e9 / link_gbs,
                              "note": "e2e moves 16 B/env in and 1 bit/env out; a bare cudaMemcpyAsync of the same 16 MiB (best of 7, "

@@ -542,7 +542,10 @@ int host_slice_bounds(long long n, int slices, long long* bound) {
 int fpv_drone_step_host(const fpv_drone_params_t* p, const fpv_drone_io_t* io, const float* actions_host,
                         uint8_t* done_host, int32_t slices, void* stream) {
   if (!p || !io) return fail(FPV_EINVAL, "fpv_drone_step_host: null params/io");
-  if (!actions_host || !done_host) return fail(FPV_EINVAL, "fpv_drone_step_host: null host buffer");
+  if (!actions_host) return fail(FPV_EINVAL, "fpv_drone_step_host: null host buffer");
+  if (!done_host && !io->done_bits)
+    return fail(FPV_EINVAL, "fpv_drone_step_host: done_host may be NULL only if io.done_bits points at (pinned host) memory the "
+                            "step kernels write the flags to themselves");
   if (!io->actions || !io->done) return fail(FPV_EINVAL, "fpv_drone_step_host: io.actions / io.done must be device staging buffers");
   if (io->n < 0 || io->plane_stride < io->n) return fail(FPV_EINVAL, "fpv_drone_step_host: bad n/stride");
   if (io->n == 0) return FPV_OK;
@@ -583,15 +586,19 @@ int fpv_drone_step_host(const fpv_drone_params_t* p, const fpv_drone_io_t* io, c
       cudaStreamWaitEvent(st, hp.joined, 0);
       return rc;
     }
-    cudaEventRecord(hp.stepped[c], st);
-    cudaStreamWaitEvent(hp.out, hp.stepped[c], 0);
-    if (io->done_bits)   // bitmask form: slices start on 64-env boundaries, so every slice owns whole 32-bit words
-      cudaMemcpyAsync(done_host + a / 8, (const char*)io->done_bits + a / 8, (size_t)((b - a + 31) / 32 * 4), cudaMemcpyDeviceToHost, hp.out);
-    else
-      cudaMemcpyAsync(done_host + a, io->done + a, (size_t)(b - a), cudaMemcpyDeviceToHost, hp.out);
+    if (done_host) {
+      cudaEventRecord(hp.stepped[c], st);
+      cudaStreamWaitEvent(hp.out, hp.stepped[c], 0);
+      if (io->done_bits)   // bitmask form: slices start on 64-env boundaries, so every slice owns whole 32-bit words
+        cudaMemcpyAsync(done_host + a / 8, (const char*)io->done_bits + a / 8, (size_t)((b - a + 31) / 32 * 4), cudaMemcpyDeviceToHost, hp.out);
+      else
+        cudaMemcpyAsync(done_host + a, io->done + a, (size_t)(b - a), cudaMemcpyDeviceToHost, hp.out);
+    }
   }
-  cudaEventRecord(hp.joined, hp.out);
-  cudaStreamWaitEvent(st, hp.joined, 0);
+  if (done_host) {   // (without done_host the flags are written by the step kernels themselves: `stream` alone orders them)
+    cudaEventRecord(hp.joined, hp.out);
+    cudaStreamWaitEvent(st, hp.joined, 0);
+  }
   return check_launch("fpv_drone_step_host");
 }
 

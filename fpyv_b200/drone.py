@@ -116,11 +116,13 @@ class BatchedDrone:
         # cta_slots > 0: the step kernel takes at most that many CTA slots per SM, so that chained launches of
         # INDEPENDENT batches stepped round-robin run side by side (fpv_drone_io_t.max_ctas_per_sm)
         self._io.max_ctas_per_sm = int(cta_slots)
+        self._static = None          # (has_ground, ctypes array, count) of set_static_objects()
         self._host_done = None
         self._sticks_dev = None
         self._last_action = None
         self._is_reset = False
         self._fast_ok = False
+        self._fast_flags = self._flags
         self._act_shape = torch.Size((n, 4))
         self._step_fn = self._lib.fpv_drone_step
         self._p_ref, self._io_ref = C.byref(self._p), C.byref(self._io)
@@ -248,6 +250,20 @@ class BatchedDrone:
         self._is_reset = True
         self._chain_ready = False
 
+    def set_static_objects(self, object_list):
+        """Register a world that does not change between steps (the reference passes the same `object_list` to every
+        `step`, simulator.py:84-85, :156): it is lowered once, `step(action)` without an object_list then steps against it,
+        and such steps ride the allocation-free fast path (and may be chained).  Objects are read NOW: call again after
+        moving one (e.g. `Target.update()`); `None` clears it.  An explicit `object_list=` in a call still wins."""
+        if object_list is None:
+            self._static = None
+        else:
+            has_ground, lowered = lower_object_list(object_list)
+            arr = (_lib.Object * len(lowered))(*lowered) if lowered else None
+            self._static = (has_ground, arr, len(lowered))
+        self._fast_ok = False
+        self._chain_ready = False
+
     def read_sticks(self):
         """components.py:250-253 on the batched joystick source."""
         return self.rc.read_actions()
@@ -289,7 +305,7 @@ class BatchedDrone:
                 and action.shape == self._act_shape and action.is_contiguous()):
             self._last_action = action
             self._io.actions = action.data_ptr()
-            self._p.flags = (self._flags | _lib.F_CHAINED) if chain_now else self._flags
+            self._p.flags = (self._fast_flags | _lib.F_CHAINED) if chain_now else self._fast_flags
             rc = self._step_fn(self._p_ref, self._io_ref, _lib.raw_stream(self._dev_index))
             if rc:
                 _lib.check(rc)
@@ -323,6 +339,9 @@ class BatchedDrone:
             if lowered:
                 objs = (_lib.Object * len(lowered))(*lowered)
                 p.n_objects = len(lowered)
+        elif self._static is not None:        # the world registered with set_static_objects()
+            has_ground, objs, p.n_objects = self._static
+            p.flags = (p.flags & ~_lib.F_GROUND) | (_lib.F_GROUND if has_ground else 0)
         ovr_q = ovr_t = None
         if rotation_matrix is not None:
             if thrust_force is None:
@@ -353,9 +372,11 @@ class BatchedDrone:
         if chained:
             self._epoch += 1
             self._chain_ready = True
-        # the fast path may reuse p / io as they are only if this call left them in the plain configuration
+        # the fast path may reuse p / io as they are only if this call left them in the plain configuration (incl. the
+        # static world, whose lowered objects and ground flag stay in p / io)
         self._fast_ok = (wind_velocity_vector is None and object_list is None and rotation_matrix is None
                          and getattr(self, "_trace", None) is None)
+        self._fast_flags = p.flags & ~_lib.F_CHAINED
         if return_obs:
             return self.observe()
         return None
@@ -365,6 +386,9 @@ class BatchedDrone:
         what the slow path of step() leaves behind after such a call, so the allocation-free fast path may follow."""
         p, io = self._p, self._io
         p.flags, p.n_objects = self._flags, 0
+        if self._static is not None:
+            self._fast_ok = False        # the static world is configured by the slow path of step()
+            return
         p.wind[0] = p.wind[1] = p.wind[2] = 0.0
         io.state, io.n, io.plane_stride = self._state.data_ptr(), self.num_envs, self._stride
         io.actions = self._actions.data_ptr()
@@ -379,6 +403,7 @@ class BatchedDrone:
         io.stats, io.work = self._stats.data_ptr(), self._work.data_ptr()
         io.chunk_epoch = io.trace = None
         self._chain_armed = False
+        self._fast_flags = self._flags
         self._fast_ok = getattr(self, "_trace", None) is None
 
     @property
@@ -417,7 +442,7 @@ class BatchedDrone:
             first = 1
         else:
             first = 0
-        if fused and first < T and not (self._flags & (_lib.F_SCALAR | _lib.F_FREEZE_DONE)):
+        if fused and first < T and self._static is None and not (self._flags & (_lib.F_SCALAR | _lib.F_FREEZE_DONE)):
             if not self._is_reset:
                 raise RuntimeError("call reset() before step() (the reference's state is None until reset)")
             self._p.flags = self._flags
@@ -452,7 +477,7 @@ class BatchedDrone:
 
     # ------------------------------------------------------------------ host-buffer entry (end-to-end path)
     def step_host(self, actions_host: torch.Tensor, done_host: torch.Tensor | None = None, slices: int = 4,
-                  zero_copy: bool = False):
+                  zero_copy: bool = False, flags_direct: bool = False):
         """One control step with HOST buffers: pinned actions [n,4] -> device, step, done flags -> pinned host.
         This is the call timed as `e2e` in bench.py.
 
@@ -462,9 +487,13 @@ class BatchedDrone:
         output (fpv_drone_io_t: "may be a pinned host pointer"): the kernel's TMA engine fetches every 64-env chunk of
         actions straight over PCIe while earlier chunks compute, and the flags go back as 32-bit words written by the warps.
         No staging copy, no copy-engine hand-offs; needs a drone built with done_bits=True and page-locked buffers.
+        flags_direct=True (sliced form, done_bits drones, pinned done_host): the slices' step kernels write the flag words
+        straight into done_host instead of a device buffer + D2H copies (no third stream, no copy hand-offs at the end).
         Either way the caller's current stream is ordered after the flags: synchronising it means they are on the host."""
         n, dev = self.num_envs, self.device
         done_host = self._check_done_host(done_host)
+        if self._static is not None:
+            raise RuntimeError("step_host serves the hot-path configuration; a drone with set_static_objects() steps with step()")
         if not self._is_reset:
             raise RuntimeError("call reset() before step() (the reference's state is None until reset)")
         if not isinstance(actions_host, torch.Tensor) or tuple(actions_host.shape) != (n, 4):
@@ -492,6 +521,15 @@ class BatchedDrone:
             self._last_action = None          # the actions never existed on the device
             return done_host
         self._io.actions = self._actions.data_ptr()
+        if flags_direct:
+            self._require_zero_copy(actions_host, done_host)
+            self._io.done_bits = done_host.data_ptr()
+            try:
+                _lib.check(self._lib.fpv_drone_step_host(self._p_ref, self._io_ref, actions_host.data_ptr(), None, int(slices),
+                                                         torch.cuda.current_stream(dev).cuda_stream))
+            finally:
+                self._io.done_bits = self._done_bits.data_ptr()
+            return done_host
         _lib.check(self._lib.fpv_drone_step_host(self._p_ref, self._io_ref, actions_host.data_ptr(), done_host.data_ptr(),
                                                  int(slices), torch.cuda.current_stream(dev).cuda_stream))
         return done_host
@@ -516,6 +554,8 @@ class BatchedDrone:
         n, dev = self.num_envs, self.device
         if self.rc._c is None:
             raise RuntimeError("Joystick is not calibrated: call calibrate(path) first")
+        if self._static is not None:
+            raise RuntimeError("step_host_sticks serves the hot-path configuration; a drone with set_static_objects() steps with step()")
         done_host = self._check_done_host(done_host)
         ok16 = isinstance(sticks_host, torch.Tensor) and sticks_host.dtype is torch.uint16 and tuple(sticks_host.shape) == (n, 4)
         ok11 = isinstance(sticks_host, torch.Tensor) and sticks_host.dtype is torch.uint8 and tuple(sticks_host.shape) == (n, 6)

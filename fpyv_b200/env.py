@@ -112,7 +112,7 @@ class GateRaceEnv:
                 action = torch.stack([torch.as_tensor(action[k]).to(self.device, torch.float32) for k in self.agent_names], dim=1)
             act = torch.as_tensor(action).to(self.device, torch.float32).reshape(self.n_agents, 4).contiguous()
         d = self.drone
-        if fused and d._fast_ok and not (d._flags & (_lib.F_FREEZE_DONE | _lib.F_SCALAR)):
+        if fused and d._fast_ok and d._static is None and not (d._flags & (_lib.F_FREEZE_DONE | _lib.F_SCALAR)):
             d._last_action = act
             if chained and torch.cuda.is_current_stream_capturing():
                 chained = False

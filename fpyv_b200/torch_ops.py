@@ -50,6 +50,8 @@ def drone_step(state: torch.Tensor, actions: torch.Tensor, done: torch.Tensor, a
         if t.shape != like.shape or t.dtype != like.dtype or t.device != like.device or not t.is_contiguous():
             raise RuntimeError(f"fpyv_b200::drone_step: `{name}` must be a contiguous {like.dtype} tensor of shape "
                                f"{tuple(like.shape)} on {like.device}")
+    if d._static is not None:
+        raise RuntimeError("fpyv_b200::drone_step serves the hot-path configuration; a drone with set_static_objects() steps with step()")
     if not d._fast_ok:
         d._configure_plain_io()
     io = _lib.DroneIO.from_buffer_copy(d._io)

@@ -226,7 +226,9 @@ int fpv_drone_step(const fpv_drone_params_t* params, const fpv_drone_io_t* io, v
  * extra streams and the events are created once per device and cached inside the library (the only state it keeps).
  * io->chunk_epoch / FPV_F_CHAINED are ignored.  slices <= 0: 4.
  * With io->done_bits set, done_host receives the BITMASK instead (uint32[ceil(n / 32)], 1/8 of the bytes; done_host must
- * then be 4-byte aligned and hold ceil(n / 32) * 4 bytes). */
+ * then be 4-byte aligned and hold ceil(n / 32) * 4 bytes).  done_host == NULL (only with io->done_bits): no device-to-host
+ * copies at all -- io->done_bits then points at pinned HOST memory and the step kernels write the flag words there
+ * themselves; synchronising `stream` means they have arrived. */
 int fpv_drone_step_host(const fpv_drone_params_t* params, const fpv_drone_io_t* io, const float* actions_host,
                         uint8_t* done_host, int32_t slices, void* stream);
 

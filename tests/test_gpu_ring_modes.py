@@ -186,9 +186,10 @@ def test_step_host_returns_the_done_bitmask():
     with pytest.raises(ValueError):
         a.step_host(host_a, torch.empty(n, dtype=torch.uint8, pin_memory=True))
     crashed = 0
-    for t in range(5):
+    for t in range(6):
         host_a.copy_(torch.as_tensor(rng.uniform(-1, 1, (n, 4)), dtype=torch.float32))
-        a.step_host(host_a, bits_host, slices=4)
+        # even steps: flags copied back by the library; odd steps: flag words written to the host buffer by the kernels
+        a.step_host(host_a, bits_host, slices=4 if t % 2 == 0 else 3, flags_direct=t % 2 == 1)
         b.step(host_a.to(DEV), return_obs=False)
         torch.cuda.synchronize()
         words = bits_host.numpy().view(np.uint32)
@@ -303,4 +304,38 @@ def test_host_stick_formats_match_the_joystick_path(fmt, zero_copy):
         b.step(None, return_obs=False)
         torch.cuda.synchronize()
         assert np.array_equal(_bits_to_bool(bits_host, n), b._done.cpu().numpy().astype(bool)), t
+    assert torch.equal(a._state, b._state)
+
+
+def test_static_world_steps_on_the_fast_path_and_chains():
+    """set_static_objects(): the object list is lowered once, `step(action)` then runs the general kernel from the
+    allocation-free fast path -- plain and chained -- with the bits of passing the same list to every call."""
+    from fpyv_b200 import BatchedDrone, Cylinder, Ground, Target
+    n = 180_000
+    rng = np.random.default_rng(17)
+    pos = np.stack([rng.normal(0, 6, n), rng.normal(0, 6, n), rng.uniform(0.05, 6.0, n)], 1)
+    vel, rpy = rng.normal(0, 2, (n, 3)), rng.uniform(-30, 30, (n, 3))
+    objs = [Target(np.array([0.0, 0.0, 3.0]), 1.0), Cylinder(np.array([5.0, -4.0, 0.0]), 1.0, 6.0), Ground()]
+    kw = dict(num_envs=n, device=DEV, substeps=8, dt=1e-3, auto_reset=True, thrust_lut=2049)
+    a, b, c = BatchedDrone(None, **kw), BatchedDrone(None, **kw), BatchedDrone(None, **kw)
+    for d in (a, b, c):
+        d.reset(pos, vel, rpy)
+    a.set_static_objects(objs)
+    c.set_static_objects(objs)
+    acts = [torch.as_tensor(rng.uniform(-1, 1, (n, 4)), dtype=torch.float32, device=DEV) for _ in range(4)]
+    for t in range(12):
+        a.step(acts[t % 4], return_obs=False)
+        b.step(acts[t % 4], None, objs, return_obs=False)
+        c.step(acts[t % 4], return_obs=False, chained=True)
+        assert a._fast_ok
+    torch.cuda.synchronize()
+    assert torch.equal(a._state, b._state) and torch.equal(a._done, b._done)
+    assert torch.equal(c._state, b._state) and c.episode_stats()["chain_timeouts"] == 0
+    assert a.episode_stats()["crashes"] == b.episode_stats()["crashes"] > 0
+    hb = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    with pytest.raises(RuntimeError):
+        a.step_host(torch.empty(n, 4, pin_memory=True), hb)
+    a.set_static_objects(None)                      # back to the hot path
+    a.step(acts[0], return_obs=False)
+    b.step(acts[0], return_obs=False)
     assert torch.equal(a._state, b._state)
