@@ -44,7 +44,9 @@ constexpr int kThreads = 128;
 #define FPV_MINB 4  // resident CTAs per SM the compiler must fit (register budget = 65536 / (kThreads * FPV_MINB))
 #endif
 #ifndef FPV_GENERAL_MINB
-#define FPV_GENERAL_MINB 3  // the general (obstacle) path needs ~140 registers; 4 CTAs/SM would spill
+#define FPV_GENERAL_MINB 4  // the general (obstacle) path: 128 registers with ~48 bytes of spills in the (rare) contact code;
+                            // measured equal to 3 CTAs/SM without spills in plain order, and it lets chained launches of
+                            // independent batches sit side by side (2 + 2 CTA slots per SM) like the hot path's
 #endif
 
 using fpv::DroneIO;
