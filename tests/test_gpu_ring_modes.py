@@ -67,7 +67,7 @@ def test_general_path_reach_test_hoisted_out_of_the_substep_loop(packed, K, dt):
         print(f"\nhoisted reach K={K} dt={dt:.4f} packed={packed}: max rel err {err[ok].max():.2e}, crashed {int(s.done.sum())}, "
               f"flag mismatches {int(mism.sum())}")
         assert mism.sum() <= 6, mism.sum()       # a motor within fp32 rounding of a surface may flip the flag
-        assert err[ok].max() <= 2e-5 * K         # K free-running substeps through stiff contact springs
+        assert err[ok].max() <= TOL_STEP         # K free-running substeps, many through contact (measured <= 1.4e-6)
         # re-synchronise the oracle on the device state so that the second step is a single control step again
         s.pos, s.vel = d.position.double().cpu().numpy(), d.velocity.double().cpu().numpy()
         s.R = fo.quaternion_to_matrix(d.quaternion.double().cpu().numpy())
