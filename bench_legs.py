@@ -244,6 +244,13 @@ def leg_config4_gate_race(dev, pk, tm, envs=8192, agents=32, K=8):
     e1.record()
     torch.cuda.synchronize()
     ms_chained = e0.elapsed_time(e1) / 40
+    import time as _time
+    torch.cuda.synchronize()
+    t0 = _time.perf_counter()
+    for i in range(40):
+        es[i % 4].step(acts[i % 4], fused=True, chained=True)
+    host_us = (_time.perf_counter() - t0) / 40 * 1e6       # enqueue cost of one call (the device runs behind)
+    torch.cuda.synchronize()
     for e in es:
         e.drone.cta_slots = 0
     flop = FLOP_DRONE_SUBSTEP * K + FLOP_GATE_ENV_STEP
@@ -251,6 +258,7 @@ def leg_config4_gate_race(dev, pk, tm, envs=8192, agents=32, K=8):
     return {"workload": f"BASELINE.json configs[4]: {n} drones = {envs} envs x {agents} agents, {K} substeps x 1 ms, 8-gate track, "
                         "per-env team reward / termination by warp reduction (reward rules: ours, parity unpinned)",
             "ms_isolated": ms_iso, "ms_stream": ms_str, "ms_chained": ms_chained, "ms_two_launches_isolated": ms_two,
+            "host_us_per_call": host_us,
             "agent_steps_per_sec": n / (ms_chained * 1e-3), "env_steps_per_sec": envs / (ms_chained * 1e-3),
             "agent_steps_per_sec_plain_stream_order": n / (ms_str * 1e-3),
             "roofline": _roof(n, ms_chained, flop, byt, pk, "fused gate-race step (fpv_gate_race_step)",

@@ -53,6 +53,7 @@ class GateRaceEnv:
         self._obs_views = None
         self._chain_env = False
         self._fused_args = None
+        self._done_view = None
 
     # -- helpers
     def _obs_dict(self):
@@ -142,7 +143,9 @@ class GateRaceEnv:
             self._chain_env = False
             d.step(act, return_obs=False)      # (also the first call: it configures the drone's io block)
             self._run_env_kernel(d._done)
-        return self._obs_dict(), self._env_reward, self._env_done.view(torch.bool), {}
+        if self._done_view is None:
+            self._done_view = self._env_done.view(torch.bool)      # a view of the persistent flag buffer, built once
+        return self._obs_dict(), self._env_reward, self._done_view, {}
 
     @property
     def next_gate(self):
