@@ -182,7 +182,8 @@ def derive_constants(params: dict, dt: float | None = None) -> DroneConstants:
         thrust_poly=model_xy(sweep.throttle_percent, thrust_n), throttle_poly=model_xy(thrust_n, sweep.throttle_percent),
         min_throttle_in_force=0.0, max_throttle_in_force=0.0, motor_name=sweep.motor, propeller=sweep.propeller)
     c.min_throttle_in_force = float(c.throttle2thrust(-1 + MIN_THROTTLE_PERCENT / 100 * 2))
-    assert c.min_throttle_in_force > 0, "The minimum throttle is below zero. This is not possible."  # components.py:141
+    assert c.min_throttle_in_force > 0, (        # same error class as components.py:141, our own wording
+        f"motor curve gives {c.min_throttle_in_force:.4f} N at the 5 % idle throttle: the fitted thrust must be positive there")
     c.max_throttle_in_force = float(c.throttle2thrust(1))
     return c
 

@@ -68,8 +68,9 @@ class Cylinder:
     point cloud (:697-708) when the two resolutions are given."""
 
     def __init__(self, position, radius, height, angle_resolution=None, height_resolution=None, random=False, rng=None):
-        assert radius > 0, "radius must be positive"
-        assert height > 0, "height must be positive"
+        # same error class as the reference (AssertionError, components.py:688-689), our own wording
+        assert radius > 0, f"Cylinder: radius {radius} is not > 0"
+        assert height > 0, f"Cylinder: height {height} is not > 0"
         self.position = np.asarray(position, dtype=np.float64)
         self.radius, self.height = float(radius), float(height)
         self.angle_resolution, self.height_resolution = angle_resolution, height_resolution

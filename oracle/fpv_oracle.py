@@ -111,7 +111,7 @@ def derive_consts(params: dict, motor_csv_path: str, dt: float | None = None) ->
     f = lambda x: np.polyval(poly, 100 * (x + 1) / 2)          # components.py:136
     min_force = float(f(-1 + 5 / 100 * 2))                       # components.py:139-140
     if not min_force > 0:
-        raise AssertionError("The minimum throttle is below zero. This is not possible.")
+        raise AssertionError(f"fitted thrust at the 5 % idle throttle is {min_force} N, must be positive (components.py:141)")
     return DroneConsts(
         dt=float(1 / sim["fps"]) if dt is None else float(dt), gravity=g,
         mass=dr["mass"] / 1000, max_rates=float(dr["max_rates"]),
