@@ -301,12 +301,23 @@ def leg_general_path(dev, pk, tm, n=1 << 20, K=8):
     out = {"workload": f"mode A general path: {n} drones, {K} substeps x 1 ms, LUT, auto-reset, object_list = 1 sphere target + "
                        "5 cylinders (r 2 m, h 10 m) + ground (the stock world of params.yaml)"}
 
-    def run(spread, zhi, tag, note):
+    def run(spread, zhi, tag, note, clear_of=0.0):
         ds, acts = [], []
         for j in range(4):
             d = BatchedDrone(None, num_envs=n, device=dev, substeps=K, dt=1e-3, auto_reset=True, thrust_lut=2049)
             pos = torch.randn(n, 3, device=dev, generator=g) * spread
             pos[:, 2] = 0.3 + torch.rand(n, device=dev, generator=g) * zhi
+            if clear_of > 0:      # push every spawn point radially out of the obstacles, `clear_of` metres off their surfaces
+                for o in objs[:-1]:
+                    c = torch.as_tensor(np.asarray(o.position, dtype=np.float32), device=dev)
+                    horiz = hasattr(o, "height")
+                    dvec = pos - c
+                    if horiz:
+                        dvec[:, 2] = 0.0
+                    dist = dvec.norm(dim=1).clamp_min(1e-3)
+                    need = float(o.radius) + clear_of
+                    inside = dist < need
+                    pos[inside] = (pos + dvec / dist[:, None] * (need - dist)[:, None])[inside]
             d.reset(pos, torch.randn(n, 3, device=dev, generator=g) * 2, (torch.rand(n, 3, device=dev, generator=g) * 2 - 1) * 30)
             ds.append(d)
             acts.append((torch.rand(n, 4, device=dev, generator=g) * 2 - 1).contiguous())
@@ -318,6 +329,8 @@ def leg_general_path(dev, pk, tm, n=1 << 20, K=8):
 
     run(8.0, 8.0, "contact_heavy", "spawn sigma 8 m around the obstacles: ~20 % of the drones start INSIDE a cylinder, every warp "
                                   "takes the contact path every substep")
+    run(10.0, 8.0, "among_obstacles", "spawn sigma 10 m around the obstacles, every spawn point at least 0.6 m off their surfaces: "
+                                     "drones fly AMONG the obstacles, some brush or hit them during the steps", clear_of=0.6)
     # clear: the same world, drones spawned in a ring 60-80 m from the origin (no obstacle in reach of any drone)
     def run_clear():
         ds, acts = [], []

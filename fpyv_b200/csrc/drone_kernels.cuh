@@ -31,6 +31,7 @@ struct DroneK {
   float motor_xy[4][2];
   float motor_radius;
   float arm_reach;          // max |motor offset| + motor_radius + margin: beyond it an obstacle cannot touch any motor
+  float bound[4];           // a sphere (centre xyz, radius) that contains every obstacle of the list: broad-phase culling
   float spring_k, spring_c; // components.py:198
   float poly[4];            // throttle% -> N, high->low; evaluated at 100*(x+1)/2   components.py:136
   float wind[3];
@@ -155,7 +156,15 @@ __device__ __forceinline__ typename Lane<V>::Mask drone_substeps(const DroneK& k
     const M closes = vle(Kdt * acc_bound(v0 + G), G);      // false for NaN as well
     const V travel = Kdt * (v0 + G);
     const V reach = S<V>(k.arm_reach) + travel;
-    for (int o = 0; o < k.n_objects; ++o) {
+    // broad phase: an env outside the sphere that contains ALL obstacles (grown by its reach) can reach none of them
+    bool any_candidate = true;
+    {
+      const V bx = s.px - S<V>(k.bound[0]), by = s.py - S<V>(k.bound[1]), bz = s.pz - S<V>(k.bound[2]);
+      const V lim = S<V>(k.bound[3]) + reach;
+      const M outside = vand(vlt(lim * lim, vfma(bx, bx, vfma(by, by, bz * bz))), closes);
+      any_candidate = vany(vnot(outside));
+    }
+    for (int o = 0; any_candidate && o < k.n_objects; ++o) {
       const fpv_object_t& ob = k.objects[o];               // warp-uniform index: kernel-parameter constant bank
       const V dx = s.px - S<V>(ob.x), dy = s.py - S<V>(ob.y);
       const V lim = S<V>(ob.a) + reach;

@@ -416,10 +416,23 @@ int prepare_drone(const fpv_drone_params_t* p, const fpv_drone_io_t* io, bool ne
   k.lut_scale = (float)((io->lut_n - 1) * 0.5);
   k.flags = p->flags;
   k.n_objects = p->n_objects;
+  double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};   // bounding box of all obstacles
   for (int i = 0; i < p->n_objects; ++i) {
     k.objects[i] = io->objects[i];
-    if (k.objects[i].kind != FPV_OBJ_SPHERE && k.objects[i].kind != FPV_OBJ_CYLINDER)
-      return fail(FPV_EINVAL, "fpv_drone_step: object %d has unknown kind %d", i, k.objects[i].kind);
+    const fpv_object_t& o = k.objects[i];
+    if (o.kind != FPV_OBJ_SPHERE && o.kind != FPV_OBJ_CYLINDER)
+      return fail(FPV_EINVAL, "fpv_drone_step: object %d has unknown kind %d", i, o.kind);
+    const double r = std::fabs((double)o.a), zlo = o.kind == FPV_OBJ_SPHERE ? o.z - r : std::fmin((double)o.z, (double)o.z + o.b),
+                 zhi = o.kind == FPV_OBJ_SPHERE ? o.z + r : std::fmax((double)o.z, (double)o.z + o.b);
+    lo[0] = std::fmin(lo[0], o.x - r); hi[0] = std::fmax(hi[0], o.x + r);
+    lo[1] = std::fmin(lo[1], o.y - r); hi[1] = std::fmax(hi[1], o.y + r);
+    lo[2] = std::fmin(lo[2], zlo);     hi[2] = std::fmax(hi[2], zhi);
+  }
+  if (p->n_objects > 0) {   // the sphere around that box (plus a margin for the float32 rounding of the test itself)
+    double r2 = 0.0;
+    for (int a = 0; a < 3; ++a) { k.bound[a] = (float)(0.5 * (lo[a] + hi[a])); r2 += 0.25 * (hi[a] - lo[a]) * (hi[a] - lo[a]); }
+    k.bound[3] = (float)(std::sqrt(r2) * 1.0001 + 1e-3);
+    if (!(k.bound[3] < 1e18f)) k.bound[3] = INFINITY;   // non-finite obstacle data: the broad phase never culls
   }
 
   d.state = (float4*)io->state;
