@@ -30,7 +30,9 @@ class _Block:
 
 def pinned(shape, dtype=torch.float32, write_combined=False, pad_to=16):
     """A page-locked CPU tensor of `shape` / `dtype`, its storage padded to a multiple of `pad_to` bytes (the step's bulk
-    copies move multiples of 16 bytes).  The tensor keeps its allocation alive."""
+    copies move multiples of 16 bytes).  The tensor keeps its allocation alive; like any buffer handed to an asynchronous
+    launch it must outlive the work that reads or writes it (synchronise the stream before dropping the last reference --
+    a zero-copy step reads it from the kernel itself)."""
     shape = tuple(int(x) for x in (shape if isinstance(shape, (tuple, list, torch.Size)) else (shape,)))
     n = int(np.prod(shape)) if shape else 1
     item = torch.empty((), dtype=dtype).element_size()
