@@ -207,7 +207,9 @@ def workload_config(n_gpus, **extra):
                      f"chained (FPV_F_CHAINED: no grid-wide wait, state ordered per 64-env chunk) and each takes {CTA_SLOTS or 'all'} "
                      f"of the 4 CTA slots per SM, so launches of consecutive (independent) batches overlap; "
                      f"ms_per_step_chained_full_grid = chained with all slots, ms_per_step_unchained = every launch waits "
-                     f"for the previous grid, ms_per_step_flushed = one isolated launch"}
+                     f"for the previous grid, ms_per_step_two_streams = plain stream order on TWO streams (independent halves of "
+                     f"the population, 2 CTA slots per launch: the closed-loop form; ..._closed_loop: with a stand-in policy kernel "
+                     f"rewriting the batch's actions in front of every step, its time included), ms_per_step_flushed = one isolated launch"}
     c.update(extra)
     return c
 
@@ -317,6 +319,54 @@ def run_gpu(args):
     ms_unchained = timed_rotation(drones, K, W, chained=False)                 # every launch waits for the previous grid
     ms_flushed = timed_loop(drone, min(K, 200), W)
     K_fl = min(K, 200)
+
+    def timed_two_streams(ds, steps, warm, policy=False):
+        """Plain stream order in a form a CLOSED-LOOP trainer can use: the population is split into independent halves
+        (here: batches 0, 2 on one stream and 1, 3 on the other), every launch waits for its predecessor ON ITS STREAM
+        (no chaining, no knowledge of future sticks) and takes 2 of the 4 CTA slots per SM, so the two streams' launches run
+        side by side and the start-up / tail of one stream's launch is covered by the other stream's bulk.
+        policy=True puts a stand-in policy kernel in front of every step ON THE SAME STREAM (it rewrites that batch's 16 MiB
+        action buffer after the batch's previous step has finished -- a real policy would read the new state there), so the
+        loop is closed: no launch can start before the previous step of its batch AND the policy that followed it are done."""
+        sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+        acts_b = [torch.empty_like(ring[0]) for _ in ds] if policy else None
+        for d_ in ds:
+            d_.cta_slots = 2
+        cur = torch.cuda.current_stream()
+
+        def run(count):
+            for i in range(count):
+                with torch.cuda.stream(sa if i % 2 == 0 else sb):
+                    if policy:
+                        j = i % len(ds)
+                        acts_b[j].copy_(ring[(i // len(ds) + j) % 4])
+                        ds[j].step(acts_b[j], return_obs=False)
+                    else:
+                        ds[i % len(ds)].step(ring[i % 4], return_obs=False)
+        sa.wait_stream(cur)
+        sb.wait_stream(cur)
+        run(warm + (warm % 2))
+        cur.wait_stream(sa)
+        cur.wait_stream(sb)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda._sleep(SPIN_CYCLES)
+        e0.record()
+        sa.wait_stream(cur)
+        sb.wait_stream(cur)
+        run(steps)
+        cur.wait_stream(sa)
+        cur.wait_stream(sb)
+        e1.record()
+        torch.cuda.synchronize()
+        for d_ in ds:
+            d_.cta_slots = 0
+        return e0.elapsed_time(e1)
+
+    ms_two_streams = timed_two_streams(drones, K, W)
+    ms_two_streams_policy = timed_two_streams(drones, K, W, policy=True)
 
     if args.profile:      # ncu / launch-list runs: only the kernel loops (K=8 then K=1)
         if sampler:
@@ -500,12 +550,12 @@ def run_gpu(args):
                 extra["config3_sharded"] = {"error": f"{type(e).__name__}: {e}"}
             dist.barrier()
         extra.update(bench_legs.run_extra(dev, pk_legs, world, rank))
-    t = torch.tensor([ms, ms_e2e, ms_k1, ms_rollout, ms_full_grid, ms_unchained, ms_e2e_sticks], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, ms_e2e, ms_k1, ms_rollout, ms_full_grid, ms_unchained, ms_e2e_sticks, ms_two_streams, ms_two_streams_policy], dtype=torch.float64, device=dev)
     t_forms = torch.tensor([ms_e2e_zero, ms_e2e_sliced] + [ms_st[k_] for k_ in sorted(ms_st)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(t_forms, op=dist.ReduceOp.MAX)
-    ms, ms_e2e, ms_k1, ms_rollout, ms_full_grid, ms_unchained, ms_e2e_sticks = t.tolist()
+    ms, ms_e2e, ms_k1, ms_rollout, ms_full_grid, ms_unchained, ms_e2e_sticks, ms_two_streams, ms_two_streams_policy = t.tolist()
     ms_e2e_zero, ms_e2e_sliced = t_forms.tolist()[:2]
     ms_st = dict(zip(sorted(ms_st), t_forms.tolist()[2:]))
     ms_e2e, ms_e2e_sticks = min(ms_e2e_zero, ms_e2e_sliced), min(ms_st.values())
@@ -534,6 +584,8 @@ def run_gpu(args):
             "algorithmic": f"{FLOP_PER_ENV_SUBSTEP} flop/env/substep x {SUBSTEPS} substeps x {n} envs per launch",
             "frac_chained_full_grid": FLOP_PER_ENV_SUBSTEP * SUBSTEPS * n / (ms_full_grid * 1e-3 / K) / 1e12 / fp32_peak,
             "frac_unchained": FLOP_PER_ENV_SUBSTEP * SUBSTEPS * n / (ms_unchained * 1e-3 / K) / 1e12 / fp32_peak,
+            "frac_two_streams": FLOP_PER_ENV_SUBSTEP * SUBSTEPS * n / (ms_two_streams * 1e-3 / K) / 1e12 / fp32_peak,
+            "frac_two_streams_closed_loop": FLOP_PER_ENV_SUBSTEP * SUBSTEPS * n / (ms_two_streams_policy * 1e-3 / K) / 1e12 / fp32_peak,
             "frac_isolated_launch": FLOP_PER_ENV_SUBSTEP * SUBSTEPS * n / (ms_flushed_per_step * 1e-3) / 1e12 / fp32_peak,
             "peak_measured": dict(peak_meas, unit="TFLOP/s", frac_of_measured_scalar=fp32_ach / peak_meas["ffma_scalar_tflops"],
                                   how="fpv_probe_fp32: SMs x 8 CTAs x 256 threads x 4096 iterations x 16 independent FMA chains with "
@@ -582,6 +634,7 @@ def run_gpu(args):
                                       "itself reads the sticks from host memory and calibrates them in registers; extra metric"},
             "ms_per_step_flushed": ms_flushed_per_step,
             "ms_per_step_chained_full_grid": ms_full_grid / K, "ms_per_step_unchained": ms_unchained / K,
+            "ms_per_step_two_streams": ms_two_streams / K, "ms_per_step_two_streams_closed_loop": ms_two_streams_policy / K,
             "rollout_fused": {"ms_per_step": ms_rollout, "env_steps_per_sec": total_envs / (ms_rollout * 1e-3),
                               "steps_per_launch": T_ro, "fp32_frac": FLOP_PER_ENV_SUBSTEP * SUBSTEPS * n / (ms_rollout * 1e-3) / 1e12 / (sm_count * FP32_LANES_PER_SM * 2 * pk["sm_max_mhz"] * 1e6 / 1e12),
                               "api": "BatchedDrone.rollout(actions[16, n, 4]): fpv_drone_rollout, bit-identical to 16 step() calls; "
