@@ -36,12 +36,19 @@ struct AcroK {
   unsigned flags;
 };
 
+// Table index without float<->int conversions (F2I / I2F / FRND run on the quarter-rate XU pipe, and mode C does four
+// lookups per substep): t = (x - 0.5) + 1.5 * 2^23 rounds x - 0.5 to the nearest integer INTO THE MANTISSA of t, so the
+// index is t's low bits and its float value is t - 1.5 * 2^23.  The rounding is to nearest-even, so the index is floor(x)
+// or -- at an exact knot -- floor(x) - 1 with f = 1: the interpolation is continuous, the result is the same.  u is
+// clamped to [u_min, u_max] within [-1, 1] (checked by the host), so 0 <= x <= lut_n - 1 and the index can reach
+// lut_n - 1 (with f = 0): the staged table carries one padding entry behind its last.
+#define FPV_LUT_MAGIC 12582912.f
 __device__ __forceinline__ float acro_motor_thrust(const AcroK& k, const float* lut_s, float u) {
   if (k.flags & FPV_F_THRUST_LUT) {
-    float x = (u + 1.f) * k.lut_scale;
-    int i = (int)floorf(x);
-    i = max(0, min(i, k.lut_n - 2));
-    const float f = x - (float)i;
+    const float x = fmaf(u, k.lut_scale, k.lut_scale);
+    const float t = (x - 0.5f) + FPV_LUT_MAGIC;
+    const float f = x - (t - FPV_LUT_MAGIC);
+    const int i = __float_as_int(t) & 0x3fffff;
     const float a = lut_s[i], b = lut_s[i + 1];
     return 0.25f * fmaf(f, b - a, a);
   }
@@ -49,6 +56,11 @@ __device__ __forceinline__ float acro_motor_thrust(const AcroK& k, const float* 
   float p = fmaf(k.poly[0], pct, k.poly[1]);
   p = fmaf(p, pct, k.poly[2]);
   return 0.25f * fmaf(p, pct, k.poly[3]);
+}
+
+// the motor-curve table as both step kernels stage it: lut_n entries + one copy of the last (see above)
+__device__ __forceinline__ void acro_stage_lut(const AcroK& k, const float* lut, float* lut_s, int tid, int nthreads) {
+  for (int i = tid; i <= k.lut_n; i += nthreads) lut_s[i] = lut[min(i, k.lut_n - 1)];
 }
 
 __global__ void acro_reset_kernel(float4* state, long long n, long long stride, const float* pos, const float* vel,
@@ -79,10 +91,15 @@ template <> __device__ __forceinline__ float acro_motor_thrust_v<float>(const Ac
   return acro_motor_thrust(k, lut_s, u);
 }
 template <> __device__ __forceinline__ F2 acro_motor_thrust_v<F2>(const AcroK& k, const float* lut_s, F2 u) {
-  if (k.flags & FPV_F_THRUST_LUT) {   // table lookups are per lane
-    float a, b;
-    f2_unpack(u, a, b);
-    return f2_pack(acro_motor_thrust(k, lut_s, a), acro_motor_thrust(k, lut_s, b));
+  if (k.flags & FPV_F_THRUST_LUT) {   // the index arithmetic and the interpolation packed, the two lookups per lane
+    const F2 x = vfma(u, S<F2>(k.lut_scale), S<F2>(k.lut_scale));
+    const F2 t = (x - S<F2>(0.5f)) + S<F2>(FPV_LUT_MAGIC);
+    const F2 f = x - (t - S<F2>(FPV_LUT_MAGIC));
+    float t0, t1;
+    f2_unpack(t, t0, t1);
+    const int i0 = __float_as_int(t0) & 0x3fffff, i1 = __float_as_int(t1) & 0x3fffff;
+    const F2 a = f2_pack(lut_s[i0], lut_s[i1]), b = f2_pack(lut_s[i0 + 1], lut_s[i1 + 1]);
+    return vfma(f, b - a, a) * S<F2>(0.25f);
   }
   const F2 pct = vfma(u, S<F2>(50.f), S<F2>(50.f));
   F2 p = vfma(S<F2>(k.poly[0]), pct, S<F2>(k.poly[1]));
@@ -323,7 +340,7 @@ __global__ void __launch_bounds__(THREADS) acro_step_kernel(const __grid_constan
   constexpr int TILE = THREADS * L;
   extern __shared__ float lut_s[];
   if (k.flags & FPV_F_THRUST_LUT) {
-    for (int i = threadIdx.x; i < k.lut_n; i += THREADS) lut_s[i] = lut[i];
+    acro_stage_lut(k, lut, lut_s, threadIdx.x, THREADS);
     __syncthreads();
   }
   const long long base = (long long)blockIdx.x * TILE + threadIdx.x;
@@ -378,8 +395,7 @@ struct AcroMode {
   }
   static __device__ __forceinline__ void stage(const K& k, const IO& io, unsigned char* smem, int tid, int nthreads) {
     float* lut_s = reinterpret_cast<float*>(smem);
-    if (k.flags & FPV_F_THRUST_LUT)
-      for (int i = tid; i < k.lut_n; i += nthreads) lut_s[i] = io.lut[i];
+    if (k.flags & FPV_F_THRUST_LUT) acro_stage_lut(k, io.lut, lut_s, tid, nthreads);
   }
   static __device__ __forceinline__ Ctx begin(const K&, const IO&) { return Ctx{TileStats{0.f, 0.f, 0.f, 0.f, 0.f}}; }
   template <class PreStore>

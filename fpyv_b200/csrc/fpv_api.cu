@@ -1082,6 +1082,8 @@ int acro_launch(const fpv_acro_params_t* p, void* state, int64_t n, int64_t plan
     if ((size_t)lut_n * sizeof(float) > 200 * 1024) return fail(FPV_EINVAL, "fpv_acro_step: lut_n=%d does not fit in shared memory", lut_n);
   }
   if (!(p->u_min < p->u_max)) return fail(FPV_EINVAL, "fpv_acro_step: u_min must be below u_max");
+  if ((p->flags & FPV_F_THRUST_LUT) && !(p->u_min >= -1.f && p->u_max <= 1.f))
+    return fail(FPV_EINVAL, "fpv_acro_step: with FPV_F_THRUST_LUT the motor throttle limits must lie in [-1, 1] (the table's range)");
   fpv::AcroK k;
   std::memset(&k, 0, sizeof(k));
   k.dt = p->dt; k.inv_dt = (float)(1.0 / (double)p->dt); k.substeps = p->substeps;
@@ -1119,7 +1121,7 @@ int acro_launch(const fpv_acro_params_t* p, void* state, int64_t n, int64_t plan
   k.motor_radius = p->motor_radius; k.spring_k = p->spring_k;
   k.flags = p->flags;
   if (n == 0) return FPV_OK;
-  const size_t smem = (p->flags & FPV_F_THRUST_LUT) ? sizeof(float) * (size_t)lut_n : 0;
+  const size_t smem = (p->flags & FPV_F_THRUST_LUT) ? sizeof(float) * ((size_t)lut_n + 1) : 0;   // + the padding entry
   auto launch = [&](auto kern, int envs_per_thread) {
     static SmemOptIn opted;
     opt_in_smem(kern, opted, smem);
