@@ -320,7 +320,9 @@ __device__ __forceinline__ typename Lane<V>::Mask drone_substeps(const DroneK& k
             const V dm = object_distance<V>(ob, wxm, wym, wzm);
             hit = vor(hit, vlt(dm, zero));
             const V pen = dm - S<V>(k.motor_radius);
-            const M act = vlt(pen, zero);
+            // an env this object has already penetrated (an earlier motor, or this one) gets nothing from it (`live`
+            // below), so it does not ask for the normals
+            const M act = vand(vlt(pen, zero), vnot(hit));
             if (vany(act)) {   // spring force of a motor inside the contact shell, :207-214
               V nx, ny, nz;
               object_normal<V>(ob, wxm, wym, wzm, nx, ny, nz);
