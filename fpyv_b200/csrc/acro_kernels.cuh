@@ -29,6 +29,7 @@ struct AcroK {
   int lut_n;
   float rc_cen[3], rc_span[3], rc_expo[3];   // stick curve: centre sensitivity, max(0, max - centre), expo (FPV_F_RATE_CURVE)
   float kd[3];            // k_drag, kinematics.py:36
+  float kd_a, kd_b;       // kd[1] - kd[0], kd[2] - kd[0] (column form of the drag, see acro_body)
   float wind[3];
   float grav_z;           // -g m
   float inv_mass;
@@ -43,19 +44,32 @@ struct AcroK {
 // clamped to [u_min, u_max] within [-1, 1] (checked by the host), so 0 <= x <= lut_n - 1 and the index can reach
 // lut_n - 1 (with f = 0): the staged table carries one padding entry behind its last.
 #define FPV_LUT_MAGIC 12582912.f
-__device__ __forceinline__ float acro_motor_thrust(const AcroK& k, const float* lut_s, float u) {
-  if (k.flags & FPV_F_THRUST_LUT) {
-    const float x = fmaf(u, k.lut_scale, k.lut_scale);
-    const float t = (x - 0.5f) + FPV_LUT_MAGIC;
-    const float f = x - (t - FPV_LUT_MAGIC);
-    const int i = __float_as_int(t) & 0x3fffff;
-    const float a = lut_s[i], b = lut_s[i + 1];
-    return 0.25f * fmaf(f, b - a, a);
-  }
-  const float pct = fmaf(u, 50.f, 50.f);
-  float p = fmaf(k.poly[0], pct, k.poly[1]);
-  p = fmaf(p, pct, k.poly[2]);
-  return 0.25f * fmaf(p, pct, k.poly[3]);
+template <class V> __device__ __forceinline__ V acro_thrust_lut(const AcroK& k, const float* lut_s, V u);
+template <> __device__ __forceinline__ float acro_thrust_lut<float>(const AcroK& k, const float* lut_s, float u) {
+  const float x = fmaf(u, k.lut_scale, k.lut_scale);
+  const float t = (x - 0.5f) + FPV_LUT_MAGIC;
+  const float f = x - (t - FPV_LUT_MAGIC);
+  const int i = __float_as_int(t) & 0x3fffff;
+  const float a = lut_s[i], b = lut_s[i + 1];
+  return 0.25f * fmaf(f, b - a, a);
+}
+template <> __device__ __forceinline__ F2 acro_thrust_lut<F2>(const AcroK& k, const float* lut_s, F2 u) {
+  // the index arithmetic and the interpolation packed, the two lookups per lane
+  const F2 x = vfma(u, S<F2>(k.lut_scale), S<F2>(k.lut_scale));
+  const F2 t = (x - S<F2>(0.5f)) + S<F2>(FPV_LUT_MAGIC);
+  const F2 f = x - (t - S<F2>(FPV_LUT_MAGIC));
+  float t0, t1;
+  f2_unpack(t, t0, t1);
+  const int i0 = __float_as_int(t0) & 0x3fffff, i1 = __float_as_int(t1) & 0x3fffff;
+  const F2 a = f2_pack(lut_s[i0], lut_s[i1]), b = f2_pack(lut_s[i0 + 1], lut_s[i1 + 1]);
+  return vfma(f, b - a, a) * S<F2>(0.25f);
+}
+// 4-motor bench cubic / 4 (components.py:136)
+template <class V> __device__ __forceinline__ V acro_thrust_poly(const AcroK& k, V u) {
+  const V pct = vfma(u, S<V>(50.f), S<V>(50.f));
+  V p = vfma(S<V>(k.poly[0]), pct, S<V>(k.poly[1]));
+  p = vfma(p, pct, S<V>(k.poly[2]));
+  return vfma(p, pct, S<V>(k.poly[3])) * S<V>(0.25f);
 }
 
 // the motor-curve table as both step kernels stage it: lut_n entries + one copy of the last (see above)
@@ -84,27 +98,6 @@ __global__ void acro_reset_kernel(float4* state, long long n, long long stride, 
   state[4 * stride + e] = zero;
   state[5 * stride + e] = zero;
   state[6 * stride + e] = zero;
-}
-
-template <class V> __device__ __forceinline__ V acro_motor_thrust_v(const AcroK& k, const float* lut_s, V u);
-template <> __device__ __forceinline__ float acro_motor_thrust_v<float>(const AcroK& k, const float* lut_s, float u) {
-  return acro_motor_thrust(k, lut_s, u);
-}
-template <> __device__ __forceinline__ F2 acro_motor_thrust_v<F2>(const AcroK& k, const float* lut_s, F2 u) {
-  if (k.flags & FPV_F_THRUST_LUT) {   // the index arithmetic and the interpolation packed, the two lookups per lane
-    const F2 x = vfma(u, S<F2>(k.lut_scale), S<F2>(k.lut_scale));
-    const F2 t = (x - S<F2>(0.5f)) + S<F2>(FPV_LUT_MAGIC);
-    const F2 f = x - (t - S<F2>(FPV_LUT_MAGIC));
-    float t0, t1;
-    f2_unpack(t, t0, t1);
-    const int i0 = __float_as_int(t0) & 0x3fffff, i1 = __float_as_int(t1) & 0x3fffff;
-    const F2 a = f2_pack(lut_s[i0], lut_s[i1]), b = f2_pack(lut_s[i0 + 1], lut_s[i1 + 1]);
-    return vfma(f, b - a, a) * S<F2>(0.25f);
-  }
-  const F2 pct = vfma(u, S<F2>(50.f), S<F2>(50.f));
-  F2 p = vfma(S<F2>(k.poly[0]), pct, S<F2>(k.poly[1]));
-  p = vfma(p, pct, S<F2>(k.poly[2]));
-  return vfma(p, pct, S<F2>(k.poly[3])) * S<F2>(0.25f);
 }
 
 // sin(a)/a and cos(a) of the half rotation angle from a^2.  |a| < 0.1 (|omega| < 200 rad/s at dt = 1 ms): series to a^6
@@ -216,12 +209,23 @@ __device__ __forceinline__ void acro_body(const AcroK& k, float4* state, long lo
     notfirst = one;
     // ---- mixer in throttle units, per-motor saturation, bench curve (shared-memory LUT) -> per-motor thrust
     V tx = zero, ty = zero, tz = zero, fsum = zero;
+    V u4[4];
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
-      V u = vfma(S<V>(k.mix[m][0]), pid[0], vfma(S<V>(k.mix[m][1]), pid[1], vfma(S<V>(k.mix[m][2]), pid[2], thr)));
-      u = vmin(vmax(u, S<V>(k.u_min)), S<V>(k.u_max));
-      const V f = acro_motor_thrust_v<V>(k, lut_s, u);
-      fm[m] = f;
+      const V u = vfma(S<V>(k.mix[m][0]), pid[0], vfma(S<V>(k.mix[m][1]), pid[1], vfma(S<V>(k.mix[m][2]), pid[2], thr)));
+      u4[m] = vmin(vmax(u, S<V>(k.u_min)), S<V>(k.u_max));
+    }
+    // ONE branch on the table flag around all four motors, so that the eight table reads of a lane are in flight together
+    if (k.flags & FPV_F_THRUST_LUT) {
+#pragma unroll
+      for (int m = 0; m < 4; ++m) fm[m] = acro_thrust_lut<V>(k, lut_s, u4[m]);
+    } else {
+#pragma unroll
+      for (int m = 0; m < 4; ++m) fm[m] = acro_thrust_poly<V>(k, u4[m]);
+    }
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const V f = fm[m];
       fsum = fsum + f;
       tx = vfma(S<V>(k.motor_xy[m][1]), f, tx);     // arm x thrust: roll torque  =  sum y_m f_m
       ty = vfma(S<V>(-k.motor_xy[m][0]), f, ty);    //               pitch torque = -sum x_m f_m
@@ -232,27 +236,35 @@ __device__ __forceinline__ void acro_body(const AcroK& k, float4* state, long lo
     const V wd0 = (tx - vfma(w[1], Iw2, vneg(w[2] * Iw1))) * S<V>(k.inv_inertia[0]);
     const V wd1 = (ty - vfma(w[2], Iw0, vneg(w[0] * Iw2))) * S<V>(k.inv_inertia[1]);
     const V wd2 = (tz - vfma(w[0], Iw1, vneg(w[1] * Iw0))) * S<V>(k.inv_inertia[2]);
-    // ---- the reference's force model on the current attitude (components.py:233-243)
-    const V two = S<V>(2.f);
-    const V xx = qx * qx, yy = qy * qy, zz = qz * qz, xy = qx * qy, xz = qx * qz, yz = qy * qz;
-    const V wx_ = qw * qx, wy_ = qw * qy, wz_ = qw * qz;
-    const V R0 = vfma(vneg(two), yy + zz, one), R1 = two * (xy - wz_), R2 = two * (xz + wy_);
-    const V R3 = two * (xy + wz_), R4 = vfma(vneg(two), xx + zz, one), R5 = two * (yz - wx_);
-    const V R6 = two * (xz - wy_), R7 = two * (yz + wx_), R8 = vfma(vneg(two), xx + yy, one);
+    // ---- the reference's force model on the current attitude (components.py:233-243), in mode A's column form
+    //      (drone_kernels.cuh): R diag(k)|u| R^T u = |u| (k0 u + (k1-k0)(c1.u) c1 + (k2-k0)(c2.u) c2) needs only the columns
+    //      c1, c2 of R(q) (plus R[2][0] for the motor heights); the thrust rides on the c2 coefficient.  Every "2 q_a q_b"
+    //      of the matrix is one product with the doubled component (2 q is exact, so K substeps in one step and K steps
+    //      of one substep still give the same bits).
+    const V nqw = vneg(qw);
+    const V dqx = qx + qx, dqy = qy + qy, dqz = qz + qz;
+    const V xz = qx * dqz, yz = qy * dqz, xy = qx * dqy;
+    const V r02 = vfma(qw, dqy, xz), r20 = vfma(nqw, dqy, xz);
+    const V r21 = vfma(qw, dqx, yz), r12 = vfma(nqw, dqx, yz);
+    const V r01 = vfma(nqw, dqz, xy);
+    const V t1 = vfma(vneg(qx), dqx, one);
+    const V r11 = vfma(vneg(qz), dqz, t1), r22 = vfma(vneg(qy), dqy, t1);
     const V ux = vx + S<V>(k.wind[0]), uy = vy + S<V>(k.wind[1]), uz = vz + S<V>(k.wind[2]);   // kinematics.py:34 (PLUS wind)
     const V nrm = vsqrt_fast(vfma(ux, ux, vfma(uy, uy, uz * uz)));
-    const V b0 = (S<V>(k.kd[0]) * nrm) * vfma(R0, ux, vfma(R3, uy, R6 * uz));
-    const V b1 = (S<V>(k.kd[1]) * nrm) * vfma(R1, ux, vfma(R4, uy, R7 * uz));
-    const V b2 = vfma(S<V>(k.kd[2]) * nrm, vfma(R2, ux, vfma(R5, uy, R8 * uz)), fsum);   // thrust rides on body z
-    const V Fx = vfma(R0, b0, vfma(R1, b1, R2 * b2));
-    const V Fy = vfma(R3, b0, vfma(R4, b1, R5 * b2));
-    V Fz = vfma(R6, b0, vfma(R7, b1, vfma(R8, b2, S<V>(k.grav_z))));
+    const V d1 = vfma(r01, ux, vfma(r11, uy, r21 * uz));
+    const V d2 = vfma(r02, ux, vfma(r12, uy, r22 * uz));
+    const V ks = S<V>(k.kd[0]) * nrm;
+    const V g1 = (S<V>(k.kd_a) * nrm) * d1;
+    const V g2 = vfma(S<V>(k.kd_b) * nrm, d2, fsum);
+    const V Fx = vfma(g2, r02, vfma(g1, r01, ks * ux));
+    const V Fy = vfma(g2, r12, vfma(g1, r11, ks * uy));
+    V Fz = vfma(g2, r22, vfma(g1, r21, vfma(ks, uz, S<V>(k.grav_z))));
     if (k.flags & FPV_F_GROUND) {   // components.py:198-214, :239 with the plane z = 0
       M crashed = vlt(one, zero);
       V comp = zero;
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
-        const V mz = vfma(S<V>(k.motor_xy[m][0]), R6, vfma(S<V>(k.motor_xy[m][1]), R7, pz));
+        const V mz = vfma(S<V>(k.motor_xy[m][0]), r20, vfma(S<V>(k.motor_xy[m][1]), r21, pz));
         crashed = vor(crashed, vlt(mz, zero));
         comp = comp + vmax(S<V>(k.motor_radius) - mz, zero);   // spring compression of motor m
       }

@@ -1112,6 +1112,8 @@ int acro_launch(const fpv_acro_params_t* p, void* state, int64_t n, int64_t plan
     k.mix[m][2] = p->spin[m];
     k.spin_kappa[m] = p->spin[m] * p->kappa;
   }
+  k.kd_a = (float)((double)p->k_drag[1] - (double)p->k_drag[0]);
+  k.kd_b = (float)((double)p->k_drag[2] - (double)p->k_drag[0]);
   k.u_min = p->u_min; k.u_max = p->u_max;
   for (int i = 0; i < 4; ++i) k.poly[i] = p->thrust_poly[i];
   k.lut_n = (p->flags & FPV_F_THRUST_LUT) ? lut_n : 0;
