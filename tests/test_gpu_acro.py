@@ -140,6 +140,37 @@ def test_ground_crash_auto_reset_and_errors():
         bad = BatchedAcroDrone(None, num_envs=4, device=DEV, inertia=[0.0, 1e-3, 1e-3])
         bad.reset(np.zeros((4, 3)), np.zeros((4, 3)), np.zeros((4, 3)))
         bad.step(np.zeros((4, 4)))
+    with pytest.raises(FpvError):            # the table covers throttle [-1, 1]: limits outside it are refused, not extrapolated
+        bad = BatchedAcroDrone(None, num_envs=4, device=DEV, u_max=1.2, thrust_lut=2049)
+        bad.reset(np.zeros((4, 3)), np.zeros((4, 3)), np.zeros((4, 3)))
+        bad.step(np.zeros((4, 4)))
+
+
+@pytest.mark.parametrize("lut_n", [2, 3, 2048, 2049])
+def test_motor_table_ends_and_knots(lut_n):
+    """The table index comes out of the float mantissa (acro_thrust_lut): full throttle lands on the LAST entry (index lut_n - 1,
+    interpolation weight 0 -- the staged table carries a padding entry there), idle on the first, and a throttle exactly on a
+    knot returns that entry.  Gains are zero, so every motor sees the filtered collective throttle only."""
+    from fpyv_b200 import BatchedAcroDrone
+    n = 64
+    zero_gains = [[0.0, 0.0, 0.0]] * 3
+    d = BatchedAcroDrone(None, num_envs=n, device=DEV, substeps=1, dt=1e-3, thrust_lut=lut_n, u_min=-1.0, u_max=1.0, gains=zero_gains)
+    table = d._lut.double().cpu().numpy()
+    pos = np.tile([0.0, 0.0, 50.0], (n, 1))
+    d.reset(pos, np.zeros((n, 3)), np.zeros((n, 3)))
+    knots = np.linspace(-1.0, 1.0, lut_n)
+    thr = np.resize(np.concatenate([[1.0, -1.0], knots[:: max(1, lut_n // 16)], np.random.default_rng(3).uniform(-1, 1, 32)]), n)
+    d.throttle.copy_(torch.as_tensor(thr, dtype=torch.float32, device=DEV))
+    act = np.zeros((n, 4))
+    act[:, 3] = thr                          # the low-pass filter of a throttle equal to its input is the identity
+    d.step(act)
+    x = (d.throttle.double().cpu().numpy() + 1.0) * (lut_n - 1) * 0.5
+    i = np.clip(np.floor(x).astype(int), 0, lut_n - 2)
+    want = (table[i] + (x - i) * (table[i + 1] - table[i])) / 4.0
+    got = d.motor_thrust.double().cpu().numpy()
+    assert np.isfinite(got).all()
+    np.testing.assert_allclose(got, np.repeat(want[:, None], 4, 1), rtol=3e-6, atol=3e-6)
+    assert abs(got[0, 0] - table[-1] / 4.0) <= 1e-6 * abs(table[-1]) and abs(got[1, 0] - table[0] / 4.0) <= 1e-6
 
 
 @pytest.mark.parametrize("n", [1, 127, 129, 1000])
