@@ -241,7 +241,7 @@ def leg_config1_small(dev, pk, tm, n=4096, K=8):
             "env_steps_per_sec": {"step_call": n / us_step * 1e6, "cuda_graph_16_steps": n / us_graph * 1e6,
                                   "rollout_64_steps_per_launch": n / us_roll * 1e6},
             "roofline": dict(_roof(n, best * 1e-3, FLOP_DRONE_SUBSTEP * K, 17 if best == us_roll else BYTES_DRONE_STEP, pk,
-                                   "drone_rollout_kernel" if best == us_roll else "drone_step_tma_kernel", "best of the three forms"),
+                                   "drone_rollout_kernel" if best == us_roll else "ring_step_kernel<DroneMode hot path>", "best of the three forms"),
                              note=f"{n} envs = {n // 64} warp-chunks on 2,368 resident warps: latency-bound by construction "
                                   "(one chunk's 8 substeps are a dependent chain); the fraction is reported for completeness")}
 
@@ -532,7 +532,7 @@ def leg_config3_sharded(dev, pk, tm, world, rank, K=8, total=1 << 24, steps=12):
                        "LUT, ground, auto-reset; plain stream order (state >> L2); statistics all-reduced over NCCL after the loop",
            "envs_per_gpu": n, "total_envs": total, "ms_per_step": ms, "env_steps_per_sec": total / (ms * 1e-3),
            "env_substeps_per_sec": total * K / (ms * 1e-3), "stats_allreduce_ms_incl_d2h": e2.elapsed_time(e3) / 10,
-           "roofline": _roof(n, ms, FLOP_DRONE_SUBSTEP * K, BYTES_DRONE_STEP, pk, "drone_step_tma_kernel", "plain stream order, max over ranks"),
+           "roofline": _roof(n, ms, FLOP_DRONE_SUBSTEP * K, BYTES_DRONE_STEP, pk, "ring_step_kernel<DroneMode hot path>", "plain stream order, max over ranks"),
            "episode_stats": stats}
     del d, acts
     torch.cuda.empty_cache()
