@@ -5,7 +5,7 @@ from . import config
 from ._lib import FpvError
 
 __all__ = ["config", "FpvError", "BatchedDrone", "Drone", "BatchedRacer", "Racer", "Joystick", "Ground",
-           "Cylinder", "Target", "Gate", "BatchedCamera", "World", "Autopilot", "PID", "BatchedAcroDrone"]
+           "Cylinder", "Target", "Gate", "BatchedCamera", "World", "Autopilot", "PID", "BatchedAcroDrone", "TwoStreamDrones"]
 
 
 def __getattr__(name):
@@ -27,6 +27,9 @@ def __getattr__(name):
     if name in ("Autopilot", "PID"):
         from . import autopilot
         return getattr(autopilot, name)
+    if name == "TwoStreamDrones":
+        from .closed_loop import TwoStreamDrones
+        return TwoStreamDrones
     if name == "BatchedAcroDrone":
         from .acro import BatchedAcroDrone
         return BatchedAcroDrone

@@ -339,3 +339,40 @@ def test_static_world_steps_on_the_fast_path_and_chains():
     a.step(acts[0], return_obs=False)
     b.step(acts[0], return_obs=False)
     assert torch.equal(a._state, b._state)
+
+
+@pytest.mark.parametrize("parts,n", [(2, 200_000), (4, 70_001), (1, 5_000)])
+def test_two_stream_population_equals_one_batch(parts, n):
+    """`TwoStreamDrones`: the population split over CUDA streams (closed-loop form of side-by-side launches), policy and step
+    of every part on the part's own stream.  The envs are independent, so state, flags and statistics equal those of ONE
+    BatchedDrone given the same per-env sticks, bit for bit -- through crashes and restarts, with a state-dependent policy."""
+    from fpyv_b200 import BatchedDrone, TwoStreamDrones
+    rng = np.random.default_rng(5)
+    pos = np.stack([rng.normal(0, 5, n), rng.normal(0, 5, n), rng.uniform(0.05, 3.0, n)], 1)
+    vel, rpy = rng.normal(0, 1, (n, 3)), rng.uniform(-30, 30, (n, 3))
+    kw = dict(device=DEV, substeps=8, dt=1e-3, auto_reset=True, thrust_lut=2049)
+    one = BatchedDrone(None, num_envs=n, **kw)
+    pop = TwoStreamDrones(None, num_envs=n, parts=parts, **kw)
+    assert [d.cta_slots for d in pop.parts] == [4 // parts if parts > 1 else 0] * parts and sum(d.num_envs for d in pop.parts) == n
+    one.reset(pos, vel, rpy)
+    pop.reset(torch.as_tensor(pos, dtype=torch.float32, device=DEV), vel, rpy)
+    noise = torch.as_tensor(rng.uniform(-1, 1, (n, 4)), dtype=torch.float32, device=DEV)
+
+    def sticks(d, extra):          # depends on the CURRENT state: the loop is closed
+        a = extra.clone()
+        a[:, :3] = (a[:, :3] + 0.5 * d.prev_rates / d.max_rates).clamp(-1, 1)
+        a[:, 3] = (a[:, 3] + 0.3 * (1.5 - d.position[:, 2])).clamp(-1, 1)
+        return a
+
+    for t in range(25):
+        one.step(sticks(one, noise), return_obs=False)
+        pop.step(lambda d, i: sticks(d, noise[pop.bounds[i]:pop.bounds[i + 1]]))
+    assert torch.equal(pop.position, one.position) and torch.equal(pop.velocity, one.velocity)
+    assert torch.equal(pop.quaternion, one.quaternion) and torch.equal(pop.done, one.done)
+    a, b = pop.episode_stats(), one.episode_stats()
+    assert a["crashes"] == b["crashes"] > 0 and a["env_steps"] == b["env_steps"]
+    pop.step_actions(noise)
+    one.step(noise, return_obs=False)
+    assert torch.equal(pop.position, one.position)
+    with pytest.raises(ValueError):
+        TwoStreamDrones(None, num_envs=n, parts=3, **kw)
