@@ -116,6 +116,17 @@ def motor_thrust_curve(c: AcroConsts, u, lut=None):
     return (lut[i] + f * (lut[i + 1] - lut[i])) / 4.0
 
 
+def rate_pid(c: AcroConsts, s: AcroState, err, dt):
+    """PID.step (racer_drone_test.py:22-32: no derivative term on the first call) on the rate error, plus a clamp on the
+    integrator; updates the PID state in `s`.  tests/test_acro_oracle_pieces.py pins it to the Racer restatement."""
+    lim = c.integral_limit / np.maximum(c.gains[:, 1], 1e-12)
+    s.integral = np.clip(s.integral + err * dt, -lim, lim)
+    der = np.where(s.first[:, None], 0.0, (err - s.e_prev) / dt)
+    s.e_prev = err
+    s.first = np.zeros(len(err), dtype=bool)
+    return c.gains[:, 0] * err + c.gains[:, 1] * s.integral + c.gains[:, 2] * der
+
+
 def acro_substep(c: AcroConsts, s: AcroState, action, wind=None, dt=None, lut=None):
     b = c.base
     dt = b.dt if dt is None else dt
@@ -128,13 +139,7 @@ def acro_substep(c: AcroConsts, s: AcroState, action, wind=None, dt=None, lut=No
     s.throttle = action[:, 3] * b.ttr + s.throttle * (1 - b.ttr)
     sp = np.deg2rad(s.rate_sp)
     # --- rate PID (racer_drone_test.py:22-32) with an integrator clamp
-    err = sp - s.omega
-    s.integral = np.clip(s.integral + err * dt, -c.integral_limit / np.maximum(c.gains[:, 1], 1e-12),
-                         c.integral_limit / np.maximum(c.gains[:, 1], 1e-12))
-    der = np.where(s.first[:, None], 0.0, (err - s.e_prev) / dt)
-    s.e_prev = err
-    s.first = np.zeros(n, dtype=bool)
-    pid = c.gains[:, 0] * err + c.gains[:, 1] * s.integral + c.gains[:, 2] * der          # [n,3], throttle units
+    pid = rate_pid(c, s, sp - s.omega, dt)                                                  # [n,3], throttle units
     # --- mixer in throttle units, per-motor saturation, bench curve -> per-motor thrust
     u = np.clip(s.throttle[:, None] + pid @ c.mix.T, c.u_min, c.u_max)                      # [n,4]
     f = motor_thrust_curve(c, u, lut)
