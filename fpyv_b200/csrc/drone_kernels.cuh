@@ -273,7 +273,6 @@ __device__ __forceinline__ typename Lane<V>::Mask drone_substeps(const DroneK& k
       // the extra objects first, the ground plane last; the first object any motor penetrates raises `done` and ends
       // the collision pass with the forces gathered so far (components.py:205-210).
       crashed = vlt(one, zero);
-      V cfx = zero, cfy = zero, cfz = zero;
       // (1) reach tests for ALL obstacles, branch-free (independent, so their latencies overlap): every motor lies
       //     within the arm length of the drone's centre, so an obstacle whose surface is further away than
       //     arm + motor_radius contributes exactly nothing and skipping it leaves the result bit-identical.
@@ -305,6 +304,7 @@ __device__ __forceinline__ typename Lane<V>::Mask drone_substeps(const DroneK& k
         // stalled on instruction fetch.  One copy: the loop over the motors is NOT unrolled and every motor position is
         // recomputed from the (warp-uniform) offset table.
         const V r00 = vfma(vneg(s.qy), s.qy, vfma(vneg(s.qz), s.qz, one)), r10 = vfma(s.qw, s.qz, xy);
+        V cfx = zero, cfy = zero, cfz = zero;
         while (near_mask) {
           const int o = __ffs(near_mask) - 1;
           near_mask &= near_mask - 1u;
@@ -340,6 +340,7 @@ __device__ __forceinline__ typename Lane<V>::Mask drone_substeps(const DroneK& k
           cfy = cfy + vsel(live, oy, zero);
           cfz = cfz + vsel(live, oz, zero);
         }
+        Fx = Fx + cfx; Fy = Fy + cfy; Fz = Fz + cfz;   // (only where something was in reach: the no-contact path adds nothing)
       }
       // (3) the ground plane, last in the list (distance = z, normal = +z, components.py:674-680), and the crash test
       //     on the motor heights that holds with or without it (:239)
@@ -373,11 +374,10 @@ __device__ __forceinline__ typename Lane<V>::Mask drone_substeps(const DroneK& k
             const V f = vneg(vfma(S<V>(k.spring_k), pen, S<V>(k.spring_c) * s.vz));
             oz = oz + vsel(vlt(pen, zero), f, zero);
           }
-          cfz = cfz + vsel(live, oz, zero);
+          Fz = Fz + vsel(live, oz, zero);
         }
         crashed = vor(crashed, below);  // components.py:239
       }
-      Fx = Fx + cfx; Fy = Fy + cfy; Fz = Fz + cfz;
     }
     done = vor(done, crashed);
     // ---- translation: x += v*dt with the OLD v, then v += (F/m)*dt, kinematics.py:21-22, components.py:243
