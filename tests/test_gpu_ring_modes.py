@@ -376,3 +376,51 @@ def test_two_stream_population_equals_one_batch(parts, n):
     assert torch.equal(pop.position, one.position)
     with pytest.raises(ValueError):
         TwoStreamDrones(None, num_envs=n, parts=3, **kw)
+
+
+@pytest.mark.parametrize("mode", ["hot", "hot_k1", "general", "acro", "racer"])
+def test_results_do_not_depend_on_the_neighbours(mode):
+    """Size-independent property of every dynamics mode: stepping a PERMUTED population gives the permuted results, bit for
+    bit.  A permutation changes which env shares a thread's packed registers with which (lanes t and t + 32 of a 64-env
+    chunk), which envs share a warp (the general path's warp-uniform decisions, the accurate-sin/cos fallbacks taken per
+    thread) and which chunk a warp pulls when -- none of it may leak into an env's arithmetic.  Ragged size, crashes and
+    restarts inside the run."""
+    from fpyv_b200 import BatchedAcroDrone, BatchedDrone, BatchedRacer, Cylinder, Ground, Target
+    n, steps = 300_007, 6
+    rng = np.random.default_rng(31)
+    perm = rng.permutation(n)
+    pt = torch.as_tensor(perm, device=DEV)
+    pos = np.stack([rng.normal(0, 6, n), rng.normal(0, 6, n), rng.uniform(0.05, 4.0, n)], 1)
+    vel, rpy = rng.normal(0, 2, (n, 3)), rng.uniform(-40, 40, (n, 3))
+    acts = [torch.as_tensor(rng.uniform(-1, 1, (n, 4)), dtype=torch.float32, device=DEV) for _ in range(steps)]
+    if mode in ("hot", "hot_k1", "general"):
+        kw = dict(num_envs=n, device=DEV, substeps=1 if mode == "hot_k1" else 8, dt=1e-3, auto_reset=True, thrust_lut=2049)
+        a, b = BatchedDrone(None, **kw), BatchedDrone(None, **kw)
+        a.reset(pos, vel, rpy)
+        b.reset(pos[perm], vel[perm], rpy[perm])
+        objs = [Target(np.array([0.0, 0.0, 3.0]), 1.0), Cylinder(np.array([4.0, -3.0, 0.0]), 1.0, 6.0), Ground()] if mode == "general" else None
+        for t in range(steps):
+            a.step(acts[t], None, objs, return_obs=False)
+            b.step(acts[t][pt].contiguous(), None, objs, return_obs=False)
+            assert torch.equal(a._done[pt], b._done), t
+        assert a.episode_stats()["crashes"] == b.episode_stats()["crashes"] > 0
+    elif mode == "acro":
+        kw = dict(num_envs=n, device=DEV, substeps=8, dt=1e-3, auto_reset=True, thrust_lut=2049)
+        a, b = BatchedAcroDrone(None, **kw), BatchedAcroDrone(None, **kw)
+        a.reset(pos, vel, rpy)
+        b.reset(pos[perm], vel[perm], rpy[perm])
+        for t in range(steps):
+            da, db = a.step(acts[t]), b.step(acts[t][pt].contiguous())
+            assert torch.equal(da[pt], db), t
+    else:
+        gains = {"roll": [2.0, 0.1, 0.01], "pitch": [2.0, 0.1, 0.01], "yaw": [0.1, 0.0, 0.0]}
+        a = BatchedRacer(5, gains, num_envs=n, device=DEV, substeps=8)
+        b = BatchedRacer(5, gains, num_envs=n, device=DEV, substeps=8)
+        a.reset()
+        b.reset()
+        for t in range(steps):
+            sp = acts[t] * torch.tensor([60.0, 60.0, 20.0, 4.0], device=DEV)      # rate set-points up to 60 rad/s: reduced sin/cos
+            a.step(sp)
+            b.step(sp[pt].contiguous())
+    sa, sb = a._state[:, :n], b._state[:, :n]
+    assert torch.equal(sa[:, pt].view(torch.int32), sb.view(torch.int32))
