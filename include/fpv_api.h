@@ -179,7 +179,12 @@ typedef struct fpv_drone_io {
                                per SM, so that CHAINED launches of INDEPENDENT batches stepped round-robin are resident
                                side by side (the idle tail and start-up of one launch are covered by the others' bulk);
                                do not combine with chaining consecutive steps of the SAME batch -- the trailing launch
-                               would hold its slots while it waits for the leading one chunk by chunk.            */
+                               would hold its slots while it waits for the leading one chunk by chunk.
+                               The same field serves the CLOSED-LOOP form: split the population into 4 / k independent
+                               parts, one CUDA stream each, plain (unchained) launches with max_ctas_per_sm = k --
+                               the parts' launches then run side by side without anything being known ahead of time
+                               (fpyv_b200.TwoStreamDrones; 37 us per 1,048,576-env K = 8 step on B200 against 44-48 us
+                               for one launch at a time).                                                          */
   void* trace;              /* developer profiling hook: device uint64[3 * warps] receiving per-warp
                                (start ns, end ns, SM id) of the hot kernel; NULL in production           */
 } fpv_drone_io_t;
